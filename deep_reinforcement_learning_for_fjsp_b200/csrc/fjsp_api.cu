@@ -1,0 +1,278 @@
+// CUDA kernels and the C ABI (include/fjsp_b200.h) of the B200 vector FJSP environment.
+// One warp owns one environment copy; a persistent grid (a multiple of the SM count)
+// walks the batch.  Build: nvcc -gencode arch=compute_100a,code=sm_100a (build.py).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/fjsp_b200.h"
+#include "fjsp_host.h"
+#include "fjsp_core.cuh"
+
+#define FJ_BLOCK 128
+#define FJ_WARPS_PER_BLOCK (FJ_BLOCK / 32)
+
+static thread_local std::string g_err;
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return -10;                                                                            \
+        }                                                                                          \
+    } while (0)
+
+template <int VARIANT, int SUM_MODE>
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_step_kernel(FjParams P, FjStepArgs A)
+{
+    const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
+    unsigned char *lp = P.lp + (size_t)gw * P.lp_stride;
+    for (int env = gw; env < P.B; env += total) fj_env_rollout<VARIANT, SUM_MODE>(P, A, env, lp);
+}
+
+template <int VARIANT, int SUM_MODE>
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_kernel(FjParams P, double *state64, float *state32)
+{
+    const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
+    unsigned char *lp = P.lp + (size_t)gw * P.lp_stride;
+    for (int env = gw; env < P.B; env += total) fj_env_reset<VARIANT, SUM_MODE>(P, env, lp, state64, state32);
+}
+
+struct fjsp_vec {
+    FjTables tb;
+    FjParams P;
+    int variant, sum_mode, B, device, grid, nstate;
+    int32_t *d_inst, *d_env_inst;
+    unsigned char *d_env, *d_lp;
+    long long launches;
+    // staging for the host-buffer entry points
+    cudaStream_t stream;
+    int stage_T;
+    int32_t *d_actions, *d_done, *d_rec;
+    uint32_t *d_rnd;
+    double *d_state64, *d_reward;
+    float *d_state32;
+};
+
+template <typename F> static int dispatch(fjsp_vec *v, F f)
+{
+    switch (v->variant * 2 + (v->sum_mode ? 1 : 0)) {
+    case 0: return f(std::integral_constant<int, FJSP_SO_DFJSP>(), std::integral_constant<int, 0>());
+    case 1: return f(std::integral_constant<int, FJSP_SO_DFJSP>(), std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, FJSP_MO_DFJSP>(), std::integral_constant<int, 0>());
+    case 3: return f(std::integral_constant<int, FJSP_MO_DFJSP>(), std::integral_constant<int, 1>());
+    case 4: return f(std::integral_constant<int, FJSP_MO_BREAKDOWN>(), std::integral_constant<int, 0>());
+    case 5: return f(std::integral_constant<int, FJSP_MO_BREAKDOWN>(), std::integral_constant<int, 1>());
+    }
+    g_err = "unsupported variant";
+    return -2;
+}
+
+extern "C" {
+
+const char *fjsp_last_error(void) { return g_err.c_str(); }
+int fjsp_abi_version(void) { return 1; }
+
+int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_instances,
+                    const int32_t *env_instance, int n_envs, int variant, int sum_mode, int device,
+                    fjsp_vec **out)
+{
+    if (!blobs || !blob_offsets || !env_instance || !out || n_instances < 1 || n_envs < 1) {
+        g_err = "fjsp_vec_create: null or empty argument"; return -1;
+    }
+    if (variant < 0 || variant > 2) {
+        g_err = "fjsp_vec_create: variant must be 0 (SO_DFJSP), 1 (MO_DFJSP) or 2 (MO_DFJSP_breakdown)"; return -2;
+    }
+    for (int e = 0; e < n_envs; ++e)
+        if (env_instance[e] < 0 || env_instance[e] >= n_instances) { g_err = "fjsp_vec_create: env_instance out of range"; return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_err = "fjsp_vec_create: no CUDA device (this library has no CPU path)"; return -3;
+    }
+    CK(cudaSetDevice(device));
+    fjsp_vec *v = new fjsp_vec();
+    if (!fj_build_tables(blobs, blob_offsets, n_instances, v->tb, g_err)) { delete v; return -1; }
+    v->variant = variant; v->sum_mode = sum_mode ? 1 : 0; v->B = n_envs; v->device = device; v->launches = 0;
+    v->nstate = variant == FJSP_SO_DFJSP ? 20 : 30;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    // persistent grid: a multiple of the SM count, 8 CTAs (32 warps) per SM at most
+    int want = (n_envs + FJ_WARPS_PER_BLOCK - 1) / FJ_WARPS_PER_BLOCK;
+    int cap = prop.multiProcessorCount * 8;
+    v->grid = want < cap ? want : cap;
+    const unsigned long long lp_stride = fj_lp_scratch_bytes(v->tb.d);
+    const size_t lp_bytes = (size_t)lp_stride * v->grid * FJ_WARPS_PER_BLOCK;
+    const size_t env_bytes = (size_t)n_envs * v->tb.eo.stride;
+    CK(cudaMalloc(&v->d_inst, v->tb.inst.size() * 4));
+    CK(cudaMalloc(&v->d_env_inst, (size_t)n_envs * 4));
+    CK(cudaMalloc(&v->d_env, env_bytes));
+    CK(cudaMalloc(&v->d_lp, lp_bytes));
+    CK(cudaMemcpy(v->d_inst, v->tb.inst.data(), v->tb.inst.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(v->d_env_inst, env_instance, (size_t)n_envs * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(v->d_env, 0, env_bytes));
+    CK(cudaMemset(v->d_lp, 0, lp_bytes));
+    FjParams &P = v->P;
+    P.d = v->tb.d; P.io = v->tb.io; P.eo = v->tb.eo;
+    P.inst = v->d_inst; P.env_inst = v->d_env_inst; P.env = v->d_env; P.lp = v->d_lp; P.lp_stride = lp_stride;
+    P.B = n_envs; P.variant = variant; P.sum_mode = v->sum_mode; P.nobs = v->nstate / 2;
+    CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+    v->stage_T = 0;
+    v->d_actions = v->d_done = v->d_rec = nullptr; v->d_rnd = nullptr;
+    v->d_state64 = v->d_reward = nullptr; v->d_state32 = nullptr;
+    *out = v;
+    return 0;
+}
+
+static void free_stage(fjsp_vec *v)
+{
+    cudaFree(v->d_actions); cudaFree(v->d_rnd); cudaFree(v->d_done); cudaFree(v->d_rec);
+    cudaFree(v->d_state64); cudaFree(v->d_state32); cudaFree(v->d_reward);
+    v->d_actions = v->d_done = v->d_rec = nullptr; v->d_rnd = nullptr;
+    v->d_state64 = v->d_reward = nullptr; v->d_state32 = nullptr;
+    v->stage_T = 0;
+}
+
+int fjsp_vec_destroy(fjsp_vec *v)
+{
+    if (!v) return 0;
+    cudaSetDevice(v->device);
+    free_stage(v);
+    cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
+    cudaStreamDestroy(v->stream);
+    delete v;
+    return 0;
+}
+
+int fjsp_vec_query(fjsp_vec *v, int64_t *o)
+{
+    if (!v || !o) { g_err = "fjsp_vec_query: null argument"; return -1; }
+    o[0] = v->B; o[1] = v->nstate; o[2] = v->tb.eo.stride; o[3] = (int64_t)v->tb.io.stride * 4;
+    o[4] = v->grid; o[5] = FJ_BLOCK; o[6] = (int64_t)v->P.lp_stride; o[7] = v->launches;
+    return 0;
+}
+
+int fjsp_vec_reset(fjsp_vec *v, void *stream, double *d_state64, float *d_state32)
+{
+    if (!v) { g_err = "fjsp_vec_reset: null handle"; return -1; }
+    CK(cudaSetDevice(v->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dispatch(v, [&](auto V, auto SM) {
+        fjsp_reset_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, 0, st>>>(v->P, d_state64, d_state32);
+        return 0;
+    });
+    if (rc) return rc;
+    v->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, const uint32_t *d_rnd,
+                  int reward_policy, double completion, double tardiness, double energy, int autoreset,
+                  double *d_state64, float *d_state32, double *d_reward, int32_t *d_done, int32_t *d_rec)
+{
+    if (!v || !d_actions || T < 1) { g_err = "fjsp_vec_step: null handle/actions or T < 1"; return -1; }
+    if (v->variant != FJSP_SO_DFJSP && (reward_policy < 0 || reward_policy > 3)) {
+        g_err = "fjsp_vec_step: reward_policy must be 0..3 (the reference raises MyError otherwise)"; return -4;
+    }
+    CK(cudaSetDevice(v->device));
+    FjStepArgs A;
+    A.T = T; A.actions = d_actions; A.rnd = d_rnd; A.reward_policy = reward_policy; A.autoreset = autoreset;
+    A.completion = completion; A.tardiness = tardiness; A.energy = energy;
+    A.state = d_state64; A.state32 = d_state32; A.reward = d_reward; A.done = d_done; A.rec = d_rec;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dispatch(v, [&](auto V, auto SM) {
+        fjsp_step_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, 0, st>>>(v->P, A);
+        return 0;
+    });
+    if (rc) return rc;
+    v->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int ensure_stage(fjsp_vec *v, int T)
+{
+    if (T <= v->stage_T) return 0;
+    free_stage(v);
+    const size_t n = (size_t)T * v->B;
+    CK(cudaMalloc(&v->d_actions, n * 2 * 4));
+    CK(cudaMalloc(&v->d_rnd, n * 2 * 4));
+    CK(cudaMalloc(&v->d_done, n * 4));
+    CK(cudaMalloc(&v->d_rec, n * 8 * 4));
+    CK(cudaMalloc(&v->d_state64, n * v->nstate * 8));
+    CK(cudaMalloc(&v->d_state32, n * v->nstate * 4));
+    CK(cudaMalloc(&v->d_reward, n * 8));
+    v->stage_T = T;
+    return 0;
+}
+
+int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint32_t *h_rnd,
+                       int reward_policy, double completion, double tardiness, double energy, int autoreset,
+                       double *h_state64, float *h_state32, double *h_reward, int32_t *h_done, int32_t *h_rec)
+{
+    if (!v || !h_actions || T < 1) { g_err = "fjsp_vec_step_host: null handle/actions or T < 1"; return -1; }
+    CK(cudaSetDevice(v->device));
+    int rc = ensure_stage(v, T);
+    if (rc) return rc;
+    const size_t n = (size_t)T * v->B;
+    cudaStream_t st = v->stream;
+    CK(cudaMemcpyAsync(v->d_actions, h_actions, n * 2 * 4, cudaMemcpyHostToDevice, st));
+    if (h_rnd) CK(cudaMemcpyAsync(v->d_rnd, h_rnd, n * 2 * 4, cudaMemcpyHostToDevice, st));
+    rc = fjsp_vec_step(v, st, T, v->d_actions, h_rnd ? v->d_rnd : nullptr, reward_policy, completion, tardiness,
+                       energy, autoreset, h_state64 ? v->d_state64 : nullptr, h_state32 ? v->d_state32 : nullptr,
+                       h_reward ? v->d_reward : nullptr, h_done ? v->d_done : nullptr, h_rec ? v->d_rec : nullptr);
+    if (rc) return rc;
+    if (h_state64) CK(cudaMemcpyAsync(h_state64, v->d_state64, n * v->nstate * 8, cudaMemcpyDeviceToHost, st));
+    if (h_state32) CK(cudaMemcpyAsync(h_state32, v->d_state32, n * v->nstate * 4, cudaMemcpyDeviceToHost, st));
+    if (h_reward) CK(cudaMemcpyAsync(h_reward, v->d_reward, n * 8, cudaMemcpyDeviceToHost, st));
+    if (h_done) CK(cudaMemcpyAsync(h_done, v->d_done, n * 4, cudaMemcpyDeviceToHost, st));
+    if (h_rec) CK(cudaMemcpyAsync(h_rec, v->d_rec, n * 8 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int fjsp_vec_reset_host(fjsp_vec *v, double *h_state64, float *h_state32)
+{
+    if (!v) { g_err = "fjsp_vec_reset_host: null handle"; return -1; }
+    CK(cudaSetDevice(v->device));
+    int rc = ensure_stage(v, 1);
+    if (rc) return rc;
+    cudaStream_t st = v->stream;
+    rc = fjsp_vec_reset(v, st, h_state64 ? v->d_state64 : nullptr, h_state32 ? v->d_state32 : nullptr);
+    if (rc) return rc;
+    const size_t n = (size_t)v->B * v->nstate;
+    if (h_state64) CK(cudaMemcpyAsync(h_state64, v->d_state64, n * 8, cudaMemcpyDeviceToHost, st));
+    if (h_state32) CK(cudaMemcpyAsync(h_state32, v->d_state32, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+__global__ void fjsp_info_kernel(FjParams P, long long *out)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.B) return;
+    const int32_t *s = (const int32_t *)(P.env + (size_t)e * P.eo.stride + P.eo.scal);
+    long long *o = out + (size_t)e * 12;
+    const long long dp = *(const long long *)(s + FJ_S_DELAY_PROC), du = *(const long long *)(s + FJ_S_DELAY_UNPROC);
+    o[0] = s[FJ_S_TIME]; o[1] = s[FJ_S_STEPS]; o[2] = s[FJ_S_COMPLETION]; o[3] = dp + du;
+    o[4] = *(const long long *)(s + FJ_S_ENERGY); o[5] = s[FJ_S_LPSOLVES]; o[6] = s[FJ_S_LPITERS];
+    o[7] = s[FJ_S_ERROR]; o[8] = s[FJ_S_DONE]; o[9] = s[FJ_S_NEXTORDER]; o[10] = s[FJ_S_EPISODES]; o[11] = du;
+}
+
+int fjsp_vec_info(fjsp_vec *v, int64_t *h_out)
+{
+    if (!v || !h_out) { g_err = "fjsp_vec_info: null argument"; return -1; }
+    CK(cudaSetDevice(v->device));
+    CK(cudaDeviceSynchronize());   // steps may have been queued on a caller's stream
+    long long *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)v->B * 12 * 8));
+    fjsp_info_kernel<<<(v->B + 255) / 256, 256, 0, v->stream>>>(v->P, d);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_out, d, (size_t)v->B * 12 * 8, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+    CK(cudaFree(d));
+    return 0;
+}
+}

@@ -1,0 +1,1043 @@
+// One warp = one FJSP environment.  This file is the whole per-environment algorithm:
+// dispatching-rule selection, dispatch, discrete-event clock, order arrival with the
+// fluid LP, state features, reward, auto-reset.  It is written against a tiny warp
+// abstraction (fj_lane / fj_sync / fj_bcast / reductions) so that the SAME source
+//   * compiles with nvcc for sm_100a with 32 cooperating lanes (the product), and
+//   * compiles with g++ as a 1-lane program (tests/hostsim) so the CPU test-suite can
+//     check the compressed state machine against the oracle without a GPU.
+//
+// Reference behaviour being reproduced (see DESIGN.md for the mapping):
+//   environments/SO_DFJSP.py, MO_DFJSP.py, MO_DFJSP_breakdown.py (step / state_extract /
+//   update_parameter / task_select / machine_select / compute_reward) on
+//   environments/class_FJSP.py, class_MODFJSP.py (reset_parameter, reset_object_add,
+//   fluid_model, update_fluid_parameter).
+//
+// Exactness rules: every float that feeds a dispatching decision (urgency, estimated
+// delay, gap, machine gap_ave, fluid rates) is computed with the reference's operation
+// order, CPython's compensated sum() included, using explicitly rounded add/mul (no FMA
+// contraction).  Floats that only feed the observation vector use warp tree sums.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include "fjsp_layout.h"
+
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
+#define FJ_DEVICE_CODE 1
+#endif
+
+#ifdef __CUDACC__
+#define FJ_FN __device__ __forceinline__
+#define FJ_FN_NOINLINE __device__ __noinline__
+#define FJ_NL 32
+FJ_FN int fj_lane() { return threadIdx.x & 31; }
+FJ_FN void fj_sync() { __syncwarp(); }
+FJ_FN int fj_bcast_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+FJ_FN double fj_bcast_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+FJ_FN long long fj_bcast_ll(long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+FJ_FN int fj_any(int p) { return __any_sync(0xffffffffu, p); }
+FJ_FN int fj_xor_i(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+FJ_FN double fj_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+FJ_FN long long fj_xor_ll(long long v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+// explicitly rounded double arithmetic: never contracted into FMA
+FJ_FN double fj_add(double a, double b) { return __dadd_rn(a, b); }
+FJ_FN double fj_sub(double a, double b) { return __dsub_rn(a, b); }
+FJ_FN double fj_mul(double a, double b) { return __dmul_rn(a, b); }
+FJ_FN double fj_div(double a, double b) { return __ddiv_rn(a, b); }
+#else
+#define FJ_FN static inline
+#define FJ_FN_NOINLINE static
+#define FJ_NL 1
+FJ_FN int fj_lane() { return 0; }
+FJ_FN void fj_sync() {}
+FJ_FN int fj_bcast_i(int v, int) { return v; }
+FJ_FN double fj_bcast_d(double v, int) { return v; }
+FJ_FN long long fj_bcast_ll(long long v, int) { return v; }
+FJ_FN int fj_any(int p) { return p != 0; }
+FJ_FN int fj_xor_i(int v, int) { return v; }
+FJ_FN double fj_xor_d(double v, int) { return v; }
+FJ_FN long long fj_xor_ll(long long v, int) { return v; }
+// the host simulation is built with -ffp-contract=off
+FJ_FN double fj_add(double a, double b) { return a + b; }
+FJ_FN double fj_sub(double a, double b) { return a - b; }
+FJ_FN double fj_mul(double a, double b) { return a * b; }
+FJ_FN double fj_div(double a, double b) { return a / b; }
+#endif
+
+// ---------------------------------------------------------------- warp reductions
+FJ_FN long long fj_sum_ll(long long v)
+{
+    for (int m = FJ_NL / 2; m > 0; m >>= 1) v += fj_xor_ll(v, m);
+    return v;
+}
+FJ_FN int fj_sum_i(int v)
+{
+    for (int m = FJ_NL / 2; m > 0; m >>= 1) v += fj_xor_i(v, m);
+    return v;
+}
+FJ_FN int fj_min_i(int v)
+{
+    for (int m = FJ_NL / 2; m > 0; m >>= 1) { int o = fj_xor_i(v, m); v = o < v ? o : v; }
+    return v;
+}
+FJ_FN unsigned fj_or_u(unsigned v)
+{
+    for (int m = FJ_NL / 2; m > 0; m >>= 1) v |= (unsigned)fj_xor_i((int)v, m);
+    return v;
+}
+FJ_FN double fj_sum_d(double v)   // observation-only sums (fixed butterfly order)
+{
+    for (int m = FJ_NL / 2; m > 0; m >>= 1) v = fj_add(v, fj_xor_d(v, m));
+    return v;
+}
+
+// running "first extremal element" of Python's max()/min() over a list in index order
+struct FjBest {
+    double key; int idx;
+};
+FJ_FN void fj_best_init(FjBest &b) { b.key = 0.0; b.idx = 0x7fffffff; }
+// local update; candidates arrive in ascending idx on a lane, so strict comparison keeps the first
+FJ_FN void fj_best_max(FjBest &b, double key, int idx) { if (b.idx == 0x7fffffff || key > b.key) { b.key = key; b.idx = idx; } }
+FJ_FN void fj_best_min(FjBest &b, double key, int idx) { if (b.idx == 0x7fffffff || key < b.key) { b.key = key; b.idx = idx; } }
+FJ_FN void fj_best_reduce(FjBest &b, int want_max)
+{
+    for (int m = FJ_NL / 2; m > 0; m >>= 1) {
+        double ok = fj_xor_d(b.key, m);
+        int oi = fj_xor_i(b.idx, m);
+        if (oi == 0x7fffffff) continue;
+        bool better = (b.idx == 0x7fffffff) || (want_max ? ok > b.key : ok < b.key) || (ok == b.key && oi < b.idx);
+        if (better) { b.key = ok; b.idx = oi; }
+    }
+}
+
+// ---------------------------------------------------------------- CPython sum()
+struct FjPySum { double f, c; };
+FJ_FN void fj_pysum_init(FjPySum &s) { s.f = 0.0; s.c = 0.0; }
+template <int MODE> FJ_FN void fj_pysum_add(FjPySum &s, double x)
+{
+    if (MODE == 0) { s.f = fj_add(s.f, x); return; }
+    double t = fj_add(s.f, x);
+    if (fabs(s.f) >= fabs(x)) s.c = fj_add(s.c, fj_add(fj_sub(s.f, t), x));
+    else s.c = fj_add(s.c, fj_add(fj_sub(x, t), s.f));
+    s.f = t;
+}
+template <int MODE> FJ_FN double fj_pysum_result(const FjPySum &s)
+{
+    if (MODE != 0 && s.c != 0.0 && isfinite(s.c)) return fj_add(s.f, s.c);
+    return s.f;
+}
+
+// ---------------------------------------------------------------- per-env context
+struct FjCtx {
+    const FjParams *P;
+    const int32_t *I;
+    int M, K, KT, S, Mx, Kx, Sx;
+    unsigned mmask;
+    int32_t *scal; double *obs, *obs2, *gapave; int32_t *choice; uint32_t *avmask, *favmask;
+    int32_t *mend, *mlast, *mjob; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
+    double *rsum, *tsum; uint16_t *cntunp, *cntnow, *pk, *slot; double *fu, *fa, *ff; uint16_t *next;
+    unsigned char *lp;
+};
+
+FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp)
+{
+    c.P = &P;
+    c.I = P.inst + (size_t)P.env_inst[env] * P.io.stride;
+    const int32_t *h = c.I + P.io.hdr;
+    c.M = h[0]; c.K = h[1]; c.KT = h[2]; c.S = h[3];
+    c.Mx = P.d.Mx; c.Kx = P.d.Kx; c.Sx = P.d.Sx;
+    c.mmask = c.M >= 32 ? 0xffffffffu : ((1u << c.M) - 1u);
+    unsigned char *E = P.env + (size_t)env * P.eo.stride;
+    const FjEnvOff &o = P.eo;
+    c.scal = (int32_t *)(E + o.scal); c.obs = (double *)(E + o.obs); c.obs2 = (double *)(E + o.obs2);
+    c.gapave = (double *)(E + o.gapave); c.choice = (int32_t *)(E + o.choice);
+    c.avmask = (uint32_t *)(E + o.avmask); c.favmask = (uint32_t *)(E + o.favmask);
+    c.mend = (int32_t *)(E + o.mend); c.mlast = (int32_t *)(E + o.mlast); c.mjob = (int32_t *)(E + o.mjob);
+    c.qhead = (uint16_t *)(E + o.qhead); c.qtail = (uint16_t *)(E + o.qtail); c.qlen = (uint16_t *)(E + o.qlen);
+    c.proc = (int32_t *)(E + o.proc); c.fstart = (int32_t *)(E + o.fstart); c.flmask = (uint32_t *)(E + o.flmask);
+    c.rsum = (double *)(E + o.rsum); c.tsum = (double *)(E + o.tsum);
+    c.cntunp = (uint16_t *)(E + o.cntunp); c.cntnow = (uint16_t *)(E + o.cntnow);
+    c.pk = (uint16_t *)(E + o.pk); c.slot = (uint16_t *)(E + o.slot);
+    c.fu = (double *)(E + o.fu); c.fa = (double *)(E + o.fa); c.ff = (double *)(E + o.ff);
+    c.next = (uint16_t *)(E + o.next);
+    c.lp = lp;
+}
+
+#define FJ_I(c, field) ((c).I + (c).P->io.field)
+FJ_FN long long fj_get_ll(const int32_t *scal, int i) { return *(const long long *)(scal + i); }
+FJ_FN void fj_set_ll(int32_t *scal, int i, long long v) { *(long long *)(scal + i) = v; }
+FJ_FN double fj_get_d(const int32_t *scal, int i) { return *(const double *)(scal + i); }
+FJ_FN void fj_set_d(int32_t *scal, int i, double v) { *(double *)(scal + i) = v; }
+FJ_FN int fj_is_mo(int variant) { return variant == FJSP_MO_DFJSP || variant == FJSP_MO_BREAKDOWN; }
+FJ_FN int fj_popc(unsigned v)
+{
+#ifdef FJ_DEVICE_CODE
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+FJ_FN int fj_ffs0(unsigned v)   // index of lowest set bit, v != 0
+{
+#ifdef FJ_DEVICE_CODE
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+FJ_FN int fj_order_of(const FjCtx &c, int r, int n)   // which order job n of kind r came with
+{
+    const int32_t *cum = FJ_I(c, cum);
+    int s = 0;
+    while (s + 1 < c.S && n >= cum[(s + 1) * c.Kx + r]) ++s;
+    return s;
+}
+
+// ---------------------------------------------------------------- fluid LP
+// Same pivoting specification as oracle/fjsp_lp.c (DESIGN.md "fluid LP specification"),
+// executed cooperatively by the warp on a scratch slab in global memory.
+#define FJ_LP_EPS_D 1e-9
+#define FJ_LP_EPS_PIV 1e-9
+#define FJ_LP_EPS_ZERO 1e-9
+
+struct FjLp {
+    double *Binv, *xB, *w, *adem, *rate;
+    int *basis, *pos, *colq, *colm, *prec, *colbase;
+    int R, C, NP;
+};
+
+FJ_FN void fj_lp_carve(FjLp &L, unsigned char *slab, const FjDims &d)
+{
+    size_t R = d.Rx, C = d.NPx + 1;
+    double *p = (double *)slab;
+    L.Binv = p; p += R * R;
+    L.xB = p; p += R;
+    L.w = p; p += R;
+    L.adem = p; p += C;
+    L.rate = p; p += C;
+    int *q = (int *)p;
+    L.basis = q; q += R;
+    L.pos = q; q += C + R;
+    L.colq = q; q += C;
+    L.colm = q; q += C;
+    L.prec = q; q += d.KTx;
+    L.colbase = q; q += d.KTx;
+}
+
+// reduced cost of column j given the row `pt` of Binv where t is basic (y = -Binv[pt])
+FJ_FN double fj_lp_colvec_dot(const FjCtx &c, const FjLp &L, const double *brow, int j, int negate)
+{
+    // returns sum_k (negate ? -brow[row_k] : brow[row_k]) * val_k in CSC (ascending row) order
+    int M = c.M, KT = c.KT;
+    double acc = 0.0;
+    if (j == L.NP) {   // the t column: +1 in every demand row
+        for (int q = 0; q < KT; ++q) { double b = brow[M + q]; acc = fj_add(acc, fj_mul(negate ? -b : b, 1.0)); }
+        return acc;
+    }
+    int q = L.colq[j], m = L.colm[j];
+    double b0 = brow[m];
+    acc = fj_add(acc, fj_mul(negate ? -b0 : b0, 1.0));
+    double b1 = brow[M + q];
+    acc = fj_add(acc, fj_mul(negate ? -b1 : b1, L.adem[j]));
+    int stage = FJ_I(c, rjstage)[q];
+    if (stage > 0 && L.prec[q - 1] >= 0) { double b = brow[L.prec[q - 1]]; acc = fj_add(acc, fj_mul(negate ? -b : b, L.rate[j])); }
+    if (L.prec[q] >= 0) { double b = brow[L.prec[q]]; acc = fj_add(acc, fj_mul(negate ? -b : b, -L.rate[j])); }
+    return acc;
+}
+
+FJ_FN_NOINLINE int fj_lp_solve(FjCtx &c, FjLp &L, int *iters_out)
+{
+    const int lane = fj_lane();
+    const int M = c.M, KT = c.KT, Mx = c.Mx;
+    const int32_t *elig = FJ_I(c, elig), *ptime = FJ_I(c, ptime), *rjstage = FJ_I(c, rjstage), *rjlast = FJ_I(c, rjlast);
+    // column bases and precedence rows (sequential prefix work: one lane)
+    if (lane == 0) {
+        int np = 0, nprec = 0;
+        for (int q = 0; q < KT; ++q) {
+            L.colbase[q] = np; np += fj_popc((unsigned)elig[q]);
+            L.prec[q] = -1;
+            if (!rjlast[q] && c.qlen[q + 1] == 0) L.prec[q] = M + KT + nprec++;
+        }
+        L.pos[0] = np; L.pos[1] = nprec;   // hand-off to the other lanes
+    }
+    fj_sync();
+    const int NP = L.pos[0], R = M + KT + L.pos[1], C = NP + 1;
+    fj_sync();
+    L.NP = NP; L.R = R; L.C = C;
+    for (int q = lane; q < KT; q += FJ_NL) {
+        unsigned em = (unsigned)elig[q];
+        int col = L.colbase[q];
+        double fs = (double)c.fstart[q];
+        while (em) {
+            int m = fj_ffs0(em); em &= em - 1;
+            double rate = fj_div(1.0, (double)ptime[q * Mx + m]);
+            L.colq[col] = q; L.colm[col] = m;
+            L.rate[col] = rate;
+            L.adem[col] = -fj_div(rate, fs);
+            ++col;
+        }
+    }
+    for (int j = lane; j < C + R; j += FJ_NL) L.pos[j] = j >= C ? j - C : -1;
+    for (int i = lane; i < R; i += FJ_NL) { L.basis[i] = C + i; L.xB[i] = i < M ? 1.0 : 0.0; }
+    for (int i = 0; i < R; ++i)
+        for (int k = lane; k < R; k += FJ_NL) L.Binv[(size_t)i * R + k] = (i == k) ? 1.0 : 0.0;
+    fj_sync();
+    const int dantzig_iters = 20 * R + 100, hard_iters = 200 * R + 1000;
+    const int nvar = C + R, t_col = NP;
+    int it = 0, rc = 0;
+    (void)rjstage;
+    for (;; ++it) {
+        if (it >= hard_iters) { rc = 2; break; }
+        const int pt = L.pos[t_col];
+        const double *yrow = L.Binv + (size_t)(pt >= 0 ? pt : 0) * R;
+        const int bland = it >= dantzig_iters;
+        // pricing: most negative reduced cost (lowest column on ties) / Bland: lowest column
+        FjBest e; fj_best_init(e);
+        for (int j = lane; j < nvar; j += FJ_NL) {
+            if (L.pos[j] >= 0) continue;
+            double d;
+            if (j < C) {
+                double acc = pt >= 0 ? fj_lp_colvec_dot(c, L, yrow, j, 1) : 0.0;
+                d = fj_sub((j == t_col) ? -1.0 : 0.0, acc);
+            } else {
+                d = pt >= 0 ? -(-yrow[j - C]) : -0.0;
+            }
+            if (d < -FJ_LP_EPS_D) {
+                if (bland) { if (e.idx == 0x7fffffff) { e.key = d; e.idx = j; } }
+                else fj_best_min(e, d, j);
+            }
+        }
+        if (bland) { int q0 = fj_min_i(e.idx); e.idx = q0; } else fj_best_reduce(e, 0);
+        const int qin = e.idx;
+        if (qin == 0x7fffffff) break;   // optimal
+        // w = Binv * A_q
+        for (int i = lane; i < R; i += FJ_NL) {
+            const double *brow = L.Binv + (size_t)i * R;
+            L.w[i] = qin < C ? fj_lp_colvec_dot(c, L, brow, qin, 0) : brow[qin - C];
+        }
+        fj_sync();
+        // ratio test: min max(xB,0)/w over w > eps, ties -> lowest basic variable
+        FjBest rb; fj_best_init(rb);
+        int rrow = -1;
+        for (int i = lane; i < R; i += FJ_NL) {
+            double wi = L.w[i];
+            if (wi > FJ_LP_EPS_PIV) {
+                double xb = L.xB[i] > 0.0 ? L.xB[i] : 0.0;
+                double r = fj_div(xb, wi);
+                int bi = L.basis[i];
+                if (rb.idx == 0x7fffffff || r < rb.key || (r == rb.key && bi < rb.idx)) { rb.key = r; rb.idx = bi; rrow = i; }
+            }
+        }
+        for (int m = FJ_NL / 2; m > 0; m >>= 1) {
+            double ok = fj_xor_d(rb.key, m); int oi = fj_xor_i(rb.idx, m); int orow = fj_xor_i(rrow, m);
+            if (oi == 0x7fffffff) continue;
+            if (rb.idx == 0x7fffffff || ok < rb.key || (ok == rb.key && oi < rb.idx)) { rb.key = ok; rb.idx = oi; rrow = orow; }
+        }
+        if (rb.idx == 0x7fffffff) { rc = 3; break; }
+        const int p = rrow;
+        const double theta = rb.key, wp = L.w[p];
+        for (int i = lane; i < R; i += FJ_NL)
+            L.xB[i] = (i == p) ? theta : fj_sub(L.xB[i], fj_mul(theta, L.w[i]));
+        double *rowp = L.Binv + (size_t)p * R;
+        for (int k = lane; k < R; k += FJ_NL) rowp[k] = fj_div(rowp[k], wp);
+        fj_sync();
+        for (int i = 0; i < R; ++i) {
+            if (i == p) continue;
+            const double wi = L.w[i];
+            if (wi == 0.0) continue;
+            double *rowi = L.Binv + (size_t)i * R;
+            for (int k = lane; k < R; k += FJ_NL) rowi[k] = fj_sub(rowi[k], fj_mul(wi, rowp[k]));
+        }
+        if (lane == 0) {
+            L.pos[L.basis[p]] = -1;
+            L.basis[p] = qin;
+            L.pos[qin] = p;
+        }
+        fj_sync();
+    }
+    if (iters_out) *iters_out = it;
+    return rc;
+}
+
+// class_FJSP.py:218-254 reset_object_add + 292-316 update_fluid_parameter
+template <int SUM_MODE>
+FJ_FN_NOINLINE void fj_order_arrives(FjCtx &c, int s)
+{
+    const int lane = fj_lane();
+    const int KT = c.KT, Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
+    const int32_t *rjkind = FJ_I(c, rjkind), *rjstage = FJ_I(c, rjstage), *count = FJ_I(c, count);
+    const int32_t *elig = FJ_I(c, elig), *ptime = FJ_I(c, ptime), *poord = FJ_I(c, poord), *nelig = FJ_I(c, nelig);
+    for (int q = lane; q < KT; q += FJ_NL) {
+        int cnt = count[s * Kx + rjkind[q]];
+        c.cntunp[q * Sx + s] = (uint16_t)cnt;
+        if (rjstage[q] == 0) {
+            c.cntnow[q * Sx + s] = (uint16_t)cnt;
+            int ql = c.qlen[q] + cnt;
+            if (ql > 65000) c.scal[FJ_S_ERROR] |= FJ_E_OVERFLOW;
+            c.qlen[q] = (uint16_t)ql;
+        }
+        int fs = 0;
+        for (int k = 0; k < c.S; ++k) fs += c.cntunp[q * Sx + k];
+        c.fstart[q] = fs;
+        c.flmask[q] = 0;
+    }
+    for (int i = lane; i < KT * Mx; i += FJ_NL) { c.pk[i] = 0; c.slot[i] = 0xFFFF; }
+    fj_sync();
+    FjLp L;
+    fj_lp_carve(L, c.lp, c.P->d);
+    int iters = 0;
+    int rc = fj_lp_solve(c, L, &iters);
+    if (lane == 0) {
+        c.scal[FJ_S_LPSOLVES] += 1; c.scal[FJ_S_LPITERS] += iters;
+        if (rc) c.scal[FJ_S_ERROR] |= FJ_E_LP;
+    }
+    // x and fluid rate per column (reuse adem/rate slabs: xs -> adem, fr -> rate)
+    for (int j = lane; j < L.NP; j += FJ_NL) {
+        double x = L.pos[j] >= 0 ? L.xB[L.pos[j]] : 0.0;
+        if (x < FJ_LP_EPS_ZERO) x = 0.0;
+        double fr = fj_mul(x, L.rate[j]);
+        L.adem[j] = x; L.rate[j] = fr;
+    }
+    fj_sync();
+    for (int q = lane; q < KT; q += FJ_NL) {
+        unsigned em = (unsigned)elig[q], fm = 0;
+        FjPySum ps; fj_pysum_init(ps);
+        for (int k = 0; k < nelig[q]; ++k) {
+            int m = poord[q * Mx + k];
+            int col = L.colbase[q] + fj_popc(em & ((1u << m) - 1u));
+            fj_pysum_add<SUM_MODE>(ps, L.rate[col]);
+            if (L.adem[col] != 0.0) fm |= 1u << m;
+        }
+        double rs = fj_pysum_result<SUM_MODE>(ps);
+        c.rsum[q] = rs;
+        c.tsum[q] = fj_div(1.0, rs);
+        c.flmask[q] = fm;
+        (void)ptime;
+    }
+    fj_sync();
+    if (lane == 0) {
+        int nfl = 0;
+        for (int j = 0; j < L.NP; ++j) {
+            if (L.adem[j] == 0.0) continue;
+            int q = L.colq[j], m = L.colm[j];
+            if (nfl >= c.P->d.NFx) { c.scal[FJ_S_ERROR] |= FJ_E_OVERFLOW; break; }
+            double arr = fj_div(fj_mul((double)c.fstart[q], L.rate[j]), c.rsum[q]);
+            c.slot[q * Mx + m] = (uint16_t)nfl;
+            c.ff[nfl] = L.rate[j]; c.fa[nfl] = arr; c.fu[nfl] = arr;
+            ++nfl;
+        }
+        c.scal[FJ_S_NFL] = nfl;
+    }
+    fj_sync();
+}
+
+// ---------------------------------------------------------------- observation + rule cache
+// state_extract + update_parameter (SO_DFJSP.py:81-169 / MO_DFJSP.py:91-187), plus the
+// operation-type choice every deterministic task rule would make in THIS state (the next
+// step() only looks the answer up).  Writes v(t) to c.obs2.
+template <int VARIANT, int SUM_MODE>
+FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
+{
+    const int lane = fj_lane();
+    const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
+    const int M = c.M, KT = c.KT, S = c.S, Mx = c.Mx, Sx = c.Sx;
+    const int32_t *elig = FJ_I(c, elig), *due = FJ_I(c, due), *rjlast = FJ_I(c, rjlast);
+    const int32_t *ptime = FJ_I(c, ptime), *energy = FJ_I(c, energy);
+    const int t = c.scal[FJ_S_TIME];
+    const double td = (double)t;
+    const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
+    const double gt = fj_get_d(c.scal, FJ_S_GAPTIME);
+    long long da = 0, de = 0, tn = 0, ja = 0, je = 0, jn = 0, dunp = 0;
+    int nav = 0, nfav = 0;
+    double s_fr = 0.0, s_gr = 0.0;
+    FjBest b_urg_av, b_de, b_da, b_gap_av, b_gap_fav, b_urg_fav, b_due_av, b_due_fav, b_en_av, b_en_fav, b_tm_av, b_tm_fav;
+    fj_best_init(b_urg_av); fj_best_init(b_de); fj_best_init(b_da); fj_best_init(b_gap_av); fj_best_init(b_gap_fav);
+    fj_best_init(b_urg_fav); fj_best_init(b_due_av); fj_best_init(b_due_fav); fj_best_init(b_en_av); fj_best_init(b_en_fav);
+    fj_best_init(b_tm_av); fj_best_init(b_tm_fav);
+    const int rounds = (KT + FJ_NL - 1) / FJ_NL;
+    for (int rd = 0; rd < rounds; ++rd) {
+        const int q = rd * FJ_NL + lane;
+        int av = 0, fav = 0;
+        if (q < KT) {
+            int residue = 0;
+            for (int s = 0; s < S; ++s) residue += c.cntunp[q * Sx + s];
+            const int qn = c.qlen[q];
+            av = qn > 0 && ((unsigned)elig[q] & idle) != 0;
+            fav = qn > 0 && (c.flmask[q] & idle) != 0;
+            const double f = c.tsum[q];
+            // walk the unprocessed operations in list order: positions are consecutive and
+            // the due date is constant inside an order, so only per-order counts are needed
+            int a_cnt = 0, e_cnt = 0, k = 0;
+            long long max_a = 0; double max_e = 0.0; bool first = true;
+            long long late_sum = 0;
+            FjPySum ps; fj_pysum_init(ps);
+            for (int s = 0; s < S; ++s) {
+                const int cnt = c.cntunp[q * Sx + s];
+                if (cnt == 0) continue;
+                const int d = due[s];
+                const double dd = (double)d;
+                if (t > d) { a_cnt += cnt; late_sum += (long long)cnt * (t - d); }
+                const long long va = (long long)t - d;
+                if (first || va > max_a) max_a = va;
+                for (int i = 0; i < cnt; ++i) {
+                    ++k;
+                    const double est = fj_add(td, fj_mul(f, (double)k));
+                    const double ve = fj_sub(est, dd);
+                    if (est > dd) ++e_cnt;
+                    if (first || ve > max_e) max_e = ve;
+                    first = false;
+                    fj_pysum_add<SUM_MODE>(ps, ve);
+                }
+            }
+            tn += residue; da += a_cnt; de += e_cnt;
+            if (rjlast[q]) { jn += residue; ja += a_cnt; je += e_cnt; dunp += late_sum; }
+            const double fluid_unp = fj_sub((double)c.fstart[q], fj_mul(c.rsum[q], gt));
+            const double gap = fj_sub((double)residue, fluid_unp);
+            const int pr = c.proc[q];
+            s_fr = fj_add(s_fr, fj_div((double)pr, (double)(residue + pr)));
+            s_gr = fj_add(s_gr, fj_div(gap, (double)c.fstart[q]));
+            if (av) {
+                ++nav;
+                const double urgency = fj_div(fj_pysum_result<SUM_MODE>(ps), (double)residue);
+                int dmin = 0; bool fd = true;
+                for (int s = 0; s < S; ++s)
+                    if (c.cntnow[q * Sx + s] > 0 && (fd || due[s] < dmin)) { dmin = due[s]; fd = false; }
+                fj_best_max(b_urg_av, urgency, q);
+                if (e_cnt > 0) fj_best_max(b_de, max_e, q);
+                if (a_cnt > 0) fj_best_max(b_da, (double)max_a, q);
+                fj_best_max(b_gap_av, gap, q);
+                fj_best_min(b_due_av, (double)dmin, q);
+                if (fav) {
+                    ++nfav;
+                    fj_best_max(b_gap_fav, gap, q);
+                    fj_best_max(b_urg_fav, urgency, q);
+                    fj_best_min(b_due_fav, (double)dmin, q);
+                }
+                if (MO) {   // MO_DFJSP.py:429-451: min time / energy over idle (fluid) machines
+                    unsigned sm = (unsigned)elig[q] & idle;
+                    int tmin = 0x7fffffff, emin = 0x7fffffff;
+                    while (sm) { int m = fj_ffs0(sm); sm &= sm - 1;
+                        int pt = ptime[q * Mx + m], en = energy[q * Mx + m];
+                        tmin = pt < tmin ? pt : tmin; emin = en < emin ? en : emin; }
+                    fj_best_min(b_tm_av, (double)tmin, q); fj_best_min(b_en_av, (double)emin, q);
+                    if (fav) {
+                        unsigned fm = c.flmask[q] & idle;
+                        tmin = 0x7fffffff; emin = 0x7fffffff;
+                        while (fm) { int m = fj_ffs0(fm); fm &= fm - 1;
+                            int pt = ptime[q * Mx + m], en = energy[q * Mx + m];
+                            tmin = pt < tmin ? pt : tmin; emin = en < emin ? en : emin; }
+                        fj_best_min(b_tm_fav, (double)tmin, q); fj_best_min(b_en_fav, (double)emin, q);
+                    }
+                }
+            }
+        }
+        // availability masks, one 32-bit word per round
+#ifdef FJ_DEVICE_CODE
+        unsigned wa = __ballot_sync(0xffffffffu, av), wf = __ballot_sync(0xffffffffu, fav);
+        if (lane == 0) { c.avmask[rd] = wa; c.favmask[rd] = wf; }
+#else
+        if ((q & 31) == 0) { c.avmask[q >> 5] = 0; c.favmask[q >> 5] = 0; }
+        if (av) c.avmask[q >> 5] |= 1u << (q & 31);
+        if (fav) c.favmask[q >> 5] |= 1u << (q & 31);
+#endif
+    }
+    tn = fj_sum_ll(tn); da = fj_sum_ll(da); de = fj_sum_ll(de);
+    jn = fj_sum_ll(jn); ja = fj_sum_ll(ja); je = fj_sum_ll(je); dunp = fj_sum_ll(dunp);
+    nav = fj_sum_i(nav); nfav = fj_sum_i(nfav);
+    const double cro_ave = fj_div(fj_sum_d(s_fr), (double)KT);
+    const double gap_ave = fj_div(fj_sum_d(s_gr), (double)KT);
+    fj_best_reduce(b_urg_av, 1); fj_best_reduce(b_de, 1); fj_best_reduce(b_da, 1);
+    fj_best_reduce(b_gap_av, 1); fj_best_reduce(b_gap_fav, 1); fj_best_reduce(b_urg_fav, 1);
+    fj_best_reduce(b_due_av, 0); fj_best_reduce(b_due_fav, 0);
+    if (MO) { fj_best_reduce(b_en_av, 0); fj_best_reduce(b_en_fav, 0); fj_best_reduce(b_tm_av, 0); fj_best_reduce(b_tm_fav, 0); }
+    // second pass: variances (observation only)
+    double v_fr = 0.0, v_gr = 0.0;
+    for (int q = lane; q < KT; q += FJ_NL) {
+        int residue = 0;
+        for (int s = 0; s < S; ++s) residue += c.cntunp[q * Sx + s];
+        const int pr = c.proc[q];
+        const double fr = fj_div((double)pr, (double)(residue + pr));
+        const double fluid_unp = fj_sub((double)c.fstart[q], fj_mul(c.rsum[q], gt));
+        const double gr = fj_div(fj_sub((double)residue, fluid_unp), (double)c.fstart[q]);
+        v_fr = fj_add(v_fr, fj_mul(fr - cro_ave, fr - cro_ave));
+        v_gr = fj_add(v_gr, fj_mul(gr - gap_ave, gr - gap_ave));
+    }
+    const double cro_std = sqrt(fj_div(fj_sum_d(v_fr), (double)KT));
+    const double gap_std = sqrt(fj_div(fj_sum_d(v_gr), (double)KT));
+    // machines: completion-time spread and the exact gap_ave of every machine (a machine
+    // rule key, so CPython's sum order over its operation types is reproduced)
+    long long tsum_m = 0;
+    for (int m = lane; m < M; m += FJ_NL) tsum_m += c.mend[m];
+    tsum_m = fj_sum_ll(tsum_m);
+    const double ct_ave = fj_div((double)tsum_m, (double)M);
+    double v_ct = 0.0, s_gm = 0.0;
+    for (int m = lane; m < M; m += FJ_NL) {
+        const double dv = fj_sub((double)c.mend[m], ct_ave);
+        v_ct = fj_add(v_ct, fj_mul(dv, dv));
+        FjPySum ps; fj_pysum_init(ps);
+        int n = 0;
+        for (int q = 0; q < KT; ++q) {
+            if (!((unsigned)elig[q] >> m & 1u)) continue;
+            const int sl = c.slot[q * Mx + m];
+            double term;
+            if (sl == 0xFFFF) term = fj_sub(0.0, (double)c.pk[q * Mx + m]);
+            else term = fj_sub(c.fu[sl], fj_sub(c.fa[sl], fj_mul(gt, c.ff[sl])));
+            fj_pysum_add<SUM_MODE>(ps, term);
+            ++n;
+        }
+        const double ga = fj_div(fj_pysum_result<SUM_MODE>(ps), (double)n);
+        c.gapave[m] = ga;
+        s_gm = fj_add(s_gm, ga);
+    }
+    const double ct_std = sqrt(fj_div(fj_sum_d(v_ct), (double)M));
+    double gm_ave = 0.0, gm_std = 0.0;
+    if (MO) {
+        gm_ave = fj_div(fj_sum_d(s_gm), (double)M);
+        fj_sync();
+        double v_gm = 0.0;
+        for (int m = lane; m < M; m += FJ_NL) { const double dv = fj_sub(c.gapave[m], gm_ave); v_gm = fj_add(v_gm, fj_mul(dv, dv)); }
+        gm_std = sqrt(fj_div(fj_sum_d(v_gm), (double)M));
+    }
+    if (lane == 0) {
+        fj_set_ll(c.scal, FJ_S_DELAY_UNPROC, dunp);
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+        if (!rates_zero) {
+            r0 = fj_div((double)da, (double)tn); r1 = fj_div((double)de, (double)tn);
+            r2 = fj_div((double)ja, (double)jn); r3 = fj_div((double)je, (double)jn);
+        }
+        double *o = c.obs2;
+        if (MO) {
+            uint64_t bits = (uint32_t)FJ_I(c, hdr)[5] | ((uint64_t)(uint32_t)FJ_I(c, hdr)[6] << 32);
+            double ddt; memcpy(&ddt, &bits, 8);
+            o[0] = ddt; o[1] = (double)M; o[2] = (double)S; o[3] = ct_std;
+            o[4] = fj_div((double)nfav, fj_add((double)nav, 1e-08));
+            o[5] = cro_ave; o[6] = cro_std; o[7] = gap_ave; o[8] = gap_std; o[9] = gm_ave; o[10] = gm_std;
+            o[11] = r0; o[12] = r1; o[13] = r2; o[14] = r3;
+        } else {
+            o[0] = (double)M; o[1] = ct_std; o[2] = cro_ave; o[3] = cro_std; o[4] = gap_ave; o[5] = gap_std;
+            o[6] = r0; o[7] = r1; o[8] = r2; o[9] = r3;
+        }
+        // rule cache: index = task rule number (1-based)
+        int *ch = c.choice;
+        const bool hf = nfav > 0;
+        ch[1] = b_de.idx != 0x7fffffff ? b_de.idx : b_urg_av.idx;
+        ch[2] = b_da.idx != 0x7fffffff ? b_da.idx : b_urg_av.idx;
+        ch[3] = hf ? b_gap_fav.idx : b_gap_av.idx;
+        ch[4] = hf ? b_urg_fav.idx : b_urg_av.idx;
+        ch[5] = hf ? b_due_fav.idx : b_due_av.idx;
+        if (MO) {
+            ch[6] = b_due_av.idx;
+            ch[7] = hf ? b_en_fav.idx : b_en_av.idx;
+            ch[8] = b_en_av.idx;
+            ch[9] = hf ? b_tm_fav.idx : b_tm_av.idx;
+            ch[10] = b_tm_av.idx;
+        }
+        ch[0] = nav; ch[11] = nfav;
+    }
+    fj_sync();
+}
+
+// ---------------------------------------------------------------- machine_select
+FJ_FN int fj_pyset_order_dev(const int *seq, int n, int *out)
+{
+    if (n >= 5) {
+        unsigned mask = 0;
+        for (int i = 0; i < n; ++i) mask |= 1u << seq[i];
+        int k = 0;
+        while (mask) { out[k++] = fj_ffs0(mask); mask &= mask - 1; }
+        return k;
+    }
+    int slot[8];
+    for (int i = 0; i < 8; ++i) slot[i] = -1;
+    for (int e = 0; e < n; ++e) {
+        unsigned i = (unsigned)seq[e] & 7u, perturb = (unsigned)seq[e];
+        while (slot[i] >= 0) { perturb >>= 5; i = (i * 5u + 1u + perturb) & 7u; }
+        slot[i] = seq[e];
+    }
+    int k = 0;
+    for (int i = 0; i < 8; ++i) if (slot[i] >= 0) out[k++] = slot[i];
+    return k;
+}
+
+// list(set(idle) & set(other)) with `other_ord` = iteration order of set(other)
+FJ_FN int fj_selectable(unsigned idle, const int *other_ord, int nother, int *out)
+{
+    int ia[32], io_[32], keep[32];
+    int ni = 0;
+    unsigned mk = idle;
+    while (mk) { ia[ni++] = fj_ffs0(mk); mk &= mk - 1; }
+    ni = fj_pyset_order_dev(ia, ni, io_);
+    unsigned om = 0;
+    for (int i = 0; i < nother; ++i) om |= 1u << other_ord[i];
+    int nk = 0;
+    if (nother > ni) { for (int i = 0; i < ni; ++i) if (om >> io_[i] & 1u) keep[nk++] = io_[i]; }
+    else { for (int i = 0; i < nother; ++i) if (idle >> other_ord[i] & 1u) keep[nk++] = other_ord[i]; }
+    return fj_pyset_order_dev(keep, nk, out);
+}
+
+FJ_FN double fj_gap_mrj(const FjCtx &c, int q, int m, double gt)
+{
+    const int sl = c.slot[q * c.Mx + m];
+    if (sl == 0xFFFF) return fj_sub(0.0, (double)c.pk[q * c.Mx + m]);
+    return fj_sub(c.fu[sl], fj_sub(c.fa[sl], fj_mul(gt, c.ff[sl])));
+}
+
+// executed by one lane; returns the machine or -1
+template <int VARIANT>
+FJ_FN int fj_machine_select(const FjCtx &c, int rule, int q, uint32_t rnd)
+{
+    const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
+    const int Mx = c.Mx;
+    const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
+    const double gt = fj_get_d(c.scal, FJ_S_GAPTIME);
+    int mt[32], fl[32], flo[32], sl[32], fs[32];
+    const int32_t *mtset = FJ_I(c, mtset) + q * Mx, *poord = FJ_I(c, poord) + q * Mx;
+    const int ne = FJ_I(c, nelig)[q];
+    for (int i = 0; i < ne; ++i) mt[i] = mtset[i];
+    int ns = fj_selectable(idle, mt, ne, sl);
+    if (ns == 0) return -1;
+    int nfl = 0;
+    const unsigned fm = c.flmask[q];
+    for (int i = 0; i < ne; ++i) if (fm >> poord[i] & 1u) fl[nfl++] = poord[i];
+    nfl = fj_pyset_order_dev(fl, nfl, flo);
+    int nf = fj_selectable(idle, flo, nfl, fs);
+    const int *lst = sl; int n = ns;
+    const int *flst = nf ? fs : sl; const int fn = nf ? nf : ns;
+    int key_kind;       // 0 gap_rj(max) 1 time(min) 2 gap_ave(max) 3 energy(min) 4 idle power(min) 5 random
+    bool use_f;
+    if (!MO) {
+        switch (rule) {
+        case 1: key_kind = 0; use_f = true; break;
+        case 2: key_kind = 0; use_f = false; break;
+        case 3: key_kind = 1; use_f = false; break;
+        case 4: key_kind = 2; use_f = true; break;
+        case 5: key_kind = 5; use_f = false; break;
+        default: return -1;
+        }
+    } else {
+        switch (rule) {
+        case 1: key_kind = 0; use_f = true; break;
+        case 2: key_kind = 1; use_f = true; break;
+        case 3: key_kind = 1; use_f = false; break;
+        case 4: key_kind = 2; use_f = true; break;
+        case 5: key_kind = 3; use_f = true; break;
+        case 6: key_kind = 3; use_f = false; break;
+        case 7: key_kind = 4; use_f = true; break;
+        case 8: key_kind = 4; use_f = false; break;
+        case 9: key_kind = 5; use_f = true; break;
+        case 10: key_kind = 5; use_f = false; break;
+        default: return -1;
+        }
+    }
+    if (use_f) { lst = flst; n = fn; }
+    if (key_kind == 5) return lst[rnd % (uint32_t)n];
+    int best = -1; double bk = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const int m = lst[i];
+        double k;
+        switch (key_kind) {
+        case 0: k = fj_gap_mrj(c, q, m, gt); break;
+        case 1: k = (double)FJ_I(c, ptime)[q * Mx + m]; break;
+        case 2: k = c.gapave[m]; break;
+        case 3: k = (double)FJ_I(c, energy)[q * Mx + m]; break;
+        default: k = (double)FJ_I(c, idlep)[m]; break;
+        }
+        const bool want_max = (key_kind == 0 || key_kind == 2);
+        if (best < 0 || (want_max ? k > bk : k < bk)) { best = m; bk = k; }
+    }
+    return best;
+}
+
+FJ_FN int fj_nth_set(const uint32_t *mask, int words, int nth)
+{
+    for (int w = 0; w < words; ++w) {
+        unsigned v = mask[w];
+        int pc = fj_popc(v);
+        if (nth < pc) { while (nth--) v &= v - 1; return w * 32 + fj_ffs0(v); }
+        nth -= pc;
+    }
+    return -1;
+}
+
+// ---------------------------------------------------------------- reset
+// reset() of the reference incl. its re-reset quirks (oracle/fjsp_oracle.c explains them):
+// busy flags, order_arrive_time and the `done` seen by the first observation survive.
+template <int VARIANT, int SUM_MODE>
+FJ_FN_NOINLINE void fj_reset(FjCtx &c, int fresh)
+{
+    const int lane = fj_lane();
+    const int KT = c.KT, Sx = c.Sx, M = c.M;
+    int was_done = 0;
+    if (fresh) {
+        for (int i = lane; i < FJ_S_COUNT; i += FJ_NL) c.scal[i] = 0;
+        for (int i = lane; i < 16; i += FJ_NL) { c.obs[i] = 0.0; c.choice[i] = -1; }
+        fj_sync();
+    } else {
+        was_done = c.scal[FJ_S_DONE];
+    }
+    for (int q = lane; q < KT; q += FJ_NL) {
+        c.qhead[q] = 0xFFFF; c.qtail[q] = 0xFFFF; c.qlen[q] = 0; c.proc[q] = 0;
+        for (int s = 0; s < Sx; ++s) { c.cntunp[q * Sx + s] = 0; c.cntnow[q * Sx + s] = 0; }
+    }
+    for (int m = lane; m < M; m += FJ_NL) { c.mend[m] = 0; c.mlast[m] = 0; c.mjob[m] = -1; }
+    fj_sync();
+    if (lane == 0) {
+        c.scal[FJ_S_NEXTORDER] = 1; c.scal[FJ_S_TIME] = 0; c.scal[FJ_S_STEPS] = 0; c.scal[FJ_S_HASTASK] = 0;
+        c.scal[FJ_S_COMPLETION] = 0; c.scal[FJ_S_COMPLETION_LAST] = 0;
+        fj_set_ll(c.scal, FJ_S_ENERGY, 0); fj_set_ll(c.scal, FJ_S_ENERGY_LAST, 0);
+        fj_set_ll(c.scal, FJ_S_DELAY_PROC, 0); fj_set_ll(c.scal, FJ_S_DELAY_LAST, 0);
+        fj_set_ll(c.scal, FJ_S_DELAY_UNPROC, 0);
+        fj_set_d(c.scal, FJ_S_GAPTIME, 0.0);
+    }
+    fj_sync();
+    fj_order_arrives<SUM_MODE>(c, 0);
+    fj_observe<VARIANT, SUM_MODE>(c, was_done);
+    for (int i = lane; i < 16; i += FJ_NL) c.obs[i] = c.obs2[i];
+    if (lane == 0) c.scal[FJ_S_DONE] = 0;
+    fj_sync();
+}
+
+// ---------------------------------------------------------------- step
+struct FjStepOut { double reward; int done; int rec[8]; };
+
+template <int VARIANT, int SUM_MODE>
+FJ_FN_NOINLINE void fj_step(FjCtx &c, int task_rule0, int mach_rule0, uint32_t rnd_task, uint32_t rnd_mach,
+                            int reward_policy, double completion_n, double tardiness_n, double energy_n,
+                            FjStepOut &out)
+{
+    const int lane = fj_lane();
+    const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
+    const int M = c.M, KT = c.KT, S = c.S, Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
+    const int32_t *rjkind = FJ_I(c, rjkind), *rjstage = FJ_I(c, rjstage), *rjlast = FJ_I(c, rjlast);
+    const int32_t *elig = FJ_I(c, elig), *due = FJ_I(c, due), *arrive = FJ_I(c, arrive), *cum = FJ_I(c, cum);
+    const int32_t *jobbase = FJ_I(c, jobbase);
+    int t = c.scal[FJ_S_TIME];
+    // ---- task_select: cached answer, or a draw from the availability masks
+    const int trule = task_rule0 + 1, mrule = mach_rule0 + 1;
+    int q = -1, m = -1;
+    if (lane == 0) {
+        const int nav = c.choice[0], nfav = c.choice[11];
+        const int KTW = (KT + 31) / 32;   // words this instance's observe() wrote
+        if (nav > 0) {
+            if (!MO) {
+                if (trule >= 1 && trule <= 5) q = c.choice[trule];
+                else if (trule == 6) q = fj_nth_set(c.avmask, KTW, (int)(rnd_task % (uint32_t)nav));
+            } else {
+                if (trule >= 1 && trule <= 10) q = c.choice[trule];
+                else if (trule == 11) q = nfav > 0 ? fj_nth_set(c.favmask, KTW, (int)(rnd_task % (uint32_t)nfav))
+                                                   : fj_nth_set(c.avmask, KTW, (int)(rnd_task % (uint32_t)nav));
+                else if (trule == 12) q = fj_nth_set(c.avmask, KTW, (int)(rnd_task % (uint32_t)nav));
+            }
+        }
+        if (q >= 0) m = fj_machine_select<VARIANT>(c, mrule, q, rnd_mach);
+    }
+    q = fj_bcast_i(q, 0); m = fj_bcast_i(m, 0);
+    if (q < 0 || m < 0) {
+        if (lane == 0) c.scal[FJ_S_ERROR] |= (q < 0 ? FJ_E_NO_TASK : FJ_E_NO_MACHINE);
+        out.reward = 0.0; out.done = c.scal[FJ_S_DONE];
+        for (int i = 0; i < 8; ++i) out.rec[i] = -1;
+        fj_sync();
+        return;
+    }
+    // ---- dispatch (one lane; a handful of scalar updates)
+    if (lane == 0) {
+        const int r = rjkind[q], stage = rjstage[q];
+        const int norder = c.scal[FJ_S_NEXTORDER];
+        int n;
+        if (stage == 0) n = cum[norder * Kx + r] - c.qlen[q];
+        else { n = c.qhead[q]; c.qhead[q] = c.next[jobbase[r] + n]; }
+        c.qlen[q] = (uint16_t)(c.qlen[q] - 1);
+        if (stage > 0 && c.qlen[q] == 0) { c.qhead[q] = 0xFFFF; c.qtail[q] = 0xFFFF; }
+        const int s = fj_order_of(c, r, n);
+        c.cntunp[q * Sx + s] = (uint16_t)(c.cntunp[q * Sx + s] - 1);
+        c.cntnow[q * Sx + s] = (uint16_t)(c.cntnow[q * Sx + s] - 1);
+        c.proc[q] += 1;
+        const int dur = FJ_I(c, ptime)[q * Mx + m];
+        int t_begin = t, t_end = t + dur, m_end = t_end;
+        if (VARIANT == FJSP_MO_BREAKDOWN) {   // MO_DFJSP_breakdown.py:204-231
+            const int32_t *bp = FJ_I(c, bdptr), *bs_ = FJ_I(c, bds), *be_ = FJ_I(c, bde);
+            for (int i = bp[m]; i < bp[m + 1]; ++i) {
+                const int bs = bs_[i], be = be_[i];
+                if (bs <= t && t < be) { int d = be - t; t_begin += d; t_end += d; m_end = t_end; }
+                else if (t < bs && bs < t_end) { t_end += be - bs; m_end = t_end; }
+                else if (bs == t_end) { m_end += be - bs; }
+                else if (bs > t_end) break;
+            }
+        }
+        const int prev_last = c.mlast[m];
+        const unsigned bit = 1u << m;
+        const int had = ((unsigned)c.scal[FJ_S_HASTASK] & bit) != 0;
+        c.mend[m] = m_end; c.mlast[m] = t_end; c.mjob[m] = (q << 16) | n;
+        c.scal[FJ_S_BUSY] = (int)((unsigned)c.scal[FJ_S_BUSY] | bit);
+        c.scal[FJ_S_HASTASK] = (int)((unsigned)c.scal[FJ_S_HASTASK] | bit);
+        const int sl = c.slot[q * Mx + m];
+        if (sl == 0xFFFF) c.pk[q * Mx + m] = (uint16_t)(c.pk[q * Mx + m] + 1);
+        else c.fu[sl] = fj_sub(c.fu[sl], 1.0);
+        if (MO) {
+            if (t_end > c.scal[FJ_S_COMPLETION]) c.scal[FJ_S_COMPLETION] = t_end;
+            long long en = fj_get_ll(c.scal, FJ_S_ENERGY) + FJ_I(c, energy)[q * Mx + m];
+            if (had) en += (long long)(t - prev_last) * FJ_I(c, idlep)[m];
+            fj_set_ll(c.scal, FJ_S_ENERGY, en);
+        }
+        if (rjlast[q]) {
+            long long late = (long long)t_end - due[s];
+            if (late > 0) fj_set_ll(c.scal, FJ_S_DELAY_PROC, fj_get_ll(c.scal, FJ_S_DELAY_PROC) + late);
+        }
+        out.rec[0] = q; out.rec[1] = r; out.rec[2] = stage; out.rec[3] = n; out.rec[4] = m;
+        out.rec[5] = t_begin; out.rec[6] = t_end; out.rec[7] = m_end;
+    }
+    fj_sync();
+    // ---- advance the clock while nothing can be dispatched
+    int done = 0;
+    for (;;) {
+        const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
+        int any = 0;
+        for (int x = lane; x < KT; x += FJ_NL) any |= (c.qlen[x] > 0 && ((unsigned)elig[x] & idle) != 0);
+        if (fj_any(any)) break;
+        int tmin = 0x7fffffff;
+        for (int i = lane; i < M; i += FJ_NL) { int e = c.mend[i]; if (e > t && e < tmin) tmin = e; }
+        tmin = fj_min_i(tmin);
+        if (tmin == 0x7fffffff) { if (lane == 0) c.scal[FJ_S_ERROR] |= FJ_E_NO_EVENT; break; }
+        t = tmin;
+        if (lane == 0) {   // machines release their jobs in ascending machine order
+            for (int i = 0; i < M; ++i) {
+                if (c.mend[i] != t || c.mjob[i] < 0) continue;
+                const int jq = c.mjob[i] >> 16, n = c.mjob[i] & 0xffff;
+                if (rjlast[jq]) continue;
+                const int q2 = jq + 1, r = rjkind[jq];
+                if (c.qlen[q2] == 0) c.qhead[q2] = (uint16_t)n;
+                else c.next[jobbase[r] + c.qtail[q2]] = (uint16_t)n;
+                c.qtail[q2] = (uint16_t)n;
+                c.qlen[q2] = (uint16_t)(c.qlen[q2] + 1);
+                const int s = fj_order_of(c, r, n);
+                c.cntnow[q2 * Sx + s] = (uint16_t)(c.cntnow[q2 * Sx + s] + 1);
+            }
+        }
+        fj_sync();
+        long long left = 0;
+        for (int x = lane; x < KT; x += FJ_NL)
+            if (rjlast[x]) for (int s = 0; s < S; ++s) left += c.cntunp[x * Sx + s];
+        left = fj_sum_ll(left);
+        int norder = c.scal[FJ_S_NEXTORDER];
+        int arr_time = c.scal[FJ_S_ARRTIME];
+        fj_sync();
+        if (norder < S && arrive[norder] <= t) {
+            if (lane == 0) { c.scal[FJ_S_NEXTORDER] = norder + 1; c.scal[FJ_S_ARRTIME] = arrive[norder]; }
+            fj_sync();
+            fj_order_arrives<SUM_MODE>(c, norder);
+            arr_time = arrive[norder]; ++norder; left = 1;
+        } else if (norder < S && left == 0) {
+            if (lane == 0) { c.scal[FJ_S_NEXTORDER] = norder + 1; c.scal[FJ_S_ARRTIME] = arrive[norder]; }
+            fj_sync();
+            fj_order_arrives<SUM_MODE>(c, norder);
+            arr_time = arrive[norder]; t = arr_time; ++norder; left = 1;
+        }
+        unsigned freed = 0;
+        for (int i = lane; i < M; i += FJ_NL) if (c.mend[i] <= t) freed |= 1u << i;
+        freed = fj_or_u(freed);
+        if (lane == 0) {
+            c.scal[FJ_S_BUSY] = (int)((unsigned)c.scal[FJ_S_BUSY] & ~freed);
+            fj_set_d(c.scal, FJ_S_GAPTIME, (double)(t - arr_time));
+        }
+        fj_sync();
+        if (norder >= S && left == 0) { done = 1; break; }
+    }
+    if (lane == 0) {
+        c.scal[FJ_S_TIME] = t; c.scal[FJ_S_STEPS] += 1;
+        if (done) c.scal[FJ_S_DONE] = 1;
+    }
+    fj_sync();
+    // ---- new observation, rule cache, reward
+    fj_observe<VARIANT, SUM_MODE>(c, done);
+    if (lane == 0) {
+        const long long dsum = fj_get_ll(c.scal, FJ_S_DELAY_PROC) + fj_get_ll(c.scal, FJ_S_DELAY_UNPROC);
+        const long long dlast = fj_get_ll(c.scal, FJ_S_DELAY_LAST);
+        double rew = 0.0;
+        if (!MO) rew = -(double)(dsum - dlast);
+        else {
+            const long long comp = c.scal[FJ_S_COMPLETION], compl_ = c.scal[FJ_S_COMPLETION_LAST];
+            const long long en = fj_get_ll(c.scal, FJ_S_ENERGY), enl = fj_get_ll(c.scal, FJ_S_ENERGY_LAST);
+            if (reward_policy == 0) rew = (double)(compl_ - comp);
+            else if (reward_policy == 1) rew = (double)(dlast - dsum);
+            else if (reward_policy == 2) rew = (double)(enl - en);
+            else if (reward_policy == 3) {
+                const double a = fj_div((double)(compl_ - comp), completion_n);
+                const double e = fj_div((double)(enl - en), energy_n);
+                if (tardiness_n > 0) rew = fj_add(fj_add(a, fj_div((double)(dlast - dsum), tardiness_n)), e);
+                else rew = fj_add(a, e);
+            }
+            c.scal[FJ_S_COMPLETION_LAST] = (int)comp;
+            fj_set_ll(c.scal, FJ_S_ENERGY_LAST, en);
+        }
+        fj_set_ll(c.scal, FJ_S_DELAY_LAST, dsum);
+        out.reward = rew;
+    }
+    out.done = done;
+    fj_sync();
+}
+
+// ---------------------------------------------------------------- per-env driver
+// T steps of one environment: emit [v(t+1), v(t+1)-v(t)], reward, done and the dispatch
+// record; auto-reset a finished environment before its next action.
+template <int VARIANT, int SUM_MODE>
+FJ_FN void fj_env_rollout(const FjParams &P, const FjStepArgs &A, int env, unsigned char *lp)
+{
+    const int lane = fj_lane();
+    FjCtx c;
+    fj_ctx_init(c, P, env, lp);
+    const int nobs = P.nobs, ns = 2 * nobs;
+    for (int tt = 0; tt < A.T; ++tt) {
+        const size_t i = (size_t)tt * P.B + env;
+        if (c.scal[FJ_S_DONE]) {
+            if (!A.autoreset) {   // a finished env without auto-reset repeats its terminal output
+                if (A.done && lane == 0) A.done[i] = 1;
+                if (A.reward && lane == 0) A.reward[i] = 0.0;
+                for (int k = lane; k < ns; k += FJ_NL) {
+                    double v = k < nobs ? c.obs[k] : 0.0;
+                    if (A.state) A.state[i * ns + k] = v;
+                    if (A.state32) A.state32[i * ns + k] = (float)v;
+                }
+                if (A.rec) for (int k = lane; k < 8; k += FJ_NL) A.rec[i * 8 + k] = -1;
+                continue;
+            }
+            fj_reset<VARIANT, SUM_MODE>(c, 0);
+            if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
+            fj_sync();
+        }
+        FjStepOut out;
+        out.reward = 0.0; out.done = 0;
+        fj_step<VARIANT, SUM_MODE>(c, A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
+                                   A.rnd ? A.rnd[2 * i + 1] : 0u, A.reward_policy, A.completion, A.tardiness,
+                                   A.energy, out);
+        // outputs: lanes stream the state vector, lane 0 the scalars
+        for (int k = lane; k < ns; k += FJ_NL) {
+            const int j = k < nobs ? k : k - nobs;
+            const double v = k < nobs ? c.obs2[j] : fj_sub(c.obs2[j], c.obs[j]);
+            if (A.state) A.state[i * ns + k] = v;
+            if (A.state32) A.state32[i * ns + k] = (float)v;
+        }
+        fj_sync();
+        for (int k = lane; k < nobs; k += FJ_NL) c.obs[k] = c.obs2[k];
+        if (lane == 0) {
+            if (A.reward) A.reward[i] = out.reward;
+            if (A.done) A.done[i] = out.done;
+            if (A.rec) for (int k = 0; k < 8; ++k) A.rec[i * 8 + k] = out.rec[k];
+        }
+        fj_sync();
+    }
+}
+
+template <int VARIANT, int SUM_MODE>
+FJ_FN void fj_env_reset(const FjParams &P, int env, unsigned char *lp, double *state_out, float *state32_out)
+{
+    const int lane = fj_lane();
+    FjCtx c;
+    fj_ctx_init(c, P, env, lp);
+    fj_reset<VARIANT, SUM_MODE>(c, 1);
+    const int nobs = P.nobs, ns = 2 * nobs;
+    for (int k = lane; k < ns; k += FJ_NL) {
+        const double v = k < nobs ? c.obs[k] : 0.0;
+        if (state_out) state_out[(size_t)env * ns + k] = v;
+        if (state32_out) state32_out[(size_t)env * ns + k] = (float)v;
+    }
+}

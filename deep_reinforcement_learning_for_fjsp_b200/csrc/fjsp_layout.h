@@ -1,0 +1,120 @@
+// Layout of the device-resident vector environment (shared by host and device code).
+//
+// Two tables live in HBM:
+//   * the INSTANCE table: one read-only int32 record per distinct problem instance
+//     (shared by every environment copy that plays it; stays hot in L2);
+//   * the ENV table: one mutable record per environment copy, contiguous per env so
+//     that the warp that owns an env streams it with coalesced loads.
+// All offsets are computed once on the host (fjsp_host.h) from the batch maxima and
+// passed to the kernels by value.
+#pragma once
+#include <stdint.h>
+
+#define FJSP_MAGIC 0x464A5350
+#define FJSP_MAX_M 32
+#define FJSP_MAX_KT 256
+#define FJSP_MAX_S 16
+
+enum { FJSP_SO_DFJSP = 0, FJSP_MO_DFJSP = 1, FJSP_MO_BREAKDOWN = 2, FJSP_SO_FJSSP = 3 };
+
+struct FjDims {
+    int Mx, Kx, KTx, Sx, NBDx, NJx;   // batch maxima
+    int NFx;                          // fluid-pair slots per env (max LP rows)
+    int KTW;                          // 32-bit words per operation-type mask
+    int Rx, NPx;                      // LP: max rows, max pair columns
+};
+
+// instance record: word (int32) offsets
+struct FjInstOff {
+    int hdr;       // [8]: M, K, KT, S, NJ, ddt_lo, ddt_hi, NP
+    int ntask;     // [Kx]
+    int first;     // [Kx]  first operation type of a kind
+    int jobbase;   // [Kx]  offset of a kind's jobs in the per-env link array
+    int rjkind;    // [KTx]
+    int rjstage;   // [KTx]
+    int rjlast;    // [KTx] 1 if last stage of its kind
+    int elig;      // [KTx] machine bit mask
+    int nelig;     // [KTx]
+    int mtset;     // [KTx*Mx] iteration order of set(machine_tuple) (CPython slot order)
+    int poord;     // [KTx*Mx] machines of the type in x.items() (pair) order
+    int ptime;     // [KTx*Mx]
+    int energy;    // [KTx*Mx] power * time
+    int idlep;     // [Mx]
+    int arrive;    // [Sx]
+    int due;       // [Sx]
+    int count;     // [Sx*Kx]
+    int cum;       // [(Sx+1)*Kx] jobs of kind r arrived before order s
+    int bdptr;     // [Mx+1]
+    int bds;       // [NBDx]
+    int bde;       // [NBDx]
+    int stride;    // words per instance
+};
+
+// env record: BYTE offsets
+struct FjEnvOff {
+    int scal;      // int32[32] scalars, see FJ_S_* below
+    int obs;       // double[16] v(t)
+    int obs2;      // double[16] staging for v(t+1)
+    int gapave;    // double[Mx] cached machine gap_ave
+    int choice;    // int32[16] cached operation-type choice per deterministic task rule
+    int avmask;    // uint32[KTW] available operation types
+    int favmask;   // uint32[KTW] fluid-available operation types
+    int mend;      // int32[Mx] machine completion time
+    int mlast;     // int32[Mx] end time of the machine's previous operation
+    int mjob;      // int32[Mx] (rj << 16 | job number) of the job on the machine, -1 none
+    int qhead;     // uint16[KTx] stage>0 waiting queue (linked through `next`)
+    int qtail;     // uint16[KTx]
+    int qlen;      // uint16[KTx]
+    int proc;      // int32[KTx] operations dispatched this episode
+    int fstart;    // int32[KTx] unprocessed count at the last order arrival
+    int flmask;    // uint32[KTx] machines with non-zero fluid rate
+    int rsum;      // double[KTx] fluid_rate_sum
+    int tsum;      // double[KTx] fluid_time_sum
+    int cntunp;    // uint16[KTx*Sx] unprocessed operations per order
+    int cntnow;    // uint16[KTx*Sx] waiting jobs per order
+    int pk;        // uint16[KTx*Mx] dispatches of type on machine since the last arrival
+    int slot;      // uint16[KTx*Mx] fluid slot of the pair, 0xFFFF = none
+    int fu;        // double[NFx] unprocessed_rj_dict of fluid pairs
+    int fa;        // double[NFx] fluid_unprocessed_rj_arrival_dict
+    int ff;        // double[NFx] fluid_process_rate_rj_dict
+    int next;      // uint16[NJx] queue links, indexed jobbase[r] + n
+    int stride;    // bytes per env (multiple of 16)
+};
+
+// scalar slots (int32 index into scal[])
+enum {
+    FJ_S_TIME = 0, FJ_S_ARRTIME = 1, FJ_S_NEXTORDER = 2, FJ_S_DONE = 3, FJ_S_STEPS = 4, FJ_S_BUSY = 5,
+    FJ_S_ERROR = 6, FJ_S_HASTASK = 7, FJ_S_COMPLETION = 8, FJ_S_COMPLETION_LAST = 9, FJ_S_EPISODES = 10,
+    FJ_S_LPSOLVES = 11, FJ_S_LPITERS = 12, FJ_S_NFL = 13,
+    // 64-bit values occupy two slots (even index)
+    FJ_S_ENERGY = 16, FJ_S_ENERGY_LAST = 18, FJ_S_DELAY_PROC = 20, FJ_S_DELAY_LAST = 22, FJ_S_DELAY_UNPROC = 24,
+    FJ_S_GAPTIME = 26 /* double */, FJ_S_COUNT = 32
+};
+
+// error flags (FJ_S_ERROR), same meaning as the oracle's
+enum { FJ_E_LP = 1, FJ_E_NO_TASK = 2, FJ_E_NO_MACHINE = 4, FJ_E_NO_EVENT = 8, FJ_E_OVERFLOW = 16 };
+
+struct FjParams {
+    FjDims d;
+    FjInstOff io;
+    FjEnvOff eo;
+    const int32_t *inst;        // instance table
+    const int32_t *env_inst;    // [B] instance index of each env
+    unsigned char *env;         // env table
+    unsigned char *lp;          // LP scratch, one slab per resident warp
+    unsigned long long lp_stride;
+    int B, variant, sum_mode, nobs;
+};
+
+struct FjStepArgs {
+    int T;                      // steps per launch
+    const int32_t *actions;     // [T][B][2]
+    const uint32_t *rnd;        // [T][B][2]
+    int reward_policy, autoreset;
+    double completion, tardiness, energy;
+    double *state;              // [T][B][2*nobs] or null
+    float *state32;             // [T][B][2*nobs] or null
+    double *reward;             // [T][B] or null
+    int32_t *done;              // [T][B] or null
+    int32_t *rec;               // [T][B][8] or null
+};

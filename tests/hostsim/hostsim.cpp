@@ -1,0 +1,122 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles the kernel source (csrc/fjsp_core.cuh) and the
+// table builder (csrc/fjsp_host.h) with g++ as a ONE-LANE program, behind the same entry
+// points as the CUDA library, so `pytest -m "not gpu"` can check the compressed state
+// machine, the rule cache, the set-order emulation and the in-kernel simplex against the
+// oracle on a machine without a GPU.  It is never loaded by the product package; the
+// 32-lane cooperation itself is covered by the `-m gpu` parity tests.
+// Build: g++ -O2 -ffp-contract=off -fPIC -shared (see tests/hostsim/build.py)
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include "../../deep_reinforcement_learning_for_fjsp_b200/csrc/fjsp_host.h"
+#include "../../deep_reinforcement_learning_for_fjsp_b200/csrc/fjsp_core.cuh"
+
+struct HostVec {
+    FjTables tb;
+    FjParams P;
+    std::vector<int32_t> env_inst;
+    std::vector<unsigned char> env, lp;
+    int variant, sum_mode;
+};
+
+static std::string g_err;
+
+template <int V, int SM>
+static void run_reset(HostVec *h, double *state)
+{
+    for (int e = 0; e < h->P.B; ++e) fj_env_reset<V, SM>(h->P, e, h->lp.data(), state, nullptr);
+}
+template <int V, int SM>
+static void run_step(HostVec *h, const FjStepArgs &A)
+{
+    for (int e = 0; e < h->P.B; ++e) fj_env_rollout<V, SM>(h->P, A, e, h->lp.data());
+}
+
+#define DISPATCH(fn, ...)                                                                      \
+    do {                                                                                       \
+        int key = h->variant * 2 + (h->sum_mode ? 1 : 0);                                      \
+        switch (key) {                                                                         \
+        case 0: fn<FJSP_SO_DFJSP, 0>(__VA_ARGS__); break;                                      \
+        case 1: fn<FJSP_SO_DFJSP, 1>(__VA_ARGS__); break;                                      \
+        case 2: fn<FJSP_MO_DFJSP, 0>(__VA_ARGS__); break;                                      \
+        case 3: fn<FJSP_MO_DFJSP, 1>(__VA_ARGS__); break;                                      \
+        case 4: fn<FJSP_MO_BREAKDOWN, 0>(__VA_ARGS__); break;                                  \
+        case 5: fn<FJSP_MO_BREAKDOWN, 1>(__VA_ARGS__); break;                                  \
+        }                                                                                      \
+    } while (0)
+
+extern "C" {
+
+const char *fjsp_hostsim_last_error(void) { return g_err.c_str(); }
+
+int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst, const int32_t *env_instance,
+                        int n_envs, int variant, int sum_mode, void **out)
+{
+    if (variant < 0 || variant > 2) { g_err = "variant not supported on the device path"; return -2; }
+    HostVec *h = new HostVec();
+    if (!fj_build_tables(blobs, offsets, n_inst, h->tb, g_err)) { delete h; return -1; }
+    h->variant = variant; h->sum_mode = sum_mode;
+    h->env_inst.assign(env_instance, env_instance + n_envs);
+    h->env.assign((size_t)n_envs * h->tb.eo.stride, 0);
+    h->lp.assign(fj_lp_scratch_bytes(h->tb.d), 0);
+    FjParams &P = h->P;
+    P.d = h->tb.d; P.io = h->tb.io; P.eo = h->tb.eo;
+    P.inst = h->tb.inst.data(); P.env_inst = h->env_inst.data(); P.env = h->env.data();
+    P.lp = h->lp.data(); P.lp_stride = 0;
+    P.B = n_envs; P.variant = variant; P.sum_mode = sum_mode;
+    P.nobs = (variant == FJSP_SO_DFJSP) ? 10 : 15;
+    *out = h;
+    return 0;
+}
+
+int fjsp_hostsim_destroy(void *v) { delete (HostVec *)v; return 0; }
+
+int fjsp_hostsim_reset(void *v, double *state)
+{
+    HostVec *h = (HostVec *)v;
+    DISPATCH(run_reset, h, state);
+    return 0;
+}
+
+int fjsp_hostsim_step(void *v, int T, const int32_t *actions, const uint32_t *rnd, int reward_policy,
+                      double completion, double tardiness, double energy, int autoreset,
+                      double *state, float *state32, double *reward, int32_t *done, int32_t *rec)
+{
+    HostVec *h = (HostVec *)v;
+    FjStepArgs A;
+    A.T = T; A.actions = actions; A.rnd = rnd; A.reward_policy = reward_policy; A.autoreset = autoreset;
+    A.completion = completion; A.tardiness = tardiness; A.energy = energy;
+    A.state = state; A.state32 = state32; A.reward = reward; A.done = done; A.rec = rec;
+    DISPATCH(run_step, h, A);
+    return 0;
+}
+
+int fjsp_hostsim_info(void *v, int64_t *out)
+{
+    HostVec *h = (HostVec *)v;
+    for (int e = 0; e < h->P.B; ++e) {
+        const int32_t *s = (const int32_t *)(h->env.data() + (size_t)e * h->tb.eo.stride + h->tb.eo.scal);
+        int64_t *o = out + (size_t)e * 12;
+        long long dp = *(const long long *)(s + FJ_S_DELAY_PROC), du = *(const long long *)(s + FJ_S_DELAY_UNPROC);
+        o[0] = s[FJ_S_TIME]; o[1] = s[FJ_S_STEPS]; o[2] = s[FJ_S_COMPLETION]; o[3] = dp + du;
+        o[4] = *(const long long *)(s + FJ_S_ENERGY); o[5] = s[FJ_S_LPSOLVES]; o[6] = s[FJ_S_LPITERS];
+        o[7] = s[FJ_S_ERROR]; o[8] = s[FJ_S_DONE]; o[9] = s[FJ_S_NEXTORDER]; o[10] = s[FJ_S_EPISODES]; o[11] = du;
+    }
+    return 0;
+}
+
+int fjsp_hostsim_query(void *v, int64_t *out8)
+{
+    HostVec *h = (HostVec *)v;
+    out8[0] = h->P.B; out8[1] = 2 * h->P.nobs; out8[2] = h->tb.eo.stride; out8[3] = (int64_t)h->tb.io.stride * 4;
+    out8[4] = 0; out8[5] = 0; out8[6] = (int64_t)fj_lp_scratch_bytes(h->tb.d); out8[7] = 0;
+    return 0;
+}
+
+/* CPython set-order emulation of the table builder, exported for tests/test_pyemu.py */
+int fjsp_hostsim_pyset_order(const int *seq, int n, int *out) { return fj_pyset_order(seq, n, out); }
+int fjsp_hostsim_selectable(unsigned idle, const int *other_ord, int nother, int *out)
+{
+    return fj_selectable(idle, other_ord, nother, out);
+}
+}

@@ -1,0 +1,109 @@
+"""Shared checks: a vector-environment backend (the CUDA library through its C ABI, or the
+one-lane host build of the same kernel source) against the golden reference trajectories
+and against the CPU oracle."""
+import os
+
+import numpy as np
+
+import oracle_py
+from deep_reinforcement_learning_for_fjsp_b200.instance import FJSPInstance
+
+# state features: the task's bar is 1e-5 relative to the reference's float64; the kernel's
+# observation-only sums use a warp tree instead of CPython's compensated sum, which moves
+# the last bits only, so the tests hold it to a far tighter bound.
+STATE_RTOL, STATE_ATOL = 1e-9, 1e-12
+NRULES = {"SO_DFJSP": (6, 5), "MO_DFJSP": (12, 10), "MO_DFJSP_breakdown": (12, 10)}
+
+
+def assert_states_close(got, want, what):
+    ok = np.isclose(got, want, rtol=STATE_RTOL, atol=STATE_ATOL)
+    assert ok.all(), f"{what}: state feature mismatch at {np.argwhere(~ok)[:5].tolist()} " \
+                     f"got {got[~ok][:5]} want {want[~ok][:5]}"
+
+
+def replay_golden(make_vec, golden_dir, case):
+    g = np.load(os.path.join(golden_dir, case + ".npz"), allow_pickle=False)
+    variant = str(g["variant"])
+    vec = make_vec([g["blob"]], [0], variant)
+    actions, rnd, rp = g["actions"], g["rnd"], int(g["reward_policy"])
+    T = len(actions)
+    s0 = vec.reset_host()
+    assert_states_close(s0[0], g["resets"][0], "reset")
+    # the whole trajectory, auto-reset between the recorded episodes, in launches of up to 64 steps
+    t = 0
+    while t < T:
+        n = min(64, T - t)
+        st, rw, dn, rec = vec.step_host(actions[t:t + n, None, :], rnd[t:t + n, None, :], rp, 1.0, 1.0, 1.0, True)
+        assert np.array_equal(rec[:, 0], g["recs"][t:t + n]), f"{case}: schedule records differ in steps {t}..{t + n}"
+        assert np.array_equal(rw[:, 0], g["rewards"][t:t + n]), f"{case}: rewards differ in steps {t}..{t + n}"
+        assert np.array_equal(dn[:, 0], g["dones"][t:t + n]), f"{case}: done flags differ in steps {t}..{t + n}"
+        assert_states_close(st[:, 0], g["states"][t:t + n], f"{case} steps {t}..{t + n}")
+        t += n
+    info = vec.info()
+    assert int(info["error"][0]) == 0
+    return vec
+
+
+def random_batch(seed, variant, n_inst, copies, profile_mix=True, breakdowns=False, M=None):
+    rng = np.random.default_rng(seed)
+    insts = []
+    for i in range(n_inst):
+        prof = ("DA3C", "HMPSAC")[i % 2] if profile_mix else "DA3C"
+        m = M or int(rng.integers(4, 13))
+        inst = FJSPInstance.generate(seed * 1000 + i, float(rng.choice([0.5, 1.0, 1.5])), m, int(rng.integers(1, 4)),
+                                     prof, breakdowns=breakdowns, scale=0.12 if prof == "DA3C" else 0.4)
+        inst.ddt = float(int(inst.ddt))
+        insts.append(inst)
+    env_instance = np.repeat(np.arange(n_inst), copies)
+    return insts, env_instance
+
+
+def compare_with_oracle(make_vec, variant, seed, n_inst=6, copies=3, T=48, launches=4, reward_policy=1,
+                        breakdowns=False):
+    """Random rule actions on a mixed batch with auto-reset; every output of every step must
+    agree with the oracle stepping the same instances one by one."""
+    insts, env_instance = random_batch(seed, variant, n_inst, copies, breakdowns=breakdowns)
+    blobs = [i.to_blob() for i in insts]
+    B = len(env_instance)
+    vec = make_vec(blobs, env_instance, variant)
+    envs = [oracle_py.OracleEnv(blobs[k], variant) for k in env_instance]
+    s0 = vec.reset_host()
+    o0 = np.stack([e.reset() for e in envs])
+    assert_states_close(s0, o0, "reset")
+    rng = np.random.default_rng(seed + 77)
+    nt, nm = NRULES[variant]
+    for L in range(launches):
+        actions = np.stack([rng.integers(0, nt, (T, B)), rng.integers(0, nm, (T, B))], -1).astype(np.int32)
+        rnd = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
+        st, rw, dn, rec = vec.step_host(actions, rnd, reward_policy, 1.0, 1.0, 1.0, True)
+        ref = oracle_py.batch_rollout(envs, actions, rnd, reward_policy)
+        assert np.array_equal(rec, ref["rec"]), f"launch {L}: schedule records differ"
+        assert np.array_equal(dn, ref["done"]), f"launch {L}: done flags differ"
+        assert np.array_equal(rw, ref["reward"]), f"launch {L}: rewards differ"
+        assert_states_close(st, ref["state"], f"launch {L}")
+    info = vec.info()
+    assert (info["error"] == 0).all()
+    oi = [e.info() for e in envs]
+    assert np.array_equal(info["step_time"], [x["step_time"] for x in oi])
+    assert np.array_equal(info["lp_solves"] >= 1, np.ones(B, bool))
+    return vec, envs
+
+
+def schedule_is_feasible(rec, dn, ntask_of_env):
+    """Size-independent property: inside an episode no machine runs two operations at once
+    and a job's stages run in order, each starting after the previous stage ended."""
+    T, B = rec.shape[:2]
+    for b in range(B):
+        mach_free, job_end, job_stage = {}, {}, {}
+        for t in range(T):
+            q, r, j, n, m, tb, te, me = rec[t, b]
+            assert tb >= mach_free.get(m, 0), (b, t, "machine overlap")
+            assert j == job_stage.get((r, n), 0), (b, t, "stage order")
+            assert tb >= job_end.get((r, n), 0), (b, t, "job precedence")
+            assert te > tb and me >= te
+            mach_free[m] = me
+            job_end[(r, n)] = te
+            job_stage[(r, n)] = j + 1
+            if dn[t, b]:
+                mach_free, job_end, job_stage = {}, {}, {}
+    return True

@@ -1,0 +1,129 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+of libfjsp_b200.so (ctypes, host buffers or torch device pointers); the oracle and the
+committed golden trajectories are the checkers."""
+import numpy as np
+import pytest
+
+import parity_common as pc
+from conftest import golden_cases
+
+pytestmark = pytest.mark.gpu
+DEVICE_CASES = [c for c in golden_cases() if "fjssp" not in c]
+
+
+def make_vec(blobs, env_instance, variant):
+    from deep_reinforcement_learning_for_fjsp_b200.vec_env import FJSPVecEnv
+    return FJSPVecEnv(None, env_instance, variant, blobs=blobs)
+
+
+@pytest.mark.parametrize("case", DEVICE_CASES)
+def test_golden_reference_trajectories(case, golden_dir):
+    pc.replay_golden(make_vec, golden_dir, case)
+
+
+@pytest.mark.parametrize("variant,seed,rp,bd", [("SO_DFJSP", 11, 1, False), ("MO_DFJSP", 12, 0, False),
+                                                 ("MO_DFJSP", 13, 1, False), ("MO_DFJSP", 14, 3, False),
+                                                 ("MO_DFJSP_breakdown", 15, 2, True)])
+def test_random_batch_vs_oracle(variant, seed, rp, bd):
+    pc.compare_with_oracle(make_vec, variant, seed, n_inst=8, copies=8, T=64, launches=4, reward_policy=rp,
+                           breakdowns=bd)
+
+
+def test_single_steps_equal_fused_rollout():
+    """T steps in one launch == T launches of one step (state lives in HBM between launches)."""
+    insts, env_instance = pc.random_batch(21, "MO_DFJSP", 4, 16)
+    blobs = [i.to_blob() for i in insts]
+    a, b = make_vec(blobs, env_instance, "MO_DFJSP"), make_vec(blobs, env_instance, "MO_DFJSP")
+    B, T = len(env_instance), 96
+    rng = np.random.default_rng(3)
+    actions = np.stack([rng.integers(0, 12, (T, B)), rng.integers(0, 10, (T, B))], -1).astype(np.int32)
+    rnd = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(a.reset_host(), b.reset_host())
+    fused = a.step_host(actions, rnd, 1)
+    for t in range(T):
+        one = b.step_host(actions[t:t + 1], rnd[t:t + 1], 1)
+        for x, y in zip(fused, one):
+            assert np.array_equal(x[t], y[0])
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (4096 copies): replicas of one instance fed the same actions
+    stay bit-identical, reruns are deterministic, schedules are feasible, and a sample of
+    environments agrees with the oracle."""
+    import torch
+    from deep_reinforcement_learning_for_fjsp_b200.instance import FJSPInstance
+    n_inst, copies, T = 64, 64, 128
+    insts = []
+    for i in range(n_inst):
+        inst = FJSPInstance.generate(500 + i, [0.5, 1.0, 1.5][i % 3], 10, 3, "DA3C", scale=0.3)
+        inst.ddt = float(int(inst.ddt))
+        insts.append(inst)
+    blobs = [i.to_blob() for i in insts]
+    env_instance = np.repeat(np.arange(n_inst), copies)
+    B = len(env_instance)
+    rng = np.random.default_rng(9)
+    act1 = np.stack([rng.integers(0, 12, (T, n_inst)), rng.integers(0, 10, (T, n_inst))], -1).astype(np.int32)
+    rnd1 = rng.integers(0, 2**32, (T, n_inst, 2), dtype=np.uint64).astype(np.uint32)
+    actions = np.repeat(act1, copies, axis=1)
+    rnd = np.repeat(rnd1, copies, axis=1)
+    outs = []
+    for rep in range(2):
+        vec = make_vec(blobs, env_instance, "MO_DFJSP")
+        vec.reset()
+        o = vec.rollout(torch.from_numpy(actions).cuda(), torch.from_numpy(rnd.view(np.int32)).cuda(),
+                        reward_policy=1, want_rec=True)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items()})
+        assert (vec.info()["error"] == 0).all()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), f"{k}: rerun differs"
+    rec = outs[0]["rec"].reshape(T, n_inst, copies, 8)
+    assert (rec == rec[:, :, :1]).all(), "replicas of one instance diverged"
+    st = outs[0]["state"].reshape(T, n_inst, copies, -1)
+    assert np.array_equal(st, np.broadcast_to(st[:, :, :1], st.shape))
+    assert pc.schedule_is_feasible(outs[0]["rec"][:, ::copies], outs[0]["done"][:, ::copies], None)
+    # oracle on a sample of instances
+    import oracle_py
+    sample = [0, 17, 63]
+    envs = [oracle_py.OracleEnv(blobs[k], "MO_DFJSP") for k in sample]
+    for e in envs:
+        e.reset()
+    ref = oracle_py.batch_rollout(envs, act1[:, sample], rnd1[:, sample], 1)
+    assert np.array_equal(ref["rec"], rec[:, sample, 0])
+    assert np.array_equal(ref["reward"], outs[0]["reward"].reshape(T, n_inst, copies)[:, sample, 0])
+    pc.assert_states_close(st[:, sample, 0], ref["state"], "full size sample")
+
+
+def test_error_behaviour():
+    from deep_reinforcement_learning_for_fjsp_b200.vec_env import FJSPVecEnv, FJSPEnv, MyError
+    with pytest.raises(RuntimeError):
+        FJSPVecEnv(None, [0], "MO_DFJSP", blobs=[np.zeros(64, np.int32)])
+    with pytest.raises(MyError):
+        FJSPVecEnv(None, [0], "NOT_AN_ENV", blobs=[np.zeros(64, np.int32)])
+    insts, _ = pc.random_batch(31, "MO_DFJSP", 1, 1)
+    env = FJSPEnv(variant="MO_DFJSP", instance=insts[0])
+    env.reset()
+    with pytest.raises(MyError):
+        env.step((12, 0), reward_policy=1)      # the reference raises MyError for an undefined rule
+    with pytest.raises(MyError):
+        env.step((0, 0), reward_policy=7)       # ... and for an undefined reward function
+
+
+def test_single_env_drop_in_episode():
+    """FJSPEnv: the reference's reset()/step(action) loop, one DDQN-style rule episode."""
+    import oracle_py
+    from deep_reinforcement_learning_for_fjsp_b200.vec_env import FJSPEnv
+    insts, _ = pc.random_batch(41, "SO_DFJSP", 1, 1)
+    env = FJSPEnv(variant="SO_DFJSP", instance=insts[0])
+    ora = oracle_py.OracleEnv(insts[0].to_blob(), "SO_DFJSP")
+    s, so = env.reset(), ora.reset()
+    pc.assert_states_close(s, so, "reset")
+    n = 0
+    while not env.done:
+        a = (n % 5, (n // 5) % 4)
+        s, r, d = env.step(a)
+        so, ro, do, _ = ora.step(a)
+        assert r == ro and d == do
+        pc.assert_states_close(s, so, f"step {n}")
+        n += 1
+    assert env.delay_time_sum == ora.info()["delay_sum"]

@@ -1,0 +1,54 @@
+"""CPU parity of the KERNEL SOURCE: csrc/fjsp_core.cuh compiled by g++ as a one-lane program
+(tests/hostsim) must reproduce the golden reference trajectories and agree with the oracle
+on random mixed batches.  This covers the compressed device state (per-order counters,
+linked queues, rule cache, fluid slots), the set-order emulation, the in-kernel simplex
+and the table builder; the 32-lane cooperation is covered by tests/test_gpu_parity.py."""
+import sys, os
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+import build as hostsim  # noqa: E402
+import parity_common as pc  # noqa: E402
+from conftest import golden_cases  # noqa: E402
+
+DEVICE_CASES = [c for c in golden_cases() if "fjssp" not in c]
+
+
+def make_vec(blobs, env_instance, variant):
+    return hostsim.HostSimVec(blobs, env_instance, variant)
+
+
+@pytest.mark.parametrize("case", DEVICE_CASES)
+def test_golden(case, golden_dir):
+    pc.replay_golden(make_vec, golden_dir, case)
+
+
+@pytest.mark.parametrize("variant,seed,rp,bd", [("SO_DFJSP", 1, 1, False), ("MO_DFJSP", 2, 0, False),
+                                                 ("MO_DFJSP", 3, 3, False), ("MO_DFJSP_breakdown", 4, 2, True)])
+def test_random_batch_vs_oracle(variant, seed, rp, bd):
+    pc.compare_with_oracle(make_vec, variant, seed, n_inst=4, copies=2, T=40, launches=3, reward_policy=rp,
+                           breakdowns=bd)
+
+
+def test_table_builder_set_order_matches_cpython():
+    L = hostsim.lib()
+    rng = np.random.default_rng(5)
+    out = np.zeros(32, np.int32)
+    for _ in range(5000):
+        M = int(rng.integers(1, 33))
+        tup = np.ascontiguousarray(rng.permutation(M)[:int(rng.integers(1, M + 1))], np.int32)
+        k = L.fjsp_hostsim_pyset_order(tup.ctypes.data, len(tup), out.ctypes.data)
+        ord_tup = list(set(int(v) for v in tup))
+        assert list(out[:k]) == ord_tup
+        idle = [m for m in range(M) if rng.random() < 0.5]
+        mask = sum(1 << m for m in idle)
+        o = np.ascontiguousarray(ord_tup, np.int32)
+        k = L.fjsp_hostsim_selectable(mask, o.ctypes.data, len(o), out.ctypes.data)
+        assert list(out[:k]) == list(set(idle) & set(int(v) for v in tup))
+
+
+def test_bad_blob_is_rejected():
+    with pytest.raises(RuntimeError):
+        hostsim.HostSimVec([np.zeros(32, np.int32)], [0], "SO_DFJSP")
