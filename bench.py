@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""FJSP env-steps/sec benchmark (BASELINE.json metric) for the B200 vector environment.
+
+Workload (BASELINE.json configs[1]): MO_DFJSP, 4096 generated instances per GPU
+(Instance_generate.py distributions: 10 machines, 3 orders), random composite-rule
+actions (task rule 0..11, machine rule 0..9, with the random rules' draws), auto-reset.
+One bench "step" = ONE launch of the step kernel = `--rollout` env steps for every
+environment copy.  `value` is device-timed (CUDA events on the launching stream, inputs
+resident in HBM, L2 flushed between timed launches); `e2e` goes through the host-buffer
+C-ABI call with pinned host buffers, H2D of actions/draws and D2H of state/reward/done
+inside the timed region.
+
+  python bench.py [--gpus N --steps K --warmup W]      (N > 1: launched under torchrun)
+  python bench.py --impl reference ...                 (the CPU port of the reference env)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fjsp_env_steps_per_sec"
+UNIT = "env_steps/s"
+WORKLOAD = "MO_DFJSP_4096_generated_instances_random_rules"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environment copies per GPU")
+    ap.add_argument("--rollout", type=int, default=32, help="env steps per kernel launch")
+    ap.add_argument("--variant", default="MO_DFJSP")
+    ap.add_argument("--machines", type=int, default=10)
+    ap.add_argument("--orders", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_instances(n, seed, M, S):
+    from deep_reinforcement_learning_for_fjsp_b200.instance import FJSPInstance
+    insts = []
+    for i in range(n):
+        inst = FJSPInstance.generate(seed * 100003 + i, [0.5, 1.0, 1.5][i % 3], M, S, "DA3C")
+        insts.append(inst)
+    return insts
+
+
+def make_actions(rng, T, B, variant):
+    nt, nm = (6, 5) if variant == "SO_DFJSP" else (12, 10)
+    a = np.stack([rng.integers(0, nt, (T, B)), rng.integers(0, nm, (T, B))], -1).astype(np.int32)
+    r = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
+    return a, r
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_port_throughput(insts, variant, seconds, rollout, seed):
+    """The oracle (C port of the reference env) on the host cores, a bounded sample of the
+    same workload: as many environments as threads, `rollout`-step chunks until the budget."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    threads = oracle_py.lib().fjsp_oracle_max_threads()
+    B = max(threads * 2, 8)
+    envs = [oracle_py.OracleEnv(insts[i % len(insts)].to_blob(), variant) for i in range(B)]
+    for e in envs:
+        e.reset()
+    rng = np.random.default_rng(seed)
+    a, r = make_actions(rng, rollout, B, variant)
+    oracle_py.batch_rollout(envs, a, r, 1, want_state=True, want_rec=False, threads=threads)  # warm-up
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        a, r = make_actions(rng, rollout, B, variant)
+        oracle_py.batch_rollout(envs, a, r, 1, want_state=True, want_rec=False, threads=threads)
+        steps += rollout * B
+    dt = time.perf_counter() - t0
+    return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{B} envs x {steps // B} steps of the same workload in {dt:.1f}s on {threads} host threads "
+                      f"(oracle/fjsp_oracle.c, the C port pinned bit-exact to the Python reference)"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    insts = make_instances(64, args.seed, args.machines, args.orders)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    threads = oracle_py.lib().fjsp_oracle_max_threads()
+    B = max(threads * 2, 8)
+    envs = [oracle_py.OracleEnv(insts[i % len(insts)].to_blob(), args.variant) for i in range(B)]
+    for e in envs:
+        e.reset()
+    rng = np.random.default_rng(args.seed)
+    T = args.rollout
+    for _ in range(args.warmup):
+        a, r = make_actions(rng, T, B, args.variant)
+        oracle_py.batch_rollout(envs, a, r, 1, want_rec=False, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, r = make_actions(rng, T, B, args.variant)
+        oracle_py.batch_rollout(envs, a, r, 1, want_rec=False, threads=threads)
+    dt = time.perf_counter() - t0
+    value = args.steps * T * B / dt
+    sample = f"{B} envs x {args.steps * T} steps on {threads} host threads (C port of the reference env; the Python " \
+             f"reference itself needs CPLEX and runs ~20-200 steps/s, see BASELINE.md)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_sampled": B, "env_steps_per_step": T,
+                       "machines": args.machines, "orders": args.orders},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    from deep_reinforcement_learning_for_fjsp_b200.vec_env import FJSPVecEnv
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, K, W = args.envs, args.rollout, args.steps, max(args.warmup, 3)
+    # every rank plays its own shard of distinct instances: no data-path collective
+    insts = make_instances(B, args.seed + 7919 * rank, args.machines, args.orders)
+    vec = FJSPVecEnv(insts, np.arange(B), args.variant, device=local_rank)
+    q = vec.query()
+    vec.reset()
+    rng = np.random.default_rng(args.seed + rank)
+    # inputs for every launch, resident in HBM before the timed region
+    acts, rnds = [], []
+    for _ in range(W + K):
+        a, r = make_actions(rng, T, B, args.variant)
+        acts.append(torch.from_numpy(a).to(dev))
+        rnds.append(torch.from_numpy(r.view(np.int32)).to(dev))
+    out = {"state": torch.empty((T, B, vec.state_size), dtype=torch.float32, device=dev),
+           "reward": torch.empty((T, B), dtype=torch.float64, device=dev),
+           "done": torch.empty((T, B), dtype=torch.int32, device=dev)}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        vec.rollout(acts[i], rnds[i], reward_policy=1, out=out, state_dtype=torch.float32)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = vec.query()["launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xff)                       # evict L2 between timed launches (not timed)
+        ev[i][0].record(stream)
+        vec.rollout(acts[W + i], rnds[W + i], reward_policy=1, out=out, state_dtype=torch.float32)
+        ev[i][1].record(stream)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    per_launch_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = float(sum(per_launch_ms))
+    launches = vec.query()["launches"] - launches0
+    errors = int((vec.info()["error"] != 0).sum())
+    # ---- e2e: the host-buffer C-ABI call, pinned host buffers, copies inside the timed region
+    ha = [torch.from_numpy(make_actions(rng, T, B, args.variant)[0]).pin_memory() for _ in range(2)]
+    hr = [torch.from_numpy(make_actions(rng, T, B, args.variant)[1].view(np.int32)).pin_memory() for _ in range(2)]
+    hs = torch.empty((T, B, vec.state_size), dtype=torch.float32).pin_memory()
+    hrw = torch.empty((T, B), dtype=torch.float64).pin_memory()
+    hdn = torch.empty((T, B), dtype=torch.int32).pin_memory()
+    L = vec._L
+    from deep_reinforcement_learning_for_fjsp_b200 import _lib
+
+    def e2e_call(i):
+        _lib.check(L.fjsp_vec_step_host(vec._h, T, ha[i % 2].data_ptr(), hr[i % 2].data_ptr(), 1, 1.0, 1.0, 1.0, 1,
+                                        None, hs.data_ptr(), hrw.data_ptr(), hdn.data_ptr(), None))
+    for i in range(W):
+        e2e_call(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_call(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.summary()
+    h2d = ha[0].numel() * 4 + hr[0].numel() * 4
+    d2h = hs.numel() * 4 + hrw.numel() * 8 + hdn.numel() * 4
+    # ---- max over ranks
+    tm = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(tm[0]), float(tm[1])
+    total_steps = world * B * T * K
+    value = total_steps / (dev_ms_max / 1e3)
+    e2e_value = total_steps / (e2e_ms_max / 1e3)
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        # algorithmic bytes of one launch (DESIGN.md "roofline"): each env record read and
+        # written once, plus per env-step inputs (2 x int32 action + 2 x uint32 draw) and
+        # outputs (float32 state, float64 reward, int32 done)
+        per_env_step_io = 16 + vec.state_size * 4 + 8 + 4
+        algo_bytes = B * (2 * q["env_record_bytes"] + T * per_env_step_io)
+        launch_s = (dev_ms / K) / 1e3
+        achieved = algo_bytes / launch_s / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64+int32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "envs_per_gpu": B, "env_steps_per_step": T,
+                           "machines": args.machines, "orders": args.orders, "variant": args.variant,
+                           "l2": "flushed between timed launches (256 MiB fill)", "parallelism": f"shard{world}",
+                           "env_record_bytes": q["env_record_bytes"], "grid": q["grid"], "block": q["block"]},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "fjsp_vec_step_host (C ABI, pinned host buffers, float32 state out)"},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "fjsp_step_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                             "launch_ms": launch_s * 1e3,
+                             "note": "latency/FP64-bound discrete-event kernel, not HBM-bound; see DESIGN.md"},
+                "wall_s_timed_region": wall, "env_errors": errors,
+                "launch_ms_min_max": [min(per_launch_ms), max(per_launch_ms)]}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_port_throughput(insts[:64], args.variant, args.cpu_seconds, T, args.seed)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -681,6 +681,8 @@ void fjsp_oracle_info(void *h, long long *info)
     info[9] = e->next_order;
 }
 
+int fjsp_oracle_done(void *h) { return ((Env *)h)->done; }
+
 /* machine completion times, for makespan checks in the SO variants */
 void fjsp_oracle_machine_end(void *h, int *out)
 {

@@ -10,6 +10,7 @@ int fjsp_oracle_step(void *h, int task_rule, int machine_rule, uint32_t rnd_task
                      int reward_policy, double completion, double tardiness, double energy_norm,
                      double *state_out, double *reward_out, int *done_out, int *rec);
 int fjsp_oracle_reset(void *h, double *state_out);
+int fjsp_oracle_done(void *h);
 
 int fjsp_oracle_max_threads(void)
 {
@@ -33,6 +34,7 @@ static void *worker(void *arg)
         double st[64], rw = 0; int dn = 0; int rc[8];
         for (int t = 0; t < jb->T; ++t) {
             size_t i = (size_t)t * jb->B + b;
+            if (fjsp_oracle_done(jb->envs[b])) jb->err |= fjsp_oracle_reset(jb->envs[b], st);
             jb->err |= fjsp_oracle_step(jb->envs[b], jb->actions[2 * i], jb->actions[2 * i + 1],
                                         jb->rnd[2 * i], jb->rnd[2 * i + 1], jb->reward_policy,
                                         1.0, 1.0, 1.0, st, &rw, &dn, rc);
@@ -40,7 +42,6 @@ static void *worker(void *arg)
             if (jb->reward) jb->reward[i] = rw;
             if (jb->done) jb->done[i] = dn;
             if (jb->rec) for (int k = 0; k < 8; ++k) jb->rec[i * 8 + k] = rc[k];
-            if (dn) jb->err |= fjsp_oracle_reset(jb->envs[b], st);
         }
     }
     return NULL;
@@ -48,7 +49,7 @@ static void *worker(void *arg)
 
 /* T steps for each of B environments; actions [T][B][2], rnd [T][B][2];
  * outputs state [T][B][nstate], reward [T][B], done [T][B], rec [T][B][8] (any may be NULL).
- * A finished environment is reset before its next action (auto-reset). */
+ * A finished environment is reset right before its next action (lazy auto-reset, like the device). */
 int fjsp_oracle_batch_rollout(void **envs, int B, int T, const int *actions, const uint32_t *rnd,
                               int reward_policy, int nstate, double *state, double *reward,
                               int *done, int *rec, int threads)
