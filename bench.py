@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--machines", type=int, default=10)
     ap.add_argument("--orders", type=int, default=3)
     ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--burnin", type=int, default=2048,
+                    help="untimed env steps per copy before timing, so episodes (order arrivals, resets) desynchronise")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -197,9 +199,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    for i in range((args.burnin + T - 1) // T):      # untimed burn-in: reach the steady mix of episode phases
+        vec.rollout(acts[i % (W + K)], rnds[(i * 7 + 3) % (W + K)], reward_policy=1, out=out, state_dtype=torch.float32)
     for i in range(W):
         vec.rollout(acts[i], rnds[i], reward_policy=1, out=out, state_dtype=torch.float32)
     barrier()
+    info0 = vec.info()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = vec.query()["launches"]
@@ -215,7 +220,10 @@ def main():
     per_launch_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = float(sum(per_launch_ms))
     launches = vec.query()["launches"] - launches0
-    errors = int((vec.info()["error"] != 0).sum())
+    info1 = vec.info()
+    errors = int((info1["error"] != 0).sum())
+    lp_solves = int((info1["lp_solves"] - info0["lp_solves"]).sum())
+    episodes = int((info1["episodes"] - info0["episodes"]).sum())
     # ---- e2e: the host-buffer C-ABI call, pinned host buffers, copies inside the timed region
     ha = [torch.from_numpy(make_actions(rng, T, B, args.variant)[0]).pin_memory() for _ in range(2)]
     hr = [torch.from_numpy(make_actions(rng, T, B, args.variant)[1].view(np.int32)).pin_memory() for _ in range(2)]
@@ -265,7 +273,7 @@ def main():
                 "dtype": "f64+int32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "envs_per_gpu": B, "env_steps_per_step": T,
                            "machines": args.machines, "orders": args.orders, "variant": args.variant,
-                           "l2": "flushed between timed launches (256 MiB fill)", "parallelism": f"shard{world}",
+                           "l2": "flushed between timed launches (256 MiB fill)", "kernels_per_step": "step + LP + resume", "parallelism": f"shard{world}",
                            "env_record_bytes": q["env_record_bytes"], "grid": q["grid"], "block": q["block"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "fjsp_vec_step_host (C ABI, pinned host buffers, float32 state out)"},
@@ -277,6 +285,8 @@ def main():
                              "launch_ms": launch_s * 1e3,
                              "note": "latency/FP64-bound discrete-event kernel, not HBM-bound; see DESIGN.md"},
                 "wall_s_timed_region": wall, "env_errors": errors,
+                "timed_region_events": {"fluid_lp_solves": lp_solves, "episodes_finished": episodes,
+                                        "burnin_env_steps_per_copy": args.burnin},
                 "launch_ms_min_max": [min(per_launch_ms), max(per_launch_ms)]}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_port_throughput(insts[:64], args.variant, args.cpu_seconds, T, args.seed)

@@ -22,28 +22,67 @@ static thread_local std::string g_err;
         }                                                                                          \
     } while (0)
 
+// main step kernel: every env; parks an env on the first fluid LP it needs
 template <int VARIANT, int SUM_MODE>
-__global__ void __launch_bounds__(FJ_BLOCK) fjsp_step_kernel(FjParams P, FjStepArgs A)
+__global__ void __launch_bounds__(FJ_BLOCK, 4) fjsp_step_kernel(FjParams P, FjStepArgs A)
+{
+    const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
+    for (int env = gw; env < P.B; env += total) fj_env_rollout<VARIANT, SUM_MODE, 1>(P, A, env, nullptr);
+}
+
+// resume kernel: parked envs only; picks up the LP solution, finishes the launch
+template <int VARIANT, int SUM_MODE>
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(FjParams P, FjStepArgs A)
 {
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
     unsigned char *lp = P.lp + (size_t)gw * P.lp_stride;
-    for (int env = gw; env < P.B; env += total) fj_env_rollout<VARIANT, SUM_MODE>(P, A, env, lp);
+    const int n = *P.pend_count;
+    for (int i = gw; i < n; i += total) fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, P.pend_env[i], lp);
+}
+
+// LP kernel: one CTA per parked LP, basis inverse in shared memory when it fits
+#define FJ_LP_THREADS 256
+template <int SMEM_BINV>
+__global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(FjParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    int n = *P.pend_count;
+    if (n > P.lp_slots) n = P.lp_slots;
+    const size_t binv_bytes = (size_t)P.d.Rx * P.d.Rx * 8;
+    unsigned char *binv = SMEM_BINV ? smem : P.lp + (size_t)blockIdx.x * P.lp_stride;
+    unsigned char *small_ = SMEM_BINV ? smem + binv_bytes : smem;
+    unsigned char *red = small_ + (fj_lp_small_bytes(P.d) + 7) / 8 * 8;
+    FjCtaGroup g;
+    g.rk = (double *)red; g.ri = (int *)(red + 32 * 8); g.ra = g.ri + 32;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) fj_lp_service(P, g, i, binv, small_);
+}
+
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(FjParams P)
+{
+    const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
+    for (int env = gw; env < P.B; env += total) fj_env_reset_begin(P, env);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *P.pend_count = P.B;
 }
 
 template <int VARIANT, int SUM_MODE>
-__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_kernel(FjParams P, double *state64, float *state32)
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_finish_kernel(FjParams P, double *state64, float *state32)
 {
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
     unsigned char *lp = P.lp + (size_t)gw * P.lp_stride;
-    for (int env = gw; env < P.B; env += total) fj_env_reset<VARIANT, SUM_MODE>(P, env, lp, state64, state32);
+    for (int env = gw; env < P.B; env += total) fj_env_reset_finish<VARIANT, SUM_MODE>(P, env, lp, state64, state32);
 }
 
 struct fjsp_vec {
     FjTables tb;
     FjParams P;
-    int variant, sum_mode, B, device, grid, nstate;
+    int variant, sum_mode, B, device, grid, resume_grid, lp_grid, lp_smem_binv, nstate;
+    size_t lp_smem_bytes;
+    int *d_pend_count, *d_pend_env, *d_lp_meta;
+    double *d_lp_x;
     int32_t *d_inst, *d_env_inst;
     unsigned char *d_env, *d_lp;
     long long launches;
@@ -55,6 +94,12 @@ struct fjsp_vec {
     double *d_state64, *d_reward;
     float *d_state32;
 };
+
+static void launch_lp(fjsp_vec *v, cudaStream_t st)
+{
+    if (v->lp_smem_binv) fjsp_lp_kernel<1><<<v->lp_grid, FJ_LP_THREADS, v->lp_smem_bytes, st>>>(v->P);
+    else fjsp_lp_kernel<0><<<v->lp_grid, FJ_LP_THREADS, v->lp_smem_bytes, st>>>(v->P);
+}
 
 template <typename F> static int dispatch(fjsp_vec *v, F f)
 {
@@ -103,7 +148,19 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     int cap = prop.multiProcessorCount * 8;
     v->grid = want < cap ? want : cap;
     const unsigned long long lp_stride = fj_lp_scratch_bytes(v->tb.d);
-    const size_t lp_bytes = (size_t)lp_stride * v->grid * FJ_WARPS_PER_BLOCK;
+    // the resume kernel (in-line LP fallback) and the LP kernel (global Binv fallback) share the slabs
+    int rcap = prop.multiProcessorCount * 4;
+    v->resume_grid = want < rcap ? want : rcap;
+    v->lp_grid = prop.multiProcessorCount * 2;
+    const size_t small_b = (fj_lp_small_bytes_host(v->tb.d) + 7) / 8 * 8 + 32 * 16;
+    const size_t binv_b = (size_t)v->tb.d.Rx * v->tb.d.Rx * 8;
+    v->lp_smem_binv = (binv_b + small_b <= 200 * 1024) ? 1 : 0;
+    v->lp_smem_bytes = v->lp_smem_binv ? binv_b + small_b : small_b;
+    if (v->lp_smem_bytes > 200 * 1024) { g_err = "fjsp_vec_create: instance too large for the LP kernel's shared memory"; delete v; return -5; }
+    if (v->lp_smem_binv && binv_b + small_b > 100 * 1024) v->lp_grid = prop.multiProcessorCount;
+    int slabs = v->resume_grid * FJ_WARPS_PER_BLOCK;
+    if (v->lp_grid > slabs) slabs = v->lp_grid;
+    const size_t lp_bytes = (size_t)lp_stride * slabs;
     const size_t env_bytes = (size_t)n_envs * v->tb.eo.stride;
     CK(cudaMalloc(&v->d_inst, v->tb.inst.size() * 4));
     CK(cudaMalloc(&v->d_env_inst, (size_t)n_envs * 4));
@@ -113,10 +170,23 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaMemcpy(v->d_env_inst, env_instance, (size_t)n_envs * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(v->d_env, 0, env_bytes));
     CK(cudaMemset(v->d_lp, 0, lp_bytes));
+    // parked-LP list and solution slots (one per env unless that would exceed 2 GiB)
+    size_t slots = (size_t)n_envs;
+    const size_t per_slot = (size_t)v->tb.d.NPx * 8;
+    if (slots * per_slot > ((size_t)2 << 30)) slots = ((size_t)2 << 30) / per_slot;
+    CK(cudaMalloc(&v->d_pend_count, 4));
+    CK(cudaMalloc(&v->d_pend_env, (size_t)n_envs * 4));
+    CK(cudaMalloc(&v->d_lp_x, slots * per_slot));
+    CK(cudaMalloc(&v->d_lp_meta, slots * 8));
+    CK(cudaMemset(v->d_pend_count, 0, 4));
+    CK(cudaFuncSetAttribute(fjsp_lp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->lp_smem_bytes));
+    CK(cudaFuncSetAttribute(fjsp_lp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->lp_smem_bytes));
     FjParams &P = v->P;
     P.d = v->tb.d; P.io = v->tb.io; P.eo = v->tb.eo;
     P.inst = v->d_inst; P.env_inst = v->d_env_inst; P.env = v->d_env; P.lp = v->d_lp; P.lp_stride = lp_stride;
     P.B = n_envs; P.variant = variant; P.sum_mode = v->sum_mode; P.nobs = v->nstate / 2;
+    P.pend_count = v->d_pend_count; P.pend_env = v->d_pend_env; P.lp_x = v->d_lp_x; P.lp_meta = v->d_lp_meta;
+    P.lp_slots = (int)slots;
     CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
     v->stage_T = 0;
     v->d_actions = v->d_done = v->d_rec = nullptr; v->d_rnd = nullptr;
@@ -140,6 +210,7 @@ int fjsp_vec_destroy(fjsp_vec *v)
     cudaSetDevice(v->device);
     free_stage(v);
     cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
+    cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
     cudaStreamDestroy(v->stream);
     delete v;
     return 0;
@@ -158,12 +229,14 @@ int fjsp_vec_reset(fjsp_vec *v, void *stream, double *d_state64, float *d_state3
     if (!v) { g_err = "fjsp_vec_reset: null handle"; return -1; }
     CK(cudaSetDevice(v->device));
     cudaStream_t st = (cudaStream_t)stream;
+    fjsp_reset_begin_kernel<<<v->grid, FJ_BLOCK, 0, st>>>(v->P);
+    launch_lp(v, st);
     int rc = dispatch(v, [&](auto V, auto SM) {
-        fjsp_reset_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, 0, st>>>(v->P, d_state64, d_state32);
+        fjsp_reset_finish_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, 0, st>>>(v->P, d_state64, d_state32);
         return 0;
     });
     if (rc) return rc;
-    v->launches += 1;
+    v->launches += 3;
     CK(cudaGetLastError());
     return 0;
 }
@@ -182,12 +255,15 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     A.completion = completion; A.tardiness = tardiness; A.energy = energy;
     A.state = d_state64; A.state32 = d_state32; A.reward = d_reward; A.done = d_done; A.rec = d_rec;
     cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(v->d_pend_count, 0, 4, st));
     int rc = dispatch(v, [&](auto V, auto SM) {
         fjsp_step_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, 0, st>>>(v->P, A);
+        launch_lp(v, st);
+        fjsp_resume_kernel<decltype(V)::value, decltype(SM)::value><<<v->resume_grid, FJ_BLOCK, 0, st>>>(v->P, A);
         return 0;
     });
     if (rc) return rc;
-    v->launches += 1;
+    v->launches += 3;
     CK(cudaGetLastError());
     return 0;
 }

@@ -28,6 +28,7 @@
 
 #ifdef __CUDACC__
 #define FJ_FN __device__ __forceinline__
+#define FJ_MFN __device__ __forceinline__
 #define FJ_FN_NOINLINE __device__ __noinline__
 #define FJ_NL 32
 FJ_FN int fj_lane() { return threadIdx.x & 31; }
@@ -46,6 +47,7 @@ FJ_FN double fj_mul(double a, double b) { return __dmul_rn(a, b); }
 FJ_FN double fj_div(double a, double b) { return __ddiv_rn(a, b); }
 #else
 #define FJ_FN static inline
+#define FJ_MFN inline
 #define FJ_FN_NOINLINE static
 #define FJ_NL 1
 FJ_FN int fj_lane() { return 0; }
@@ -194,23 +196,100 @@ FJ_FN int fj_order_of(const FjCtx &c, int r, int n)   // which order job n of ki
 }
 
 // ---------------------------------------------------------------- fluid LP
-// Same pivoting specification as oracle/fjsp_lp.c (DESIGN.md "fluid LP specification"),
-// executed cooperatively by the warp on a scratch slab in global memory.
+// Same pivoting specification as oracle/fjsp_lp.c (DESIGN.md "fluid LP specification").
+// The solver is written once against a "group" policy: FjWarpGroup (the 32 lanes of the
+// env's own warp, scratch in global memory: the in-line fallback) or FjCtaGroup (a whole
+// CTA, basis inverse in shared memory: the LP kernel).  Both perform the identical
+// floating-point operations; only the work split differs.
 #define FJ_LP_EPS_D 1e-9
 #define FJ_LP_EPS_PIV 1e-9
 #define FJ_LP_EPS_ZERO 1e-9
 
+struct FjWarpGroup {
+    FJ_MFN int rank() const { return fj_lane(); }
+    FJ_MFN int size() const { return FJ_NL; }
+    FJ_MFN int lane() const { return fj_lane(); }
+    FJ_MFN int warp() const { return 0; }
+    FJ_MFN int nwarps() const { return 1; }
+    FJ_MFN void sync() const { fj_sync(); }
+    FJ_MFN int min_i(int v) const { return fj_min_i(v); }
+    // lexicographic (key, idx) minimum, idx 0x7fffffff = empty; `aux` travels with the winner
+    FJ_MFN void argmin(double &key, int &idx, int &aux) const
+    {
+        for (int m = FJ_NL / 2; m > 0; m >>= 1) {
+            double ok = fj_xor_d(key, m); int oi = fj_xor_i(idx, m); int oa = fj_xor_i(aux, m);
+            if (oi == 0x7fffffff) continue;
+            if (idx == 0x7fffffff || ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; aux = oa; }
+        }
+    }
+};
+
+#ifdef __CUDACC__
+struct FjCtaGroup {
+    double *rk; int *ri, *ra;    // shared scratch: one entry per warp (<= 32)
+    FJ_MFN int rank() const { return threadIdx.x; }
+    FJ_MFN int size() const { return blockDim.x; }
+    FJ_MFN int lane() const { return threadIdx.x & 31; }
+    FJ_MFN int warp() const { return threadIdx.x >> 5; }
+    FJ_MFN int nwarps() const { return blockDim.x >> 5; }
+    FJ_MFN void sync() const { __syncthreads(); }
+    FJ_MFN int min_i(int v) const
+    {
+        v = fj_min_i(v);
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) ri[w] = v;
+        __syncthreads();
+        int r = ri[0];
+        for (int i = 1; i < nw; ++i) r = ri[i] < r ? ri[i] : r;
+        return r;
+    }
+    FJ_MFN void argmin(double &key, int &idx, int &aux) const
+    {
+        FjWarpGroup wg; wg.argmin(key, idx, aux);
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { rk[w] = key; ri[w] = idx; ra[w] = aux; }
+        __syncthreads();
+        key = rk[0]; idx = ri[0]; aux = ra[0];
+        for (int i = 1; i < nw; ++i) {
+            const double ok = rk[i]; const int oi = ri[i];
+            if (oi == 0x7fffffff) continue;
+            if (idx == 0x7fffffff || ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; aux = ra[i]; }
+        }
+    }
+};
+#else
+struct FjCtaGroup {   // host simulation: one thread
+    double *rk; int *ri, *ra;
+    FJ_MFN int rank() const { return 0; }
+    FJ_MFN int size() const { return 1; }
+    FJ_MFN int lane() const { return 0; }
+    FJ_MFN int warp() const { return 0; }
+    FJ_MFN int nwarps() const { return 1; }
+    FJ_MFN void sync() const {}
+    FJ_MFN int min_i(int v) const { return v; }
+    FJ_MFN void argmin(double &, int &, int &) const {}
+};
+#endif
+
 struct FjLp {
     double *Binv, *xB, *w, *adem, *rate;
-    int *basis, *pos, *colq, *colm, *prec, *colbase;
+    int *basis, *pos, *colq, *colm, *prec;
     int R, C, NP;
 };
 
-FJ_FN void fj_lp_carve(FjLp &L, unsigned char *slab, const FjDims &d)
+// bytes of the small arrays (everything but Binv) and carving of a slab
+FJ_FN size_t fj_lp_small_bytes(const FjDims &d)
 {
     size_t R = d.Rx, C = d.NPx + 1;
-    double *p = (double *)slab;
-    L.Binv = p; p += R * R;
+    return (2 * R + 2 * C) * 8 + (R + (C + R) + 2 * C + d.KTx) * 4;
+}
+FJ_FN void fj_lp_carve(FjLp &L, unsigned char *binv, unsigned char *small_, const FjDims &d)
+{
+    size_t R = d.Rx, C = d.NPx + 1;
+    L.Binv = (double *)binv;
+    double *p = (double *)small_;
     L.xB = p; p += R;
     L.w = p; p += R;
     L.adem = p; p += C;
@@ -221,13 +300,11 @@ FJ_FN void fj_lp_carve(FjLp &L, unsigned char *slab, const FjDims &d)
     L.colq = q; q += C;
     L.colm = q; q += C;
     L.prec = q; q += d.KTx;
-    L.colbase = q; q += d.KTx;
 }
 
-// reduced cost of column j given the row `pt` of Binv where t is basic (y = -Binv[pt])
+// sum_k (negate ? -brow[row_k] : brow[row_k]) * val_k of column j in ascending row order
 FJ_FN double fj_lp_colvec_dot(const FjCtx &c, const FjLp &L, const double *brow, int j, int negate)
 {
-    // returns sum_k (negate ? -brow[row_k] : brow[row_k]) * val_k in CSC (ascending row) order
     int M = c.M, KT = c.KT;
     double acc = 0.0;
     if (j == L.NP) {   // the t column: +1 in every demand row
@@ -245,28 +322,30 @@ FJ_FN double fj_lp_colvec_dot(const FjCtx &c, const FjLp &L, const double *brow,
     return acc;
 }
 
-FJ_FN_NOINLINE int fj_lp_solve(FjCtx &c, FjLp &L, int *iters_out)
+// Builds the canonical LP from the env record (after fj_arrival_begin) and solves it.
+// On return x[0..NP) holds the structural solution (values < 1e-9 flushed to 0).
+template <class G>
+FJ_FN int fj_lp_solve(const G &g, FjCtx &c, FjLp &L, double *x_out, int *iters_out)
 {
-    const int lane = fj_lane();
+    const int tid = g.rank(), nt = g.size();
     const int M = c.M, KT = c.KT, Mx = c.Mx;
-    const int32_t *elig = FJ_I(c, elig), *ptime = FJ_I(c, ptime), *rjstage = FJ_I(c, rjstage), *rjlast = FJ_I(c, rjlast);
-    // column bases and precedence rows (sequential prefix work: one lane)
-    if (lane == 0) {
-        int np = 0, nprec = 0;
+    const int32_t *elig = FJ_I(c, elig), *ptime = FJ_I(c, ptime), *rjlast = FJ_I(c, rjlast);
+    const int32_t *colbase = FJ_I(c, colbase);
+    if (tid == 0) {   // precedence rows: sequential numbering
+        int nprec = 0;
         for (int q = 0; q < KT; ++q) {
-            L.colbase[q] = np; np += fj_popc((unsigned)elig[q]);
             L.prec[q] = -1;
             if (!rjlast[q] && c.qlen[q + 1] == 0) L.prec[q] = M + KT + nprec++;
         }
-        L.pos[0] = np; L.pos[1] = nprec;   // hand-off to the other lanes
+        L.pos[0] = nprec;
     }
-    fj_sync();
-    const int NP = L.pos[0], R = M + KT + L.pos[1], C = NP + 1;
-    fj_sync();
+    g.sync();
+    const int NP = FJ_I(c, hdr)[7], R = M + KT + L.pos[0], C = NP + 1;
+    g.sync();
     L.NP = NP; L.R = R; L.C = C;
-    for (int q = lane; q < KT; q += FJ_NL) {
+    for (int q = tid; q < KT; q += nt) {
         unsigned em = (unsigned)elig[q];
-        int col = L.colbase[q];
+        int col = colbase[q];
         double fs = (double)c.fstart[q];
         while (em) {
             int m = fj_ffs0(em); em &= em - 1;
@@ -277,23 +356,21 @@ FJ_FN_NOINLINE int fj_lp_solve(FjCtx &c, FjLp &L, int *iters_out)
             ++col;
         }
     }
-    for (int j = lane; j < C + R; j += FJ_NL) L.pos[j] = j >= C ? j - C : -1;
-    for (int i = lane; i < R; i += FJ_NL) { L.basis[i] = C + i; L.xB[i] = i < M ? 1.0 : 0.0; }
-    for (int i = 0; i < R; ++i)
-        for (int k = lane; k < R; k += FJ_NL) L.Binv[(size_t)i * R + k] = (i == k) ? 1.0 : 0.0;
-    fj_sync();
+    for (int j = tid; j < C + R; j += nt) L.pos[j] = j >= C ? j - C : -1;
+    for (int i = tid; i < R; i += nt) { L.basis[i] = C + i; L.xB[i] = i < M ? 1.0 : 0.0; }
+    for (int e = tid; e < R * R; e += nt) L.Binv[e] = (e / R == e % R) ? 1.0 : 0.0;
+    g.sync();
     const int dantzig_iters = 20 * R + 100, hard_iters = 200 * R + 1000;
     const int nvar = C + R, t_col = NP;
     int it = 0, rc = 0;
-    (void)rjstage;
     for (;; ++it) {
         if (it >= hard_iters) { rc = 2; break; }
         const int pt = L.pos[t_col];
         const double *yrow = L.Binv + (size_t)(pt >= 0 ? pt : 0) * R;
         const int bland = it >= dantzig_iters;
         // pricing: most negative reduced cost (lowest column on ties) / Bland: lowest column
-        FjBest e; fj_best_init(e);
-        for (int j = lane; j < nvar; j += FJ_NL) {
+        double ek = 0.0; int ei = 0x7fffffff, ea = 0;
+        for (int j = tid; j < nvar; j += nt) {
             if (L.pos[j] >= 0) continue;
             double d;
             if (j < C) {
@@ -303,70 +380,71 @@ FJ_FN_NOINLINE int fj_lp_solve(FjCtx &c, FjLp &L, int *iters_out)
                 d = pt >= 0 ? -(-yrow[j - C]) : -0.0;
             }
             if (d < -FJ_LP_EPS_D) {
-                if (bland) { if (e.idx == 0x7fffffff) { e.key = d; e.idx = j; } }
-                else fj_best_min(e, d, j);
+                if (bland) { if (ei == 0x7fffffff) { ek = d; ei = j; } }
+                else if (ei == 0x7fffffff || d < ek) { ek = d; ei = j; }
             }
         }
-        if (bland) { int q0 = fj_min_i(e.idx); e.idx = q0; } else fj_best_reduce(e, 0);
-        const int qin = e.idx;
+        if (bland) ei = g.min_i(ei); else g.argmin(ek, ei, ea);
+        const int qin = ei;
         if (qin == 0x7fffffff) break;   // optimal
         // w = Binv * A_q
-        for (int i = lane; i < R; i += FJ_NL) {
+        for (int i = tid; i < R; i += nt) {
             const double *brow = L.Binv + (size_t)i * R;
             L.w[i] = qin < C ? fj_lp_colvec_dot(c, L, brow, qin, 0) : brow[qin - C];
         }
-        fj_sync();
+        g.sync();
         // ratio test: min max(xB,0)/w over w > eps, ties -> lowest basic variable
-        FjBest rb; fj_best_init(rb);
-        int rrow = -1;
-        for (int i = lane; i < R; i += FJ_NL) {
+        double rk = 0.0; int ri = 0x7fffffff, rrow = -1;
+        for (int i = tid; i < R; i += nt) {
             double wi = L.w[i];
             if (wi > FJ_LP_EPS_PIV) {
                 double xb = L.xB[i] > 0.0 ? L.xB[i] : 0.0;
                 double r = fj_div(xb, wi);
                 int bi = L.basis[i];
-                if (rb.idx == 0x7fffffff || r < rb.key || (r == rb.key && bi < rb.idx)) { rb.key = r; rb.idx = bi; rrow = i; }
+                if (ri == 0x7fffffff || r < rk || (r == rk && bi < ri)) { rk = r; ri = bi; rrow = i; }
             }
         }
-        for (int m = FJ_NL / 2; m > 0; m >>= 1) {
-            double ok = fj_xor_d(rb.key, m); int oi = fj_xor_i(rb.idx, m); int orow = fj_xor_i(rrow, m);
-            if (oi == 0x7fffffff) continue;
-            if (rb.idx == 0x7fffffff || ok < rb.key || (ok == rb.key && oi < rb.idx)) { rb.key = ok; rb.idx = oi; rrow = orow; }
-        }
-        if (rb.idx == 0x7fffffff) { rc = 3; break; }
+        g.argmin(rk, ri, rrow);
+        if (ri == 0x7fffffff) { rc = 3; break; }
         const int p = rrow;
-        const double theta = rb.key, wp = L.w[p];
-        for (int i = lane; i < R; i += FJ_NL)
+        const double theta = rk, wp = L.w[p];
+        for (int i = tid; i < R; i += nt)
             L.xB[i] = (i == p) ? theta : fj_sub(L.xB[i], fj_mul(theta, L.w[i]));
         double *rowp = L.Binv + (size_t)p * R;
-        for (int k = lane; k < R; k += FJ_NL) rowp[k] = fj_div(rowp[k], wp);
-        fj_sync();
-        for (int i = 0; i < R; ++i) {
+        for (int k = tid; k < R; k += nt) rowp[k] = fj_div(rowp[k], wp);
+        g.sync();
+        // rank-1 update of every other row: warps own rows, lanes own columns
+        for (int i = g.warp(); i < R; i += g.nwarps()) {
             if (i == p) continue;
             const double wi = L.w[i];
             if (wi == 0.0) continue;
             double *rowi = L.Binv + (size_t)i * R;
-            for (int k = lane; k < R; k += FJ_NL) rowi[k] = fj_sub(rowi[k], fj_mul(wi, rowp[k]));
+            for (int k = g.lane(); k < R; k += FJ_NL) rowi[k] = fj_sub(rowi[k], fj_mul(wi, rowp[k]));
         }
-        if (lane == 0) {
+        if (tid == 0) {
             L.pos[L.basis[p]] = -1;
             L.basis[p] = qin;
             L.pos[qin] = p;
         }
-        fj_sync();
+        g.sync();
     }
+    for (int j = tid; j < NP; j += nt) {
+        double x = L.pos[j] >= 0 ? L.xB[L.pos[j]] : 0.0;
+        if (x < FJ_LP_EPS_ZERO) x = 0.0;
+        x_out[j] = x;
+    }
+    g.sync();
     if (iters_out) *iters_out = it;
     return rc;
 }
 
-// class_FJSP.py:218-254 reset_object_add + 292-316 update_fluid_parameter
-template <int SUM_MODE>
-FJ_FN_NOINLINE void fj_order_arrives(FjCtx &c, int s)
+// class_FJSP.py:218-248 reset_object_add up to the LP: the new order's jobs join the
+// counters, fluid start counts are taken, per-pair fluid bookkeeping is cleared.
+FJ_FN void fj_arrival_begin(FjCtx &c, int s)
 {
     const int lane = fj_lane();
     const int KT = c.KT, Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
     const int32_t *rjkind = FJ_I(c, rjkind), *rjstage = FJ_I(c, rjstage), *count = FJ_I(c, count);
-    const int32_t *elig = FJ_I(c, elig), *ptime = FJ_I(c, ptime), *poord = FJ_I(c, poord), *nelig = FJ_I(c, nelig);
     for (int q = lane; q < KT; q += FJ_NL) {
         int cnt = count[s * Kx + rjkind[q]];
         c.cntunp[q * Sx + s] = (uint16_t)cnt;
@@ -383,52 +461,72 @@ FJ_FN_NOINLINE void fj_order_arrives(FjCtx &c, int s)
     }
     for (int i = lane; i < KT * Mx; i += FJ_NL) { c.pk[i] = 0; c.slot[i] = 0xFFFF; }
     fj_sync();
-    FjLp L;
-    fj_lp_carve(L, c.lp, c.P->d);
-    int iters = 0;
-    int rc = fj_lp_solve(c, L, &iters);
+}
+
+// class_FJSP.py:292-316 update_fluid_parameter from the LP solution x (canonical columns)
+template <int SUM_MODE>
+FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
+{
+    const int lane = fj_lane();
+    const int KT = c.KT, Mx = c.Mx;
+    const int32_t *elig = FJ_I(c, elig), *ptime = FJ_I(c, ptime), *poord = FJ_I(c, poord), *nelig = FJ_I(c, nelig);
+    const int32_t *colbase = FJ_I(c, colbase);
     if (lane == 0) {
         c.scal[FJ_S_LPSOLVES] += 1; c.scal[FJ_S_LPITERS] += iters;
         if (rc) c.scal[FJ_S_ERROR] |= FJ_E_LP;
     }
-    // x and fluid rate per column (reuse adem/rate slabs: xs -> adem, fr -> rate)
-    for (int j = lane; j < L.NP; j += FJ_NL) {
-        double x = L.pos[j] >= 0 ? L.xB[L.pos[j]] : 0.0;
-        if (x < FJ_LP_EPS_ZERO) x = 0.0;
-        double fr = fj_mul(x, L.rate[j]);
-        L.adem[j] = x; L.rate[j] = fr;
-    }
-    fj_sync();
     for (int q = lane; q < KT; q += FJ_NL) {
         unsigned em = (unsigned)elig[q], fm = 0;
         FjPySum ps; fj_pysum_init(ps);
         for (int k = 0; k < nelig[q]; ++k) {
             int m = poord[q * Mx + k];
-            int col = L.colbase[q] + fj_popc(em & ((1u << m) - 1u));
-            fj_pysum_add<SUM_MODE>(ps, L.rate[col]);
-            if (L.adem[col] != 0.0) fm |= 1u << m;
+            int col = colbase[q] + fj_popc(em & ((1u << m) - 1u));
+            double xv = x[col];
+            double fr = fj_mul(xv, fj_div(1.0, (double)ptime[q * Mx + m]));
+            fj_pysum_add<SUM_MODE>(ps, fr);
+            if (xv != 0.0) fm |= 1u << m;
         }
         double rs = fj_pysum_result<SUM_MODE>(ps);
         c.rsum[q] = rs;
         c.tsum[q] = fj_div(1.0, rs);
         c.flmask[q] = fm;
-        (void)ptime;
     }
     fj_sync();
-    if (lane == 0) {
+    if (lane == 0) {   // fluid slots in canonical column order
         int nfl = 0;
-        for (int j = 0; j < L.NP; ++j) {
-            if (L.adem[j] == 0.0) continue;
-            int q = L.colq[j], m = L.colm[j];
-            if (nfl >= c.P->d.NFx) { c.scal[FJ_S_ERROR] |= FJ_E_OVERFLOW; break; }
-            double arr = fj_div(fj_mul((double)c.fstart[q], L.rate[j]), c.rsum[q]);
-            c.slot[q * Mx + m] = (uint16_t)nfl;
-            c.ff[nfl] = L.rate[j]; c.fa[nfl] = arr; c.fu[nfl] = arr;
-            ++nfl;
+        for (int q = 0; q < KT && nfl >= 0; ++q) {
+            unsigned fm = c.flmask[q], em = (unsigned)elig[q];
+            while (fm) {
+                int m = fj_ffs0(fm); fm &= fm - 1;
+                if (nfl >= c.P->d.NFx) { c.scal[FJ_S_ERROR] |= FJ_E_OVERFLOW; nfl = -1; break; }
+                int col = colbase[q] + fj_popc(em & ((1u << m) - 1u));
+                double fr = fj_mul(x[col], fj_div(1.0, (double)ptime[q * Mx + m]));
+                double arr = fj_div(fj_mul((double)c.fstart[q], fr), c.rsum[q]);
+                c.slot[q * Mx + m] = (uint16_t)nfl;
+                c.ff[nfl] = fr; c.fa[nfl] = arr; c.fu[nfl] = arr;
+                ++nfl;
+            }
         }
-        c.scal[FJ_S_NFL] = nfl;
+        c.scal[FJ_S_NFL] = nfl < 0 ? 0 : nfl;
     }
     fj_sync();
+}
+
+// in-line arrival: the env's own warp solves the LP on its global scratch slab
+template <int SUM_MODE>
+FJ_FN_NOINLINE void fj_order_arrives_inline(FjCtx &c, int s, int do_begin)
+{
+    if (do_begin) fj_arrival_begin(c, s);
+    FjLp L;
+    const FjDims &d = c.P->d;
+    unsigned char *binv = c.lp;
+    unsigned char *small_ = c.lp + (size_t)d.Rx * d.Rx * 8;
+    fj_lp_carve(L, binv, small_, d);
+    double *x = (double *)(small_ + (fj_lp_small_bytes(d) + 7) / 8 * 8);
+    int iters = 0;
+    FjWarpGroup g;
+    int rc = fj_lp_solve(g, c, L, x, &iters);
+    fj_arrival_finish<SUM_MODE>(c, x, iters, rc);
 }
 
 // ---------------------------------------------------------------- observation + rule cache
@@ -759,11 +857,44 @@ FJ_FN int fj_nth_set(const uint32_t *mask, int words, int nth)
     return -1;
 }
 
+// ---------------------------------------------------------------- suspension
+// An environment whose clock loop (or auto-reset) reaches an order arrival needs the fluid
+// LP.  In the main step kernel (SUSPEND = 1) it parks itself on the pending list; the LP
+// kernel solves all parked LPs one CTA each; the resume kernel (SUSPEND = 0) picks the
+// solution up and finishes the step and the rest of the launch, solving any FURTHER
+// arrival of the same launch in line.
+enum { FJ_PH_RUN = 0, FJ_PH_LP_STEP = 1, FJ_PH_LP_RESET = 2 };
+
+FJ_FN void fj_suspend(FjCtx &c, const FjParams &P, int env, int phase, int tt)
+{
+    if (fj_lane() == 0) {
+        c.scal[FJ_S_PHASE] = phase; c.scal[FJ_S_TT] = tt;
+#ifdef FJ_DEVICE_CODE
+        const int idx = atomicAdd(P.pend_count, 1);
+#else
+        const int idx = (*P.pend_count)++;
+#endif
+        P.pend_env[idx] = env;
+        c.scal[FJ_S_LPSLOT] = idx < P.lp_slots ? idx : -1;
+    }
+    fj_sync();
+}
+
+// picks up the parked arrival's LP solution (or solves in line when no slot was free)
+template <int SUM_MODE>
+FJ_FN void fj_arrival_resume(FjCtx &c, const FjParams &P)
+{
+    const int slot = c.scal[FJ_S_LPSLOT];
+    if (slot >= 0) fj_arrival_finish<SUM_MODE>(c, P.lp_x + (size_t)slot * P.d.NPx, P.lp_meta[2 * slot], P.lp_meta[2 * slot + 1]);
+    else fj_order_arrives_inline<SUM_MODE>(c, 0, 0);
+    if (fj_lane() == 0) c.scal[FJ_S_PHASE] = FJ_PH_RUN;
+    fj_sync();
+}
+
 // ---------------------------------------------------------------- reset
 // reset() of the reference incl. its re-reset quirks (oracle/fjsp_oracle.c explains them):
 // busy flags, order_arrive_time and the `done` seen by the first observation survive.
-template <int VARIANT, int SUM_MODE>
-FJ_FN_NOINLINE void fj_reset(FjCtx &c, int fresh)
+FJ_FN void fj_reset_begin(FjCtx &c, int fresh)
 {
     const int lane = fj_lane();
     const int KT = c.KT, Sx = c.Sx, M = c.M;
@@ -783,15 +914,21 @@ FJ_FN_NOINLINE void fj_reset(FjCtx &c, int fresh)
     fj_sync();
     if (lane == 0) {
         c.scal[FJ_S_NEXTORDER] = 1; c.scal[FJ_S_TIME] = 0; c.scal[FJ_S_STEPS] = 0; c.scal[FJ_S_HASTASK] = 0;
-        c.scal[FJ_S_COMPLETION] = 0; c.scal[FJ_S_COMPLETION_LAST] = 0;
+        c.scal[FJ_S_COMPLETION] = 0; c.scal[FJ_S_COMPLETION_LAST] = 0; c.scal[FJ_S_WASDONE] = was_done;
         fj_set_ll(c.scal, FJ_S_ENERGY, 0); fj_set_ll(c.scal, FJ_S_ENERGY_LAST, 0);
         fj_set_ll(c.scal, FJ_S_DELAY_PROC, 0); fj_set_ll(c.scal, FJ_S_DELAY_LAST, 0);
         fj_set_ll(c.scal, FJ_S_DELAY_UNPROC, 0);
         fj_set_d(c.scal, FJ_S_GAPTIME, 0.0);
     }
     fj_sync();
-    fj_order_arrives<SUM_MODE>(c, 0);
-    fj_observe<VARIANT, SUM_MODE>(c, was_done);
+    fj_arrival_begin(c, 0);
+}
+
+template <int VARIANT, int SUM_MODE>
+FJ_FN void fj_reset_finish(FjCtx &c)
+{
+    const int lane = fj_lane();
+    fj_observe<VARIANT, SUM_MODE>(c, c.scal[FJ_S_WASDONE]);
     for (int i = lane; i < 16; i += FJ_NL) c.obs[i] = c.obs2[i];
     if (lane == 0) c.scal[FJ_S_DONE] = 0;
     fj_sync();
@@ -800,18 +937,17 @@ FJ_FN_NOINLINE void fj_reset(FjCtx &c, int fresh)
 // ---------------------------------------------------------------- step
 struct FjStepOut { double reward; int done; int rec[8]; };
 
-template <int VARIANT, int SUM_MODE>
-FJ_FN_NOINLINE void fj_step(FjCtx &c, int task_rule0, int mach_rule0, uint32_t rnd_task, uint32_t rnd_mach,
-                            int reward_policy, double completion_n, double tardiness_n, double energy_n,
-                            FjStepOut &out)
+// task_select + machine_select + dispatch; returns 0 when nothing could be dispatched
+template <int VARIANT>
+FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint32_t rnd_task, uint32_t rnd_mach,
+                                 FjStepOut &out)
 {
     const int lane = fj_lane();
     const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
-    const int M = c.M, KT = c.KT, S = c.S, Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
+    const int KT = c.KT, Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
     const int32_t *rjkind = FJ_I(c, rjkind), *rjstage = FJ_I(c, rjstage), *rjlast = FJ_I(c, rjlast);
-    const int32_t *elig = FJ_I(c, elig), *due = FJ_I(c, due), *arrive = FJ_I(c, arrive), *cum = FJ_I(c, cum);
-    const int32_t *jobbase = FJ_I(c, jobbase);
-    int t = c.scal[FJ_S_TIME];
+    const int32_t *due = FJ_I(c, due), *cum = FJ_I(c, cum), *jobbase = FJ_I(c, jobbase);
+    const int t = c.scal[FJ_S_TIME];
     // ---- task_select: cached answer, or a draw from the availability masks
     const int trule = task_rule0 + 1, mrule = mach_rule0 + 1;
     int q = -1, m = -1;
@@ -834,10 +970,9 @@ FJ_FN_NOINLINE void fj_step(FjCtx &c, int task_rule0, int mach_rule0, uint32_t r
     q = fj_bcast_i(q, 0); m = fj_bcast_i(m, 0);
     if (q < 0 || m < 0) {
         if (lane == 0) c.scal[FJ_S_ERROR] |= (q < 0 ? FJ_E_NO_TASK : FJ_E_NO_MACHINE);
-        out.reward = 0.0; out.done = c.scal[FJ_S_DONE];
         for (int i = 0; i < 8; ++i) out.rec[i] = -1;
         fj_sync();
-        return;
+        return 0;
     }
     // ---- dispatch (one lane; a handful of scalar updates)
     if (lane == 0) {
@@ -887,50 +1022,75 @@ FJ_FN_NOINLINE void fj_step(FjCtx &c, int task_rule0, int mach_rule0, uint32_t r
         out.rec[5] = t_begin; out.rec[6] = t_end; out.rec[7] = m_end;
     }
     fj_sync();
-    // ---- advance the clock while nothing can be dispatched
-    int done = 0;
+    return 1;
+}
+
+// advance the clock while nothing can be dispatched (SO_DFJSP.py:206-253).
+// returns 1 when parked on an order arrival (SUSPEND only); `resume` re-enters right
+// after that arrival.
+template <int SUM_MODE, int SUSPEND>
+FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
+{
+    const int lane = fj_lane();
+    const int M = c.M, KT = c.KT, S = c.S, Sx = c.Sx;
+    const int32_t *rjkind = FJ_I(c, rjkind), *rjlast = FJ_I(c, rjlast), *elig = FJ_I(c, elig);
+    const int32_t *arrive = FJ_I(c, arrive), *jobbase = FJ_I(c, jobbase);
+    int t = c.scal[FJ_S_TIME];
+    done = 0;
     for (;;) {
-        const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
-        int any = 0;
-        for (int x = lane; x < KT; x += FJ_NL) any |= (c.qlen[x] > 0 && ((unsigned)elig[x] & idle) != 0);
-        if (fj_any(any)) break;
-        int tmin = 0x7fffffff;
-        for (int i = lane; i < M; i += FJ_NL) { int e = c.mend[i]; if (e > t && e < tmin) tmin = e; }
-        tmin = fj_min_i(tmin);
-        if (tmin == 0x7fffffff) { if (lane == 0) c.scal[FJ_S_ERROR] |= FJ_E_NO_EVENT; break; }
-        t = tmin;
-        if (lane == 0) {   // machines release their jobs in ascending machine order
-            for (int i = 0; i < M; ++i) {
-                if (c.mend[i] != t || c.mjob[i] < 0) continue;
-                const int jq = c.mjob[i] >> 16, n = c.mjob[i] & 0xffff;
-                if (rjlast[jq]) continue;
-                const int q2 = jq + 1, r = rjkind[jq];
-                if (c.qlen[q2] == 0) c.qhead[q2] = (uint16_t)n;
-                else c.next[jobbase[r] + c.qtail[q2]] = (uint16_t)n;
-                c.qtail[q2] = (uint16_t)n;
-                c.qlen[q2] = (uint16_t)(c.qlen[q2] + 1);
-                const int s = fj_order_of(c, r, n);
-                c.cntnow[q2 * Sx + s] = (uint16_t)(c.cntnow[q2 * Sx + s] + 1);
+        long long left = 1;
+        int norder, arr_time;
+        if (!resume) {
+            const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
+            int any = 0;
+            for (int x = lane; x < KT; x += FJ_NL) any |= (c.qlen[x] > 0 && ((unsigned)elig[x] & idle) != 0);
+            if (fj_any(any)) break;
+            int tmin = 0x7fffffff;
+            for (int i = lane; i < M; i += FJ_NL) { int e = c.mend[i]; if (e > t && e < tmin) tmin = e; }
+            tmin = fj_min_i(tmin);
+            if (tmin == 0x7fffffff) { if (lane == 0) c.scal[FJ_S_ERROR] |= FJ_E_NO_EVENT; break; }
+            t = tmin;
+            if (lane == 0) {   // machines release their jobs in ascending machine order
+                for (int i = 0; i < M; ++i) {
+                    if (c.mend[i] != t || c.mjob[i] < 0) continue;
+                    const int jq = c.mjob[i] >> 16, n = c.mjob[i] & 0xffff;
+                    if (rjlast[jq]) continue;
+                    const int q2 = jq + 1, r = rjkind[jq];
+                    if (c.qlen[q2] == 0) c.qhead[q2] = (uint16_t)n;
+                    else c.next[jobbase[r] + c.qtail[q2]] = (uint16_t)n;
+                    c.qtail[q2] = (uint16_t)n;
+                    c.qlen[q2] = (uint16_t)(c.qlen[q2] + 1);
+                    const int s = fj_order_of(c, r, n);
+                    c.cntnow[q2 * Sx + s] = (uint16_t)(c.cntnow[q2 * Sx + s] + 1);
+                }
             }
-        }
-        fj_sync();
-        long long left = 0;
-        for (int x = lane; x < KT; x += FJ_NL)
-            if (rjlast[x]) for (int s = 0; s < S; ++s) left += c.cntunp[x * Sx + s];
-        left = fj_sum_ll(left);
-        int norder = c.scal[FJ_S_NEXTORDER];
-        int arr_time = c.scal[FJ_S_ARRTIME];
-        fj_sync();
-        if (norder < S && arrive[norder] <= t) {
-            if (lane == 0) { c.scal[FJ_S_NEXTORDER] = norder + 1; c.scal[FJ_S_ARRTIME] = arrive[norder]; }
             fj_sync();
-            fj_order_arrives<SUM_MODE>(c, norder);
-            arr_time = arrive[norder]; ++norder; left = 1;
-        } else if (norder < S && left == 0) {
-            if (lane == 0) { c.scal[FJ_S_NEXTORDER] = norder + 1; c.scal[FJ_S_ARRTIME] = arrive[norder]; }
+            left = 0;
+            for (int x = lane; x < KT; x += FJ_NL)
+                if (rjlast[x]) for (int s = 0; s < S; ++s) left += c.cntunp[x * Sx + s];
+            left = fj_sum_ll(left);
+            norder = c.scal[FJ_S_NEXTORDER];
+            arr_time = c.scal[FJ_S_ARRTIME];
             fj_sync();
-            fj_order_arrives<SUM_MODE>(c, norder);
-            arr_time = arrive[norder]; t = arr_time; ++norder; left = 1;
+            const int by_time = norder < S && arrive[norder] <= t;
+            if (by_time || (norder < S && left == 0)) {
+                arr_time = arrive[norder];
+                if (!by_time) t = arr_time;
+                if (lane == 0) { c.scal[FJ_S_NEXTORDER] = norder + 1; c.scal[FJ_S_ARRTIME] = arr_time; }
+                fj_sync();
+                fj_arrival_begin(c, norder);
+                if (SUSPEND) {
+                    if (lane == 0) c.scal[FJ_S_TIME] = t;
+                    fj_sync();
+                    return 1;
+                }
+                fj_order_arrives_inline<SUM_MODE>(c, norder, 0);
+                ++norder; left = 1;
+            }
+        } else {
+            resume = 0;
+            norder = c.scal[FJ_S_NEXTORDER];
+            arr_time = c.scal[FJ_S_ARRTIME];
         }
         unsigned freed = 0;
         for (int i = lane; i < M; i += FJ_NL) if (c.mend[i] <= t) freed |= 1u << i;
@@ -942,12 +1102,23 @@ FJ_FN_NOINLINE void fj_step(FjCtx &c, int task_rule0, int mach_rule0, uint32_t r
         fj_sync();
         if (norder >= S && left == 0) { done = 1; break; }
     }
+    if (lane == 0) c.scal[FJ_S_TIME] = t;
+    fj_sync();
+    return 0;
+}
+
+// bookkeeping after the clock loop: new observation, rule cache, reward
+template <int VARIANT, int SUM_MODE>
+FJ_FN_NOINLINE void fj_step_back(FjCtx &c, int done, int reward_policy, double completion_n, double tardiness_n,
+                                 double energy_n, FjStepOut &out)
+{
+    const int lane = fj_lane();
+    const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
     if (lane == 0) {
-        c.scal[FJ_S_TIME] = t; c.scal[FJ_S_STEPS] += 1;
+        c.scal[FJ_S_STEPS] += 1;
         if (done) c.scal[FJ_S_DONE] = 1;
     }
     fj_sync();
-    // ---- new observation, rule cache, reward
     fj_observe<VARIANT, SUM_MODE>(c, done);
     if (lane == 0) {
         const long long dsum = fj_get_ll(c.scal, FJ_S_DELAY_PROC) + fj_get_ll(c.scal, FJ_S_DELAY_UNPROC);
@@ -977,18 +1148,22 @@ FJ_FN_NOINLINE void fj_step(FjCtx &c, int task_rule0, int mach_rule0, uint32_t r
 }
 
 // ---------------------------------------------------------------- per-env driver
-// T steps of one environment: emit [v(t+1), v(t+1)-v(t)], reward, done and the dispatch
-// record; auto-reset a finished environment before its next action.
-template <int VARIANT, int SUM_MODE>
+// Steps tt0..T-1 of one environment: emit [v(t+1), v(t+1)-v(t)], reward, done and the
+// dispatch record; auto-reset a finished environment before its next action.
+// SUSPEND = 1: main kernel, parks on the first LP it needs.  SUSPEND = 0: resume kernel
+// (starts from the parked phase / step) and the one-lane host build's second pass.
+template <int VARIANT, int SUM_MODE, int SUSPEND>
 FJ_FN void fj_env_rollout(const FjParams &P, const FjStepArgs &A, int env, unsigned char *lp)
 {
     const int lane = fj_lane();
     FjCtx c;
     fj_ctx_init(c, P, env, lp);
     const int nobs = P.nobs, ns = 2 * nobs;
-    for (int tt = 0; tt < A.T; ++tt) {
+    int tt = SUSPEND ? 0 : c.scal[FJ_S_TT];
+    for (; tt < A.T; ++tt) {
         const size_t i = (size_t)tt * P.B + env;
-        if (c.scal[FJ_S_DONE]) {
+        int phase = c.scal[FJ_S_PHASE];
+        if (phase == FJ_PH_RUN && c.scal[FJ_S_DONE]) {
             if (!A.autoreset) {   // a finished env without auto-reset repeats its terminal output
                 if (A.done && lane == 0) A.done[i] = 1;
                 if (A.reward && lane == 0) A.reward[i] = 0.0;
@@ -1000,15 +1175,37 @@ FJ_FN void fj_env_rollout(const FjParams &P, const FjStepArgs &A, int env, unsig
                 if (A.rec) for (int k = lane; k < 8; k += FJ_NL) A.rec[i * 8 + k] = -1;
                 continue;
             }
-            fj_reset<VARIANT, SUM_MODE>(c, 0);
+            fj_reset_begin(c, 0);
             if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
             fj_sync();
+            if (SUSPEND) { fj_suspend(c, P, env, FJ_PH_LP_RESET, tt); return; }
+            fj_order_arrives_inline<SUM_MODE>(c, 0, 0);
+            fj_reset_finish<VARIANT, SUM_MODE>(c);
+        } else if (phase == FJ_PH_LP_RESET) {
+            fj_arrival_resume<SUM_MODE>(c, P);
+            fj_reset_finish<VARIANT, SUM_MODE>(c);
+            phase = FJ_PH_RUN;
         }
         FjStepOut out;
         out.reward = 0.0; out.done = 0;
-        fj_step<VARIANT, SUM_MODE>(c, A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
-                                   A.rnd ? A.rnd[2 * i + 1] : 0u, A.reward_policy, A.completion, A.tardiness,
-                                   A.energy, out);
+        int resume = 0, ok = 1;
+        if (phase == FJ_PH_LP_STEP) {
+            fj_arrival_resume<SUM_MODE>(c, P);
+            resume = 1;
+        } else {
+            ok = fj_step_front<VARIANT>(c, A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
+                                        A.rnd ? A.rnd[2 * i + 1] : 0u, out);
+            if (A.rec && lane == 0) for (int k = 0; k < 8; ++k) A.rec[i * 8 + k] = out.rec[k];
+        }
+        int done = 0;
+        if (ok) {
+            if (fj_clock<SUM_MODE, SUSPEND>(c, resume, done)) { fj_suspend(c, P, env, FJ_PH_LP_STEP, tt); return; }
+            fj_step_back<VARIANT, SUM_MODE>(c, done, A.reward_policy, A.completion, A.tardiness, A.energy, out);
+        } else {
+            out.done = c.scal[FJ_S_DONE];
+            for (int k = lane; k < nobs; k += FJ_NL) c.obs2[k] = c.obs[k];
+            fj_sync();
+        }
         // outputs: lanes stream the state vector, lane 0 the scalars
         for (int k = lane; k < ns; k += FJ_NL) {
             const int j = k < nobs ? k : k - nobs;
@@ -1021,23 +1218,51 @@ FJ_FN void fj_env_rollout(const FjParams &P, const FjStepArgs &A, int env, unsig
         if (lane == 0) {
             if (A.reward) A.reward[i] = out.reward;
             if (A.done) A.done[i] = out.done;
-            if (A.rec) for (int k = 0; k < 8; ++k) A.rec[i * 8 + k] = out.rec[k];
         }
         fj_sync();
     }
 }
 
+// reset() entry: phase 1 parks every env on its order-0 LP, phase 2 finishes
+FJ_FN void fj_env_reset_begin(const FjParams &P, int env)
+{
+    FjCtx c;
+    fj_ctx_init(c, P, env, nullptr);
+    fj_reset_begin(c, 1);
+    if (fj_lane() == 0) {
+        c.scal[FJ_S_PHASE] = FJ_PH_LP_RESET;
+        c.scal[FJ_S_LPSLOT] = env < P.lp_slots ? env : -1;
+        P.pend_env[env] = env;
+    }
+    fj_sync();
+}
+
 template <int VARIANT, int SUM_MODE>
-FJ_FN void fj_env_reset(const FjParams &P, int env, unsigned char *lp, double *state_out, float *state32_out)
+FJ_FN void fj_env_reset_finish(const FjParams &P, int env, unsigned char *lp, double *state_out, float *state32_out)
 {
     const int lane = fj_lane();
     FjCtx c;
     fj_ctx_init(c, P, env, lp);
-    fj_reset<VARIANT, SUM_MODE>(c, 1);
+    fj_arrival_resume<SUM_MODE>(c, P);
+    fj_reset_finish<VARIANT, SUM_MODE>(c);
     const int nobs = P.nobs, ns = 2 * nobs;
     for (int k = lane; k < ns; k += FJ_NL) {
         const double v = k < nobs ? c.obs[k] : 0.0;
         if (state_out) state_out[(size_t)env * ns + k] = v;
         if (state32_out) state32_out[(size_t)env * ns + k] = (float)v;
     }
+}
+
+// one parked LP, solved by a whole CTA (device) / one thread (host build)
+FJ_FN void fj_lp_service(const FjParams &P, const FjCtaGroup &g, int idx, unsigned char *binv, unsigned char *small_)
+{
+    const int env = P.pend_env[idx];
+    FjCtx c;
+    fj_ctx_init(c, P, env, nullptr);
+    FjLp L;
+    fj_lp_carve(L, binv, small_, P.d);
+    int iters = 0;
+    const int rc = fj_lp_solve(g, c, L, P.lp_x + (size_t)idx * P.d.NPx, &iters);
+    if (g.rank() == 0) { P.lp_meta[2 * idx] = iters; P.lp_meta[2 * idx + 1] = rc; }
+    g.sync();
 }

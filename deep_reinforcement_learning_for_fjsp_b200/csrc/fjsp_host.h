@@ -125,6 +125,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     io.bdptr = o; o += d.Mx + 1;
     io.bds = o; o += d.NBDx;
     io.bde = o; o += d.NBDx;
+    io.colbase = o; o += d.KTx;
     io.stride = fj_align(o, 4);
     t.io = io;
     // env offsets (bytes)
@@ -212,6 +213,11 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
                 w[io.energy + q * d.Mx + m] = v.power[q * v.M + m] * v.ptime[q * v.M + m];
             }
         }
+        {
+            int cb = 0;
+            for (int q = 0; q < v.KT; ++q) { w[io.colbase + q] = cb; cb += v.nelig[q]; }
+            if (cb != v.NP) { err = "instance blob: NP != sum(nelig)"; return false; }
+        }
         for (int m = 0; m < v.M; ++m) w[io.idlep + m] = v.idle_power[m];
         for (int s = 0; s < v.S; ++s) { w[io.arrive + s] = v.arrive[s]; w[io.due + s] = v.due[s]; }
         for (int m = 0; m <= d.Mx; ++m) w[io.bdptr + m] = v.bd_ptr[m <= v.M ? m : v.M];
@@ -220,12 +226,16 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     return true;
 }
 
-// bytes of LP scratch per resident warp (see fjsp_core.cuh: struct Lp)
-static inline unsigned long long fj_lp_scratch_bytes(const FjDims &d)
+// bytes of LP scratch per resident warp: Binv, the small arrays, the solution vector
+// (see fjsp_core.cuh: fj_lp_carve / fj_order_arrives_inline)
+static inline unsigned long long fj_lp_small_bytes_host(const FjDims &d)
 {
     unsigned long long R = d.Rx, C = d.NPx + 1;
-    unsigned long long dbl = R * R + 2 * R + 2 * C;          // Binv, xB, w, a_dem, rate
-    unsigned long long i32 = R + (C + R) + 2 * C + 2 * d.KTx; // basis, pos, col_q/col_m, prec_row, col_base
-    unsigned long long bytes = dbl * 8 + i32 * 4;
+    return (2 * R + 2 * C) * 8 + (R + (C + R) + 2 * C + d.KTx) * 4;
+}
+static inline unsigned long long fj_lp_scratch_bytes(const FjDims &d)
+{
+    unsigned long long R = d.Rx;
+    unsigned long long bytes = R * R * 8 + (fj_lp_small_bytes_host(d) + 7) / 8 * 8 + (unsigned long long)d.NPx * 8;
     return (bytes + 127) / 128 * 128;
 }

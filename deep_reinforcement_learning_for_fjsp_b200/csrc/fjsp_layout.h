@@ -47,6 +47,7 @@ struct FjInstOff {
     int bdptr;     // [Mx+1]
     int bds;       // [NBDx]
     int bde;       // [NBDx]
+    int colbase;   // [KTx] first LP column of an operation type (prefix of popcount(elig))
     int stride;    // words per instance
 };
 
@@ -85,10 +86,10 @@ struct FjEnvOff {
 enum {
     FJ_S_TIME = 0, FJ_S_ARRTIME = 1, FJ_S_NEXTORDER = 2, FJ_S_DONE = 3, FJ_S_STEPS = 4, FJ_S_BUSY = 5,
     FJ_S_ERROR = 6, FJ_S_HASTASK = 7, FJ_S_COMPLETION = 8, FJ_S_COMPLETION_LAST = 9, FJ_S_EPISODES = 10,
-    FJ_S_LPSOLVES = 11, FJ_S_LPITERS = 12, FJ_S_NFL = 13,
+    FJ_S_LPSOLVES = 11, FJ_S_LPITERS = 12, FJ_S_NFL = 13, FJ_S_PHASE = 14, FJ_S_LPSLOT = 15,
     // 64-bit values occupy two slots (even index)
     FJ_S_ENERGY = 16, FJ_S_ENERGY_LAST = 18, FJ_S_DELAY_PROC = 20, FJ_S_DELAY_LAST = 22, FJ_S_DELAY_UNPROC = 24,
-    FJ_S_GAPTIME = 26 /* double */, FJ_S_COUNT = 32
+    FJ_S_GAPTIME = 26 /* double */, FJ_S_TT = 28, FJ_S_WASDONE = 29, FJ_S_COUNT = 32
 };
 
 // error flags (FJ_S_ERROR), same meaning as the oracle's
@@ -103,6 +104,11 @@ struct FjParams {
     unsigned char *env;         // env table
     unsigned char *lp;          // LP scratch, one slab per resident warp
     unsigned long long lp_stride;
+    int *pend_count;            // parked LPs of the current launch
+    int *pend_env;              // [B] env of each parked LP
+    double *lp_x;               // [lp_slots][NPx] LP solutions
+    int *lp_meta;               // [lp_slots][2] iterations, return code
+    int lp_slots;
     int B, variant, sum_mode, nobs;
 };
 

@@ -14,22 +14,42 @@
 struct HostVec {
     FjTables tb;
     FjParams P;
-    std::vector<int32_t> env_inst;
+    std::vector<int32_t> env_inst, pend_env, lp_meta;
     std::vector<unsigned char> env, lp;
+    std::vector<double> lp_x;
+    int pend_count;
     int variant, sum_mode;
 };
+
+static void run_lp_service(HostVec *h)
+{
+    // the CTA-group LP kernel, one thread: Binv and the small arrays on the host slab
+    const FjDims &d = h->tb.d;
+    unsigned char *binv = h->lp.data();
+    unsigned char *small_ = h->lp.data() + (size_t)d.Rx * d.Rx * 8;
+    FjCtaGroup g; g.rk = nullptr; g.ri = nullptr; g.ra = nullptr;
+    int n = h->pend_count < h->P.lp_slots ? h->pend_count : h->P.lp_slots;
+    for (int i = 0; i < n; ++i) fj_lp_service(h->P, g, i, binv, small_);
+}
 
 static std::string g_err;
 
 template <int V, int SM>
 static void run_reset(HostVec *h, double *state)
 {
-    for (int e = 0; e < h->P.B; ++e) fj_env_reset<V, SM>(h->P, e, h->lp.data(), state, nullptr);
+    for (int e = 0; e < h->P.B; ++e) fj_env_reset_begin(h->P, e);
+    h->pend_count = h->P.B;
+    run_lp_service(h);
+    for (int e = 0; e < h->P.B; ++e) fj_env_reset_finish<V, SM>(h->P, e, h->lp.data(), state, nullptr);
 }
 template <int V, int SM>
 static void run_step(HostVec *h, const FjStepArgs &A)
 {
-    for (int e = 0; e < h->P.B; ++e) fj_env_rollout<V, SM>(h->P, A, e, h->lp.data());
+    h->pend_count = 0;
+    for (int e = 0; e < h->P.B; ++e) fj_env_rollout<V, SM, 1>(h->P, A, e, h->lp.data());   // main kernel
+    run_lp_service(h);                                                                    // LP kernel
+    const int n = h->pend_count;
+    for (int i = 0; i < n; ++i) fj_env_rollout<V, SM, 0>(h->P, A, h->pend_env[i], h->lp.data());   // resume kernel
 }
 
 #define DISPATCH(fn, ...)                                                                      \
@@ -63,6 +83,13 @@ int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst
     P.d = h->tb.d; P.io = h->tb.io; P.eo = h->tb.eo;
     P.inst = h->tb.inst.data(); P.env_inst = h->env_inst.data(); P.env = h->env.data();
     P.lp = h->lp.data(); P.lp_stride = 0;
+    h->pend_env.assign(n_envs, 0);
+    const char *ov = getenv("FJSP_HOSTSIM_LP_SLOTS");   // tests: force the "no free slot" in-line path
+    P.lp_slots = ov ? atoi(ov) : n_envs;
+    h->lp_x.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * h->tb.d.NPx, 0.0);
+    h->lp_meta.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * 2, 0);
+    h->pend_count = 0;
+    P.pend_count = &h->pend_count; P.pend_env = h->pend_env.data(); P.lp_x = h->lp_x.data(); P.lp_meta = h->lp_meta.data();
     P.B = n_envs; P.variant = variant; P.sum_mode = sum_mode;
     P.nobs = (variant == FJSP_SO_DFJSP) ? 10 : 15;
     *out = h;
