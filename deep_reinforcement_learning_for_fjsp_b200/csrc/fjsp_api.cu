@@ -26,9 +26,11 @@ static thread_local std::string g_err;
 template <int VARIANT, int SUM_MODE>
 __global__ void __launch_bounds__(FJ_BLOCK, 4) fjsp_step_kernel(FjParams P, FjStepArgs A)
 {
+    extern __shared__ __align__(16) unsigned char stage_smem[];
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
-    for (int env = gw; env < P.B; env += total) fj_env_rollout<VARIANT, SUM_MODE, 1>(P, A, env, nullptr);
+    unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.eo.hot : nullptr;
+    for (int env = gw; env < P.B; env += total) fj_env_rollout<VARIANT, SUM_MODE, 1>(P, A, env, nullptr, stage);
 }
 
 // resume kernel: parked envs only; picks up the LP solution, finishes the launch
@@ -37,9 +39,11 @@ __global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(FjParams P, FjSte
 {
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
+    extern __shared__ __align__(16) unsigned char stage_smem[];
     unsigned char *lp = P.lp + (size_t)gw * P.lp_stride;
+    unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.eo.hot : nullptr;
     const int n = *P.pend_count;
-    for (int i = gw; i < n; i += total) fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, P.pend_env[i], lp);
+    for (int i = gw; i < n; i += total) fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, P.pend_env[i], lp, stage);
 }
 
 // LP kernel: one CTA per parked LP, basis inverse in shared memory when it fits
@@ -80,7 +84,7 @@ struct fjsp_vec {
     FjTables tb;
     FjParams P;
     int variant, sum_mode, B, device, grid, resume_grid, lp_grid, lp_smem_binv, nstate;
-    size_t lp_smem_bytes;
+    size_t lp_smem_bytes, stage_bytes;
     int *d_pend_count, *d_pend_env, *d_lp_meta;
     double *d_lp_x;
     int32_t *d_inst, *d_env_inst;
@@ -187,6 +191,18 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     P.B = n_envs; P.variant = variant; P.sum_mode = v->sum_mode; P.nobs = v->nstate / 2;
     P.pend_count = v->d_pend_count; P.pend_env = v->d_pend_env; P.lp_x = v->d_lp_x; P.lp_meta = v->d_lp_meta;
     P.lp_slots = (int)slots;
+    // hot part of the env records staged in shared memory for the whole launch when four
+    // warps' worth fits with at least two CTAs per SM
+    v->stage_bytes = (size_t)FJ_WARPS_PER_BLOCK * v->tb.eo.hot;
+    P.stage = v->stage_bytes <= 100 * 1024 ? 1 : 0;
+    if (!P.stage) v->stage_bytes = 0;
+    if (dispatch(v, [&](auto V, auto SM) {
+            cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->stage_bytes);
+            cudaFuncSetAttribute(fjsp_resume_kernel<decltype(V)::value, decltype(SM)::value>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->stage_bytes);
+            return 0;
+        })) return -2;
     CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
     v->stage_T = 0;
     v->d_actions = v->d_done = v->d_rec = nullptr; v->d_rnd = nullptr;
@@ -257,9 +273,9 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(v->d_pend_count, 0, 4, st));
     int rc = dispatch(v, [&](auto V, auto SM) {
-        fjsp_step_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, 0, st>>>(v->P, A);
+        fjsp_step_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, v->stage_bytes, st>>>(v->P, A);
         launch_lp(v, st);
-        fjsp_resume_kernel<decltype(V)::value, decltype(SM)::value><<<v->resume_grid, FJ_BLOCK, 0, st>>>(v->P, A);
+        fjsp_resume_kernel<decltype(V)::value, decltype(SM)::value><<<v->resume_grid, FJ_BLOCK, v->stage_bytes, st>>>(v->P, A);
         return 0;
     });
     if (rc) return rc;

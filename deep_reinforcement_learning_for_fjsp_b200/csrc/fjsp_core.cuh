@@ -135,13 +135,13 @@ struct FjCtx {
     const int32_t *I;
     int M, K, KT, S, Mx, Kx, Sx;
     unsigned mmask;
-    int32_t *scal; double *obs, *obs2, *gapave; int32_t *choice; uint32_t *avmask, *favmask;
+    int32_t *scal; double *obs, *obs2, *gapave, *urg, *maxe; uint32_t *avmask, *favmask, *demask, *damask;
     int32_t *mend, *mlast, *mjob; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
     double *rsum, *tsum; uint16_t *cntunp, *cntnow, *pk, *slot; double *fu, *fa, *ff; uint16_t *next;
     unsigned char *lp;
 };
 
-FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp)
+FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, unsigned char *hot = nullptr)
 {
     c.P = &P;
     c.I = P.inst + (size_t)P.env_inst[env] * P.io.stride;
@@ -149,11 +149,13 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp)
     c.M = h[0]; c.K = h[1]; c.KT = h[2]; c.S = h[3];
     c.Mx = P.d.Mx; c.Kx = P.d.Kx; c.Sx = P.d.Sx;
     c.mmask = c.M >= 32 ? 0xffffffffu : ((1u << c.M) - 1u);
-    unsigned char *E = P.env + (size_t)env * P.eo.stride;
+    unsigned char *G = P.env + (size_t)env * P.eo.stride;   // record in HBM
+    unsigned char *E = hot ? hot : G;                       // hot part, possibly staged in shared memory
     const FjEnvOff &o = P.eo;
     c.scal = (int32_t *)(E + o.scal); c.obs = (double *)(E + o.obs); c.obs2 = (double *)(E + o.obs2);
-    c.gapave = (double *)(E + o.gapave); c.choice = (int32_t *)(E + o.choice);
+    c.gapave = (double *)(E + o.gapave); c.urg = (double *)(E + o.urg); c.maxe = (double *)(E + o.maxe);
     c.avmask = (uint32_t *)(E + o.avmask); c.favmask = (uint32_t *)(E + o.favmask);
+    c.demask = (uint32_t *)(E + o.demask); c.damask = (uint32_t *)(E + o.damask);
     c.mend = (int32_t *)(E + o.mend); c.mlast = (int32_t *)(E + o.mlast); c.mjob = (int32_t *)(E + o.mjob);
     c.qhead = (uint16_t *)(E + o.qhead); c.qtail = (uint16_t *)(E + o.qtail); c.qlen = (uint16_t *)(E + o.qlen);
     c.proc = (int32_t *)(E + o.proc); c.fstart = (int32_t *)(E + o.fstart); c.flmask = (uint32_t *)(E + o.flmask);
@@ -161,11 +163,26 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp)
     c.cntunp = (uint16_t *)(E + o.cntunp); c.cntnow = (uint16_t *)(E + o.cntnow);
     c.pk = (uint16_t *)(E + o.pk); c.slot = (uint16_t *)(E + o.slot);
     c.fu = (double *)(E + o.fu); c.fa = (double *)(E + o.fa); c.ff = (double *)(E + o.ff);
-    c.next = (uint16_t *)(E + o.next);
+    c.next = (uint16_t *)(G + o.next);
     c.lp = lp;
 }
 
-#define FJ_I(c, field) ((c).I + (c).P->io.field)
+// read-only instance table: loads go through the non-coherent path (L1-cached, never
+// invalidated by the env-state stores)
+struct FjRO {
+    const int32_t *p;
+    FJ_MFN int operator[](int i) const
+    {
+#ifdef FJ_DEVICE_CODE
+        return __ldg(p + i);
+#else
+        return p[i];
+#endif
+    }
+    FJ_MFN FjRO operator+(int o) const { FjRO r; r.p = p + o; return r; }
+};
+FJ_FN FjRO fj_ro(const int32_t *p) { FjRO r; r.p = p; return r; }
+#define FJ_I(c, field) (fj_ro((c).I + (c).P->io.field))
 FJ_FN long long fj_get_ll(const int32_t *scal, int i) { return *(const long long *)(scal + i); }
 FJ_FN void fj_set_ll(int32_t *scal, int i, long long v) { *(long long *)(scal + i) = v; }
 FJ_FN double fj_get_d(const int32_t *scal, int i) { return *(const double *)(scal + i); }
@@ -189,7 +206,7 @@ FJ_FN int fj_ffs0(unsigned v)   // index of lowest set bit, v != 0
 }
 FJ_FN int fj_order_of(const FjCtx &c, int r, int n)   // which order job n of kind r came with
 {
-    const int32_t *cum = FJ_I(c, cum);
+    const FjRO cum = FJ_I(c, cum);
     int s = 0;
     while (s + 1 < c.S && n >= cum[(s + 1) * c.Kx + r]) ++s;
     return s;
@@ -329,8 +346,8 @@ FJ_FN int fj_lp_solve(const G &g, FjCtx &c, FjLp &L, double *x_out, int *iters_o
 {
     const int tid = g.rank(), nt = g.size();
     const int M = c.M, KT = c.KT, Mx = c.Mx;
-    const int32_t *elig = FJ_I(c, elig), *ptime = FJ_I(c, ptime), *rjlast = FJ_I(c, rjlast);
-    const int32_t *colbase = FJ_I(c, colbase);
+    const FjRO elig = FJ_I(c, elig), ptime = FJ_I(c, ptime), rjlast = FJ_I(c, rjlast);
+    const FjRO colbase = FJ_I(c, colbase);
     if (tid == 0) {   // precedence rows: sequential numbering
         int nprec = 0;
         for (int q = 0; q < KT; ++q) {
@@ -444,7 +461,7 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
 {
     const int lane = fj_lane();
     const int KT = c.KT, Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
-    const int32_t *rjkind = FJ_I(c, rjkind), *rjstage = FJ_I(c, rjstage), *count = FJ_I(c, count);
+    const FjRO rjkind = FJ_I(c, rjkind), rjstage = FJ_I(c, rjstage), count = FJ_I(c, count);
     for (int q = lane; q < KT; q += FJ_NL) {
         int cnt = count[s * Kx + rjkind[q]];
         c.cntunp[q * Sx + s] = (uint16_t)cnt;
@@ -469,8 +486,8 @@ FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
 {
     const int lane = fj_lane();
     const int KT = c.KT, Mx = c.Mx;
-    const int32_t *elig = FJ_I(c, elig), *ptime = FJ_I(c, ptime), *poord = FJ_I(c, poord), *nelig = FJ_I(c, nelig);
-    const int32_t *colbase = FJ_I(c, colbase);
+    const FjRO elig = FJ_I(c, elig), ptime = FJ_I(c, ptime), poord = FJ_I(c, poord), nelig = FJ_I(c, nelig);
+    const FjRO colbase = FJ_I(c, colbase);
     if (lane == 0) {
         c.scal[FJ_S_LPSOLVES] += 1; c.scal[FJ_S_LPITERS] += iters;
         if (rc) c.scal[FJ_S_ERROR] |= FJ_E_LP;
@@ -529,125 +546,132 @@ FJ_FN_NOINLINE void fj_order_arrives_inline(FjCtx &c, int s, int do_begin)
     fj_arrival_finish<SUM_MODE>(c, x, iters, rc);
 }
 
-// ---------------------------------------------------------------- observation + rule cache
-// state_extract + update_parameter (SO_DFJSP.py:81-169 / MO_DFJSP.py:91-187), plus the
-// operation-type choice every deterministic task rule would make in THIS state (the next
-// step() only looks the answer up).  Writes v(t) to c.obs2.
+// ---------------------------------------------------------------- observation + rule keys
+// state_extract + update_parameter (SO_DFJSP.py:81-169 / MO_DFJSP.py:91-187).  Besides v(t)
+// (written to c.obs2) it leaves what the NEXT step's task_select needs: availability /
+// delay bit masks and, per available operation type, the two keys that come out of the
+// walk over its unprocessed operations (delivery urgency, largest estimated delay).  All
+// other rule keys are cheap and recomputed lazily by fj_task_select for the one rule used.
+template <int SUM_MODE> FJ_FN void fj_neumaier(double &f, double &cc, double x)
+{
+    if (SUM_MODE == 0) { f = fj_add(f, x); return; }
+    const double t2 = fj_add(f, x);
+    const bool bigf = fabs(f) >= fabs(x);
+    const double hi = bigf ? f : x, lo = bigf ? x : f;
+    cc = fj_add(cc, fj_add(fj_sub(hi, t2), lo));
+    f = t2;
+}
+
+FJ_FN double fj_gap_mrj(const FjCtx &c, int q, int m, double gt)
+{
+    const int sl = c.slot[q * c.Mx + m];
+    if (sl == 0xFFFF) return fj_sub(0.0, (double)c.pk[q * c.Mx + m]);
+    return fj_sub(c.fu[sl], fj_sub(c.fa[sl], fj_mul(gt, c.ff[sl])));
+}
+
+// gap_ave of machine m (class_FJSP.py:156-159).  EXACT: CPython's sum order and compensation
+// (it is a machine-rule key); otherwise a plain running sum (observation feature only).
+template <int SUM_MODE, int EXACT>
+FJ_FN double fj_machine_gap_ave(const FjCtx &c, int m, double gt)
+{
+    const int KT = c.KT;
+    const FjRO elig = FJ_I(c, elig);
+    double f = 0.0, cc = 0.0;
+    int n = 0;
+    for (int q = 0; q < KT; ++q) {
+        if (!((unsigned)elig[q] >> m & 1u)) continue;
+        const double term = fj_gap_mrj(c, q, m, gt);
+        if (EXACT) fj_neumaier<SUM_MODE>(f, cc, term); else f = fj_add(f, term);
+        ++n;
+    }
+    if (EXACT && SUM_MODE != 0 && cc != 0.0 && isfinite(cc)) f = fj_add(f, cc);
+    return fj_div(f, (double)n);
+}
+
 template <int VARIANT, int SUM_MODE>
 FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
 {
     const int lane = fj_lane();
     const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
-    const int M = c.M, KT = c.KT, S = c.S, Mx = c.Mx, Sx = c.Sx;
-    const int32_t *elig = FJ_I(c, elig), *due = FJ_I(c, due), *rjlast = FJ_I(c, rjlast);
-    const int32_t *ptime = FJ_I(c, ptime), *energy = FJ_I(c, energy);
+    const int M = c.M, KT = c.KT, S = c.S, Sx = c.Sx;
+    const FjRO elig = FJ_I(c, elig), due = FJ_I(c, due), rjlast = FJ_I(c, rjlast);
     const int t = c.scal[FJ_S_TIME];
     const double td = (double)t;
     const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
     const double gt = fj_get_d(c.scal, FJ_S_GAPTIME);
-    long long da = 0, de = 0, tn = 0, ja = 0, je = 0, jn = 0, dunp = 0;
+    // packed integer partials: (tn, da) (de, jn) (ja, je) and the 64-bit tardiness of waiting jobs
+    long long p0 = 0, p1 = 0, p2 = 0, dunp = 0;
     int nav = 0, nfav = 0;
     double s_fr = 0.0, s_gr = 0.0;
-    FjBest b_urg_av, b_de, b_da, b_gap_av, b_gap_fav, b_urg_fav, b_due_av, b_due_fav, b_en_av, b_en_fav, b_tm_av, b_tm_fav;
-    fj_best_init(b_urg_av); fj_best_init(b_de); fj_best_init(b_da); fj_best_init(b_gap_av); fj_best_init(b_gap_fav);
-    fj_best_init(b_urg_fav); fj_best_init(b_due_av); fj_best_init(b_due_fav); fj_best_init(b_en_av); fj_best_init(b_en_fav);
-    fj_best_init(b_tm_av); fj_best_init(b_tm_fav);
     const int rounds = (KT + FJ_NL - 1) / FJ_NL;
     for (int rd = 0; rd < rounds; ++rd) {
         const int q = rd * FJ_NL + lane;
-        int av = 0, fav = 0;
+        int av = 0, fav = 0, dle = 0, dla = 0;
         if (q < KT) {
-            int residue = 0;
-            for (int s = 0; s < S; ++s) residue += c.cntunp[q * Sx + s];
             const int qn = c.qlen[q];
             av = qn > 0 && ((unsigned)elig[q] & idle) != 0;
             fav = qn > 0 && (c.flmask[q] & idle) != 0;
             const double f = c.tsum[q];
-            // walk the unprocessed operations in list order: positions are consecutive and
-            // the due date is constant inside an order, so only per-order counts are needed
-            int a_cnt = 0, e_cnt = 0, k = 0;
-            long long max_a = 0; double max_e = 0.0; bool first = true;
+            // walk the unprocessed operations in list order: positions are consecutive and the
+            // due date is constant inside an order, so per-order counts are all that is needed;
+            // inside an order the estimate grows with the position, so its maximum is the last
+            int residue = 0, a_cnt = 0, e_cnt = 0;
+            double kd = 0.0, max_e = 0.0, sf = 0.0, sc = 0.0;
+            bool first = true;
             long long late_sum = 0;
-            FjPySum ps; fj_pysum_init(ps);
             for (int s = 0; s < S; ++s) {
                 const int cnt = c.cntunp[q * Sx + s];
                 if (cnt == 0) continue;
+                residue += cnt;
                 const int d = due[s];
                 const double dd = (double)d;
                 if (t > d) { a_cnt += cnt; late_sum += (long long)cnt * (t - d); }
-                const long long va = (long long)t - d;
-                if (first || va > max_a) max_a = va;
+                double ve = 0.0;
                 for (int i = 0; i < cnt; ++i) {
-                    ++k;
-                    const double est = fj_add(td, fj_mul(f, (double)k));
-                    const double ve = fj_sub(est, dd);
-                    if (est > dd) ++e_cnt;
-                    if (first || ve > max_e) max_e = ve;
-                    first = false;
-                    fj_pysum_add<SUM_MODE>(ps, ve);
+                    kd += 1.0;
+                    const double est = fj_add(td, fj_mul(f, kd));
+                    ve = fj_sub(est, dd);
+                    e_cnt += est > dd;
+                    fj_neumaier<SUM_MODE>(sf, sc, ve);
                 }
+                if (first || ve > max_e) max_e = ve;
+                first = false;
             }
-            tn += residue; da += a_cnt; de += e_cnt;
-            if (rjlast[q]) { jn += residue; ja += a_cnt; je += e_cnt; dunp += late_sum; }
+            p0 += ((long long)residue << 32) + a_cnt;
+            p1 += ((long long)e_cnt << 32);
+            if (rjlast[q]) { p1 += residue; p2 += ((long long)a_cnt << 32) + e_cnt; dunp += late_sum; }
             const double fluid_unp = fj_sub((double)c.fstart[q], fj_mul(c.rsum[q], gt));
             const double gap = fj_sub((double)residue, fluid_unp);
             const int pr = c.proc[q];
             s_fr = fj_add(s_fr, fj_div((double)pr, (double)(residue + pr)));
             s_gr = fj_add(s_gr, fj_div(gap, (double)c.fstart[q]));
             if (av) {
-                ++nav;
-                const double urgency = fj_div(fj_pysum_result<SUM_MODE>(ps), (double)residue);
-                int dmin = 0; bool fd = true;
-                for (int s = 0; s < S; ++s)
-                    if (c.cntnow[q * Sx + s] > 0 && (fd || due[s] < dmin)) { dmin = due[s]; fd = false; }
-                fj_best_max(b_urg_av, urgency, q);
-                if (e_cnt > 0) fj_best_max(b_de, max_e, q);
-                if (a_cnt > 0) fj_best_max(b_da, (double)max_a, q);
-                fj_best_max(b_gap_av, gap, q);
-                fj_best_min(b_due_av, (double)dmin, q);
-                if (fav) {
-                    ++nfav;
-                    fj_best_max(b_gap_fav, gap, q);
-                    fj_best_max(b_urg_fav, urgency, q);
-                    fj_best_min(b_due_fav, (double)dmin, q);
-                }
-                if (MO) {   // MO_DFJSP.py:429-451: min time / energy over idle (fluid) machines
-                    unsigned sm = (unsigned)elig[q] & idle;
-                    int tmin = 0x7fffffff, emin = 0x7fffffff;
-                    while (sm) { int m = fj_ffs0(sm); sm &= sm - 1;
-                        int pt = ptime[q * Mx + m], en = energy[q * Mx + m];
-                        tmin = pt < tmin ? pt : tmin; emin = en < emin ? en : emin; }
-                    fj_best_min(b_tm_av, (double)tmin, q); fj_best_min(b_en_av, (double)emin, q);
-                    if (fav) {
-                        unsigned fm = c.flmask[q] & idle;
-                        tmin = 0x7fffffff; emin = 0x7fffffff;
-                        while (fm) { int m = fj_ffs0(fm); fm &= fm - 1;
-                            int pt = ptime[q * Mx + m], en = energy[q * Mx + m];
-                            tmin = pt < tmin ? pt : tmin; emin = en < emin ? en : emin; }
-                        fj_best_min(b_tm_fav, (double)tmin, q); fj_best_min(b_en_fav, (double)emin, q);
-                    }
-                }
+                if (SUM_MODE != 0 && sc != 0.0 && isfinite(sc)) sf = fj_add(sf, sc);
+                c.urg[q] = fj_div(sf, (double)residue);
+                c.maxe[q] = max_e;
+                dle = e_cnt > 0; dla = a_cnt > 0;
             }
         }
-        // availability masks, one 32-bit word per round
+        // bit masks, one 32-bit word per round
 #ifdef FJ_DEVICE_CODE
-        unsigned wa = __ballot_sync(0xffffffffu, av), wf = __ballot_sync(0xffffffffu, fav);
-        if (lane == 0) { c.avmask[rd] = wa; c.favmask[rd] = wf; }
+        const unsigned wa = __ballot_sync(0xffffffffu, av), wf = __ballot_sync(0xffffffffu, fav);
+        const unsigned we = __ballot_sync(0xffffffffu, dle), wd = __ballot_sync(0xffffffffu, dla);
+        if (lane == 0) { c.avmask[rd] = wa; c.favmask[rd] = wf; c.demask[rd] = we; c.damask[rd] = wd; }
+        nav += fj_popc(wa); nfav += fj_popc(wf);
 #else
-        if ((q & 31) == 0) { c.avmask[q >> 5] = 0; c.favmask[q >> 5] = 0; }
+        if ((q & 31) == 0) { c.avmask[q >> 5] = 0; c.favmask[q >> 5] = 0; c.demask[q >> 5] = 0; c.damask[q >> 5] = 0; }
         if (av) c.avmask[q >> 5] |= 1u << (q & 31);
         if (fav) c.favmask[q >> 5] |= 1u << (q & 31);
+        if (dle) c.demask[q >> 5] |= 1u << (q & 31);
+        if (dla) c.damask[q >> 5] |= 1u << (q & 31);
+        nav += av; nfav += fav;
 #endif
     }
-    tn = fj_sum_ll(tn); da = fj_sum_ll(da); de = fj_sum_ll(de);
-    jn = fj_sum_ll(jn); ja = fj_sum_ll(ja); je = fj_sum_ll(je); dunp = fj_sum_ll(dunp);
-    nav = fj_sum_i(nav); nfav = fj_sum_i(nfav);
+    p0 = fj_sum_ll(p0); p1 = fj_sum_ll(p1); p2 = fj_sum_ll(p2); dunp = fj_sum_ll(dunp);
+    const long long tn = p0 >> 32, da = p0 & 0xffffffffll, de = p1 >> 32, jn = p1 & 0xffffffffll;
+    const long long ja = p2 >> 32, je = p2 & 0xffffffffll;
     const double cro_ave = fj_div(fj_sum_d(s_fr), (double)KT);
     const double gap_ave = fj_div(fj_sum_d(s_gr), (double)KT);
-    fj_best_reduce(b_urg_av, 1); fj_best_reduce(b_de, 1); fj_best_reduce(b_da, 1);
-    fj_best_reduce(b_gap_av, 1); fj_best_reduce(b_gap_fav, 1); fj_best_reduce(b_urg_fav, 1);
-    fj_best_reduce(b_due_av, 0); fj_best_reduce(b_due_fav, 0);
-    if (MO) { fj_best_reduce(b_en_av, 0); fj_best_reduce(b_en_fav, 0); fj_best_reduce(b_tm_av, 0); fj_best_reduce(b_tm_fav, 0); }
     // second pass: variances (observation only)
     double v_fr = 0.0, v_gr = 0.0;
     for (int q = lane; q < KT; q += FJ_NL) {
@@ -662,42 +686,37 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
     }
     const double cro_std = sqrt(fj_div(fj_sum_d(v_fr), (double)KT));
     const double gap_std = sqrt(fj_div(fj_sum_d(v_gr), (double)KT));
-    // machines: completion-time spread and the exact gap_ave of every machine (a machine
-    // rule key, so CPython's sum order over its operation types is reproduced)
+    // machines: completion-time spread; MO also the mean / spread of the machines' gap_ave
     long long tsum_m = 0;
     for (int m = lane; m < M; m += FJ_NL) tsum_m += c.mend[m];
     tsum_m = fj_sum_ll(tsum_m);
     const double ct_ave = fj_div((double)tsum_m, (double)M);
-    double v_ct = 0.0, s_gm = 0.0;
+    double v_ct = 0.0, s_gm = 0.0, q_gm = 0.0;
     for (int m = lane; m < M; m += FJ_NL) {
         const double dv = fj_sub((double)c.mend[m], ct_ave);
         v_ct = fj_add(v_ct, fj_mul(dv, dv));
-        FjPySum ps; fj_pysum_init(ps);
-        int n = 0;
-        for (int q = 0; q < KT; ++q) {
-            if (!((unsigned)elig[q] >> m & 1u)) continue;
-            const int sl = c.slot[q * Mx + m];
-            double term;
-            if (sl == 0xFFFF) term = fj_sub(0.0, (double)c.pk[q * Mx + m]);
-            else term = fj_sub(c.fu[sl], fj_sub(c.fa[sl], fj_mul(gt, c.ff[sl])));
-            fj_pysum_add<SUM_MODE>(ps, term);
-            ++n;
+        if (MO) {
+            const double ga = fj_machine_gap_ave<SUM_MODE, 0>(c, m, gt);
+            s_gm = fj_add(s_gm, ga);
+            q_gm = fj_add(q_gm, fj_mul(ga, ga));
         }
-        const double ga = fj_div(fj_pysum_result<SUM_MODE>(ps), (double)n);
-        c.gapave[m] = ga;
-        s_gm = fj_add(s_gm, ga);
     }
     const double ct_std = sqrt(fj_div(fj_sum_d(v_ct), (double)M));
     double gm_ave = 0.0, gm_std = 0.0;
     if (MO) {
         gm_ave = fj_div(fj_sum_d(s_gm), (double)M);
-        fj_sync();
+        // E[x^2] - mean^2 would cancel badly; redo the centred sum from the per-lane values
         double v_gm = 0.0;
-        for (int m = lane; m < M; m += FJ_NL) { const double dv = fj_sub(c.gapave[m], gm_ave); v_gm = fj_add(v_gm, fj_mul(dv, dv)); }
+        for (int m = lane; m < M; m += FJ_NL) {
+            const double dv = fj_sub(fj_machine_gap_ave<SUM_MODE, 0>(c, m, gt), gm_ave);
+            v_gm = fj_add(v_gm, fj_mul(dv, dv));
+        }
         gm_std = sqrt(fj_div(fj_sum_d(v_gm), (double)M));
+        (void)q_gm;
     }
     if (lane == 0) {
         fj_set_ll(c.scal, FJ_S_DELAY_UNPROC, dunp);
+        c.scal[FJ_S_NAV] = nav; c.scal[FJ_S_NFAV] = nfav;
         double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
         if (!rates_zero) {
             r0 = fj_div((double)da, (double)tn); r1 = fj_div((double)de, (double)tn);
@@ -715,92 +734,166 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
             o[0] = (double)M; o[1] = ct_std; o[2] = cro_ave; o[3] = cro_std; o[4] = gap_ave; o[5] = gap_std;
             o[6] = r0; o[7] = r1; o[8] = r2; o[9] = r3;
         }
-        // rule cache: index = task rule number (1-based)
-        int *ch = c.choice;
-        const bool hf = nfav > 0;
-        ch[1] = b_de.idx != 0x7fffffff ? b_de.idx : b_urg_av.idx;
-        ch[2] = b_da.idx != 0x7fffffff ? b_da.idx : b_urg_av.idx;
-        ch[3] = hf ? b_gap_fav.idx : b_gap_av.idx;
-        ch[4] = hf ? b_urg_fav.idx : b_urg_av.idx;
-        ch[5] = hf ? b_due_fav.idx : b_due_av.idx;
-        if (MO) {
-            ch[6] = b_due_av.idx;
-            ch[7] = hf ? b_en_fav.idx : b_en_av.idx;
-            ch[8] = b_en_av.idx;
-            ch[9] = hf ? b_tm_fav.idx : b_tm_av.idx;
-            ch[10] = b_tm_av.idx;
-        }
-        ch[0] = nav; ch[11] = nfav;
     }
     fj_sync();
 }
 
-// ---------------------------------------------------------------- machine_select
-FJ_FN int fj_pyset_order_dev(const int *seq, int n, int *out)
+// ---------------------------------------------------------------- task_select
+FJ_FN int fj_nth_set(const uint32_t *mask, int words, int nth)
 {
-    if (n >= 5) {
-        unsigned mask = 0;
-        for (int i = 0; i < n; ++i) mask |= 1u << seq[i];
-        int k = 0;
-        while (mask) { out[k++] = fj_ffs0(mask); mask &= mask - 1; }
-        return k;
+    for (int w = 0; w < words; ++w) {
+        unsigned v = mask[w];
+        int pc = fj_popc(v);
+        if (nth < pc) { while (nth--) v &= v - 1; return w * 32 + fj_ffs0(v); }
+        nth -= pc;
     }
-    int slot[8];
-    for (int i = 0; i < 8; ++i) slot[i] = -1;
-    for (int e = 0; e < n; ++e) {
-        unsigned i = (unsigned)seq[e] & 7u, perturb = (unsigned)seq[e];
-        while (slot[i] >= 0) { perturb >>= 5; i = (i * 5u + 1u + perturb) & 7u; }
-        slot[i] = seq[e];
-    }
-    int k = 0;
-    for (int i = 0; i < 8; ++i) if (slot[i] >= 0) out[k++] = slot[i];
-    return k;
+    return -1;
 }
-
-// list(set(idle) & set(other)) with `other_ord` = iteration order of set(other)
-FJ_FN int fj_selectable(unsigned idle, const int *other_ord, int nother, int *out)
+FJ_FN int fj_mask_any(const uint32_t *mask, int words)
 {
-    int ia[32], io_[32], keep[32];
-    int ni = 0;
-    unsigned mk = idle;
-    while (mk) { ia[ni++] = fj_ffs0(mk); mk &= mk - 1; }
-    ni = fj_pyset_order_dev(ia, ni, io_);
-    unsigned om = 0;
-    for (int i = 0; i < nother; ++i) om |= 1u << other_ord[i];
-    int nk = 0;
-    if (nother > ni) { for (int i = 0; i < ni; ++i) if (om >> io_[i] & 1u) keep[nk++] = io_[i]; }
-    else { for (int i = 0; i < nother; ++i) if (idle >> other_ord[i] & 1u) keep[nk++] = other_ord[i]; }
-    return fj_pyset_order_dev(keep, nk, out);
+    unsigned v = 0;
+    for (int w = 0; w < words; ++w) v |= mask[w];
+    return v != 0;
 }
 
-FJ_FN double fj_gap_mrj(const FjCtx &c, int q, int m, double gt)
-{
-    const int sl = c.slot[q * c.Mx + m];
-    if (sl == 0xFFFF) return fj_sub(0.0, (double)c.pk[q * c.Mx + m]);
-    return fj_sub(c.fu[sl], fj_sub(c.fa[sl], fj_mul(gt, c.ff[sl])));
-}
-
-// executed by one lane; returns the machine or -1
+// SO_DFJSP.py:270-301 / MO_DFJSP.py:300-352.  Warp-cooperative: lanes own operation types,
+// one argmax/argmin reduction (lowest index on ties = Python's first extremal element).
 template <int VARIANT>
-FJ_FN int fj_machine_select(const FjCtx &c, int rule, int q, uint32_t rnd)
+FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
 {
+    const int lane = fj_lane();
     const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
-    const int Mx = c.Mx;
+    const int KT = c.KT, S = c.S, Sx = c.Sx, Mx = c.Mx;
+    const int KTW = (KT + 31) / 32;
+    const int nav = c.scal[FJ_S_NAV], nfav = c.scal[FJ_S_NFAV];
+    if (nav <= 0) return -1;
+    // key: 0 urgency 1 est. delay 2 actual delay 3 gap (all max) 4 min due 5 min energy 6 min time (all min)
+    const uint32_t *set = c.avmask;
+    int key = -1;
+    bool fluid_m = false;   // energy / time over the fluid machines
+    const uint32_t *flav = nfav > 0 ? c.favmask : c.avmask;
+    switch (rule) {
+    case 1: if (fj_mask_any(c.demask, KTW)) { set = c.demask; key = 1; } else key = 0; break;
+    case 2: if (fj_mask_any(c.damask, KTW)) { set = c.damask; key = 2; } else key = 0; break;
+    case 3: set = flav; key = 3; break;
+    case 4: set = flav; key = 0; break;
+    case 5: set = flav; key = 4; break;
+    default:
+        if (!MO) { if (rule == 6) return fj_nth_set(c.avmask, KTW, (int)(rnd % (uint32_t)nav)); return -1; }
+        switch (rule) {
+        case 6: key = 4; break;
+        case 7: set = flav; key = 5; fluid_m = nfav > 0; break;
+        case 8: key = 5; break;
+        case 9: set = flav; key = 6; fluid_m = nfav > 0; break;
+        case 10: key = 6; break;
+        case 11: return nfav > 0 ? fj_nth_set(c.favmask, KTW, (int)(rnd % (uint32_t)nfav))
+                                 : fj_nth_set(c.avmask, KTW, (int)(rnd % (uint32_t)nav));
+        case 12: return fj_nth_set(c.avmask, KTW, (int)(rnd % (uint32_t)nav));
+        default: return -1;
+        }
+    }
+    const FjRO due = FJ_I(c, due), elig = FJ_I(c, elig);
+    const int t = c.scal[FJ_S_TIME];
     const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
     const double gt = fj_get_d(c.scal, FJ_S_GAPTIME);
-    int mt[32], fl[32], flo[32], sl[32], fs[32];
-    const int32_t *mtset = FJ_I(c, mtset) + q * Mx, *poord = FJ_I(c, poord) + q * Mx;
-    const int ne = FJ_I(c, nelig)[q];
-    for (int i = 0; i < ne; ++i) mt[i] = mtset[i];
-    int ns = fj_selectable(idle, mt, ne, sl);
-    if (ns == 0) return -1;
-    int nfl = 0;
-    const unsigned fm = c.flmask[q];
-    for (int i = 0; i < ne; ++i) if (fm >> poord[i] & 1u) fl[nfl++] = poord[i];
-    nfl = fj_pyset_order_dev(fl, nfl, flo);
-    int nf = fj_selectable(idle, flo, nfl, fs);
-    const int *lst = sl; int n = ns;
-    const int *flst = nf ? fs : sl; const int fn = nf ? nf : ns;
+    const bool want_max = key <= 3;
+    FjBest b; fj_best_init(b);
+    for (int q = lane; q < KT; q += FJ_NL) {
+        if (!(set[q >> 5] >> (q & 31) & 1u)) continue;
+        double k;
+        if (key == 0) k = c.urg[q];
+        else if (key == 1) k = c.maxe[q];
+        else if (key == 2) {   // max over unprocessed operations of (t - due)
+            int mind = 0x7fffffff;
+            for (int s = 0; s < S; ++s) if (c.cntunp[q * Sx + s] > 0 && due[s] < mind) mind = due[s];
+            k = (double)((long long)t - mind);
+        } else if (key == 3) {
+            int residue = 0;
+            for (int s = 0; s < S; ++s) residue += c.cntunp[q * Sx + s];
+            k = fj_sub((double)residue, fj_sub((double)c.fstart[q], fj_mul(c.rsum[q], gt)));
+        } else if (key == 4) {
+            int mind = 0x7fffffff;
+            for (int s = 0; s < S; ++s) if (c.cntnow[q * Sx + s] > 0 && due[s] < mind) mind = due[s];
+            k = (double)mind;
+        } else {   // MO_DFJSP.py:429-451: min energy / time over the idle (fluid) machines
+            unsigned sm = (fluid_m ? c.flmask[q] : (unsigned)elig[q]) & idle;
+            const FjRO tab = (key == 5 ? FJ_I(c, energy) : FJ_I(c, ptime)) + q * Mx;
+            int mn = 0x7fffffff;
+            while (sm) { const int m = fj_ffs0(sm); sm &= sm - 1; const int v = tab[m]; mn = v < mn ? v : mn; }
+            k = (double)mn;
+        }
+        if (want_max) fj_best_max(b, k, q); else fj_best_min(b, k, q);
+    }
+    fj_best_reduce(b, want_max ? 1 : 0);
+    return b.idx == 0x7fffffff ? -1 : b.idx;
+}
+
+// ---------------------------------------------------------------- machine_select
+// Candidate lists are list(set(idle) & set(machine_tuple)) in CPython's set iteration
+// order (see oracle/pyemu.h).  Five or more members iterate in ascending order; up to four
+// live in an 8-slot table whose layout depends on insertion order, emulated here on a
+// 64-bit register (one byte per slot).
+FJ_FN unsigned fj_small_set_order(unsigned seq, int n)   // seq: members, one byte each, insertion order
+{
+    unsigned long long slots = ~0ull;
+    for (int e = 0; e < n; ++e) {
+        const unsigned v = (seq >> (8 * e)) & 0xffu;
+        unsigned i = v & 7u;
+        while (((slots >> (8 * i)) & 0xffull) != 0xffull) i = (i * 5u + 1u) & 7u;   // perturb is 0 for v < 32
+        slots = (slots & ~(0xffull << (8 * i))) | ((unsigned long long)v << (8 * i));
+    }
+    unsigned out = 0; int k = 0;
+    for (int i = 0; i < 8; ++i) {
+        const unsigned bt = (unsigned)((slots >> (8 * i)) & 0xffull);
+        if (bt != 0xffu) out |= bt << (8 * k++);
+    }
+    return out;
+}
+
+struct FjCand { unsigned mask; unsigned packed; int n; };   // n >= 5: ascending over mask; else packed order
+
+// list(set(idle) & set(other)); other given by its mask, its size and a functor-free walk:
+// `ord` = iteration order of set(other) as an int32 array (static), or, when ord_packed_n >= 0,
+// as packed bytes.
+FJ_FN FjCand fj_selectable(unsigned idle, unsigned omask, int nother, FjRO ord, unsigned ord_packed, int use_packed)
+{
+    FjCand r;
+    r.mask = idle & omask; r.n = fj_popc(r.mask); r.packed = 0;
+    if (r.n >= 5 || r.n == 0) return r;
+    const int ni = fj_popc(idle);
+    unsigned seq = 0; int k = 0;
+    if (nother > ni) {   // iterate set(idle)
+        if (ni >= 5) { unsigned mk = r.mask; while (mk) { seq |= (unsigned)fj_ffs0(mk) << (8 * k++); mk &= mk - 1; } }
+        else {
+            unsigned a = 0; int na = 0; unsigned mk = idle;
+            while (mk) { a |= (unsigned)fj_ffs0(mk) << (8 * na++); mk &= mk - 1; }
+            const unsigned ao = fj_small_set_order(a, na);
+            for (int i = 0; i < na; ++i) { const unsigned v = (ao >> (8 * i)) & 0xffu; if (omask >> v & 1u) seq |= v << (8 * k++); }
+        }
+    } else {             // iterate set(other)
+        if (nother >= 5 && !use_packed) {
+            // set(other) has >= 5 members: ascending
+            unsigned mk = r.mask; while (mk) { seq |= (unsigned)fj_ffs0(mk) << (8 * k++); mk &= mk - 1; }
+        } else if (use_packed) {
+            if (nother >= 5) { unsigned mk = r.mask; while (mk) { seq |= (unsigned)fj_ffs0(mk) << (8 * k++); mk &= mk - 1; } }
+            else for (int i = 0; i < nother; ++i) { const unsigned v = (ord_packed >> (8 * i)) & 0xffu; if (idle >> v & 1u) seq |= v << (8 * k++); }
+        } else {
+            for (int i = 0; i < nother; ++i) { const unsigned v = (unsigned)ord[i]; if (idle >> v & 1u) seq |= v << (8 * k++); }
+        }
+    }
+    r.packed = fj_small_set_order(seq, r.n);
+    return r;
+}
+
+// SO_DFJSP.py:303-325 / MO_DFJSP.py:354-398.  Warp-cooperative only for the exact gap_ave
+// keys of rule 4; the pick itself is a short scalar loop every lane runs redundantly.
+template <int VARIANT, int SUM_MODE>
+FJ_FN int fj_machine_select(FjCtx &c, int rule, int q, uint32_t rnd)
+{
+    const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
+    const int Mx = c.Mx, M = c.M;
+    const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
+    const double gt = fj_get_d(c.scal, FJ_S_GAPTIME);
     int key_kind;       // 0 gap_rj(max) 1 time(min) 2 gap_ave(max) 3 energy(min) 4 idle power(min) 5 random
     bool use_f;
     if (!MO) {
@@ -827,11 +920,40 @@ FJ_FN int fj_machine_select(const FjCtx &c, int rule, int q, uint32_t rnd)
         default: return -1;
         }
     }
-    if (use_f) { lst = flst; n = fn; }
-    if (key_kind == 5) return lst[rnd % (uint32_t)n];
+    const unsigned em = (unsigned)FJ_I(c, elig)[q], fm = c.flmask[q];
+    const int ne = FJ_I(c, nelig)[q];
+    if ((idle & em) == 0) return -1;
+    FjCand cand;
+    if (use_f && (idle & fm) != 0) {
+        // set(fluid_machine_list): members in x.items() order
+        const int nf = fj_popc(fm);
+        unsigned fo = 0;
+        if (nf < 5) {
+            const FjRO poord = FJ_I(c, poord) + q * Mx;
+            unsigned seq = 0; int k = 0;
+            for (int i = 0; i < ne; ++i) { const unsigned v = (unsigned)poord[i]; if (fm >> v & 1u) seq |= v << (8 * k++); }
+            fo = fj_small_set_order(seq, nf);
+        }
+        cand = fj_selectable(idle, fm, nf, fj_ro(nullptr), fo, 1);
+    } else {
+        cand = fj_selectable(idle, em, ne, FJ_I(c, mtset) + q * Mx, 0, 0);
+    }
+    if (key_kind == 2) {   // exact gap_ave of the candidates, one lane per machine
+        for (int m = fj_lane(); m < M; m += FJ_NL)
+            if (cand.mask >> m & 1u) c.gapave[m] = fj_machine_gap_ave<SUM_MODE, 1>(c, m, gt);
+        fj_sync();
+    }
+    const int n = cand.n;
+    if (key_kind == 5) {
+        const int pick = (int)(rnd % (uint32_t)n);
+        if (n >= 5) { unsigned mk = cand.mask; for (int i = 0; i < pick; ++i) mk &= mk - 1; return fj_ffs0(mk); }
+        return (int)((cand.packed >> (8 * pick)) & 0xffu);
+    }
     int best = -1; double bk = 0.0;
+    unsigned mk = cand.mask;
     for (int i = 0; i < n; ++i) {
-        const int m = lst[i];
+        int m;
+        if (n >= 5) { m = fj_ffs0(mk); mk &= mk - 1; } else m = (int)((cand.packed >> (8 * i)) & 0xffu);
         double k;
         switch (key_kind) {
         case 0: k = fj_gap_mrj(c, q, m, gt); break;
@@ -844,17 +966,6 @@ FJ_FN int fj_machine_select(const FjCtx &c, int rule, int q, uint32_t rnd)
         if (best < 0 || (want_max ? k > bk : k < bk)) { best = m; bk = k; }
     }
     return best;
-}
-
-FJ_FN int fj_nth_set(const uint32_t *mask, int words, int nth)
-{
-    for (int w = 0; w < words; ++w) {
-        unsigned v = mask[w];
-        int pc = fj_popc(v);
-        if (nth < pc) { while (nth--) v &= v - 1; return w * 32 + fj_ffs0(v); }
-        nth -= pc;
-    }
-    return -1;
 }
 
 // ---------------------------------------------------------------- suspension
@@ -901,7 +1012,7 @@ FJ_FN void fj_reset_begin(FjCtx &c, int fresh)
     int was_done = 0;
     if (fresh) {
         for (int i = lane; i < FJ_S_COUNT; i += FJ_NL) c.scal[i] = 0;
-        for (int i = lane; i < 16; i += FJ_NL) { c.obs[i] = 0.0; c.choice[i] = -1; }
+        for (int i = lane; i < 16; i += FJ_NL) c.obs[i] = 0.0;
         fj_sync();
     } else {
         was_done = c.scal[FJ_S_DONE];
@@ -938,35 +1049,20 @@ FJ_FN void fj_reset_finish(FjCtx &c)
 struct FjStepOut { double reward; int done; int rec[8]; };
 
 // task_select + machine_select + dispatch; returns 0 when nothing could be dispatched
-template <int VARIANT>
+template <int VARIANT, int SUM_MODE>
 FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint32_t rnd_task, uint32_t rnd_mach,
                                  FjStepOut &out)
 {
     const int lane = fj_lane();
     const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
-    const int KT = c.KT, Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
-    const int32_t *rjkind = FJ_I(c, rjkind), *rjstage = FJ_I(c, rjstage), *rjlast = FJ_I(c, rjlast);
-    const int32_t *due = FJ_I(c, due), *cum = FJ_I(c, cum), *jobbase = FJ_I(c, jobbase);
+    const int Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
+    const FjRO rjkind = FJ_I(c, rjkind), rjstage = FJ_I(c, rjstage), rjlast = FJ_I(c, rjlast);
+    const FjRO due = FJ_I(c, due), cum = FJ_I(c, cum), jobbase = FJ_I(c, jobbase);
     const int t = c.scal[FJ_S_TIME];
-    // ---- task_select: cached answer, or a draw from the availability masks
+    // ---- task_select / machine_select on the keys the previous observation left
     const int trule = task_rule0 + 1, mrule = mach_rule0 + 1;
-    int q = -1, m = -1;
-    if (lane == 0) {
-        const int nav = c.choice[0], nfav = c.choice[11];
-        const int KTW = (KT + 31) / 32;   // words this instance's observe() wrote
-        if (nav > 0) {
-            if (!MO) {
-                if (trule >= 1 && trule <= 5) q = c.choice[trule];
-                else if (trule == 6) q = fj_nth_set(c.avmask, KTW, (int)(rnd_task % (uint32_t)nav));
-            } else {
-                if (trule >= 1 && trule <= 10) q = c.choice[trule];
-                else if (trule == 11) q = nfav > 0 ? fj_nth_set(c.favmask, KTW, (int)(rnd_task % (uint32_t)nfav))
-                                                   : fj_nth_set(c.avmask, KTW, (int)(rnd_task % (uint32_t)nav));
-                else if (trule == 12) q = fj_nth_set(c.avmask, KTW, (int)(rnd_task % (uint32_t)nav));
-            }
-        }
-        if (q >= 0) m = fj_machine_select<VARIANT>(c, mrule, q, rnd_mach);
-    }
+    int q = fj_task_select<VARIANT>(c, trule, rnd_task), m = -1;
+    if (q >= 0) m = fj_machine_select<VARIANT, SUM_MODE>(c, mrule, q, rnd_mach);
     q = fj_bcast_i(q, 0); m = fj_bcast_i(m, 0);
     if (q < 0 || m < 0) {
         if (lane == 0) c.scal[FJ_S_ERROR] |= (q < 0 ? FJ_E_NO_TASK : FJ_E_NO_MACHINE);
@@ -990,7 +1086,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
         const int dur = FJ_I(c, ptime)[q * Mx + m];
         int t_begin = t, t_end = t + dur, m_end = t_end;
         if (VARIANT == FJSP_MO_BREAKDOWN) {   // MO_DFJSP_breakdown.py:204-231
-            const int32_t *bp = FJ_I(c, bdptr), *bs_ = FJ_I(c, bds), *be_ = FJ_I(c, bde);
+            const FjRO bp = FJ_I(c, bdptr), bs_ = FJ_I(c, bds), be_ = FJ_I(c, bde);
             for (int i = bp[m]; i < bp[m + 1]; ++i) {
                 const int bs = bs_[i], be = be_[i];
                 if (bs <= t && t < be) { int d = be - t; t_begin += d; t_end += d; m_end = t_end; }
@@ -1033,8 +1129,8 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
 {
     const int lane = fj_lane();
     const int M = c.M, KT = c.KT, S = c.S, Sx = c.Sx;
-    const int32_t *rjkind = FJ_I(c, rjkind), *rjlast = FJ_I(c, rjlast), *elig = FJ_I(c, elig);
-    const int32_t *arrive = FJ_I(c, arrive), *jobbase = FJ_I(c, jobbase);
+    const FjRO rjkind = FJ_I(c, rjkind), rjlast = FJ_I(c, rjlast), elig = FJ_I(c, elig);
+    const FjRO arrive = FJ_I(c, arrive), jobbase = FJ_I(c, jobbase);
     int t = c.scal[FJ_S_TIME];
     done = 0;
     for (;;) {
@@ -1152,12 +1248,39 @@ FJ_FN_NOINLINE void fj_step_back(FjCtx &c, int done, int reward_policy, double c
 // dispatch record; auto-reset a finished environment before its next action.
 // SUSPEND = 1: main kernel, parks on the first LP it needs.  SUSPEND = 0: resume kernel
 // (starts from the parked phase / step) and the one-lane host build's second pass.
+FJ_FN void fj_stage_copy(unsigned char *dst, const unsigned char *src, int bytes)
+{
+    // records are 16-byte aligned multiples of 16 bytes: 128-bit coalesced copies
+    const int n = bytes >> 4;
+#ifdef FJ_DEVICE_CODE
+    const uint4 *s4 = (const uint4 *)src; uint4 *d4 = (uint4 *)dst;
+    for (int i = fj_lane(); i < n; i += FJ_NL) d4[i] = s4[i];
+#else
+    memcpy(dst, src, (size_t)n * 16);
+#endif
+    fj_sync();
+}
+
 template <int VARIANT, int SUM_MODE, int SUSPEND>
-FJ_FN void fj_env_rollout(const FjParams &P, const FjStepArgs &A, int env, unsigned char *lp)
+FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, unsigned char *lp, unsigned char *hot);
+
+// `stage`: this warp's shared-memory slab (hot part of the env record lives there for the
+// whole launch) or null (work on the record in HBM/L2 directly).
+template <int VARIANT, int SUM_MODE, int SUSPEND>
+FJ_FN void fj_env_rollout(const FjParams &P, const FjStepArgs &A, int env, unsigned char *lp, unsigned char *stage = nullptr)
+{
+    unsigned char *G = P.env + (size_t)env * P.eo.stride;
+    if (stage) fj_stage_copy(stage, G, P.eo.hot);
+    fj_env_rollout_body<VARIANT, SUM_MODE, SUSPEND>(P, A, env, lp, stage);
+    if (stage) fj_stage_copy(G, stage, P.eo.hot);
+}
+
+template <int VARIANT, int SUM_MODE, int SUSPEND>
+FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, unsigned char *lp, unsigned char *hot)
 {
     const int lane = fj_lane();
     FjCtx c;
-    fj_ctx_init(c, P, env, lp);
+    fj_ctx_init(c, P, env, lp, hot);
     const int nobs = P.nobs, ns = 2 * nobs;
     int tt = SUSPEND ? 0 : c.scal[FJ_S_TT];
     for (; tt < A.T; ++tt) {
@@ -1193,7 +1316,7 @@ FJ_FN void fj_env_rollout(const FjParams &P, const FjStepArgs &A, int env, unsig
             fj_arrival_resume<SUM_MODE>(c, P);
             resume = 1;
         } else {
-            ok = fj_step_front<VARIANT>(c, A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
+            ok = fj_step_front<VARIANT, SUM_MODE>(c, A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
                                         A.rnd ? A.rnd[2 * i + 1] : 0u, out);
             if (A.rec && lane == 0) for (int k = 0; k < 8; ++k) A.rec[i * 8 + k] = out.rec[k];
         }

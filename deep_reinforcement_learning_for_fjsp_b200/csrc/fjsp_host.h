@@ -137,12 +137,15 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.gapave = b; b += 8 * d.Mx;
     eo.rsum = b; b += 8 * d.KTx;
     eo.tsum = b; b += 8 * d.KTx;
+    eo.urg = b; b += 8 * d.KTx;
+    eo.maxe = b; b += 8 * d.KTx;
     eo.fu = b; b += 8 * d.NFx;
     eo.fa = b; b += 8 * d.NFx;
     eo.ff = b; b += 8 * d.NFx;
-    eo.choice = b; b += 4 * 16;
     eo.avmask = b; b += 4 * d.KTW;
     eo.favmask = b; b += 4 * d.KTW;
+    eo.demask = b; b += 4 * d.KTW;
+    eo.damask = b; b += 4 * d.KTW;
     eo.mend = b; b += 4 * d.Mx;
     eo.mlast = b; b += 4 * d.Mx;
     eo.mjob = b; b += 4 * d.Mx;
@@ -155,8 +158,10 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.cntunp = b; b += 2 * d.KTx * d.Sx;
     eo.cntnow = b; b += 2 * d.KTx * d.Sx;
     eo.pk = b; b += 2 * d.KTx * d.Mx;
-    eo.next = b; b += 2 * d.NJx;
     eo.slot = b; b += 2 * d.KTx * d.Mx;
+    b = fj_align(b, 16);
+    eo.hot = b;
+    eo.next = b; b += 2 * d.NJx;
     eo.stride = fj_align(b, 16);
     t.eo = eo;
     // fill instance records

@@ -57,9 +57,12 @@ struct FjEnvOff {
     int obs;       // double[16] v(t)
     int obs2;      // double[16] staging for v(t+1)
     int gapave;    // double[Mx] cached machine gap_ave
-    int choice;    // int32[16] cached operation-type choice per deterministic task rule
+    int urg;       // double[KTx] delivery urgency of an available operation type (rule key)
+    int maxe;      // double[KTx] its largest estimated delay (rule key)
     int avmask;    // uint32[KTW] available operation types
     int favmask;   // uint32[KTW] fluid-available operation types
+    int demask;    // uint32[KTW] available with an estimated-late operation
+    int damask;    // uint32[KTW] available with an actually-late operation
     int mend;      // int32[Mx] machine completion time
     int mlast;     // int32[Mx] end time of the machine's previous operation
     int mjob;      // int32[Mx] (rj << 16 | job number) of the job on the machine, -1 none
@@ -79,6 +82,7 @@ struct FjEnvOff {
     int fa;        // double[NFx] fluid_unprocessed_rj_arrival_dict
     int ff;        // double[NFx] fluid_process_rate_rj_dict
     int next;      // uint16[NJx] queue links, indexed jobbase[r] + n
+    int hot;       // bytes of the record's hot part (everything but `next`), multiple of 16
     int stride;    // bytes per env (multiple of 16)
 };
 
@@ -89,7 +93,7 @@ enum {
     FJ_S_LPSOLVES = 11, FJ_S_LPITERS = 12, FJ_S_NFL = 13, FJ_S_PHASE = 14, FJ_S_LPSLOT = 15,
     // 64-bit values occupy two slots (even index)
     FJ_S_ENERGY = 16, FJ_S_ENERGY_LAST = 18, FJ_S_DELAY_PROC = 20, FJ_S_DELAY_LAST = 22, FJ_S_DELAY_UNPROC = 24,
-    FJ_S_GAPTIME = 26 /* double */, FJ_S_TT = 28, FJ_S_WASDONE = 29, FJ_S_COUNT = 32
+    FJ_S_GAPTIME = 26 /* double */, FJ_S_TT = 28, FJ_S_WASDONE = 29, FJ_S_NAV = 30, FJ_S_NFAV = 31, FJ_S_COUNT = 32
 };
 
 // error flags (FJ_S_ERROR), same meaning as the oracle's
@@ -109,6 +113,7 @@ struct FjParams {
     double *lp_x;               // [lp_slots][NPx] LP solutions
     int *lp_meta;               // [lp_slots][2] iterations, return code
     int lp_slots;
+    int stage;                  // 1: kernels stage the hot part of the env record in shared memory
     int B, variant, sum_mode, nobs;
 };
 

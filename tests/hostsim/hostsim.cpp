@@ -46,10 +46,14 @@ template <int V, int SM>
 static void run_step(HostVec *h, const FjStepArgs &A)
 {
     h->pend_count = 0;
-    for (int e = 0; e < h->P.B; ++e) fj_env_rollout<V, SM, 1>(h->P, A, e, h->lp.data());   // main kernel
-    run_lp_service(h);                                                                    // LP kernel
+    // FJSP_HOSTSIM_STAGE=1: run on a staged copy of the record's hot part (the shared-memory path)
+    static std::vector<unsigned char> slab;
+    slab.assign(h->tb.eo.hot + 16, 0);
+    unsigned char *stage = getenv("FJSP_HOSTSIM_STAGE") ? slab.data() : nullptr;
+    for (int e = 0; e < h->P.B; ++e) fj_env_rollout<V, SM, 1>(h->P, A, e, h->lp.data(), stage);   // main kernel
+    run_lp_service(h);                                                                           // LP kernel
     const int n = h->pend_count;
-    for (int i = 0; i < n; ++i) fj_env_rollout<V, SM, 0>(h->P, A, h->pend_env[i], h->lp.data());   // resume kernel
+    for (int i = 0; i < n; ++i) fj_env_rollout<V, SM, 0>(h->P, A, h->pend_env[i], h->lp.data(), stage);   // resume kernel
 }
 
 #define DISPATCH(fn, ...)                                                                      \
@@ -88,6 +92,7 @@ int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst
     P.lp_slots = ov ? atoi(ov) : n_envs;
     h->lp_x.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * h->tb.d.NPx, 0.0);
     h->lp_meta.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * 2, 0);
+    P.stage = 0;
     h->pend_count = 0;
     P.pend_count = &h->pend_count; P.pend_env = h->pend_env.data(); P.lp_x = h->lp_x.data(); P.lp_meta = h->lp_meta.data();
     P.B = n_envs; P.variant = variant; P.sum_mode = sum_mode;
@@ -144,6 +149,14 @@ int fjsp_hostsim_query(void *v, int64_t *out8)
 int fjsp_hostsim_pyset_order(const int *seq, int n, int *out) { return fj_pyset_order(seq, n, out); }
 int fjsp_hostsim_selectable(unsigned idle, const int *other_ord, int nother, int *out)
 {
-    return fj_selectable(idle, other_ord, nother, out);
+    unsigned omask = 0;
+    for (int i = 0; i < nother; ++i) omask |= 1u << other_ord[i];
+    FjCand cand = fj_selectable(idle, omask, nother, fj_ro(other_ord), 0, 0);
+    unsigned mk = cand.mask;
+    for (int i = 0; i < cand.n; ++i) {
+        if (cand.n >= 5) { out[i] = __builtin_ctz(mk); mk &= mk - 1; }
+        else out[i] = (int)((cand.packed >> (8 * i)) & 0xffu);
+    }
+    return cand.n;
 }
 }
