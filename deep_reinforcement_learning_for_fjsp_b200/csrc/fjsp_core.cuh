@@ -30,6 +30,8 @@
 #define FJ_FN __device__ __forceinline__
 #define FJ_MFN __device__ __forceinline__
 #define FJ_FN_NOINLINE __device__ __noinline__
+#define FJ_OUTLINE __device__ __noinline__
+#define FJ_NOUNROLL _Pragma("unroll 1")
 #define FJ_NL 32
 FJ_FN int fj_lane() { return threadIdx.x & 31; }
 FJ_FN void fj_sync() { __syncwarp(); }
@@ -44,11 +46,13 @@ FJ_FN long long fj_xor_ll(long long v, int m) { return __shfl_xor_sync(0xfffffff
 FJ_FN double fj_add(double a, double b) { return __dadd_rn(a, b); }
 FJ_FN double fj_sub(double a, double b) { return __dsub_rn(a, b); }
 FJ_FN double fj_mul(double a, double b) { return __dmul_rn(a, b); }
-FJ_FN double fj_div(double a, double b) { return __ddiv_rn(a, b); }
+FJ_FN_NOINLINE double fj_div(double a, double b) { return __ddiv_rn(a, b); }
 #else
 #define FJ_FN static inline
 #define FJ_MFN inline
 #define FJ_FN_NOINLINE static
+#define FJ_OUTLINE static
+#define FJ_NOUNROLL
 #define FJ_NL 1
 FJ_FN int fj_lane() { return 0; }
 FJ_FN void fj_sync() {}
@@ -67,27 +71,27 @@ FJ_FN double fj_div(double a, double b) { return a / b; }
 #endif
 
 // ---------------------------------------------------------------- warp reductions
-FJ_FN long long fj_sum_ll(long long v)
+FJ_OUTLINE long long fj_sum_ll(long long v)
 {
     for (int m = FJ_NL / 2; m > 0; m >>= 1) v += fj_xor_ll(v, m);
     return v;
 }
-FJ_FN int fj_sum_i(int v)
+FJ_OUTLINE int fj_sum_i(int v)
 {
     for (int m = FJ_NL / 2; m > 0; m >>= 1) v += fj_xor_i(v, m);
     return v;
 }
-FJ_FN int fj_min_i(int v)
+FJ_OUTLINE int fj_min_i(int v)
 {
     for (int m = FJ_NL / 2; m > 0; m >>= 1) { int o = fj_xor_i(v, m); v = o < v ? o : v; }
     return v;
 }
-FJ_FN unsigned fj_or_u(unsigned v)
+FJ_OUTLINE unsigned fj_or_u(unsigned v)
 {
     for (int m = FJ_NL / 2; m > 0; m >>= 1) v |= (unsigned)fj_xor_i((int)v, m);
     return v;
 }
-FJ_FN double fj_sum_d(double v)   // observation-only sums (fixed butterfly order)
+FJ_OUTLINE double fj_sum_d(double v)   // observation-only sums (fixed butterfly order)
 {
     for (int m = FJ_NL / 2; m > 0; m >>= 1) v = fj_add(v, fj_xor_d(v, m));
     return v;
@@ -101,7 +105,7 @@ FJ_FN void fj_best_init(FjBest &b) { b.key = 0.0; b.idx = 0x7fffffff; }
 // local update; candidates arrive in ascending idx on a lane, so strict comparison keeps the first
 FJ_FN void fj_best_max(FjBest &b, double key, int idx) { if (b.idx == 0x7fffffff || key > b.key) { b.key = key; b.idx = idx; } }
 FJ_FN void fj_best_min(FjBest &b, double key, int idx) { if (b.idx == 0x7fffffff || key < b.key) { b.key = key; b.idx = idx; } }
-FJ_FN void fj_best_reduce(FjBest &b, int want_max)
+FJ_OUTLINE void fj_best_reduce(FjBest &b, int want_max)
 {
     for (int m = FJ_NL / 2; m > 0; m >>= 1) {
         double ok = fj_xor_d(b.key, m);
@@ -204,10 +208,11 @@ FJ_FN int fj_ffs0(unsigned v)   // index of lowest set bit, v != 0
     return __builtin_ctz(v);
 #endif
 }
-FJ_FN int fj_order_of(const FjCtx &c, int r, int n)   // which order job n of kind r came with
+FJ_OUTLINE int fj_order_of(const FjCtx &c, int r, int n)   // which order job n of kind r came with
 {
     const FjRO cum = FJ_I(c, cum);
     int s = 0;
+    FJ_NOUNROLL
     while (s + 1 < c.S && n >= cum[(s + 1) * c.Kx + r]) ++s;
     return s;
 }
@@ -462,6 +467,7 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
     const int lane = fj_lane();
     const int KT = c.KT, Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
     const FjRO rjkind = FJ_I(c, rjkind), rjstage = FJ_I(c, rjstage), count = FJ_I(c, count);
+    FJ_NOUNROLL
     for (int q = lane; q < KT; q += FJ_NL) {
         int cnt = count[s * Kx + rjkind[q]];
         c.cntunp[q * Sx + s] = (uint16_t)cnt;
@@ -472,10 +478,12 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
             c.qlen[q] = (uint16_t)ql;
         }
         int fs = 0;
+        FJ_NOUNROLL
         for (int k = 0; k < c.S; ++k) fs += c.cntunp[q * Sx + k];
         c.fstart[q] = fs;
         c.flmask[q] = 0;
     }
+    FJ_NOUNROLL
     for (int i = lane; i < KT * Mx; i += FJ_NL) { c.pk[i] = 0; c.slot[i] = 0xFFFF; }
     fj_sync();
 }
@@ -492,9 +500,11 @@ FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
         c.scal[FJ_S_LPSOLVES] += 1; c.scal[FJ_S_LPITERS] += iters;
         if (rc) c.scal[FJ_S_ERROR] |= FJ_E_LP;
     }
+    FJ_NOUNROLL
     for (int q = lane; q < KT; q += FJ_NL) {
         unsigned em = (unsigned)elig[q], fm = 0;
         FjPySum ps; fj_pysum_init(ps);
+        FJ_NOUNROLL
         for (int k = 0; k < nelig[q]; ++k) {
             int m = poord[q * Mx + k];
             int col = colbase[q] + fj_popc(em & ((1u << m) - 1u));
@@ -511,8 +521,10 @@ FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
     fj_sync();
     if (lane == 0) {   // fluid slots in canonical column order
         int nfl = 0;
+        FJ_NOUNROLL
         for (int q = 0; q < KT && nfl >= 0; ++q) {
             unsigned fm = c.flmask[q], em = (unsigned)elig[q];
+            FJ_NOUNROLL
             while (fm) {
                 int m = fj_ffs0(fm); fm &= fm - 1;
                 if (nfl >= c.P->d.NFx) { c.scal[FJ_S_ERROR] |= FJ_E_OVERFLOW; nfl = -1; break; }
@@ -562,7 +574,7 @@ template <int SUM_MODE> FJ_FN void fj_neumaier(double &f, double &cc, double x)
     f = t2;
 }
 
-FJ_FN double fj_gap_mrj(const FjCtx &c, int q, int m, double gt)
+FJ_OUTLINE double fj_gap_mrj(const FjCtx &c, int q, int m, double gt)
 {
     const int sl = c.slot[q * c.Mx + m];
     if (sl == 0xFFFF) return fj_sub(0.0, (double)c.pk[q * c.Mx + m]);
@@ -572,12 +584,13 @@ FJ_FN double fj_gap_mrj(const FjCtx &c, int q, int m, double gt)
 // gap_ave of machine m (class_FJSP.py:156-159).  EXACT: CPython's sum order and compensation
 // (it is a machine-rule key); otherwise a plain running sum (observation feature only).
 template <int SUM_MODE, int EXACT>
-FJ_FN double fj_machine_gap_ave(const FjCtx &c, int m, double gt)
+FJ_OUTLINE double fj_machine_gap_ave(const FjCtx &c, int m, double gt)
 {
     const int KT = c.KT;
     const FjRO elig = FJ_I(c, elig);
     double f = 0.0, cc = 0.0;
     int n = 0;
+    FJ_NOUNROLL
     for (int q = 0; q < KT; ++q) {
         if (!((unsigned)elig[q] >> m & 1u)) continue;
         const double term = fj_gap_mrj(c, q, m, gt);
@@ -604,6 +617,7 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
     int nav = 0, nfav = 0;
     double s_fr = 0.0, s_gr = 0.0;
     const int rounds = (KT + FJ_NL - 1) / FJ_NL;
+    FJ_NOUNROLL
     for (int rd = 0; rd < rounds; ++rd) {
         const int q = rd * FJ_NL + lane;
         int av = 0, fav = 0, dle = 0, dla = 0;
@@ -619,6 +633,7 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
             double kd = 0.0, max_e = 0.0, sf = 0.0, sc = 0.0;
             bool first = true;
             long long late_sum = 0;
+            FJ_NOUNROLL
             for (int s = 0; s < S; ++s) {
                 const int cnt = c.cntunp[q * Sx + s];
                 if (cnt == 0) continue;
@@ -674,8 +689,10 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
     const double gap_ave = fj_div(fj_sum_d(s_gr), (double)KT);
     // second pass: variances (observation only)
     double v_fr = 0.0, v_gr = 0.0;
+    FJ_NOUNROLL
     for (int q = lane; q < KT; q += FJ_NL) {
         int residue = 0;
+        FJ_NOUNROLL
         for (int s = 0; s < S; ++s) residue += c.cntunp[q * Sx + s];
         const int pr = c.proc[q];
         const double fr = fj_div((double)pr, (double)(residue + pr));
@@ -688,31 +705,40 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
     const double gap_std = sqrt(fj_div(fj_sum_d(v_gr), (double)KT));
     // machines: completion-time spread; MO also the mean / spread of the machines' gap_ave
     long long tsum_m = 0;
+    FJ_NOUNROLL
     for (int m = lane; m < M; m += FJ_NL) tsum_m += c.mend[m];
     tsum_m = fj_sum_ll(tsum_m);
     const double ct_ave = fj_div((double)tsum_m, (double)M);
-    double v_ct = 0.0, s_gm = 0.0, q_gm = 0.0;
+    double v_ct = 0.0;
+    FJ_NOUNROLL
     for (int m = lane; m < M; m += FJ_NL) {
         const double dv = fj_sub((double)c.mend[m], ct_ave);
         v_ct = fj_add(v_ct, fj_mul(dv, dv));
-        if (MO) {
-            const double ga = fj_machine_gap_ave<SUM_MODE, 0>(c, m, gt);
-            s_gm = fj_add(s_gm, ga);
-            q_gm = fj_add(q_gm, fj_mul(ga, ga));
-        }
     }
     const double ct_std = sqrt(fj_div(fj_sum_d(v_ct), (double)M));
     double gm_ave = 0.0, gm_std = 0.0;
     if (MO) {
-        gm_ave = fj_div(fj_sum_d(s_gm), (double)M);
-        // E[x^2] - mean^2 would cancel badly; redo the centred sum from the per-lane values
-        double v_gm = 0.0;
-        for (int m = lane; m < M; m += FJ_NL) {
-            const double dv = fj_sub(fj_machine_gap_ave<SUM_MODE, 0>(c, m, gt), gm_ave);
-            v_gm = fj_add(v_gm, fj_mul(dv, dv));
+        // gap_ave of every machine as an observation feature: lanes own operation types,
+        // one warp-tree sum per machine (the exact CPython-ordered value is only needed as
+        // the key of machine rule 4 and is computed there)
+        const FjRO nkt = FJ_I(c, mnkt);
+        double s_gm = 0.0;
+        FJ_NOUNROLL
+        for (int m = 0; m < M; ++m) {
+            double part = 0.0;
+            FJ_NOUNROLL
+            for (int q = lane; q < KT; q += FJ_NL)
+                if ((unsigned)elig[q] >> m & 1u) part = fj_add(part, fj_gap_mrj(c, q, m, gt));
+            const double ga = fj_div(fj_sum_d(part), (double)nkt[m]);
+            if (lane == 0) c.gapave[m] = ga;
+            s_gm = fj_add(s_gm, ga);
         }
+        gm_ave = fj_div(s_gm, (double)M);
+        fj_sync();
+        double v_gm = 0.0;
+        FJ_NOUNROLL
+        for (int m = lane; m < M; m += FJ_NL) { const double dv = fj_sub(c.gapave[m], gm_ave); v_gm = fj_add(v_gm, fj_mul(dv, dv)); }
         gm_std = sqrt(fj_div(fj_sum_d(v_gm), (double)M));
-        (void)q_gm;
     }
     if (lane == 0) {
         fj_set_ll(c.scal, FJ_S_DELAY_UNPROC, dunp);
@@ -739,8 +765,9 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
 }
 
 // ---------------------------------------------------------------- task_select
-FJ_FN int fj_nth_set(const uint32_t *mask, int words, int nth)
+FJ_OUTLINE int fj_nth_set(const uint32_t *mask, int words, int nth)
 {
+    FJ_NOUNROLL
     for (int w = 0; w < words; ++w) {
         unsigned v = mask[w];
         int pc = fj_popc(v);
@@ -752,6 +779,7 @@ FJ_FN int fj_nth_set(const uint32_t *mask, int words, int nth)
 FJ_FN int fj_mask_any(const uint32_t *mask, int words)
 {
     unsigned v = 0;
+    FJ_NOUNROLL
     for (int w = 0; w < words; ++w) v |= mask[w];
     return v != 0;
 }
@@ -798,6 +826,7 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
     const double gt = fj_get_d(c.scal, FJ_S_GAPTIME);
     const bool want_max = key <= 3;
     FjBest b; fj_best_init(b);
+    FJ_NOUNROLL
     for (int q = lane; q < KT; q += FJ_NL) {
         if (!(set[q >> 5] >> (q & 31) & 1u)) continue;
         double k;
@@ -805,20 +834,24 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
         else if (key == 1) k = c.maxe[q];
         else if (key == 2) {   // max over unprocessed operations of (t - due)
             int mind = 0x7fffffff;
+            FJ_NOUNROLL
             for (int s = 0; s < S; ++s) if (c.cntunp[q * Sx + s] > 0 && due[s] < mind) mind = due[s];
             k = (double)((long long)t - mind);
         } else if (key == 3) {
             int residue = 0;
+            FJ_NOUNROLL
             for (int s = 0; s < S; ++s) residue += c.cntunp[q * Sx + s];
             k = fj_sub((double)residue, fj_sub((double)c.fstart[q], fj_mul(c.rsum[q], gt)));
         } else if (key == 4) {
             int mind = 0x7fffffff;
+            FJ_NOUNROLL
             for (int s = 0; s < S; ++s) if (c.cntnow[q * Sx + s] > 0 && due[s] < mind) mind = due[s];
             k = (double)mind;
         } else {   // MO_DFJSP.py:429-451: min energy / time over the idle (fluid) machines
             unsigned sm = (fluid_m ? c.flmask[q] : (unsigned)elig[q]) & idle;
             const FjRO tab = (key == 5 ? FJ_I(c, energy) : FJ_I(c, ptime)) + q * Mx;
             int mn = 0x7fffffff;
+            FJ_NOUNROLL
             while (sm) { const int m = fj_ffs0(sm); sm &= sm - 1; const int v = tab[m]; mn = v < mn ? v : mn; }
             k = (double)mn;
         }
@@ -833,16 +866,19 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
 // order (see oracle/pyemu.h).  Five or more members iterate in ascending order; up to four
 // live in an 8-slot table whose layout depends on insertion order, emulated here on a
 // 64-bit register (one byte per slot).
-FJ_FN unsigned fj_small_set_order(unsigned seq, int n)   // seq: members, one byte each, insertion order
+FJ_OUTLINE unsigned fj_small_set_order(unsigned seq, int n)   // seq: members, one byte each, insertion order
 {
     unsigned long long slots = ~0ull;
+    FJ_NOUNROLL
     for (int e = 0; e < n; ++e) {
         const unsigned v = (seq >> (8 * e)) & 0xffu;
         unsigned i = v & 7u;
+        FJ_NOUNROLL
         while (((slots >> (8 * i)) & 0xffull) != 0xffull) i = (i * 5u + 1u) & 7u;   // perturb is 0 for v < 32
         slots = (slots & ~(0xffull << (8 * i))) | ((unsigned long long)v << (8 * i));
     }
     unsigned out = 0; int k = 0;
+    FJ_NOUNROLL
     for (int i = 0; i < 8; ++i) {
         const unsigned bt = (unsigned)((slots >> (8 * i)) & 0xffull);
         if (bt != 0xffu) out |= bt << (8 * k++);
@@ -855,7 +891,7 @@ struct FjCand { unsigned mask; unsigned packed; int n; };   // n >= 5: ascending
 // list(set(idle) & set(other)); other given by its mask, its size and a functor-free walk:
 // `ord` = iteration order of set(other) as an int32 array (static), or, when ord_packed_n >= 0,
 // as packed bytes.
-FJ_FN FjCand fj_selectable(unsigned idle, unsigned omask, int nother, FjRO ord, unsigned ord_packed, int use_packed)
+FJ_OUTLINE FjCand fj_selectable(unsigned idle, unsigned omask, int nother, FjRO ord, unsigned ord_packed, int use_packed)
 {
     FjCand r;
     r.mask = idle & omask; r.n = fj_popc(r.mask); r.packed = 0;
@@ -866,8 +902,10 @@ FJ_FN FjCand fj_selectable(unsigned idle, unsigned omask, int nother, FjRO ord, 
         if (ni >= 5) { unsigned mk = r.mask; while (mk) { seq |= (unsigned)fj_ffs0(mk) << (8 * k++); mk &= mk - 1; } }
         else {
             unsigned a = 0; int na = 0; unsigned mk = idle;
+            FJ_NOUNROLL
             while (mk) { a |= (unsigned)fj_ffs0(mk) << (8 * na++); mk &= mk - 1; }
             const unsigned ao = fj_small_set_order(a, na);
+            FJ_NOUNROLL
             for (int i = 0; i < na; ++i) { const unsigned v = (ao >> (8 * i)) & 0xffu; if (omask >> v & 1u) seq |= v << (8 * k++); }
         }
     } else {             // iterate set(other)
@@ -878,6 +916,7 @@ FJ_FN FjCand fj_selectable(unsigned idle, unsigned omask, int nother, FjRO ord, 
             if (nother >= 5) { unsigned mk = r.mask; while (mk) { seq |= (unsigned)fj_ffs0(mk) << (8 * k++); mk &= mk - 1; } }
             else for (int i = 0; i < nother; ++i) { const unsigned v = (ord_packed >> (8 * i)) & 0xffu; if (idle >> v & 1u) seq |= v << (8 * k++); }
         } else {
+            FJ_NOUNROLL
             for (int i = 0; i < nother; ++i) { const unsigned v = (unsigned)ord[i]; if (idle >> v & 1u) seq |= v << (8 * k++); }
         }
     }
@@ -931,6 +970,7 @@ FJ_FN int fj_machine_select(FjCtx &c, int rule, int q, uint32_t rnd)
         if (nf < 5) {
             const FjRO poord = FJ_I(c, poord) + q * Mx;
             unsigned seq = 0; int k = 0;
+            FJ_NOUNROLL
             for (int i = 0; i < ne; ++i) { const unsigned v = (unsigned)poord[i]; if (fm >> v & 1u) seq |= v << (8 * k++); }
             fo = fj_small_set_order(seq, nf);
         }
@@ -939,6 +979,7 @@ FJ_FN int fj_machine_select(FjCtx &c, int rule, int q, uint32_t rnd)
         cand = fj_selectable(idle, em, ne, FJ_I(c, mtset) + q * Mx, 0, 0);
     }
     if (key_kind == 2) {   // exact gap_ave of the candidates, one lane per machine
+        FJ_NOUNROLL
         for (int m = fj_lane(); m < M; m += FJ_NL)
             if (cand.mask >> m & 1u) c.gapave[m] = fj_machine_gap_ave<SUM_MODE, 1>(c, m, gt);
         fj_sync();
@@ -951,6 +992,7 @@ FJ_FN int fj_machine_select(FjCtx &c, int rule, int q, uint32_t rnd)
     }
     int best = -1; double bk = 0.0;
     unsigned mk = cand.mask;
+    FJ_NOUNROLL
     for (int i = 0; i < n; ++i) {
         int m;
         if (n >= 5) { m = fj_ffs0(mk); mk &= mk - 1; } else m = (int)((cand.packed >> (8 * i)) & 0xffu);
@@ -1011,16 +1053,21 @@ FJ_FN void fj_reset_begin(FjCtx &c, int fresh)
     const int KT = c.KT, Sx = c.Sx, M = c.M;
     int was_done = 0;
     if (fresh) {
+        FJ_NOUNROLL
         for (int i = lane; i < FJ_S_COUNT; i += FJ_NL) c.scal[i] = 0;
+        FJ_NOUNROLL
         for (int i = lane; i < 16; i += FJ_NL) c.obs[i] = 0.0;
         fj_sync();
     } else {
         was_done = c.scal[FJ_S_DONE];
     }
+    FJ_NOUNROLL
     for (int q = lane; q < KT; q += FJ_NL) {
         c.qhead[q] = 0xFFFF; c.qtail[q] = 0xFFFF; c.qlen[q] = 0; c.proc[q] = 0;
+        FJ_NOUNROLL
         for (int s = 0; s < Sx; ++s) { c.cntunp[q * Sx + s] = 0; c.cntnow[q * Sx + s] = 0; }
     }
+    FJ_NOUNROLL
     for (int m = lane; m < M; m += FJ_NL) { c.mend[m] = 0; c.mlast[m] = 0; c.mjob[m] = -1; }
     fj_sync();
     if (lane == 0) {
@@ -1040,6 +1087,7 @@ FJ_FN void fj_reset_finish(FjCtx &c)
 {
     const int lane = fj_lane();
     fj_observe<VARIANT, SUM_MODE>(c, c.scal[FJ_S_WASDONE]);
+    FJ_NOUNROLL
     for (int i = lane; i < 16; i += FJ_NL) c.obs[i] = c.obs2[i];
     if (lane == 0) c.scal[FJ_S_DONE] = 0;
     fj_sync();
@@ -1066,6 +1114,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
     q = fj_bcast_i(q, 0); m = fj_bcast_i(m, 0);
     if (q < 0 || m < 0) {
         if (lane == 0) c.scal[FJ_S_ERROR] |= (q < 0 ? FJ_E_NO_TASK : FJ_E_NO_MACHINE);
+        FJ_NOUNROLL
         for (int i = 0; i < 8; ++i) out.rec[i] = -1;
         fj_sync();
         return 0;
@@ -1087,6 +1136,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
         int t_begin = t, t_end = t + dur, m_end = t_end;
         if (VARIANT == FJSP_MO_BREAKDOWN) {   // MO_DFJSP_breakdown.py:204-231
             const FjRO bp = FJ_I(c, bdptr), bs_ = FJ_I(c, bds), be_ = FJ_I(c, bde);
+            FJ_NOUNROLL
             for (int i = bp[m]; i < bp[m + 1]; ++i) {
                 const int bs = bs_[i], be = be_[i];
                 if (bs <= t && t < be) { int d = be - t; t_begin += d; t_end += d; m_end = t_end; }
@@ -1133,20 +1183,24 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
     const FjRO arrive = FJ_I(c, arrive), jobbase = FJ_I(c, jobbase);
     int t = c.scal[FJ_S_TIME];
     done = 0;
+    FJ_NOUNROLL
     for (;;) {
         long long left = 1;
         int norder, arr_time;
         if (!resume) {
             const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
             int any = 0;
+            FJ_NOUNROLL
             for (int x = lane; x < KT; x += FJ_NL) any |= (c.qlen[x] > 0 && ((unsigned)elig[x] & idle) != 0);
             if (fj_any(any)) break;
             int tmin = 0x7fffffff;
+            FJ_NOUNROLL
             for (int i = lane; i < M; i += FJ_NL) { int e = c.mend[i]; if (e > t && e < tmin) tmin = e; }
             tmin = fj_min_i(tmin);
             if (tmin == 0x7fffffff) { if (lane == 0) c.scal[FJ_S_ERROR] |= FJ_E_NO_EVENT; break; }
             t = tmin;
             if (lane == 0) {   // machines release their jobs in ascending machine order
+                FJ_NOUNROLL
                 for (int i = 0; i < M; ++i) {
                     if (c.mend[i] != t || c.mjob[i] < 0) continue;
                     const int jq = c.mjob[i] >> 16, n = c.mjob[i] & 0xffff;
@@ -1162,6 +1216,7 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
             }
             fj_sync();
             left = 0;
+            FJ_NOUNROLL
             for (int x = lane; x < KT; x += FJ_NL)
                 if (rjlast[x]) for (int s = 0; s < S; ++s) left += c.cntunp[x * Sx + s];
             left = fj_sum_ll(left);
@@ -1179,9 +1234,10 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
                     if (lane == 0) c.scal[FJ_S_TIME] = t;
                     fj_sync();
                     return 1;
+                } else {
+                    fj_order_arrives_inline<SUM_MODE>(c, norder, 0);
+                    ++norder; left = 1;
                 }
-                fj_order_arrives_inline<SUM_MODE>(c, norder, 0);
-                ++norder; left = 1;
             }
         } else {
             resume = 0;
@@ -1189,6 +1245,7 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
             arr_time = c.scal[FJ_S_ARRTIME];
         }
         unsigned freed = 0;
+        FJ_NOUNROLL
         for (int i = lane; i < M; i += FJ_NL) if (c.mend[i] <= t) freed |= 1u << i;
         freed = fj_or_u(freed);
         if (lane == 0) {
@@ -1254,6 +1311,7 @@ FJ_FN void fj_stage_copy(unsigned char *dst, const unsigned char *src, int bytes
     const int n = bytes >> 4;
 #ifdef FJ_DEVICE_CODE
     const uint4 *s4 = (const uint4 *)src; uint4 *d4 = (uint4 *)dst;
+    FJ_NOUNROLL
     for (int i = fj_lane(); i < n; i += FJ_NL) d4[i] = s4[i];
 #else
     memcpy(dst, src, (size_t)n * 16);
@@ -1283,6 +1341,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
     fj_ctx_init(c, P, env, lp, hot);
     const int nobs = P.nobs, ns = 2 * nobs;
     int tt = SUSPEND ? 0 : c.scal[FJ_S_TT];
+    FJ_NOUNROLL
     for (; tt < A.T; ++tt) {
         const size_t i = (size_t)tt * P.B + env;
         int phase = c.scal[FJ_S_PHASE];
@@ -1290,6 +1349,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
             if (!A.autoreset) {   // a finished env without auto-reset repeats its terminal output
                 if (A.done && lane == 0) A.done[i] = 1;
                 if (A.reward && lane == 0) A.reward[i] = 0.0;
+                FJ_NOUNROLL
                 for (int k = lane; k < ns; k += FJ_NL) {
                     double v = k < nobs ? c.obs[k] : 0.0;
                     if (A.state) A.state[i * ns + k] = v;
@@ -1302,9 +1362,11 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
             if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
             fj_sync();
             if (SUSPEND) { fj_suspend(c, P, env, FJ_PH_LP_RESET, tt); return; }
-            fj_order_arrives_inline<SUM_MODE>(c, 0, 0);
-            fj_reset_finish<VARIANT, SUM_MODE>(c);
-        } else if (phase == FJ_PH_LP_RESET) {
+            else {
+                fj_order_arrives_inline<SUM_MODE>(c, 0, 0);
+                fj_reset_finish<VARIANT, SUM_MODE>(c);
+            }
+        } else if (!SUSPEND && phase == FJ_PH_LP_RESET) {
             fj_arrival_resume<SUM_MODE>(c, P);
             fj_reset_finish<VARIANT, SUM_MODE>(c);
             phase = FJ_PH_RUN;
@@ -1312,7 +1374,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
         FjStepOut out;
         out.reward = 0.0; out.done = 0;
         int resume = 0, ok = 1;
-        if (phase == FJ_PH_LP_STEP) {
+        if (!SUSPEND && phase == FJ_PH_LP_STEP) {
             fj_arrival_resume<SUM_MODE>(c, P);
             resume = 1;
         } else {
@@ -1326,10 +1388,12 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
             fj_step_back<VARIANT, SUM_MODE>(c, done, A.reward_policy, A.completion, A.tardiness, A.energy, out);
         } else {
             out.done = c.scal[FJ_S_DONE];
+            FJ_NOUNROLL
             for (int k = lane; k < nobs; k += FJ_NL) c.obs2[k] = c.obs[k];
             fj_sync();
         }
         // outputs: lanes stream the state vector, lane 0 the scalars
+        FJ_NOUNROLL
         for (int k = lane; k < ns; k += FJ_NL) {
             const int j = k < nobs ? k : k - nobs;
             const double v = k < nobs ? c.obs2[j] : fj_sub(c.obs2[j], c.obs[j]);
@@ -1337,6 +1401,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
             if (A.state32) A.state32[i * ns + k] = (float)v;
         }
         fj_sync();
+        FJ_NOUNROLL
         for (int k = lane; k < nobs; k += FJ_NL) c.obs[k] = c.obs2[k];
         if (lane == 0) {
             if (A.reward) A.reward[i] = out.reward;
@@ -1369,6 +1434,7 @@ FJ_FN void fj_env_reset_finish(const FjParams &P, int env, unsigned char *lp, do
     fj_arrival_resume<SUM_MODE>(c, P);
     fj_reset_finish<VARIANT, SUM_MODE>(c);
     const int nobs = P.nobs, ns = 2 * nobs;
+    FJ_NOUNROLL
     for (int k = lane; k < ns; k += FJ_NL) {
         const double v = k < nobs ? c.obs[k] : 0.0;
         if (state_out) state_out[(size_t)env * ns + k] = v;

@@ -126,6 +126,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     io.bds = o; o += d.NBDx;
     io.bde = o; o += d.NBDx;
     io.colbase = o; o += d.KTx;
+    io.mnkt = o; o += d.Mx;
     io.stride = fj_align(o, 4);
     t.io = io;
     // env offsets (bytes)
@@ -223,7 +224,12 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
             for (int q = 0; q < v.KT; ++q) { w[io.colbase + q] = cb; cb += v.nelig[q]; }
             if (cb != v.NP) { err = "instance blob: NP != sum(nelig)"; return false; }
         }
-        for (int m = 0; m < v.M; ++m) w[io.idlep + m] = v.idle_power[m];
+        for (int m = 0; m < v.M; ++m) {
+            w[io.idlep + m] = v.idle_power[m];
+            int n = 0;
+            for (int q = 0; q < v.KT; ++q) n += v.ptime[q * v.M + m] > 0;
+            w[io.mnkt + m] = n;
+        }
         for (int s = 0; s < v.S; ++s) { w[io.arrive + s] = v.arrive[s]; w[io.due + s] = v.due[s]; }
         for (int m = 0; m <= d.Mx; ++m) w[io.bdptr + m] = v.bd_ptr[m <= v.M ? m : v.M];
         for (int k = 0; k < v.NBD; ++k) { w[io.bds + k] = v.bd_start[k]; w[io.bde + k] = v.bd_end[k]; }

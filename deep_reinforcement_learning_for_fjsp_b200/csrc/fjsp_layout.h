@@ -47,6 +47,7 @@ struct FjInstOff {
     int bdptr;     // [Mx+1]
     int bds;       // [NBDx]
     int bde;       // [NBDx]
+    int mnkt;      // [Mx] operation types a machine can process (len(kind_task_tuple))
     int colbase;   // [KTx] first LP column of an operation type (prefix of popcount(elig))
     int stride;    // words per instance
 };
