@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--burnin", type=int, default=2048,
                     help="untimed env steps per copy before timing, so episodes (order arrivals, resets) desynchronise")
+    ap.add_argument("--large-envs", type=int, default=65536,
+                    help="also time this many copies (the same instances, replicated) for a few launches; 0 = skip")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -244,6 +246,32 @@ def main():
         e2e_call(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # ---- the same kernels with enough copies to fill the machine (not the headline)
+    large = None
+    if args.large_envs and args.large_envs > B:
+        BL = args.large_envs
+        vecL = FJSPVecEnv(insts, np.arange(BL) % B, args.variant, device=local_rank)
+        vecL.reset()
+        aL = [torch.from_numpy(make_actions(rng, T, BL, args.variant)[0]).to(dev) for _ in range(2)]
+        rL = [torch.from_numpy(make_actions(rng, T, BL, args.variant)[1].view(np.int32)).to(dev) for _ in range(2)]
+        outL = {"state": torch.empty((T, BL, vec.state_size), dtype=torch.float32, device=dev),
+                "reward": torch.empty((T, BL), dtype=torch.float64, device=dev),
+                "done": torch.empty((T, BL), dtype=torch.int32, device=dev)}
+        for i in range(min(args.burnin, 1024) // T + 3):
+            vecL.rollout(aL[i % 2], rL[(i + 1) % 2], reward_policy=1, out=outL, state_dtype=torch.float32)
+        torch.cuda.synchronize(dev)
+        KL = max(3, K // 4)
+        evL = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KL)]
+        for i in range(KL):
+            evL[i][0].record(stream)
+            vecL.rollout(aL[i % 2], rL[(i + 1) % 2], reward_policy=1, out=outL, state_dtype=torch.float32)
+            evL[i][1].record(stream)
+        torch.cuda.synchronize(dev)
+        msL = sum(a.elapsed_time(b) for a, b in evL)
+        large = {"envs_per_gpu": BL, "value": BL * T * KL / (msL / 1e3), "unit": UNIT, "launches": KL,
+                 "ms_per_launch": msL / KL, "env_errors": int((vecL.info()["error"] != 0).sum()),
+                 "note": "instances replicated 16x; state 0.8 GB > L2, no flush needed"}
+        del vecL, outL, aL, rL
     clocks = sampler.summary()
     h2d = ha[0].numel() * 4 + hr[0].numel() * 4
     d2h = hs.numel() * 4 + hrw.numel() * 8 + hdn.numel() * 4
@@ -287,7 +315,7 @@ def main():
                 "wall_s_timed_region": wall, "env_errors": errors,
                 "timed_region_events": {"fluid_lp_solves": lp_solves, "episodes_finished": episodes,
                                         "burnin_env_steps_per_copy": args.burnin},
-                "launch_ms_min_max": [min(per_launch_ms), max(per_launch_ms)]}
+                "launch_ms_min_max": [min(per_launch_ms), max(per_launch_ms)], "large_batch": large}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_port_throughput(insts[:64], args.variant, args.cpu_seconds, T, args.seed)
         print(json.dumps(line), flush=True)

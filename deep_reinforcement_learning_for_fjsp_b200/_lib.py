@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfjsp_b200.so")
+LIB_PATH = os.environ.get("FJSP_B200_LIB", os.path.join(HERE, "libfjsp_b200.so"))   # override: tuning builds
 _lib = None
 
 SYMBOLS = ["fjsp_last_error", "fjsp_abi_version", "fjsp_vec_create", "fjsp_vec_destroy", "fjsp_vec_query",

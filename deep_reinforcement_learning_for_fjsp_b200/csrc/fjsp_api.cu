@@ -3,6 +3,7 @@
 // walks the batch.  Build: nvcc -gencode arch=compute_100a,code=sm_100a (build.py).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "../../include/fjsp_b200.h"
@@ -23,8 +24,11 @@ static thread_local std::string g_err;
     } while (0)
 
 // main step kernel: every env; parks an env on the first fluid LP it needs
+#ifndef FJ_STEP_MIN_BLOCKS
+#define FJ_STEP_MIN_BLOCKS 8
+#endif
 template <int VARIANT, int SUM_MODE>
-__global__ void __launch_bounds__(FJ_BLOCK, 4) fjsp_step_kernel(FjParams P, FjStepArgs A)
+__global__ void __launch_bounds__(FJ_BLOCK, FJ_STEP_MIN_BLOCKS) fjsp_step_kernel(FjParams P, FjStepArgs A)
 {
     extern __shared__ __align__(16) unsigned char stage_smem[];
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -150,6 +154,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     // persistent grid: a multiple of the SM count, 8 CTAs (32 warps) per SM at most
     int want = (n_envs + FJ_WARPS_PER_BLOCK - 1) / FJ_WARPS_PER_BLOCK;
     int cap = prop.multiProcessorCount * 8;
+    if (getenv("FJSP_GRID_PER_SM")) cap = prop.multiProcessorCount * atoi(getenv("FJSP_GRID_PER_SM"));
     v->grid = want < cap ? want : cap;
     const unsigned long long lp_stride = fj_lp_scratch_bytes(v->tb.d);
     // the resume kernel (in-line LP fallback) and the LP kernel (global Binv fallback) share the slabs
@@ -195,6 +200,9 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     // warps' worth fits with at least two CTAs per SM
     v->stage_bytes = (size_t)FJ_WARPS_PER_BLOCK * v->tb.eo.hot;
     P.stage = v->stage_bytes <= 100 * 1024 ? 1 : 0;
+    // measured on B200 (profiles/README.md): the records are L1/L2-resident anyway and the
+    // shared-memory slabs cost occupancy, so staging is opt-in
+    if (!getenv("FJSP_STAGE")) P.stage = 0;
     if (!P.stage) v->stage_bytes = 0;
     if (dispatch(v, [&](auto V, auto SM) {
             cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,

@@ -140,7 +140,7 @@ struct FjCtx {
     int M, K, KT, S, Mx, Kx, Sx;
     unsigned mmask;
     int32_t *scal; double *obs, *obs2, *gapave, *urg, *maxe; uint32_t *avmask, *favmask, *demask, *damask;
-    int32_t *mend, *mlast, *mjob; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
+    int32_t *mend, *mlast, *mjob, *mD; double *mF; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
     double *rsum, *tsum; uint16_t *cntunp, *cntnow, *pk, *slot; double *fu, *fa, *ff; uint16_t *next;
     unsigned char *lp;
 };
@@ -160,6 +160,7 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     c.gapave = (double *)(E + o.gapave); c.urg = (double *)(E + o.urg); c.maxe = (double *)(E + o.maxe);
     c.avmask = (uint32_t *)(E + o.avmask); c.favmask = (uint32_t *)(E + o.favmask);
     c.demask = (uint32_t *)(E + o.demask); c.damask = (uint32_t *)(E + o.damask);
+    c.mF = (double *)(E + o.mF); c.mD = (int32_t *)(E + o.mD);
     c.mend = (int32_t *)(E + o.mend); c.mlast = (int32_t *)(E + o.mlast); c.mjob = (int32_t *)(E + o.mjob);
     c.qhead = (uint16_t *)(E + o.qhead); c.qtail = (uint16_t *)(E + o.qtail); c.qlen = (uint16_t *)(E + o.qlen);
     c.proc = (int32_t *)(E + o.proc); c.fstart = (int32_t *)(E + o.fstart); c.flmask = (uint32_t *)(E + o.flmask);
@@ -485,6 +486,8 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
     }
     FJ_NOUNROLL
     for (int i = lane; i < KT * Mx; i += FJ_NL) { c.pk[i] = 0; c.slot[i] = 0xFFFF; }
+    FJ_NOUNROLL
+    for (int m = lane; m < c.M; m += FJ_NL) { c.mD[m] = 0; c.mF[m] = 0.0; }
     fj_sync();
 }
 
@@ -533,6 +536,7 @@ FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
                 double arr = fj_div(fj_mul((double)c.fstart[q], fr), c.rsum[q]);
                 c.slot[q * Mx + m] = (uint16_t)nfl;
                 c.ff[nfl] = fr; c.fa[nfl] = arr; c.fu[nfl] = arr;
+                c.mF[m] = fj_add(c.mF[m], fr);
                 ++nfl;
             }
         }
@@ -566,11 +570,14 @@ FJ_FN_NOINLINE void fj_order_arrives_inline(FjCtx &c, int s, int do_begin)
 // other rule keys are cheap and recomputed lazily by fj_task_select for the one rule used.
 template <int SUM_MODE> FJ_FN void fj_neumaier(double &f, double &cc, double x)
 {
+    // CPython's Neumaier step adds the exact rounding error of f + x to the compensation,
+    // picking the Fast2Sum operand order by magnitude.  Knuth's branch-free TwoSum yields
+    // the same (exactly representable) error for either order, so the result is identical.
     if (SUM_MODE == 0) { f = fj_add(f, x); return; }
     const double t2 = fj_add(f, x);
-    const bool bigf = fabs(f) >= fabs(x);
-    const double hi = bigf ? f : x, lo = bigf ? x : f;
-    cc = fj_add(cc, fj_add(fj_sub(hi, t2), lo));
+    const double bp = fj_sub(t2, f);
+    const double err = fj_add(fj_sub(f, fj_sub(t2, bp)), fj_sub(x, bp));
+    cc = fj_add(cc, err);
     f = t2;
 }
 
@@ -718,23 +725,20 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
     const double ct_std = sqrt(fj_div(fj_sum_d(v_ct), (double)M));
     double gm_ave = 0.0, gm_std = 0.0;
     if (MO) {
-        // gap_ave of every machine as an observation feature: lanes own operation types,
-        // one warp-tree sum per machine (the exact CPython-ordered value is only needed as
-        // the key of machine rule 4 and is computed there)
+        // gap_ave of every machine as an observation feature.  Summed over a machine's
+        // operation types, unprocessed - fluid_unprocessed telescopes to
+        // (gap_time * sum of its fluid rates) - (dispatches on it since the last arrival);
+        // the exact CPython-ordered value is only needed as the key of machine rule 4 and is
+        // computed there.
         const FjRO nkt = FJ_I(c, mnkt);
-        double s_gm = 0.0;
+        double s_gm = 0.0, ga_l = 0.0;
         FJ_NOUNROLL
-        for (int m = 0; m < M; ++m) {
-            double part = 0.0;
-            FJ_NOUNROLL
-            for (int q = lane; q < KT; q += FJ_NL)
-                if ((unsigned)elig[q] >> m & 1u) part = fj_add(part, fj_gap_mrj(c, q, m, gt));
-            const double ga = fj_div(fj_sum_d(part), (double)nkt[m]);
-            if (lane == 0) c.gapave[m] = ga;
-            s_gm = fj_add(s_gm, ga);
+        for (int m = lane; m < M; m += FJ_NL) {
+            ga_l = fj_div(fj_sub(fj_mul(gt, c.mF[m]), (double)c.mD[m]), (double)nkt[m]);
+            c.gapave[m] = ga_l;      // same lane reads it back below
+            s_gm = fj_add(s_gm, ga_l);
         }
-        gm_ave = fj_div(s_gm, (double)M);
-        fj_sync();
+        gm_ave = fj_div(fj_sum_d(s_gm), (double)M);
         double v_gm = 0.0;
         FJ_NOUNROLL
         for (int m = lane; m < M; m += FJ_NL) { const double dv = fj_sub(c.gapave[m], gm_ave); v_gm = fj_add(v_gm, fj_mul(dv, dv)); }
@@ -1154,6 +1158,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
         const int sl = c.slot[q * Mx + m];
         if (sl == 0xFFFF) c.pk[q * Mx + m] = (uint16_t)(c.pk[q * Mx + m] + 1);
         else c.fu[sl] = fj_sub(c.fu[sl], 1.0);
+        c.mD[m] += 1;
         if (MO) {
             if (t_end > c.scal[FJ_S_COMPLETION]) c.scal[FJ_S_COMPLETION] = t_end;
             long long en = fj_get_ll(c.scal, FJ_S_ENERGY) + FJ_I(c, energy)[q * Mx + m];

@@ -136,6 +136,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.obs = b; b += 8 * 16;
     eo.obs2 = b; b += 8 * 16;
     eo.gapave = b; b += 8 * d.Mx;
+    eo.mF = b; b += 8 * d.Mx;
     eo.rsum = b; b += 8 * d.KTx;
     eo.tsum = b; b += 8 * d.KTx;
     eo.urg = b; b += 8 * d.KTx;
@@ -150,6 +151,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.mend = b; b += 4 * d.Mx;
     eo.mlast = b; b += 4 * d.Mx;
     eo.mjob = b; b += 4 * d.Mx;
+    eo.mD = b; b += 4 * d.Mx;
     eo.proc = b; b += 4 * d.KTx;
     eo.fstart = b; b += 4 * d.KTx;
     eo.flmask = b; b += 4 * d.KTx;

@@ -66,6 +66,8 @@ struct FjEnvOff {
     int damask;    // uint32[KTW] available with an actually-late operation
     int mend;      // int32[Mx] machine completion time
     int mlast;     // int32[Mx] end time of the machine's previous operation
+    int mF;        // double[Mx] sum of the machine's fluid rates since the last arrival
+    int mD;        // int32[Mx] dispatches on the machine since the last arrival
     int mjob;      // int32[Mx] (rj << 16 | job number) of the job on the machine, -1 none
     int qhead;     // uint16[KTx] stage>0 waiting queue (linked through `next`)
     int qtail;     // uint16[KTx]
