@@ -24,17 +24,22 @@ static thread_local std::string g_err;
     } while (0)
 
 // main step kernel: every env; parks an env on the first fluid LP it needs
+#ifndef FJ_STEP_THREADS
+#define FJ_STEP_THREADS 512      // 16 warps in lockstep phases, two CTAs per SM at 64 registers
+#endif
 #ifndef FJ_STEP_MIN_BLOCKS
-#define FJ_STEP_MIN_BLOCKS 8
+#define FJ_STEP_MIN_BLOCKS (1024 / FJ_STEP_THREADS)
 #endif
 template <int VARIANT, int SUM_MODE>
-__global__ void __launch_bounds__(FJ_BLOCK, FJ_STEP_MIN_BLOCKS) fjsp_step_kernel(FjParams P, FjStepArgs A)
+__global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step_kernel(FjParams P, FjStepArgs A)
 {
-    extern __shared__ __align__(16) unsigned char stage_smem[];
-    const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
-    unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.eo.hot : nullptr;
-    for (int env = gw; env < P.B; env += total) fj_env_rollout<VARIANT, SUM_MODE, 1>(P, A, env, nullptr, stage);
+    // lockstep phases: every warp of the CTA walks the same number of env groups and steps
+    const int wpb = blockDim.x >> 5;
+    const int total = gridDim.x * wpb;
+    for (int base = blockIdx.x * wpb; base < P.B; base += total) {
+        const int env = base + (threadIdx.x >> 5);
+        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, env < P.B ? env : 0, env < P.B);
+    }
 }
 
 // resume kernel: parked envs only; picks up the LP solution, finishes the launch
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_finish_kernel(FjParams P,
 struct fjsp_vec {
     FjTables tb;
     FjParams P;
-    int variant, sum_mode, B, device, grid, resume_grid, lp_grid, lp_smem_binv, nstate;
+    int variant, sum_mode, B, device, grid, step_grid, resume_grid, lp_grid, lp_smem_binv, nstate;
     size_t lp_smem_bytes, stage_bytes;
     int *d_pend_count, *d_pend_env, *d_lp_meta;
     double *d_lp_x;
@@ -156,6 +161,11 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     int cap = prop.multiProcessorCount * 8;
     if (getenv("FJSP_GRID_PER_SM")) cap = prop.multiProcessorCount * atoi(getenv("FJSP_GRID_PER_SM"));
     v->grid = want < cap ? want : cap;
+    {
+        const int wpb = FJ_STEP_THREADS / 32;
+        int w2 = (n_envs + wpb - 1) / wpb, c2 = prop.multiProcessorCount * (1024 / FJ_STEP_THREADS);
+        v->step_grid = w2 < c2 ? w2 : c2;
+    }
     const unsigned long long lp_stride = fj_lp_scratch_bytes(v->tb.d);
     // the resume kernel (in-line LP fallback) and the LP kernel (global Binv fallback) share the slabs
     int rcap = prop.multiProcessorCount * 4;
@@ -244,7 +254,7 @@ int fjsp_vec_query(fjsp_vec *v, int64_t *o)
 {
     if (!v || !o) { g_err = "fjsp_vec_query: null argument"; return -1; }
     o[0] = v->B; o[1] = v->nstate; o[2] = v->tb.eo.stride; o[3] = (int64_t)v->tb.io.stride * 4;
-    o[4] = v->grid; o[5] = FJ_BLOCK; o[6] = (int64_t)v->P.lp_stride; o[7] = v->launches;
+    o[4] = v->step_grid; o[5] = FJ_STEP_THREADS; o[6] = (int64_t)v->P.lp_stride; o[7] = v->launches;
     return 0;
 }
 
@@ -281,7 +291,7 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(v->d_pend_count, 0, 4, st));
     int rc = dispatch(v, [&](auto V, auto SM) {
-        fjsp_step_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, v->stage_bytes, st>>>(v->P, A);
+        fjsp_step_kernel<decltype(V)::value, decltype(SM)::value><<<v->step_grid, FJ_STEP_THREADS, 0, st>>>(v->P, A);
         launch_lp(v, st);
         fjsp_resume_kernel<decltype(V)::value, decltype(SM)::value><<<v->resume_grid, FJ_BLOCK, v->stage_bytes, st>>>(v->P, A);
         return 0;

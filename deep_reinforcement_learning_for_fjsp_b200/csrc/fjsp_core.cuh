@@ -1416,6 +1416,97 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
     }
 }
 
+// ---------------------------------------------------------------- main kernel driver
+// The main step kernel runs the warps of a CTA in LOCKSTEP PHASES (front / clock / back,
+// one CTA barrier each): all warps then execute the same few KB of straight-line code at
+// the same time and share its instruction-cache lines.  Profiling the free-running
+// version (profiles/README.md) showed the per-step code (tens of KB, executed once per
+// step per warp) being re-fetched from L2 by every warp: "no instruction" was the top
+// stall.  Every warp takes every barrier; a warp whose env is finished, parked on an LP or
+// past the batch end just skips the work in between.
+#ifdef FJ_DEVICE_CODE
+#define FJ_CTA_SYNC() __syncthreads()
+#else
+#define FJ_CTA_SYNC()
+#endif
+
+FJ_FN void fj_emit_state(const FjCtx &c, const FjStepArgs &A, size_t i, int nobs, int terminal)
+{
+    const int ns = 2 * nobs;
+    FJ_NOUNROLL
+    for (int k = fj_lane(); k < ns; k += FJ_NL) {
+        const int j = k < nobs ? k : k - nobs;
+        double v;
+        if (terminal) v = k < nobs ? c.obs[j] : 0.0;
+        else v = k < nobs ? c.obs2[j] : fj_sub(c.obs2[j], c.obs[j]);
+        if (A.state) A.state[i * ns + k] = v;
+        if (A.state32) A.state32[i * ns + k] = (float)v;
+    }
+}
+
+template <int VARIANT, int SUM_MODE>
+FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, int env, int active)
+{
+    const int lane = fj_lane();
+    FjCtx c;
+    if (active) fj_ctx_init(c, P, env, nullptr, nullptr);
+    const int nobs = P.nobs;
+    int parked = !active;
+    FJ_NOUNROLL
+    for (int tt = 0; tt < A.T; ++tt) {
+        const size_t i = (size_t)tt * P.B + env;
+        FjStepOut out;
+        out.reward = 0.0; out.done = 0;
+        int stage = 0;      // 0 nothing, 1 dispatched (run the clock), 2 nothing dispatchable (emit unchanged)
+        FJ_CTA_SYNC();      // ---- phase A: auto-reset / task_select / machine_select / dispatch
+        if (!parked) {
+            if (c.scal[FJ_S_DONE]) {
+                if (!A.autoreset) {   // a finished env without auto-reset repeats its terminal output
+                    if (A.done && lane == 0) A.done[i] = 1;
+                    if (A.reward && lane == 0) A.reward[i] = 0.0;
+                    fj_emit_state(c, A, i, nobs, 1);
+                    if (A.rec) for (int k = lane; k < 8; k += FJ_NL) A.rec[i * 8 + k] = -1;
+                } else {
+                    fj_reset_begin(c, 0);
+                    if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
+                    fj_sync();
+                    fj_suspend(c, P, env, FJ_PH_LP_RESET, tt);
+                    parked = 1;
+                }
+            } else {
+                const int ok = fj_step_front<VARIANT, SUM_MODE>(c, A.actions[2 * i], A.actions[2 * i + 1],
+                                                               A.rnd ? A.rnd[2 * i] : 0u, A.rnd ? A.rnd[2 * i + 1] : 0u, out);
+                if (A.rec && lane == 0) for (int k = 0; k < 8; ++k) A.rec[i * 8 + k] = out.rec[k];
+                stage = ok ? 1 : 2;
+            }
+        }
+        FJ_CTA_SYNC();      // ---- phase B: discrete-event clock
+        int done = 0;
+        if (stage == 1) {
+            if (fj_clock<SUM_MODE, 1>(c, 0, done)) { fj_suspend(c, P, env, FJ_PH_LP_STEP, tt); parked = 1; stage = 0; }
+        }
+        FJ_CTA_SYNC();      // ---- phase C: observation, reward, outputs
+        if (stage == 1) fj_step_back<VARIANT, SUM_MODE>(c, done, A.reward_policy, A.completion, A.tardiness, A.energy, out);
+        else if (stage == 2) {
+            out.done = c.scal[FJ_S_DONE];
+            FJ_NOUNROLL
+            for (int k = lane; k < nobs; k += FJ_NL) c.obs2[k] = c.obs[k];
+            fj_sync();
+        }
+        if (stage) {
+            fj_emit_state(c, A, i, nobs, 0);
+            fj_sync();
+            FJ_NOUNROLL
+            for (int k = lane; k < nobs; k += FJ_NL) c.obs[k] = c.obs2[k];
+            if (lane == 0) {
+                if (A.reward) A.reward[i] = out.reward;
+                if (A.done) A.done[i] = out.done;
+            }
+            fj_sync();
+        }
+    }
+}
+
 // reset() entry: phase 1 parks every env on its order-0 LP, phase 2 finishes
 FJ_FN void fj_env_reset_begin(const FjParams &P, int env)
 {

@@ -50,7 +50,7 @@ static void run_step(HostVec *h, const FjStepArgs &A)
     static std::vector<unsigned char> slab;
     slab.assign(h->tb.eo.hot + 16, 0);
     unsigned char *stage = getenv("FJSP_HOSTSIM_STAGE") ? slab.data() : nullptr;
-    for (int e = 0; e < h->P.B; ++e) fj_env_rollout<V, SM, 1>(h->P, A, e, h->lp.data(), stage);   // main kernel
+    for (int e = 0; e < h->P.B; ++e) fj_cta_rollout<V, SM>(h->P, A, e, 1);                         // main kernel
     run_lp_service(h);                                                                           // LP kernel
     const int n = h->pend_count;
     for (int i = 0; i < n; ++i) fj_env_rollout<V, SM, 0>(h->P, A, h->pend_env[i], h->lp.data(), stage);   // resume kernel
