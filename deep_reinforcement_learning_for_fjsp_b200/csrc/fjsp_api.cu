@@ -25,7 +25,7 @@ static thread_local std::string g_err;
 
 // main step kernel: every env; parks an env on the first fluid LP it needs
 #ifndef FJ_STEP_THREADS
-#define FJ_STEP_THREADS 512      // 16 warps in lockstep phases, two CTAs per SM at 64 registers
+#define FJ_STEP_THREADS 256      // 8 warps in lockstep phases, four CTAs per SM at 64 registers
 #endif
 #ifndef FJ_STEP_MIN_BLOCKS
 #define FJ_STEP_MIN_BLOCKS (1024 / FJ_STEP_THREADS)
@@ -34,34 +34,34 @@ template <int VARIANT, int SUM_MODE>
 __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step_kernel(FjParams P, FjStepArgs A)
 {
     // lockstep phases: every warp of the CTA walks the same number of env groups and steps
+    extern __shared__ __align__(16) unsigned char stage_smem[];
     const int wpb = blockDim.x >> 5;
     const int total = gridDim.x * wpb;
+    unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.eo.hot : nullptr;
     for (int base = blockIdx.x * wpb; base < P.B; base += total) {
         const int env = base + (threadIdx.x >> 5);
-        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, env < P.B ? env : 0, env < P.B);
+        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, env < P.B ? env : 0, env < P.B, stage);
     }
 }
 
 // resume kernel: parked envs only; picks up the LP solution, finishes the launch
-template <int VARIANT, int SUM_MODE>
-__global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(FjParams P, FjStepArgs A)
+template <int VARIANT, int SUM_MODE, int SUSPEND>
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(FjParams P, FjStepArgs A, const int *count_in, const int *list_in)
 {
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
-    extern __shared__ __align__(16) unsigned char stage_smem[];
     unsigned char *lp = P.lp + (size_t)gw * P.lp_stride;
-    unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.eo.hot : nullptr;
-    const int n = *P.pend_count;
-    for (int i = gw; i < n; i += total) fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, P.pend_env[i], lp, stage);
+    const int n = *count_in;
+    for (int i = gw; i < n; i += total) fj_env_rollout<VARIANT, SUM_MODE, SUSPEND>(P, A, list_in[i], lp, nullptr);
 }
 
 // LP kernel: one CTA per parked LP, basis inverse in shared memory when it fits
 #define FJ_LP_THREADS 256
 template <int SMEM_BINV>
-__global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(FjParams P)
+__global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(FjParams P, const int *count_in, const int *list_in)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    int n = *P.pend_count;
+    int n = *count_in;
     if (n > P.lp_slots) n = P.lp_slots;
     const size_t binv_bytes = (size_t)P.d.Rx * P.d.Rx * 8;
     unsigned char *binv = SMEM_BINV ? smem : P.lp + (size_t)blockIdx.x * P.lp_stride;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(FjParams P)
     unsigned char *red = small_ + (fj_lp_small_bytes(P.d) + 7) / 8 * 8;
     FjCtaGroup g;
     g.rk = (double *)red; g.ri = (int *)(red + 32 * 8); g.ra = g.ri + 32;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) fj_lp_service(P, g, i, binv, small_);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) fj_lp_service(P, g, list_in, i, binv, small_);
 }
 
 __global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(FjParams P)
@@ -108,10 +108,11 @@ struct fjsp_vec {
     float *d_state32;
 };
 
-static void launch_lp(fjsp_vec *v, cudaStream_t st)
+static void launch_lp(fjsp_vec *v, cudaStream_t st, int round)
 {
-    if (v->lp_smem_binv) fjsp_lp_kernel<1><<<v->lp_grid, FJ_LP_THREADS, v->lp_smem_bytes, st>>>(v->P);
-    else fjsp_lp_kernel<0><<<v->lp_grid, FJ_LP_THREADS, v->lp_smem_bytes, st>>>(v->P);
+    const int *cnt = v->d_pend_count + round, *lst = v->d_pend_env + (size_t)(round & 1) * v->B;
+    if (v->lp_smem_binv) fjsp_lp_kernel<1><<<v->lp_grid, FJ_LP_THREADS, v->lp_smem_bytes, st>>>(v->P, cnt, lst);
+    else fjsp_lp_kernel<0><<<v->lp_grid, FJ_LP_THREADS, v->lp_smem_bytes, st>>>(v->P, cnt, lst);
 }
 
 template <typename F> static int dispatch(fjsp_vec *v, F f)
@@ -193,11 +194,11 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     size_t slots = (size_t)n_envs;
     const size_t per_slot = (size_t)v->tb.d.NPx * 8;
     if (slots * per_slot > ((size_t)2 << 30)) slots = ((size_t)2 << 30) / per_slot;
-    CK(cudaMalloc(&v->d_pend_count, 4));
-    CK(cudaMalloc(&v->d_pend_env, (size_t)n_envs * 4));
+    CK(cudaMalloc(&v->d_pend_count, 4 * (FJ_ROUNDS + 1)));
+    CK(cudaMalloc(&v->d_pend_env, (size_t)n_envs * 4 * 2));
     CK(cudaMalloc(&v->d_lp_x, slots * per_slot));
     CK(cudaMalloc(&v->d_lp_meta, slots * 8));
-    CK(cudaMemset(v->d_pend_count, 0, 4));
+    CK(cudaMemset(v->d_pend_count, 0, 4 * (FJ_ROUNDS + 1)));
     CK(cudaFuncSetAttribute(fjsp_lp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->lp_smem_bytes));
     CK(cudaFuncSetAttribute(fjsp_lp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->lp_smem_bytes));
     FjParams &P = v->P;
@@ -208,16 +209,14 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     P.lp_slots = (int)slots;
     // hot part of the env records staged in shared memory for the whole launch when four
     // warps' worth fits with at least two CTAs per SM
-    v->stage_bytes = (size_t)FJ_WARPS_PER_BLOCK * v->tb.eo.hot;
-    P.stage = v->stage_bytes <= 100 * 1024 ? 1 : 0;
-    // measured on B200 (profiles/README.md): the records are L1/L2-resident anyway and the
-    // shared-memory slabs cost occupancy, so staging is opt-in
-    if (!getenv("FJSP_STAGE")) P.stage = 0;
+    // the main kernel stages the hot prefix of its warps' records in shared memory when the
+    // CTA's slabs leave room for four CTAs per SM
+    v->stage_bytes = (size_t)(FJ_STEP_THREADS / 32) * v->tb.eo.hot;
+    P.stage = v->stage_bytes <= 56 * 1024 ? 1 : 0;
+    if (getenv("FJSP_NO_STAGE")) P.stage = 0;
     if (!P.stage) v->stage_bytes = 0;
     if (dispatch(v, [&](auto V, auto SM) {
             cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->stage_bytes);
-            cudaFuncSetAttribute(fjsp_resume_kernel<decltype(V)::value, decltype(SM)::value>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->stage_bytes);
             return 0;
         })) return -2;
@@ -264,7 +263,7 @@ int fjsp_vec_reset(fjsp_vec *v, void *stream, double *d_state64, float *d_state3
     CK(cudaSetDevice(v->device));
     cudaStream_t st = (cudaStream_t)stream;
     fjsp_reset_begin_kernel<<<v->grid, FJ_BLOCK, 0, st>>>(v->P);
-    launch_lp(v, st);
+    launch_lp(v, st, 0);
     int rc = dispatch(v, [&](auto V, auto SM) {
         fjsp_reset_finish_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, 0, st>>>(v->P, d_state64, d_state32);
         return 0;
@@ -288,16 +287,26 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     A.T = T; A.actions = d_actions; A.rnd = d_rnd; A.reward_policy = reward_policy; A.autoreset = autoreset;
     A.completion = completion; A.tardiness = tardiness; A.energy = energy;
     A.state = d_state64; A.state32 = d_state32; A.reward = d_reward; A.done = d_done; A.rec = d_rec;
+    A.park_count = nullptr; A.park_env = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemsetAsync(v->d_pend_count, 0, 4, st));
+    CK(cudaMemsetAsync(v->d_pend_count, 0, 4 * (FJ_ROUNDS + 1), st));
     int rc = dispatch(v, [&](auto V, auto SM) {
-        fjsp_step_kernel<decltype(V)::value, decltype(SM)::value><<<v->step_grid, FJ_STEP_THREADS, 0, st>>>(v->P, A);
-        launch_lp(v, st);
-        fjsp_resume_kernel<decltype(V)::value, decltype(SM)::value><<<v->resume_grid, FJ_BLOCK, v->stage_bytes, st>>>(v->P, A);
+        constexpr int VV = decltype(V)::value, MM = decltype(SM)::value;
+        A.park_count = v->d_pend_count; A.park_env = v->d_pend_env;
+        fjsp_step_kernel<VV, MM><<<v->step_grid, FJ_STEP_THREADS, v->stage_bytes, st>>>(v->P, A);
+        // resume rounds: an env can meet a reset and further order arrivals inside one launch; the
+        // last round solves whatever is left in line
+        for (int r = 0; r < FJ_ROUNDS; ++r) {
+            launch_lp(v, st, r);
+            const int *cnt = v->d_pend_count + r, *lst = v->d_pend_env + (size_t)(r & 1) * v->B;
+            A.park_count = v->d_pend_count + r + 1; A.park_env = v->d_pend_env + (size_t)((r + 1) & 1) * v->B;
+            if (r + 1 < FJ_ROUNDS) fjsp_resume_kernel<VV, MM, 1><<<v->resume_grid, FJ_BLOCK, 0, st>>>(v->P, A, cnt, lst);
+            else fjsp_resume_kernel<VV, MM, 0><<<v->resume_grid, FJ_BLOCK, 0, st>>>(v->P, A, cnt, lst);
+        }
         return 0;
     });
     if (rc) return rc;
-    v->launches += 3;
+    v->launches += 1 + 2 * FJ_ROUNDS;
     CK(cudaGetLastError());
     return 0;
 }

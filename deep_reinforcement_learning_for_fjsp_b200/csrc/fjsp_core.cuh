@@ -157,7 +157,7 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     unsigned char *E = hot ? hot : G;                       // hot part, possibly staged in shared memory
     const FjEnvOff &o = P.eo;
     c.scal = (int32_t *)(E + o.scal); c.obs = (double *)(E + o.obs); c.obs2 = (double *)(E + o.obs2);
-    c.gapave = (double *)(E + o.gapave); c.urg = (double *)(E + o.urg); c.maxe = (double *)(E + o.maxe);
+    c.gapave = (double *)(E + o.gapave); c.urg = (double *)(G + o.urg); c.maxe = (double *)(G + o.maxe);
     c.avmask = (uint32_t *)(E + o.avmask); c.favmask = (uint32_t *)(E + o.favmask);
     c.demask = (uint32_t *)(E + o.demask); c.damask = (uint32_t *)(E + o.damask);
     c.mF = (double *)(E + o.mF); c.mD = (int32_t *)(E + o.mD);
@@ -166,8 +166,8 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     c.proc = (int32_t *)(E + o.proc); c.fstart = (int32_t *)(E + o.fstart); c.flmask = (uint32_t *)(E + o.flmask);
     c.rsum = (double *)(E + o.rsum); c.tsum = (double *)(E + o.tsum);
     c.cntunp = (uint16_t *)(E + o.cntunp); c.cntnow = (uint16_t *)(E + o.cntnow);
-    c.pk = (uint16_t *)(E + o.pk); c.slot = (uint16_t *)(E + o.slot);
-    c.fu = (double *)(E + o.fu); c.fa = (double *)(E + o.fa); c.ff = (double *)(E + o.ff);
+    c.pk = (uint16_t *)(G + o.pk); c.slot = (uint16_t *)(G + o.slot);
+    c.fu = (double *)(G + o.fu); c.fa = (double *)(G + o.fa); c.ff = (double *)(G + o.ff);
     c.next = (uint16_t *)(G + o.next);
     c.lp = lp;
 }
@@ -1022,16 +1022,16 @@ FJ_FN int fj_machine_select(FjCtx &c, int rule, int q, uint32_t rnd)
 // arrival of the same launch in line.
 enum { FJ_PH_RUN = 0, FJ_PH_LP_STEP = 1, FJ_PH_LP_RESET = 2 };
 
-FJ_FN void fj_suspend(FjCtx &c, const FjParams &P, int env, int phase, int tt)
+FJ_FN void fj_suspend(FjCtx &c, const FjParams &P, const FjStepArgs &A, int env, int phase, int tt)
 {
     if (fj_lane() == 0) {
         c.scal[FJ_S_PHASE] = phase; c.scal[FJ_S_TT] = tt;
 #ifdef FJ_DEVICE_CODE
-        const int idx = atomicAdd(P.pend_count, 1);
+        const int idx = atomicAdd(A.park_count, 1);
 #else
-        const int idx = (*P.pend_count)++;
+        const int idx = (*A.park_count)++;
 #endif
-        P.pend_env[idx] = env;
+        A.park_env[idx] = env;
         c.scal[FJ_S_LPSLOT] = idx < P.lp_slots ? idx : -1;
     }
     fj_sync();
@@ -1345,7 +1345,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
     FjCtx c;
     fj_ctx_init(c, P, env, lp, hot);
     const int nobs = P.nobs, ns = 2 * nobs;
-    int tt = SUSPEND ? 0 : c.scal[FJ_S_TT];
+    int tt = c.scal[FJ_S_TT];   // this driver only runs parked envs (resume kernel)
     FJ_NOUNROLL
     for (; tt < A.T; ++tt) {
         const size_t i = (size_t)tt * P.B + env;
@@ -1366,12 +1366,12 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
             fj_reset_begin(c, 0);
             if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
             fj_sync();
-            if (SUSPEND) { fj_suspend(c, P, env, FJ_PH_LP_RESET, tt); return; }
+            if (SUSPEND) { fj_suspend(c, P, A, env, FJ_PH_LP_RESET, tt); return; }
             else {
                 fj_order_arrives_inline<SUM_MODE>(c, 0, 0);
                 fj_reset_finish<VARIANT, SUM_MODE>(c);
             }
-        } else if (!SUSPEND && phase == FJ_PH_LP_RESET) {
+        } else if (phase == FJ_PH_LP_RESET) {
             fj_arrival_resume<SUM_MODE>(c, P);
             fj_reset_finish<VARIANT, SUM_MODE>(c);
             phase = FJ_PH_RUN;
@@ -1379,7 +1379,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
         FjStepOut out;
         out.reward = 0.0; out.done = 0;
         int resume = 0, ok = 1;
-        if (!SUSPEND && phase == FJ_PH_LP_STEP) {
+        if (phase == FJ_PH_LP_STEP) {
             fj_arrival_resume<SUM_MODE>(c, P);
             resume = 1;
         } else {
@@ -1389,7 +1389,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
         }
         int done = 0;
         if (ok) {
-            if (fj_clock<SUM_MODE, SUSPEND>(c, resume, done)) { fj_suspend(c, P, env, FJ_PH_LP_STEP, tt); return; }
+            if (fj_clock<SUM_MODE, SUSPEND>(c, resume, done)) { fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt); return; }
             fj_step_back<VARIANT, SUM_MODE>(c, done, A.reward_policy, A.completion, A.tardiness, A.energy, out);
         } else {
             out.done = c.scal[FJ_S_DONE];
@@ -1417,8 +1417,8 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
 }
 
 // ---------------------------------------------------------------- main kernel driver
-// The main step kernel runs the warps of a CTA in LOCKSTEP PHASES (front / clock / back,
-// one CTA barrier each): all warps then execute the same few KB of straight-line code at
+// The main step kernel runs the warps of a CTA in LOCKSTEP PHASES (dispatch + clock /
+// observation, one CTA barrier each): all warps then execute the same few KB of straight-line code at
 // the same time and share its instruction-cache lines.  Profiling the free-running
 // version (profiles/README.md) showed the per-step code (tens of KB, executed once per
 // step per warp) being re-fetched from L2 by every warp: "no instruction" was the top
@@ -1445,11 +1445,15 @@ FJ_FN void fj_emit_state(const FjCtx &c, const FjStepArgs &A, size_t i, int nobs
 }
 
 template <int VARIANT, int SUM_MODE>
-FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, int env, int active)
+FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, int env, int active, unsigned char *stage = nullptr)
 {
     const int lane = fj_lane();
     FjCtx c;
-    if (active) fj_ctx_init(c, P, env, nullptr, nullptr);
+    unsigned char *G = P.env + (size_t)env * P.eo.stride;
+    if (active) {
+        if (stage) fj_stage_copy(stage, G, P.eo.hot);
+        fj_ctx_init(c, P, env, nullptr, stage);
+    }
     const int nobs = P.nobs;
     int parked = !active;
     FJ_NOUNROLL
@@ -1470,7 +1474,7 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, int env, int a
                     fj_reset_begin(c, 0);
                     if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
                     fj_sync();
-                    fj_suspend(c, P, env, FJ_PH_LP_RESET, tt);
+                    fj_suspend(c, P, A, env, FJ_PH_LP_RESET, tt);
                     parked = 1;
                 }
             } else {
@@ -1480,10 +1484,10 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, int env, int a
                 stage = ok ? 1 : 2;
             }
         }
-        FJ_CTA_SYNC();      // ---- phase B: discrete-event clock
+        // ---- phase B: discrete-event clock (same barrier interval as A: together they fit the I-cache)
         int done = 0;
         if (stage == 1) {
-            if (fj_clock<SUM_MODE, 1>(c, 0, done)) { fj_suspend(c, P, env, FJ_PH_LP_STEP, tt); parked = 1; stage = 0; }
+            if (fj_clock<SUM_MODE, 1>(c, 0, done)) { fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt); parked = 1; stage = 0; }
         }
         FJ_CTA_SYNC();      // ---- phase C: observation, reward, outputs
         if (stage == 1) fj_step_back<VARIANT, SUM_MODE>(c, done, A.reward_policy, A.completion, A.tardiness, A.energy, out);
@@ -1505,6 +1509,7 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, int env, int a
             fj_sync();
         }
     }
+    if (active && stage) fj_stage_copy(G, stage, P.eo.hot);
 }
 
 // reset() entry: phase 1 parks every env on its order-0 LP, phase 2 finishes
@@ -1516,7 +1521,7 @@ FJ_FN void fj_env_reset_begin(const FjParams &P, int env)
     if (fj_lane() == 0) {
         c.scal[FJ_S_PHASE] = FJ_PH_LP_RESET;
         c.scal[FJ_S_LPSLOT] = env < P.lp_slots ? env : -1;
-        P.pend_env[env] = env;
+        P.pend_env[env] = env;   // list 0
     }
     fj_sync();
 }
@@ -1539,9 +1544,9 @@ FJ_FN void fj_env_reset_finish(const FjParams &P, int env, unsigned char *lp, do
 }
 
 // one parked LP, solved by a whole CTA (device) / one thread (host build)
-FJ_FN void fj_lp_service(const FjParams &P, const FjCtaGroup &g, int idx, unsigned char *binv, unsigned char *small_)
+FJ_FN void fj_lp_service(const FjParams &P, const FjCtaGroup &g, const int *list, int idx, unsigned char *binv, unsigned char *small_)
 {
-    const int env = P.pend_env[idx];
+    const int env = list[idx];
     FjCtx c;
     fj_ctx_init(c, P, env, nullptr);
     FjLp L;

@@ -132,6 +132,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     // env offsets (bytes)
     FjEnvOff eo;
     int b = 0;
+    // hot prefix: what every step reads (staged in shared memory by the main kernel)
     eo.scal = b; b += 4 * FJ_S_COUNT;
     eo.obs = b; b += 8 * 16;
     eo.obs2 = b; b += 8 * 16;
@@ -139,11 +140,6 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.mF = b; b += 8 * d.Mx;
     eo.rsum = b; b += 8 * d.KTx;
     eo.tsum = b; b += 8 * d.KTx;
-    eo.urg = b; b += 8 * d.KTx;
-    eo.maxe = b; b += 8 * d.KTx;
-    eo.fu = b; b += 8 * d.NFx;
-    eo.fa = b; b += 8 * d.NFx;
-    eo.ff = b; b += 8 * d.NFx;
     eo.avmask = b; b += 4 * d.KTW;
     eo.favmask = b; b += 4 * d.KTW;
     eo.demask = b; b += 4 * d.KTW;
@@ -160,10 +156,16 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.qlen = b; b += 2 * d.KTx;
     eo.cntunp = b; b += 2 * d.KTx * d.Sx;
     eo.cntnow = b; b += 2 * d.KTx * d.Sx;
-    eo.pk = b; b += 2 * d.KTx * d.Mx;
-    eo.slot = b; b += 2 * d.KTx * d.Mx;
     b = fj_align(b, 16);
     eo.hot = b;
+    // the rest stays in HBM/L2: rule keys of available types, per-pair counters, fluid slots, links
+    eo.urg = b; b += 8 * d.KTx;
+    eo.maxe = b; b += 8 * d.KTx;
+    eo.fu = b; b += 8 * d.NFx;
+    eo.fa = b; b += 8 * d.NFx;
+    eo.ff = b; b += 8 * d.NFx;
+    eo.pk = b; b += 2 * d.KTx * d.Mx;
+    eo.slot = b; b += 2 * d.KTx * d.Mx;
     eo.next = b; b += 2 * d.NJx;
     eo.stride = fj_align(b, 16);
     t.eo = eo;

@@ -111,8 +111,8 @@ struct FjParams {
     unsigned char *env;         // env table
     unsigned char *lp;          // LP scratch, one slab per resident warp
     unsigned long long lp_stride;
-    int *pend_count;            // parked LPs of the current launch
-    int *pend_env;              // [B] env of each parked LP
+    int *pend_count;            // [FJ_ROUNDS + 1] parked LPs per resume round of the current launch
+    int *pend_env;              // [2][B] env of each parked LP (ping-pong between rounds)
     double *lp_x;               // [lp_slots][NPx] LP solutions
     int *lp_meta;               // [lp_slots][2] iterations, return code
     int lp_slots;
@@ -131,4 +131,8 @@ struct FjStepArgs {
     double *reward;             // [T][B] or null
     int32_t *done;              // [T][B] or null
     int32_t *rec;               // [T][B][8] or null
+    int *park_count;            // where this kernel parks envs that need a fluid LP
+    int *park_env;
 };
+
+#define FJ_ROUNDS 3   // resume rounds per launch (reset + two order arrivals inside one launch)

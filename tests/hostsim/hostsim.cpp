@@ -15,21 +15,24 @@ struct HostVec {
     FjTables tb;
     FjParams P;
     std::vector<int32_t> env_inst, pend_env, lp_meta;
+    int pend_counts[FJ_ROUNDS + 1];
     std::vector<unsigned char> env, lp;
     std::vector<double> lp_x;
     int pend_count;
     int variant, sum_mode;
 };
 
-static void run_lp_service(HostVec *h)
+static void run_lp_service(HostVec *h, int round = 0)
 {
+    const int *list = h->pend_env.data() + (size_t)(round & 1) * h->P.B;
+    h->pend_count = h->pend_counts[round];
     // the CTA-group LP kernel, one thread: Binv and the small arrays on the host slab
     const FjDims &d = h->tb.d;
     unsigned char *binv = h->lp.data();
     unsigned char *small_ = h->lp.data() + (size_t)d.Rx * d.Rx * 8;
     FjCtaGroup g; g.rk = nullptr; g.ri = nullptr; g.ra = nullptr;
     int n = h->pend_count < h->P.lp_slots ? h->pend_count : h->P.lp_slots;
-    for (int i = 0; i < n; ++i) fj_lp_service(h->P, g, i, binv, small_);
+    for (int i = 0; i < n; ++i) fj_lp_service(h->P, g, list, i, binv, small_);
 }
 
 static std::string g_err;
@@ -38,22 +41,31 @@ template <int V, int SM>
 static void run_reset(HostVec *h, double *state)
 {
     for (int e = 0; e < h->P.B; ++e) fj_env_reset_begin(h->P, e);
-    h->pend_count = h->P.B;
-    run_lp_service(h);
+    h->pend_counts[0] = h->P.B;
+    run_lp_service(h, 0);
     for (int e = 0; e < h->P.B; ++e) fj_env_reset_finish<V, SM>(h->P, e, h->lp.data(), state, nullptr);
 }
 template <int V, int SM>
 static void run_step(HostVec *h, const FjStepArgs &A)
 {
-    h->pend_count = 0;
     // FJSP_HOSTSIM_STAGE=1: run on a staged copy of the record's hot part (the shared-memory path)
     static std::vector<unsigned char> slab;
     slab.assign(h->tb.eo.hot + 16, 0);
     unsigned char *stage = getenv("FJSP_HOSTSIM_STAGE") ? slab.data() : nullptr;
-    for (int e = 0; e < h->P.B; ++e) fj_cta_rollout<V, SM>(h->P, A, e, 1);                         // main kernel
-    run_lp_service(h);                                                                           // LP kernel
-    const int n = h->pend_count;
-    for (int i = 0; i < n; ++i) fj_env_rollout<V, SM, 0>(h->P, A, h->pend_env[i], h->lp.data(), stage);   // resume kernel
+    for (int r = 0; r <= FJ_ROUNDS; ++r) h->pend_counts[r] = 0;
+    FjStepArgs B_ = A;
+    B_.park_count = &h->pend_counts[0]; B_.park_env = h->pend_env.data();
+    for (int e = 0; e < h->P.B; ++e) fj_cta_rollout<V, SM>(h->P, B_, e, 1, stage);                  // main kernel
+    for (int r = 0; r < FJ_ROUNDS; ++r) {
+        run_lp_service(h, r);                                                                       // LP kernel
+        const int *list = h->pend_env.data() + (size_t)(r & 1) * h->P.B;
+        const int n = h->pend_counts[r];
+        B_.park_count = &h->pend_counts[r + 1]; B_.park_env = h->pend_env.data() + (size_t)((r + 1) & 1) * h->P.B;
+        for (int i = 0; i < n; ++i) {                                                               // resume kernel
+            if (r + 1 < FJ_ROUNDS) fj_env_rollout<V, SM, 1>(h->P, B_, list[i], h->lp.data(), nullptr);
+            else fj_env_rollout<V, SM, 0>(h->P, B_, list[i], h->lp.data(), nullptr);
+        }
+    }
 }
 
 #define DISPATCH(fn, ...)                                                                      \
@@ -87,7 +99,7 @@ int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst
     P.d = h->tb.d; P.io = h->tb.io; P.eo = h->tb.eo;
     P.inst = h->tb.inst.data(); P.env_inst = h->env_inst.data(); P.env = h->env.data();
     P.lp = h->lp.data(); P.lp_stride = 0;
-    h->pend_env.assign(n_envs, 0);
+    h->pend_env.assign((size_t)2 * n_envs, 0);
     const char *ov = getenv("FJSP_HOSTSIM_LP_SLOTS");   // tests: force the "no free slot" in-line path
     P.lp_slots = ov ? atoi(ov) : n_envs;
     h->lp_x.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * h->tb.d.NPx, 0.0);
@@ -119,6 +131,7 @@ int fjsp_hostsim_step(void *v, int T, const int32_t *actions, const uint32_t *rn
     A.T = T; A.actions = actions; A.rnd = rnd; A.reward_policy = reward_policy; A.autoreset = autoreset;
     A.completion = completion; A.tardiness = tardiness; A.energy = energy;
     A.state = state; A.state32 = state32; A.reward = reward; A.done = done; A.rec = rec;
+    A.park_count = nullptr; A.park_env = nullptr;
     DISPATCH(run_step, h, A);
     return 0;
 }
