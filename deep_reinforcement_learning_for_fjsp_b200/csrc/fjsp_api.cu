@@ -72,6 +72,18 @@ __global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(FjParams P, cons
     for (int i = blockIdx.x; i < n; i += gridDim.x) fj_lp_service(P, g, list_in, i, binv, small_);
 }
 
+// after the first reset(): copy each instance's order-0 LP solution from its representative env
+__global__ void fjsp_plan_kernel(FjParams P, const int *rep_env, int n_inst, double *plan_x, int *plan_meta, int *plan_ok)
+{
+    const int ii = blockIdx.x;
+    if (ii >= n_inst) return;
+    const int env = rep_env[ii];
+    if (env < 0 || env >= P.lp_slots) { if (threadIdx.x == 0) plan_ok[ii] = 0; return; }
+    const int np = P.d.NPx;
+    for (int j = threadIdx.x; j < np; j += blockDim.x) plan_x[(size_t)ii * np + j] = P.lp_x[(size_t)env * np + j];
+    if (threadIdx.x == 0) { plan_meta[2 * ii] = P.lp_meta[2 * env]; plan_meta[2 * ii + 1] = P.lp_meta[2 * env + 1]; plan_ok[ii] = 1; }
+}
+
 __global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(FjParams P)
 {
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -94,8 +106,9 @@ struct fjsp_vec {
     FjParams P;
     int variant, sum_mode, B, device, grid, step_grid, resume_grid, lp_grid, lp_smem_binv, nstate;
     size_t lp_smem_bytes, stage_bytes;
-    int *d_pend_count, *d_pend_env, *d_lp_meta;
-    double *d_lp_x;
+    int *d_pend_count, *d_pend_env, *d_lp_meta, *d_rep_env, *d_plan_meta, *d_plan_ok;
+    double *d_lp_x, *d_plan_x;
+    int n_inst, plan_ready;
     int32_t *d_inst, *d_env_inst;
     unsigned char *d_env, *d_lp;
     long long launches;
@@ -199,6 +212,17 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaMalloc(&v->d_lp_x, slots * per_slot));
     CK(cudaMalloc(&v->d_lp_meta, slots * 8));
     CK(cudaMemset(v->d_pend_count, 0, 4 * (FJ_ROUNDS + 1)));
+    {   // per-instance cache of the order-0 LP solution (filled by the first reset)
+        std::vector<int> rep(n_instances, -1);
+        for (int e = n_envs - 1; e >= 0; --e) rep[env_instance[e]] = e;
+        v->n_inst = n_instances; v->plan_ready = 0;
+        CK(cudaMalloc(&v->d_rep_env, (size_t)n_instances * 4));
+        CK(cudaMalloc(&v->d_plan_x, (size_t)n_instances * per_slot));
+        CK(cudaMalloc(&v->d_plan_meta, (size_t)n_instances * 8));
+        CK(cudaMalloc(&v->d_plan_ok, (size_t)n_instances * 4));
+        CK(cudaMemcpy(v->d_rep_env, rep.data(), (size_t)n_instances * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemset(v->d_plan_ok, 0, (size_t)n_instances * 4));
+    }
     CK(cudaFuncSetAttribute(fjsp_lp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->lp_smem_bytes));
     CK(cudaFuncSetAttribute(fjsp_lp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->lp_smem_bytes));
     FjParams &P = v->P;
@@ -207,6 +231,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     P.B = n_envs; P.variant = variant; P.sum_mode = v->sum_mode; P.nobs = v->nstate / 2;
     P.pend_count = v->d_pend_count; P.pend_env = v->d_pend_env; P.lp_x = v->d_lp_x; P.lp_meta = v->d_lp_meta;
     P.lp_slots = (int)slots;
+    P.plan_x = v->d_plan_x; P.plan_meta = v->d_plan_meta; P.plan_ok = nullptr;
     // hot part of the env records staged in shared memory for the whole launch when four
     // warps' worth fits with at least two CTAs per SM
     // the main kernel stages the hot prefix of its warps' records in shared memory when the
@@ -244,6 +269,7 @@ int fjsp_vec_destroy(fjsp_vec *v)
     free_stage(v);
     cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
+    cudaFree(v->d_rep_env); cudaFree(v->d_plan_x); cudaFree(v->d_plan_meta); cudaFree(v->d_plan_ok);
     cudaStreamDestroy(v->stream);
     delete v;
     return 0;
@@ -264,6 +290,11 @@ int fjsp_vec_reset(fjsp_vec *v, void *stream, double *d_state64, float *d_state3
     cudaStream_t st = (cudaStream_t)stream;
     fjsp_reset_begin_kernel<<<v->grid, FJ_BLOCK, 0, st>>>(v->P);
     launch_lp(v, st, 0);
+    if (!v->plan_ready) {
+        fjsp_plan_kernel<<<v->n_inst, 128, 0, st>>>(v->P, v->d_rep_env, v->n_inst, v->d_plan_x, v->d_plan_meta, v->d_plan_ok);
+        v->plan_ready = 1;
+        v->P.plan_ok = v->d_plan_ok;   // later launches may reset from the cache
+    }
     int rc = dispatch(v, [&](auto V, auto SM) {
         fjsp_reset_finish_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, 0, st>>>(v->P, d_state64, d_state32);
         return 0;

@@ -137,6 +137,7 @@ template <int MODE> FJ_FN double fj_pysum_result(const FjPySum &s)
 struct FjCtx {
     const FjParams *P;
     const int32_t *I;
+    int inst;
     int M, K, KT, S, Mx, Kx, Sx;
     unsigned mmask;
     int32_t *scal; double *obs, *obs2, *gapave, *urg, *maxe; uint32_t *avmask, *favmask, *demask, *damask;
@@ -148,7 +149,8 @@ struct FjCtx {
 FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, unsigned char *hot = nullptr)
 {
     c.P = &P;
-    c.I = P.inst + (size_t)P.env_inst[env] * P.io.stride;
+    c.inst = P.env_inst[env];
+    c.I = P.inst + (size_t)c.inst * P.io.stride;
     const int32_t *h = c.I + P.io.hdr;
     c.M = h[0]; c.K = h[1]; c.KT = h[2]; c.S = h[3];
     c.Mx = P.d.Mx; c.Kx = P.d.Kx; c.Sx = P.d.Sx;
@@ -1097,6 +1099,21 @@ FJ_FN void fj_reset_finish(FjCtx &c)
     fj_sync();
 }
 
+// The order-0 fluid LP of an instance is the same at every reset (same counts, all later
+// queues empty), so after the first reset() its solution is cached per instance and an
+// auto-reset needs no LP at all.
+template <int VARIANT, int SUM_MODE>
+FJ_FN int fj_reset_from_plan(FjCtx &c, const FjParams &P)
+{
+    if (!P.plan_ok || !P.plan_ok[c.inst]) return 0;
+    fj_reset_begin(c, 0);
+    fj_arrival_finish<SUM_MODE>(c, P.plan_x + (size_t)c.inst * P.d.NPx, P.plan_meta[2 * c.inst], P.plan_meta[2 * c.inst + 1]);
+    fj_reset_finish<VARIANT, SUM_MODE>(c);
+    if (fj_lane() == 0) c.scal[FJ_S_EPISODES] += 1;
+    fj_sync();
+    return 1;
+}
+
 // ---------------------------------------------------------------- step
 struct FjStepOut { double reward; int done; int rec[8]; };
 
@@ -1363,13 +1380,15 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
                 if (A.rec) for (int k = lane; k < 8; k += FJ_NL) A.rec[i * 8 + k] = -1;
                 continue;
             }
-            fj_reset_begin(c, 0);
-            if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
-            fj_sync();
-            if (SUSPEND) { fj_suspend(c, P, A, env, FJ_PH_LP_RESET, tt); return; }
-            else {
-                fj_order_arrives_inline<SUM_MODE>(c, 0, 0);
-                fj_reset_finish<VARIANT, SUM_MODE>(c);
+            if (!fj_reset_from_plan<VARIANT, SUM_MODE>(c, P)) {
+                fj_reset_begin(c, 0);
+                if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
+                fj_sync();
+                if (SUSPEND) { fj_suspend(c, P, A, env, FJ_PH_LP_RESET, tt); return; }
+                else {
+                    fj_order_arrives_inline<SUM_MODE>(c, 0, 0);
+                    fj_reset_finish<VARIANT, SUM_MODE>(c);
+                }
             }
         } else if (phase == FJ_PH_LP_RESET) {
             fj_arrival_resume<SUM_MODE>(c, P);
@@ -1470,14 +1489,15 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, int env, int a
                     if (A.reward && lane == 0) A.reward[i] = 0.0;
                     fj_emit_state(c, A, i, nobs, 1);
                     if (A.rec) for (int k = lane; k < 8; k += FJ_NL) A.rec[i * 8 + k] = -1;
-                } else {
+                } else if (!fj_reset_from_plan<VARIANT, SUM_MODE>(c, P)) {
                     fj_reset_begin(c, 0);
                     if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
                     fj_sync();
                     fj_suspend(c, P, A, env, FJ_PH_LP_RESET, tt);
                     parked = 1;
                 }
-            } else {
+            }
+            if (!parked && !c.scal[FJ_S_DONE]) {
                 const int ok = fj_step_front<VARIANT, SUM_MODE>(c, A.actions[2 * i], A.actions[2 * i + 1],
                                                                A.rnd ? A.rnd[2 * i] : 0u, A.rnd ? A.rnd[2 * i + 1] : 0u, out);
                 if (A.rec && lane == 0) for (int k = 0; k < 8; ++k) A.rec[i * 8 + k] = out.rec[k];

@@ -116,6 +116,9 @@ struct FjParams {
     double *lp_x;               // [lp_slots][NPx] LP solutions
     int *lp_meta;               // [lp_slots][2] iterations, return code
     int lp_slots;
+    const double *plan_x;       // [n_instances][NPx] cached order-0 LP solution per instance
+    const int *plan_meta;       // [n_instances][2]
+    const int *plan_ok;         // [n_instances] 1 once cached (null before the first reset)
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory
     int B, variant, sum_mode, nobs;
 };
@@ -135,4 +138,4 @@ struct FjStepArgs {
     int *park_env;
 };
 
-#define FJ_ROUNDS 3   // resume rounds per launch (reset + two order arrivals inside one launch)
+#define FJ_ROUNDS 2   // resume rounds per launch; a third LP of one env inside a launch is solved in line

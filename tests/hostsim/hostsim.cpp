@@ -17,7 +17,8 @@ struct HostVec {
     std::vector<int32_t> env_inst, pend_env, lp_meta;
     int pend_counts[FJ_ROUNDS + 1];
     std::vector<unsigned char> env, lp;
-    std::vector<double> lp_x;
+    std::vector<double> lp_x, plan_x;
+    std::vector<int32_t> plan_meta, plan_ok;
     int pend_count;
     int variant, sum_mode;
 };
@@ -43,6 +44,18 @@ static void run_reset(HostVec *h, double *state)
     for (int e = 0; e < h->P.B; ++e) fj_env_reset_begin(h->P, e);
     h->pend_counts[0] = h->P.B;
     run_lp_service(h, 0);
+    if (!h->P.plan_ok && !getenv("FJSP_HOSTSIM_NO_PLAN")) {   // cache each instance's order-0 LP solution
+        const int np = h->tb.d.NPx, ni = h->tb.n_instances;
+        h->plan_x.assign((size_t)ni * np, 0.0); h->plan_meta.assign((size_t)ni * 2, 0); h->plan_ok.assign(ni, 0);
+        for (int e = h->P.B - 1; e >= 0; --e) {
+            if (e >= h->P.lp_slots) continue;
+            const int ii = h->env_inst[e];
+            for (int j = 0; j < np; ++j) h->plan_x[(size_t)ii * np + j] = h->lp_x[(size_t)e * np + j];
+            h->plan_meta[2 * ii] = h->lp_meta[2 * e]; h->plan_meta[2 * ii + 1] = h->lp_meta[2 * e + 1];
+            h->plan_ok[ii] = 1;
+        }
+        h->P.plan_x = h->plan_x.data(); h->P.plan_meta = h->plan_meta.data(); h->P.plan_ok = h->plan_ok.data();
+    }
     for (int e = 0; e < h->P.B; ++e) fj_env_reset_finish<V, SM>(h->P, e, h->lp.data(), state, nullptr);
 }
 template <int V, int SM>
@@ -105,6 +118,7 @@ int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst
     h->lp_x.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * h->tb.d.NPx, 0.0);
     h->lp_meta.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * 2, 0);
     P.stage = 0;
+    P.plan_x = nullptr; P.plan_meta = nullptr; P.plan_ok = nullptr;
     h->pend_count = 0;
     P.pend_count = &h->pend_count; P.pend_env = h->pend_env.data(); P.lp_x = h->lp_x.data(); P.lp_meta = h->lp_meta.data();
     P.B = n_envs; P.variant = variant; P.sum_mode = sum_mode;
