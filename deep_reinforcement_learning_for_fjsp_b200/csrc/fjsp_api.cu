@@ -35,12 +35,21 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
 {
     // lockstep phases: every warp of the CTA walks the same number of env groups and steps
     extern __shared__ __align__(16) unsigned char stage_smem[];
+    __shared__ int req_env[32], lp_meta[2], red_i[64];
+    __shared__ double red_d[32];
     const int wpb = blockDim.x >> 5;
     const int total = gridDim.x * wpb;
     unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.eo.hot : nullptr;
+    FjCtaCtx K;
+    K.warp = threadIdx.x >> 5; K.nwarps = wpb; K.cta_lp = P.cta_lp;
+    K.stage_base = P.stage ? stage_smem : nullptr;
+    K.slab = P.lp + (size_t)blockIdx.x * P.lp_stride;
+    K.x = (double *)(K.slab + (size_t)P.d.Rx * P.d.Rx * 8 + (fj_lp_small_bytes(P.d) + 7) / 8 * 8);
+    K.meta = lp_meta; K.req_env = req_env;
+    K.group.rk = red_d; K.group.ri = red_i; K.group.ra = red_i + 32;
     for (int base = blockIdx.x * wpb; base < P.B; base += total) {
         const int env = base + (threadIdx.x >> 5);
-        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, env < P.B ? env : 0, env < P.B, stage);
+        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env < P.B ? env : 0, env < P.B, stage);
     }
 }
 
@@ -193,6 +202,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (v->lp_smem_binv && binv_b + small_b > 100 * 1024) v->lp_grid = prop.multiProcessorCount;
     int slabs = v->resume_grid * FJ_WARPS_PER_BLOCK;
     if (v->lp_grid > slabs) slabs = v->lp_grid;
+    if (v->step_grid > slabs) slabs = v->step_grid;   // one slab per CTA of the main kernel (in-CTA LP service)
     const size_t lp_bytes = (size_t)lp_stride * slabs;
     const size_t env_bytes = (size_t)n_envs * v->tb.eo.stride;
     CK(cudaMalloc(&v->d_inst, v->tb.inst.size() * 4));
@@ -239,6 +249,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     v->stage_bytes = (size_t)(FJ_STEP_THREADS / 32) * v->tb.eo.hot;
     P.stage = v->stage_bytes <= 56 * 1024 ? 1 : 0;
     if (getenv("FJSP_NO_STAGE")) P.stage = 0;
+    P.cta_lp = getenv("FJSP_NO_CTA_LP") ? 0 : 1;   // 0: park order arrivals for the LP / resume kernels
     if (!P.stage) v->stage_bytes = 0;
     if (dispatch(v, [&](auto V, auto SM) {
             cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,

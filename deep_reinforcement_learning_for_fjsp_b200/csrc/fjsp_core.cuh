@@ -1463,8 +1463,29 @@ FJ_FN void fj_emit_state(const FjCtx &c, const FjStepArgs &A, size_t i, int nobs
     }
 }
 
+// per-CTA context of the main kernel: which warp this is, the staging slabs of all warps and
+// the CTA's LP service (scratch slab in global memory, solution vector, request board)
+struct FjCtaCtx {
+    int warp, nwarps, cta_lp;
+    unsigned char *stage_base;   // shared-memory staging slabs of the CTA's warps, or null
+    unsigned char *slab;         // LP scratch: Binv, small arrays
+    double *x;                   // LP solution
+    int *meta;                   // iterations, return code
+    int *req_env;                // [nwarps] env each warp wants an LP for, -1 none
+    FjCtaGroup group;
+};
+
+FJ_FN int fj_cta_sync_or(int pred)
+{
+#ifdef FJ_DEVICE_CODE
+    return __syncthreads_or(pred);
+#else
+    return pred;
+#endif
+}
+
 template <int VARIANT, int SUM_MODE>
-FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, int env, int active, unsigned char *stage = nullptr)
+FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx &K, int env, int active, unsigned char *stage = nullptr)
 {
     const int lane = fj_lane();
     FjCtx c;
@@ -1504,10 +1525,46 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, int env, int a
                 stage = ok ? 1 : 2;
             }
         }
-        // ---- phase B: discrete-event clock (same barrier interval as A: together they fit the I-cache)
+        // ---- phase B: discrete-event clock.  A warp whose clock reaches an order arrival asks
+        // the CTA for the fluid LP: at the phase barrier all warps of the CTA solve it together
+        // (FjCtaGroup, basis inverse on the CTA's scratch slab), the owner applies it and
+        // re-enters its clock loop.  No kernel boundary, no parked tail.
         int done = 0;
-        if (stage == 1) {
-            if (fj_clock<SUM_MODE, 1>(c, 0, done)) { fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt); parked = 1; stage = 0; }
+        {
+            int st = stage == 1 ? 1 : 0;     // 1 clock to run, 2 waiting for an LP, 0 nothing / finished
+            int resume = 0;
+            for (;;) {
+                int want = 0;
+                if (st == 1) {
+                    if (fj_clock<SUM_MODE, 1>(c, resume, done)) { st = 2; want = 1; } else st = 0;
+                }
+                if (!K.cta_lp) {             // no CTA service configured: park for the LP / resume kernels
+                    if (want) { fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt); parked = 1; stage = 0; }
+                    break;
+                }
+                if (lane == 0) K.req_env[K.warp] = want ? env : -1;
+                if (!fj_cta_sync_or(want)) break;
+                FJ_NOUNROLL
+                for (int w = 0; w < K.nwarps; ++w) {
+                    const int e2 = K.req_env[w];
+                    if (e2 < 0) continue;    // uniform over the CTA
+                    {
+                        FjCtx c2;
+                        fj_ctx_init(c2, P, e2, nullptr, K.stage_base ? K.stage_base + (size_t)w * P.eo.hot : nullptr);
+                        FjLp L;
+                        fj_lp_carve(L, K.slab, K.slab + (size_t)P.d.Rx * P.d.Rx * 8, P.d);
+                        int iters = 0;
+                        const int rc = fj_lp_solve(K.group, c2, L, K.x, &iters);
+                        if (K.group.rank() == 0) { K.meta[0] = iters; K.meta[1] = rc; }
+                        K.group.sync();
+                    }
+                    if (w == K.warp) {
+                        fj_arrival_finish<SUM_MODE>(c, K.x, K.meta[0], K.meta[1]);
+                        resume = 1; st = 1;
+                    }
+                    K.group.sync();
+                }
+            }
         }
         FJ_CTA_SYNC();      // ---- phase C: observation, reward, outputs
         if (stage == 1) fj_step_back<VARIANT, SUM_MODE>(c, done, A.reward_policy, A.completion, A.tardiness, A.energy, out);

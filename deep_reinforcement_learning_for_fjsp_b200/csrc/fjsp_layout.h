@@ -119,6 +119,7 @@ struct FjParams {
     const double *plan_x;       // [n_instances][NPx] cached order-0 LP solution per instance
     const int *plan_meta;       // [n_instances][2]
     const int *plan_ok;         // [n_instances] 1 once cached (null before the first reset)
+    int cta_lp;                 // 1: the main kernel's CTAs solve order-arrival LPs themselves
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory
     int B, variant, sum_mode, nobs;
 };

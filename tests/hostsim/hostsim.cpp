@@ -68,7 +68,13 @@ static void run_step(HostVec *h, const FjStepArgs &A)
     for (int r = 0; r <= FJ_ROUNDS; ++r) h->pend_counts[r] = 0;
     FjStepArgs B_ = A;
     B_.park_count = &h->pend_counts[0]; B_.park_env = h->pend_env.data();
-    for (int e = 0; e < h->P.B; ++e) fj_cta_rollout<V, SM>(h->P, B_, e, 1, stage);                  // main kernel
+    FjCtaCtx K;
+    static int req_env[1], meta[2];
+    K.warp = 0; K.nwarps = 1; K.cta_lp = h->P.cta_lp; K.stage_base = stage;
+    K.slab = h->lp.data();
+    K.x = (double *)(K.slab + (size_t)h->tb.d.Rx * h->tb.d.Rx * 8 + (fj_lp_small_bytes(h->tb.d) + 7) / 8 * 8);
+    K.meta = meta; K.req_env = req_env; K.group.rk = nullptr; K.group.ri = nullptr; K.group.ra = nullptr;
+    for (int e = 0; e < h->P.B; ++e) fj_cta_rollout<V, SM>(h->P, B_, K, e, 1, stage);               // main kernel
     for (int r = 0; r < FJ_ROUNDS; ++r) {
         run_lp_service(h, r);                                                                       // LP kernel
         const int *list = h->pend_env.data() + (size_t)(r & 1) * h->P.B;
@@ -118,6 +124,7 @@ int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst
     h->lp_x.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * h->tb.d.NPx, 0.0);
     h->lp_meta.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * 2, 0);
     P.stage = 0;
+    P.cta_lp = getenv("FJSP_HOSTSIM_NO_CTA_LP") ? 0 : 1;
     P.plan_x = nullptr; P.plan_meta = nullptr; P.plan_ok = nullptr;
     h->pend_count = 0;
     P.pend_count = &h->pend_count; P.pend_env = h->pend_env.data(); P.lp_x = h->lp_x.data(); P.lp_meta = h->lp_meta.data();
