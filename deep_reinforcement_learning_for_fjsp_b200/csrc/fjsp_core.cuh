@@ -438,13 +438,30 @@ FJ_FN int fj_lp_solve(const G &g, FjCtx &c, FjLp &L, double *x_out, int *iters_o
         double *rowp = L.Binv + (size_t)p * R;
         for (int k = tid; k < R; k += nt) rowp[k] = fj_div(rowp[k], wp);
         g.sync();
-        // rank-1 update of every other row: warps own rows, lanes own columns
-        for (int i = g.warp(); i < R; i += g.nwarps()) {
-            if (i == p) continue;
-            const double wi = L.w[i];
-            if (wi == 0.0) continue;
-            double *rowi = L.Binv + (size_t)i * R;
-            for (int k = g.lane(); k < R; k += FJ_NL) rowi[k] = fj_sub(rowi[k], fj_mul(wi, rowp[k]));
+        // rank-1 update of every other row: warps own rows (four at a time, so that the four
+        // loads of a column are in flight together), lanes own columns.  Per element it is
+        // still  B[i][k] - w[i] * B[p][k]  with separately rounded multiply and subtract.
+        for (int i0 = g.warp() * 4; i0 < R; i0 += g.nwarps() * 4) {
+            double wv0 = 0.0, wv1 = 0.0, wv2 = 0.0, wv3 = 0.0;
+            if (i0 + 0 < R && i0 + 0 != p) wv0 = L.w[i0 + 0];
+            if (i0 + 1 < R && i0 + 1 != p) wv1 = L.w[i0 + 1];
+            if (i0 + 2 < R && i0 + 2 != p) wv2 = L.w[i0 + 2];
+            if (i0 + 3 < R && i0 + 3 != p) wv3 = L.w[i0 + 3];
+            if (wv0 == 0.0 && wv1 == 0.0 && wv2 == 0.0 && wv3 == 0.0) continue;
+            double *r0 = L.Binv + (size_t)(i0 + 0) * R, *r1 = L.Binv + (size_t)(i0 + 1) * R;
+            double *r2 = L.Binv + (size_t)(i0 + 2) * R, *r3 = L.Binv + (size_t)(i0 + 3) * R;
+            for (int k = g.lane(); k < R; k += FJ_NL) {
+                const double pk_ = rowp[k];
+                double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+                if (wv0 != 0.0) e0 = r0[k];
+                if (wv1 != 0.0) e1 = r1[k];
+                if (wv2 != 0.0) e2 = r2[k];
+                if (wv3 != 0.0) e3 = r3[k];
+                if (wv0 != 0.0) r0[k] = fj_sub(e0, fj_mul(wv0, pk_));
+                if (wv1 != 0.0) r1[k] = fj_sub(e1, fj_mul(wv1, pk_));
+                if (wv2 != 0.0) r2[k] = fj_sub(e2, fj_mul(wv2, pk_));
+                if (wv3 != 0.0) r3[k] = fj_sub(e3, fj_mul(wv3, pk_));
+            }
         }
         if (tid == 0) {
             L.pos[L.basis[p]] = -1;
