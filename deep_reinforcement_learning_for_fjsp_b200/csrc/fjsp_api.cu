@@ -146,6 +146,8 @@ template <typename F> static int dispatch(fjsp_vec *v, F f)
     case 3: return f(std::integral_constant<int, FJSP_MO_DFJSP>(), std::integral_constant<int, 1>());
     case 4: return f(std::integral_constant<int, FJSP_MO_BREAKDOWN>(), std::integral_constant<int, 0>());
     case 5: return f(std::integral_constant<int, FJSP_MO_BREAKDOWN>(), std::integral_constant<int, 1>());
+    case 6: return f(std::integral_constant<int, FJSP_SO_FJSSP>(), std::integral_constant<int, 0>());
+    case 7: return f(std::integral_constant<int, FJSP_SO_FJSSP>(), std::integral_constant<int, 1>());
     }
     g_err = "unsupported variant";
     return -2;
@@ -163,8 +165,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (!blobs || !blob_offsets || !env_instance || !out || n_instances < 1 || n_envs < 1) {
         g_err = "fjsp_vec_create: null or empty argument"; return -1;
     }
-    if (variant < 0 || variant > 2) {
-        g_err = "fjsp_vec_create: variant must be 0 (SO_DFJSP), 1 (MO_DFJSP) or 2 (MO_DFJSP_breakdown)"; return -2;
+    if (variant < 0 || variant > 3) {
+        g_err = "fjsp_vec_create: variant must be 0 (SO_DFJSP), 1 (MO_DFJSP), 2 (MO_DFJSP_breakdown) or 3 (SO_FJSSP)"; return -2;
     }
     for (int e = 0; e < n_envs; ++e)
         if (env_instance[e] < 0 || env_instance[e] >= n_instances) { g_err = "fjsp_vec_create: env_instance out of range"; return -1; }
@@ -174,9 +176,9 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     }
     CK(cudaSetDevice(device));
     fjsp_vec *v = new fjsp_vec();
-    if (!fj_build_tables(blobs, blob_offsets, n_instances, v->tb, g_err)) { delete v; return -1; }
+    if (!fj_build_tables(blobs, blob_offsets, n_instances, v->tb, g_err, variant)) { delete v; return -1; }
     v->variant = variant; v->sum_mode = sum_mode ? 1 : 0; v->B = n_envs; v->device = device; v->launches = 0;
-    v->nstate = variant == FJSP_SO_DFJSP ? 20 : 30;
+    v->nstate = (variant == FJSP_SO_DFJSP || variant == FJSP_SO_FJSSP) ? 20 : 30;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     // persistent grid: a multiple of the SM count, 8 CTAs (32 warps) per SM at most
@@ -321,7 +323,7 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
                   double *d_state64, float *d_state32, double *d_reward, int32_t *d_done, int32_t *d_rec)
 {
     if (!v || !d_actions || T < 1) { g_err = "fjsp_vec_step: null handle/actions or T < 1"; return -1; }
-    if (v->variant != FJSP_SO_DFJSP && (reward_policy < 0 || reward_policy > 3)) {
+    if (v->variant != FJSP_SO_DFJSP && v->variant != FJSP_SO_FJSSP && (reward_policy < 0 || reward_policy > 3)) {
         g_err = "fjsp_vec_step: reward_policy must be 0..3 (the reference raises MyError otherwise)"; return -4;
     }
     CK(cudaSetDevice(v->device));

@@ -143,6 +143,7 @@ struct FjCtx {
     int32_t *scal; double *obs, *obs2, *gapave, *urg, *maxe; uint32_t *avmask, *favmask, *demask, *damask;
     int32_t *mend, *mlast, *mjob, *mD; double *mF; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
     double *rsum, *tsum; uint16_t *cntunp, *cntnow, *pk, *slot; double *fu, *fa, *ff; uint16_t *next;
+    uint32_t *unpmask; int32_t *duejob, *mindue;   // SO_FJSSP only (per-job due dates)
     unsigned char *lp;
 };
 
@@ -171,6 +172,7 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     c.pk = (uint16_t *)(G + o.pk); c.slot = (uint16_t *)(G + o.slot);
     c.fu = (double *)(G + o.fu); c.fa = (double *)(G + o.fa); c.ff = (double *)(G + o.ff);
     c.next = (uint16_t *)(G + o.next);
+    c.unpmask = (uint32_t *)(G + o.unpmask); c.duejob = (int32_t *)(G + o.duejob); c.mindue = (int32_t *)(G + o.mindue);
     c.lp = lp;
 }
 
@@ -507,6 +509,28 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
     for (int i = lane; i < KT * Mx; i += FJ_NL) { c.pk[i] = 0; c.slot[i] = 0xFFFF; }
     FJ_NOUNROLL
     for (int m = lane; m < c.M; m += FJ_NL) { c.mD[m] = 0; c.mF[m] = 0.0; }
+    if (c.P->variant == FJSP_SO_FJSSP) {
+        // class_FJSSP.py:214-218: every job has its own due date
+        //   r_due = round(delivery * len(tasks) / count);  due(n) = round(r_due * n / count)
+        // (Python round() of a float = round-half-even = rint), and the unprocessed sets are
+        // kept per job because the due date now varies inside an order
+        const FjRO cum = FJ_I(c, cum), due = FJ_I(c, due), ntask = FJ_I(c, ntask), jobbase = FJ_I(c, jobbase);
+        const int NWx = c.P->d.NWx;
+        FJ_NOUNROLL
+        for (int q = lane; q < KT; q += FJ_NL) {
+            const int r = rjkind[q], n0 = cum[s * Kx + r], n1 = cum[(s + 1) * Kx + r];
+            FJ_NOUNROLL
+            for (int n = n0; n < n1; ++n) c.unpmask[q * NWx + (n >> 5)] |= 1u << (n & 31);
+        }
+        FJ_NOUNROLL
+        for (int r = 0; r < c.K; ++r) {
+            const int n0 = cum[s * Kx + r], n1 = cum[(s + 1) * Kx + r], cnt = n1 - n0;
+            const long long r_due = (long long)rint(fj_div((double)((long long)due[s] * ntask[r]), (double)cnt));
+            FJ_NOUNROLL
+            for (int n = n0 + lane; n < n1; n += FJ_NL)
+                c.duejob[jobbase[r] + n] = (int)rint(fj_div((double)(r_due * n), (double)cnt));
+        }
+    }
     fj_sync();
 }
 
@@ -659,6 +683,32 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
             double kd = 0.0, max_e = 0.0, sf = 0.0, sc = 0.0;
             bool first = true;
             long long late_sum = 0;
+            if (VARIANT == FJSP_SO_FJSSP) {
+                // per-job due dates: walk the set of unprocessed jobs in job-number order
+                const int NWx = c.P->d.NWx;
+                const int r = FJ_I(c, rjkind)[q], jb = FJ_I(c, jobbase)[r];
+                const int arrived = FJ_I(c, cum)[c.scal[FJ_S_NEXTORDER] * c.Kx + r];
+                int mind = 0x7fffffff;
+                FJ_NOUNROLL
+                for (int w = 0; w * 32 < arrived; ++w) {
+                    unsigned bits = c.unpmask[q * NWx + w];
+                    while (bits) {
+                        const int n = w * 32 + fj_ffs0(bits); bits &= bits - 1;
+                        const int d = c.duejob[jb + n];
+                        const double dd = (double)d;
+                        ++residue; kd += 1.0;
+                        const double est = fj_add(td, fj_mul(f, kd));
+                        const double ve = fj_sub(est, dd);
+                        if (t > d) { ++a_cnt; late_sum += t - d; }
+                        e_cnt += est > dd;
+                        if (first || ve > max_e) max_e = ve;
+                        first = false;
+                        mind = d < mind ? d : mind;
+                        fj_neumaier<SUM_MODE>(sf, sc, ve);
+                    }
+                }
+                c.mindue[q] = mind;
+            } else {
             FJ_NOUNROLL
             for (int s = 0; s < S; ++s) {
                 const int cnt = c.cntunp[q * Sx + s];
@@ -677,6 +727,7 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
                 }
                 if (first || ve > max_e) max_e = ve;
                 first = false;
+            }
             }
             p0 += ((long long)residue << 32) + a_cnt;
             p1 += ((long long)e_cnt << 32);
@@ -855,6 +906,21 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
         double k;
         if (key == 0) k = c.urg[q];
         else if (key == 1) k = c.maxe[q];
+        else if (key == 2 && VARIANT == FJSP_SO_FJSSP) k = (double)((long long)t - c.mindue[q]);
+        else if (key == 4 && VARIANT == FJSP_SO_FJSSP) {   // min due date over the waiting jobs
+            const int r = FJ_I(c, rjkind)[q], jb = FJ_I(c, jobbase)[r];
+            int mind = 0x7fffffff, n;
+            if (FJ_I(c, rjstage)[q] == 0) {
+                const int arrived = FJ_I(c, cum)[c.scal[FJ_S_NEXTORDER] * c.Kx + r];
+                FJ_NOUNROLL
+                for (n = arrived - c.qlen[q]; n < arrived; ++n) { const int d = c.duejob[jb + n]; mind = d < mind ? d : mind; }
+            } else {
+                n = c.qhead[q];
+                FJ_NOUNROLL
+                for (int i = 0; i < c.qlen[q]; ++i) { const int d = c.duejob[jb + n]; mind = d < mind ? d : mind; n = c.next[jb + n]; }
+            }
+            k = (double)mind;
+        }
         else if (key == 2) {   // max over unprocessed operations of (t - due)
             int mind = 0x7fffffff;
             FJ_NOUNROLL
@@ -1092,6 +1158,10 @@ FJ_FN void fj_reset_begin(FjCtx &c, int fresh)
     }
     FJ_NOUNROLL
     for (int m = lane; m < M; m += FJ_NL) { c.mend[m] = 0; c.mlast[m] = 0; c.mjob[m] = -1; }
+    if (c.P->variant == FJSP_SO_FJSSP) {
+        FJ_NOUNROLL
+        for (int i = lane; i < KT * c.P->d.NWx; i += FJ_NL) c.unpmask[i] = 0;
+    }
     fj_sync();
     if (lane == 0) {
         c.scal[FJ_S_NEXTORDER] = 1; c.scal[FJ_S_TIME] = 0; c.scal[FJ_S_STEPS] = 0; c.scal[FJ_S_HASTASK] = 0;
@@ -1199,8 +1269,9 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
             if (had) en += (long long)(t - prev_last) * FJ_I(c, idlep)[m];
             fj_set_ll(c.scal, FJ_S_ENERGY, en);
         }
+        if (VARIANT == FJSP_SO_FJSSP) c.unpmask[q * c.P->d.NWx + (n >> 5)] &= ~(1u << (n & 31));
         if (rjlast[q]) {
-            long long late = (long long)t_end - due[s];
+            long long late = (long long)t_end - (VARIANT == FJSP_SO_FJSSP ? c.duejob[jobbase[r] + n] : due[s]);
             if (late > 0) fj_set_ll(c.scal, FJ_S_DELAY_PROC, fj_get_ll(c.scal, FJ_S_DELAY_PROC) + late);
         }
         out.rec[0] = q; out.rec[1] = r; out.rec[2] = stage; out.rec[3] = n; out.rec[4] = m;

@@ -81,7 +81,7 @@ struct FjTables {
 };
 
 static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets, int n_inst, FjTables &t,
-                                   std::string &err)
+                                   std::string &err, int variant = 0)
 {
     std::vector<FjBlobView> views(n_inst);
     FjDims d;
@@ -96,6 +96,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
         if (v.NBD > d.NBDx) d.NBDx = v.NBD;
         if (v.NJ > d.NJx) d.NJx = v.NJ;
         if (v.NP > d.NPx) d.NPx = v.NP;
+        if (variant == FJSP_SO_FJSSP && (v.Nmax + 31) / 32 > d.NWx) d.NWx = (v.Nmax + 31) / 32;
     }
     d.KTW = (d.KTx + 31) / 32;
     d.Rx = d.Mx + 2 * d.KTx;
@@ -167,6 +168,10 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.pk = b; b += 2 * d.KTx * d.Mx;
     eo.slot = b; b += 2 * d.KTx * d.Mx;
     eo.next = b; b += 2 * d.NJx;
+    b = fj_align(b, 4);
+    eo.unpmask = b; b += 4 * d.KTx * d.NWx;
+    eo.duejob = b; b += (d.NWx ? 4 * d.NJx : 0);
+    eo.mindue = b; b += (d.NWx ? 4 * d.KTx : 0);
     eo.stride = fj_align(b, 16);
     t.eo = eo;
     // fill instance records

@@ -22,6 +22,7 @@ struct FjDims {
     int NFx;                          // fluid-pair slots per env (max LP rows)
     int KTW;                          // 32-bit words per operation-type mask
     int Rx, NPx;                      // LP: max rows, max pair columns
+    int NWx;                          // SO_FJSSP: 32-bit words per unprocessed-job set (0 otherwise)
 };
 
 // instance record: word (int32) offsets
@@ -85,6 +86,9 @@ struct FjEnvOff {
     int fa;        // double[NFx] fluid_unprocessed_rj_arrival_dict
     int ff;        // double[NFx] fluid_process_rate_rj_dict
     int next;      // uint16[NJx] queue links, indexed jobbase[r] + n
+    int unpmask;   // uint32[KTx*NWx] SO_FJSSP: unprocessed jobs of an operation type, one bit per job
+    int duejob;    // int32[NJx]      SO_FJSSP: due date of every job
+    int mindue;    // int32[KTx]      SO_FJSSP: smallest due date among an operation type's unprocessed jobs
     int hot;       // bytes of the record's hot part (everything but `next`), multiple of 16
     int stride;    // bytes per env (multiple of 16)
 };

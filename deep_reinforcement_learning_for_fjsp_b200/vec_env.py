@@ -19,8 +19,8 @@ import numpy as np
 from . import _lib
 from .instance import FJSPInstance
 
-VARIANTS = {"SO_DFJSP": 0, "MO_DFJSP": 1, "MO_DFJSP_breakdown": 2}
-ACTIONS_SIZE = {0: [6, 5], 1: [12, 10], 2: [12, 10]}
+VARIANTS = {"SO_DFJSP": 0, "MO_DFJSP": 1, "MO_DFJSP_breakdown": 2, "SO_FJSSP": 3}
+ACTIONS_SIZE = {0: [6, 5], 1: [12, 10], 2: [12, 10], 3: [6, 5]}
 INFO_KEYS = ["step_time", "step_count", "completion_time", "delay_time_sum", "energy_consumption", "lp_solves",
              "lp_iterations", "error", "done", "next_order", "episodes", "delay_time_sum_unprocessed"]
 
@@ -53,7 +53,7 @@ class FJSPVecEnv:
                                      self.variant, sum_mode, device, ctypes.byref(h)))
         self._h, self._L = h, L
         self.actions_size = ACTIONS_SIZE[self.variant]
-        self.state_size = 20 if self.variant == 0 else 30
+        self.state_size = 20 if self.variant in (0, 3) else 30
         self.observation_space = self.state_size // 2
         self.action_tuple = tuple((a1, a2) for a1 in range(self.actions_size[0]) for a2 in range(self.actions_size[1]))
         self.action_types = "DISCRETE"
@@ -164,7 +164,7 @@ class FJSPEnv:
                                                  "DA3C")
             else:
                 instance = FJSPInstance.from_csv(kwargs["path"], kwargs["file_name"],
-                                                 "SO" if variant == "SO_DFJSP" else "MO")
+                                                 "SO" if variant in ("SO_DFJSP", "SO_FJSSP") else "MO")
         self.instance = instance
         self.vec = FJSPVecEnv([instance], [0], variant, device)
         for k in ("actions_size", "state_size", "observation_space", "action_tuple", "action_types"):
@@ -188,7 +188,7 @@ class FJSPEnv:
             raise MyError("报错：未定义该工序动作规则")
         if not (0 <= action[1] < self.actions_size[1]):
             raise MyError("报错：未定义该机器分配规则。")
-        if self.vec.variant != 0 and reward_policy not in (0, 1, 2, 3):
+        if self.vec.variant in (1, 2) and reward_policy not in (0, 1, 2, 3):
             raise MyError("未定义该回报函数")
         rnd = self._rng.integers(0, 2**32, (1, 1, 2), dtype=np.uint64).astype(np.uint32)
         st, rw, dn, _ = self.vec.step_host(np.array(action, np.int32).reshape(1, 1, 2), rnd,

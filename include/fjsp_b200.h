@@ -4,6 +4,7 @@
  *   environments/SO_DFJSP.py:13-268           SO_DFJSP_Environment.reset()/step(action)
  *   environments/MO_DFJSP.py:12-298           MO_DFJSP_Environment.reset()/step(action, reward_policy, ...)
  *   environments/MO_DFJSP_breakdown.py:12-328 same, with machine breakdown / repair intervals
+ *   environments/SO_FJSSP.py:12-265           SO_FJSSP_Environment (per-job due dates of class_FJSSP.py)
  * and for the process-pool rollout of utilities/Parallel_Experience_Generator.py:28-66
  * (play_n_episodes / play_1_episode): one call steps EVERY environment copy of a batch on
  * the GPU.  Plain pointers and sizes only; a binding needs no CUDA or torch headers.
@@ -30,7 +31,8 @@ extern "C" {
 
 typedef struct fjsp_vec fjsp_vec;
 
-enum { FJSP_VARIANT_SO_DFJSP = 0, FJSP_VARIANT_MO_DFJSP = 1, FJSP_VARIANT_MO_DFJSP_BREAKDOWN = 2 };
+enum { FJSP_VARIANT_SO_DFJSP = 0, FJSP_VARIANT_MO_DFJSP = 1, FJSP_VARIANT_MO_DFJSP_BREAKDOWN = 2,
+       FJSP_VARIANT_SO_FJSSP = 3 };
 /* sum_mode: how the reference's builtin sum() adds floats. 1 = CPython >= 3.12
  * (Neumaier-compensated), 0 = CPython <= 3.11 (left to right). */
 

@@ -44,7 +44,7 @@ def lib():
 
 INFO_KEYS = ["step_time", "step_count", "completion", "delay_sum", "energy", "lp_solves", "lp_iters", "error",
              "done", "next_order", "episodes", "delay_unprocessed"]
-VARIANTS = {"SO_DFJSP": 0, "MO_DFJSP": 1, "MO_DFJSP_breakdown": 2}
+VARIANTS = {"SO_DFJSP": 0, "MO_DFJSP": 1, "MO_DFJSP_breakdown": 2, "SO_FJSSP": 3}
 
 
 class HostSimVec:
@@ -61,7 +61,7 @@ class HostSimVec:
         if rc != 0:
             raise RuntimeError(L.fjsp_hostsim_last_error().decode())
         self.h = h
-        self.nstate = 20 if self.variant == 0 else 30
+        self.nstate = 20 if self.variant in (0, 3) else 30
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -97,6 +97,8 @@ static void run_step(HostVec *h, const FjStepArgs &A)
         case 3: fn<FJSP_MO_DFJSP, 1>(__VA_ARGS__); break;                                      \
         case 4: fn<FJSP_MO_BREAKDOWN, 0>(__VA_ARGS__); break;                                  \
         case 5: fn<FJSP_MO_BREAKDOWN, 1>(__VA_ARGS__); break;                                  \
+        case 6: fn<FJSP_SO_FJSSP, 0>(__VA_ARGS__); break;                                      \
+        case 7: fn<FJSP_SO_FJSSP, 1>(__VA_ARGS__); break;                                      \
         }                                                                                      \
     } while (0)
 
@@ -107,9 +109,9 @@ const char *fjsp_hostsim_last_error(void) { return g_err.c_str(); }
 int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst, const int32_t *env_instance,
                         int n_envs, int variant, int sum_mode, void **out)
 {
-    if (variant < 0 || variant > 2) { g_err = "variant not supported on the device path"; return -2; }
+    if (variant < 0 || variant > 3) { g_err = "unknown variant"; return -2; }
     HostVec *h = new HostVec();
-    if (!fj_build_tables(blobs, offsets, n_inst, h->tb, g_err)) { delete h; return -1; }
+    if (!fj_build_tables(blobs, offsets, n_inst, h->tb, g_err, variant)) { delete h; return -1; }
     h->variant = variant; h->sum_mode = sum_mode;
     h->env_inst.assign(env_instance, env_instance + n_envs);
     h->env.assign((size_t)n_envs * h->tb.eo.stride, 0);
@@ -129,7 +131,7 @@ int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst
     h->pend_count = 0;
     P.pend_count = &h->pend_count; P.pend_env = h->pend_env.data(); P.lp_x = h->lp_x.data(); P.lp_meta = h->lp_meta.data();
     P.B = n_envs; P.variant = variant; P.sum_mode = sum_mode;
-    P.nobs = (variant == FJSP_SO_DFJSP) ? 10 : 15;
+    P.nobs = (variant == FJSP_SO_DFJSP || variant == FJSP_SO_FJSSP) ? 10 : 15;
     *out = h;
     return 0;
 }

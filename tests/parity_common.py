@@ -12,7 +12,7 @@ from deep_reinforcement_learning_for_fjsp_b200.instance import FJSPInstance
 # observation-only sums use a warp tree instead of CPython's compensated sum, which moves
 # the last bits only, so the tests hold it to a far tighter bound.
 STATE_RTOL, STATE_ATOL = 1e-9, 1e-12
-NRULES = {"SO_DFJSP": (6, 5), "MO_DFJSP": (12, 10), "MO_DFJSP_breakdown": (12, 10)}
+NRULES = {"SO_DFJSP": (6, 5), "MO_DFJSP": (12, 10), "MO_DFJSP_breakdown": (12, 10), "SO_FJSSP": (6, 5)}
 
 
 def assert_states_close(got, want, what):

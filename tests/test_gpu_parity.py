@@ -8,7 +8,7 @@ import parity_common as pc
 from conftest import golden_cases
 
 pytestmark = pytest.mark.gpu
-DEVICE_CASES = [c for c in golden_cases() if "fjssp" not in c]
+DEVICE_CASES = golden_cases()
 
 
 def make_vec(blobs, env_instance, variant):
@@ -23,7 +23,7 @@ def test_golden_reference_trajectories(case, golden_dir):
 
 @pytest.mark.parametrize("variant,seed,rp,bd", [("SO_DFJSP", 11, 1, False), ("MO_DFJSP", 12, 0, False),
                                                  ("MO_DFJSP", 13, 1, False), ("MO_DFJSP", 14, 3, False),
-                                                 ("MO_DFJSP_breakdown", 15, 2, True)])
+                                                 ("MO_DFJSP_breakdown", 15, 2, True), ("SO_FJSSP", 16, 1, False)])
 def test_random_batch_vs_oracle(variant, seed, rp, bd):
     pc.compare_with_oracle(make_vec, variant, seed, n_inst=8, copies=8, T=64, launches=4, reward_policy=rp,
                            breakdowns=bd)

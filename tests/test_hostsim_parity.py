@@ -13,7 +13,7 @@ import build as hostsim  # noqa: E402
 import parity_common as pc  # noqa: E402
 from conftest import golden_cases  # noqa: E402
 
-DEVICE_CASES = [c for c in golden_cases() if "fjssp" not in c]
+DEVICE_CASES = golden_cases()
 
 
 def make_vec(blobs, env_instance, variant):
@@ -26,7 +26,7 @@ def test_golden(case, golden_dir):
 
 
 @pytest.mark.parametrize("variant,seed,rp,bd", [("SO_DFJSP", 1, 1, False), ("MO_DFJSP", 2, 0, False),
-                                                 ("MO_DFJSP", 3, 3, False), ("MO_DFJSP_breakdown", 4, 2, True)])
+                                                 ("MO_DFJSP", 3, 3, False), ("MO_DFJSP_breakdown", 4, 2, True), ("SO_FJSSP", 5, 1, False)])
 def test_random_batch_vs_oracle(variant, seed, rp, bd):
     pc.compare_with_oracle(make_vec, variant, seed, n_inst=4, copies=2, T=40, launches=3, reward_policy=rp,
                            breakdowns=bd)
