@@ -139,5 +139,14 @@ def main():
               FJSPInstance.from_csv(os.path.join(ref_data, "HMPSAC"), "DDT1.0_M10_S3", "MO"), 23, max_steps=250)
 
 
+def brandimarte_blobs():
+    """tests/golden/brandimarte_blobs.npz: instance blobs of the reference's Mk01-Mk10 csv
+    directories (data/benchmark/Brandimarte_Data), for the replicated-copies tests."""
+    base = os.path.join(ref_loader.REFERENCE_ROOT, "data", "benchmark", "Brandimarte_Data")
+    out = {"Mk%02d" % k: FJSPInstance.from_csv(base, "Mk%02d" % k, "SO").to_blob() for k in range(1, 11)}
+    np.savez_compressed(os.path.join(GOLDEN, "brandimarte_blobs.npz"), **out)
+
+
 if __name__ == "__main__":
     main()
+    brandimarte_blobs()

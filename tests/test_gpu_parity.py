@@ -127,3 +127,71 @@ def test_single_env_drop_in_episode():
         pc.assert_states_close(s, so, f"step {n}")
         n += 1
     assert env.delay_time_sum == ora.info()["delay_sum"]
+
+
+def _brandimarte(golden_dir):
+    import os
+    z = np.load(os.path.join(golden_dir, "brandimarte_blobs.npz"))
+    return [z["Mk%02d" % k] for k in range(1, 11)]
+
+
+def test_brandimarte_replicated_copies(golden_dir):
+    """BASELINE configs[3] shape: Brandimarte mk01-mk10 replicated (here 10 x 2048 copies, the
+    DA3C environment class SO_DFJSP): replicas fed the same rules stay bit-identical through
+    several episodes with auto-reset, and every instance agrees with the oracle."""
+    import torch
+    import oracle_py
+    blobs = _brandimarte(golden_dir)
+    copies, T, launches = 2048, 64, 3
+    env_instance = np.repeat(np.arange(10), copies)
+    B = len(env_instance)
+    vec = make_vec(blobs, env_instance, "SO_DFJSP")
+    envs = [oracle_py.OracleEnv(b, "SO_DFJSP") for b in blobs]
+    s0 = vec.reset().cpu().numpy().reshape(10, copies, -1)
+    o0 = np.stack([e.reset() for e in envs])
+    pc.assert_states_close(s0[:, 0], o0, "reset")
+    assert np.array_equal(s0, np.broadcast_to(s0[:, :1], s0.shape))
+    rng = np.random.default_rng(4)
+    for L in range(launches):
+        act1 = np.stack([rng.integers(0, 6, (T, 10)), rng.integers(0, 5, (T, 10))], -1).astype(np.int32)
+        rnd1 = rng.integers(0, 2**32, (T, 10, 2), dtype=np.uint64).astype(np.uint32)
+        o = vec.rollout(torch.from_numpy(np.repeat(act1, copies, axis=1)).cuda(),
+                        torch.from_numpy(np.repeat(rnd1, copies, axis=1).view(np.int32)).cuda(), want_rec=True)
+        torch.cuda.synchronize()
+        rec = o["rec"].cpu().numpy().reshape(T, 10, copies, 8)
+        st = o["state"].cpu().numpy().reshape(T, 10, copies, -1)
+        assert (rec == rec[:, :, :1]).all(), "replicas diverged"
+        ref = oracle_py.batch_rollout(envs, act1, rnd1, 1)
+        assert np.array_equal(ref["rec"], rec[:, :, 0]), f"launch {L}"
+        assert np.array_equal(ref["done"], o["done"].cpu().numpy().reshape(T, 10, copies)[:, :, 0])
+        assert np.array_equal(ref["reward"], o["reward"].cpu().numpy().reshape(T, 10, copies)[:, :, 0])
+        pc.assert_states_close(st[:, :, 0], ref["state"], f"launch {L}")
+    info = vec.info()
+    assert (info["error"] == 0).all() and (info["episodes"] >= 1).any()
+
+
+def test_large_dynamic_instances():
+    """BASELINE configs[4] shape: 20 machines, five orders (about 200 inserted jobs), MO_DFJSP:
+    a batch of copies against the oracle, LP rows in the hundreds."""
+    from deep_reinforcement_learning_for_fjsp_b200.instance import FJSPInstance
+    import oracle_py
+    insts = []
+    for i in range(3):
+        inst = FJSPInstance.generate(900 + i, 1.0, 20, 5, "HMPSAC", scale=0.6)
+        inst.ddt = float(int(inst.ddt))
+        insts.append(inst)
+    blobs = [i.to_blob() for i in insts]
+    env_instance = np.repeat(np.arange(3), 16)
+    B, T = len(env_instance), 64
+    vec = make_vec(blobs, env_instance, "MO_DFJSP")
+    envs = [oracle_py.OracleEnv(blobs[k], "MO_DFJSP") for k in env_instance]
+    pc.assert_states_close(vec.reset_host(), np.stack([e.reset() for e in envs]), "reset")
+    rng = np.random.default_rng(8)
+    for L in range(3):
+        actions = np.stack([rng.integers(0, 12, (T, B)), rng.integers(0, 10, (T, B))], -1).astype(np.int32)
+        rnd = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
+        st, rw, dn, rec = vec.step_host(actions, rnd, 2)
+        ref = oracle_py.batch_rollout(envs, actions, rnd, 2)
+        assert np.array_equal(rec, ref["rec"]) and np.array_equal(rw, ref["reward"]) and np.array_equal(dn, ref["done"])
+        pc.assert_states_close(st, ref["state"], f"launch {L}")
+    assert (vec.info()["error"] == 0).all()

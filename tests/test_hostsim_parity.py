@@ -52,3 +52,24 @@ def test_table_builder_set_order_matches_cpython():
 def test_bad_blob_is_rejected():
     with pytest.raises(RuntimeError):
         hostsim.HostSimVec([np.zeros(32, np.int32)], [0], "SO_DFJSP")
+
+
+def test_brandimarte_instances(golden_dir):
+    """Mk01 / Mk06 / Mk10 of the reference's benchmark data (static, one job per kind, up to 240
+    operation types and 475 LP rows): one episode and a half with auto-reset against the oracle."""
+    import oracle_py
+    z = np.load(os.path.join(golden_dir, "brandimarte_blobs.npz"))
+    for name in ("Mk01", "Mk06", "Mk10"):
+        blob = z[name]
+        vec = make_vec([blob], [0], "SO_DFJSP")
+        env = oracle_py.OracleEnv(blob, "SO_DFJSP")
+        pc.assert_states_close(vec.reset_host()[0], env.reset(), "reset")
+        T = int(blob[4] * 3 // 2)
+        rng = np.random.default_rng(1)
+        actions = np.stack([rng.integers(0, 6, (T, 1)), rng.integers(0, 5, (T, 1))], -1).astype(np.int32)
+        rnd = rng.integers(0, 2**32, (T, 1, 2), dtype=np.uint64).astype(np.uint32)
+        st, rw, dn, rec = vec.step_host(actions, rnd, 1)
+        ref = oracle_py.batch_rollout([env], actions, rnd, 1)
+        assert np.array_equal(rec, ref["rec"]) and np.array_equal(rw, ref["reward"]) and np.array_equal(dn, ref["done"])
+        pc.assert_states_close(st, ref["state"], name)
+        assert dn.sum() >= 1
