@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
              f"reference itself needs CPLEX and runs ~20-200 steps/s, see BASELINE.md)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_sampled": B, "env_steps_per_step": T,
                        "machines": args.machines, "orders": args.orders},
@@ -302,7 +302,7 @@ def main():
         achieved = algo_bytes / launch_s / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64+int32", "data": "synthetic",
+                "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "envs_per_gpu": B, "env_steps_per_step": T,
                            "machines": args.machines, "orders": args.orders, "variant": args.variant,
                            "l2": "flushed between timed launches (256 MiB fill)", "kernels_per_step": "step kernel (in-CTA LP service) + empty LP/resume fallback launches", "parallelism": f"shard{world}",

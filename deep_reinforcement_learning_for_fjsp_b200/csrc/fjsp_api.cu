@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/fjsp_b200.h"
@@ -48,8 +49,11 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
     K.meta = lp_meta; K.req_env = req_env;
     K.group.rk = red_d; K.group.ri = red_i; K.group.ra = red_i + 32;
     for (int base = blockIdx.x * wpb; base < P.B; base += total) {
-        const int env = base + (threadIdx.x >> 5);
-        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env < P.B ? env : 0, env < P.B, stage);
+        // envs are visited in order of decreasing static walk length (P.order): the warps that
+        // share a CTA's phase barriers then carry similar work, and the longest start first
+        const int slot = base + (threadIdx.x >> 5);
+        const int env = slot < P.B ? P.order[slot] : 0;
+        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env, slot < P.B, stage);
     }
 }
 
@@ -118,7 +122,7 @@ struct fjsp_vec {
     int *d_pend_count, *d_pend_env, *d_lp_meta, *d_rep_env, *d_plan_meta, *d_plan_ok;
     double *d_lp_x, *d_plan_x;
     int n_inst, plan_ready;
-    int32_t *d_inst, *d_env_inst;
+    int32_t *d_inst, *d_env_inst, *d_order;
     unsigned char *d_env, *d_lp;
     long long launches;
     // staging for the host-buffer entry points
@@ -209,6 +213,19 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     const size_t env_bytes = (size_t)n_envs * v->tb.eo.stride;
     CK(cudaMalloc(&v->d_inst, v->tb.inst.size() * 4));
     CK(cudaMalloc(&v->d_env_inst, (size_t)n_envs * 4));
+    CK(cudaMalloc(&v->d_order, (size_t)n_envs * 4));
+    {
+        // static walk length of an env: jobs of its largest kind x warp rounds over its operation types
+        std::vector<long long> key(n_instances);
+        for (int i = 0; i < n_instances; ++i) {
+            const int32_t *b = blobs + blob_offsets[i];
+            key[i] = (long long)b[10] * ((b[4] + 31) / 32);
+        }
+        std::vector<int32_t> order(n_envs);
+        for (int e = 0; e < n_envs; ++e) order[e] = e;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[env_instance[x]] > key[env_instance[y]]; });
+        CK(cudaMemcpy(v->d_order, order.data(), (size_t)n_envs * 4, cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&v->d_env, env_bytes));
     CK(cudaMalloc(&v->d_lp, lp_bytes));
     CK(cudaMemcpy(v->d_inst, v->tb.inst.data(), v->tb.inst.size() * 4, cudaMemcpyHostToDevice));
@@ -239,6 +256,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaFuncSetAttribute(fjsp_lp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->lp_smem_bytes));
     FjParams &P = v->P;
     P.d = v->tb.d; P.io = v->tb.io; P.eo = v->tb.eo;
+    P.order = v->d_order;
     P.inst = v->d_inst; P.env_inst = v->d_env_inst; P.env = v->d_env; P.lp = v->d_lp; P.lp_stride = lp_stride;
     P.B = n_envs; P.variant = variant; P.sum_mode = v->sum_mode; P.nobs = v->nstate / 2;
     P.pend_count = v->d_pend_count; P.pend_env = v->d_pend_env; P.lp_x = v->d_lp_x; P.lp_meta = v->d_lp_meta;
@@ -280,6 +298,7 @@ int fjsp_vec_destroy(fjsp_vec *v)
     if (!v) return 0;
     cudaSetDevice(v->device);
     free_stage(v);
+    cudaFree(v->d_order);
     cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
     cudaFree(v->d_rep_env); cudaFree(v->d_plan_x); cudaFree(v->d_plan_meta); cudaFree(v->d_plan_ok);

@@ -112,6 +112,7 @@ struct FjParams {
     FjEnvOff eo;
     const int32_t *inst;        // instance table
     const int32_t *env_inst;    // [B] instance index of each env
+    const int32_t *order;       // [B] envs by decreasing static walk length (main kernel's visiting order)
     unsigned char *env;         // env table
     unsigned char *lp;          // LP scratch, one slab per resident warp
     unsigned long long lp_stride;
