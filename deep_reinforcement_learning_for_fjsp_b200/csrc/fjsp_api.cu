@@ -265,9 +265,9 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     // hot part of the env records staged in shared memory for the whole launch when four
     // warps' worth fits with at least two CTAs per SM
     // the main kernel stages the hot prefix of its warps' records in shared memory when the
-    // CTA's slabs leave room for four CTAs per SM
+    // slabs of all CTAs resident on an SM fit
     v->stage_bytes = (size_t)(FJ_STEP_THREADS / 32) * v->tb.eo.hot;
-    P.stage = v->stage_bytes <= 56 * 1024 ? 1 : 0;
+    P.stage = v->stage_bytes * (1024 / FJ_STEP_THREADS) <= 200 * 1024 ? 1 : 0;
     if (getenv("FJSP_NO_STAGE")) P.stage = 0;
     P.cta_lp = getenv("FJSP_NO_CTA_LP") ? 0 : 1;   // 0: park order arrivals for the LP / resume kernels
     if (!P.stage) v->stage_bytes = 0;
