@@ -26,7 +26,7 @@ static thread_local std::string g_err;
 
 // main step kernel: every env; parks an env on the first fluid LP it needs
 #ifndef FJ_STEP_THREADS
-#define FJ_STEP_THREADS 256      // 8 warps in lockstep phases, four CTAs per SM at 64 registers
+#define FJ_STEP_THREADS 512      // 16 warps in lockstep phases, two CTAs per SM at 64 registers (measured best of 128..1024)
 #endif
 #ifndef FJ_STEP_MIN_BLOCKS
 #define FJ_STEP_MIN_BLOCKS (1024 / FJ_STEP_THREADS)
