@@ -40,13 +40,15 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
     __shared__ double red_d[32];
     const int wpb = blockDim.x >> 5;
     const int total = gridDim.x * wpb;
-    unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.eo.hot : nullptr;
+    unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.stage_stride : nullptr;
     FjCtaCtx K;
     K.warp = threadIdx.x >> 5; K.nwarps = wpb; K.cta_lp = P.cta_lp;
     K.stage_base = P.stage ? stage_smem : nullptr;
     K.slab = P.lp + (size_t)blockIdx.x * P.lp_stride;
     K.x = (double *)(K.slab + (size_t)P.d.Rx * P.d.Rx * 8 + (fj_lp_small_bytes(P.d) + 7) / 8 * 8);
     K.meta = lp_meta; K.req_env = req_env;
+    K.lp_smem_bytes = P.cta_lp_smem;
+    K.lp_smem = P.cta_lp_smem ? stage_smem + (size_t)(P.stage ? wpb * P.stage_stride : 0) : nullptr;
     K.group.rk = red_d; K.group.ri = red_i; K.group.ra = red_i + 32;
     for (int base = blockIdx.x * wpb; base < P.B; base += total) {
         // envs are visited in order of decreasing static walk length (P.order): the warps that
@@ -118,7 +120,7 @@ struct fjsp_vec {
     FjTables tb;
     FjParams P;
     int variant, sum_mode, B, device, grid, step_grid, resume_grid, lp_grid, lp_smem_binv, nstate;
-    size_t lp_smem_bytes, stage_bytes;
+    size_t lp_smem_bytes, stage_bytes, step_smem_bytes;
     int *d_pend_count, *d_pend_env, *d_lp_meta, *d_rep_env, *d_plan_meta, *d_plan_ok;
     double *d_lp_x, *d_plan_x;
     int n_inst, plan_ready;
@@ -266,14 +268,31 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     // warps' worth fits with at least two CTAs per SM
     // the main kernel stages the hot prefix of its warps' records in shared memory when the
     // slabs of all CTAs resident on an SM fit
-    v->stage_bytes = (size_t)(FJ_STEP_THREADS / 32) * v->tb.eo.hot;
+    P.stage_stride = v->tb.eo.hot + v->tb.io.hotw * 4;
+    v->stage_bytes = (size_t)(FJ_STEP_THREADS / 32) * P.stage_stride;
     P.stage = v->stage_bytes * (1024 / FJ_STEP_THREADS) <= 200 * 1024 ? 1 : 0;
     if (getenv("FJSP_NO_STAGE")) P.stage = 0;
-    P.cta_lp = getenv("FJSP_NO_CTA_LP") ? 0 : 1;   // 0: park order arrivals for the LP / resume kernels
+    if (!getenv("FJSP_INST_STAGE")) {   // staging the instance head as well measured slightly slower (less L1): opt-in
+        v->tb.io.hotw = 0; P.io.hotw = 0;
+        P.stage_stride = v->tb.eo.hot;
+        v->stage_bytes = (size_t)(FJ_STEP_THREADS / 32) * P.stage_stride;
+    }
     if (!P.stage) v->stage_bytes = 0;
+    P.cta_lp = getenv("FJSP_NO_CTA_LP") ? 0 : 1;   // 0: park order arrivals for the LP / resume kernels
+    {   // shared-memory scratch for the in-CTA LP: what is left of the SM's 200 KB per resident CTA
+        const size_t per_cta = (size_t)200 * 1024 / (1024 / FJ_STEP_THREADS);
+        size_t left = per_cta > v->stage_bytes + 1024 ? per_cta - v->stage_bytes - 1024 : 0;
+        const size_t want_lp = ((size_t)v->tb.d.Rx * v->tb.d.Rx * 8 + fj_lp_small_bytes_host(v->tb.d) + 15) / 16 * 16;
+        if (left > want_lp) left = want_lp;
+        left = left / 16 * 16;
+        // measured (profiles/README.md): the extra shared memory costs more L1 than the faster pivots win,
+        // so the shared-memory LP scratch is opt-in
+        P.cta_lp_smem = (P.cta_lp && getenv("FJSP_LP_SMEM") && left >= 8 * 1024) ? (int)left : 0;
+        v->step_smem_bytes = v->stage_bytes + (size_t)P.cta_lp_smem;
+    }
     if (dispatch(v, [&](auto V, auto SM) {
             cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->stage_bytes);
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->step_smem_bytes);
             return 0;
         })) return -2;
     CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
@@ -356,7 +375,7 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     int rc = dispatch(v, [&](auto V, auto SM) {
         constexpr int VV = decltype(V)::value, MM = decltype(SM)::value;
         A.park_count = v->d_pend_count; A.park_env = v->d_pend_env;
-        fjsp_step_kernel<VV, MM><<<v->step_grid, FJ_STEP_THREADS, v->stage_bytes, st>>>(v->P, A);
+        fjsp_step_kernel<VV, MM><<<v->step_grid, FJ_STEP_THREADS, v->step_smem_bytes, st>>>(v->P, A);
         // resume rounds: an env can meet a reset and further order arrivals inside one launch; the
         // last round solves whatever is left in line
         for (int r = 0; r < FJ_ROUNDS; ++r) {

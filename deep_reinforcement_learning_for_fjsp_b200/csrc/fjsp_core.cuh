@@ -136,7 +136,8 @@ template <int MODE> FJ_FN double fj_pysum_result(const FjPySum &s)
 // ---------------------------------------------------------------- per-env context
 struct FjCtx {
     const FjParams *P;
-    const int32_t *I;
+    const int32_t *I, *IH;   // instance record in HBM; staged copy of its hot words (or null)
+    int ihotw;
     int inst;
     int M, K, KT, S, Mx, Kx, Sx;
     unsigned mmask;
@@ -152,6 +153,8 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     c.P = &P;
     c.inst = P.env_inst[env];
     c.I = P.inst + (size_t)c.inst * P.io.stride;
+    c.IH = hot ? (const int32_t *)(hot + P.eo.hot) : c.I;
+    c.ihotw = hot ? P.io.hotw : 0;
     const int32_t *h = c.I + P.io.hdr;
     c.M = h[0]; c.K = h[1]; c.KT = h[2]; c.S = h[3];
     c.Mx = P.d.Mx; c.Kx = P.d.Kx; c.Sx = P.d.Sx;
@@ -176,22 +179,31 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     c.lp = lp;
 }
 
-// read-only instance table: loads go through the non-coherent path (L1-cached, never
-// invalidated by the env-state stores)
+// read-only instance table.  Cold arrays are loaded through the non-coherent path
+// (ld.global.nc: L1-cached, never invalidated by the env-state stores); the small arrays every
+// step touches (the record's first io.hotw words) are read from the warp's shared-memory copy
+// when the main kernel staged one.
 struct FjRO {
     const int32_t *p;
+    int plain;
     FJ_MFN int operator[](int i) const
     {
 #ifdef FJ_DEVICE_CODE
-        return __ldg(p + i);
+        return plain ? p[i] : __ldg(p + i);
 #else
         return p[i];
 #endif
     }
-    FJ_MFN FjRO operator+(int o) const { FjRO r; r.p = p + o; return r; }
+    FJ_MFN FjRO operator+(int o) const { FjRO r; r.p = p + o; r.plain = plain; return r; }
 };
-FJ_FN FjRO fj_ro(const int32_t *p) { FjRO r; r.p = p; return r; }
-#define FJ_I(c, field) (fj_ro((c).I + (c).P->io.field))
+FJ_FN FjRO fj_ro(const int32_t *p) { FjRO r; r.p = p; r.plain = 0; return r; }
+FJ_FN FjRO fj_ro_field(const FjCtx &c, int off)
+{
+    FjRO r;
+    if (off < c.ihotw) { r.p = c.IH + off; r.plain = 1; } else { r.p = c.I + off; r.plain = 0; }
+    return r;
+}
+#define FJ_I(c, field) (fj_ro_field((c), (c).P->io.field))
 FJ_FN long long fj_get_ll(const int32_t *scal, int i) { return *(const long long *)(scal + i); }
 FJ_FN void fj_set_ll(int32_t *scal, int i, long long v) { *(long long *)(scal + i) = v; }
 FJ_FN double fj_get_d(const int32_t *scal, int i) { return *(const double *)(scal + i); }
@@ -327,6 +339,29 @@ FJ_FN void fj_lp_carve(FjLp &L, unsigned char *binv, unsigned char *small_, cons
     L.colq = q; q += C;
     L.colm = q; q += C;
     L.prec = q; q += d.KTx;
+}
+
+// the same carving with the dimensions of ONE LP (R rows at most, C columns): used when the
+// scratch lives in a CTA's shared memory.  Returns the bytes of the small arrays.
+FJ_FN size_t fj_lp_carve_dims(FjLp &L, unsigned char *binv, unsigned char *small_, size_t R, size_t C, size_t KT)
+{
+    L.Binv = (double *)binv;
+    double *p = (double *)small_;
+    L.xB = p; p += R;
+    L.w = p; p += R;
+    L.adem = p; p += C;
+    L.rate = p; p += C;
+    int *q = (int *)p;
+    L.basis = q; q += R;
+    L.pos = q; q += C + R;
+    L.colq = q; q += C;
+    L.colm = q; q += C;
+    L.prec = q; q += KT;
+    return (size_t)((unsigned char *)q - small_);
+}
+FJ_FN size_t fj_lp_dims_bytes(size_t R, size_t C, size_t KT)
+{
+    return R * R * 8 + (2 * R + 2 * C) * 8 + (R + (C + R) + 2 * C + KT) * 4;
 }
 
 // sum_k (negate ? -brow[row_k] : brow[row_k]) * val_k of column j in ascending row order
@@ -1438,7 +1473,10 @@ template <int VARIANT, int SUM_MODE, int SUSPEND>
 FJ_FN void fj_env_rollout(const FjParams &P, const FjStepArgs &A, int env, unsigned char *lp, unsigned char *stage = nullptr)
 {
     unsigned char *G = P.env + (size_t)env * P.eo.stride;
-    if (stage) fj_stage_copy(stage, G, P.eo.hot);
+    if (stage) {
+        fj_stage_copy(stage, G, P.eo.hot);
+        fj_stage_copy(stage + P.eo.hot, (const unsigned char *)(P.inst + (size_t)P.env_inst[env] * P.io.stride), P.io.hotw * 4);
+    }
     fj_env_rollout_body<VARIANT, SUM_MODE, SUSPEND>(P, A, env, lp, stage);
     if (stage) fj_stage_copy(G, stage, P.eo.hot);
 }
@@ -1556,7 +1594,9 @@ FJ_FN void fj_emit_state(const FjCtx &c, const FjStepArgs &A, size_t i, int nobs
 struct FjCtaCtx {
     int warp, nwarps, cta_lp;
     unsigned char *stage_base;   // shared-memory staging slabs of the CTA's warps, or null
-    unsigned char *slab;         // LP scratch: Binv, small arrays
+    unsigned char *slab;         // LP scratch in HBM: Binv, small arrays
+    unsigned char *lp_smem;      // LP scratch in shared memory (used when an LP fits), or null
+    int lp_smem_bytes;
     double *x;                   // LP solution
     int *meta;                   // iterations, return code
     int *req_env;                // [nwarps] env each warp wants an LP for, -1 none
@@ -1579,7 +1619,10 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
     FjCtx c;
     unsigned char *G = P.env + (size_t)env * P.eo.stride;
     if (active) {
-        if (stage) fj_stage_copy(stage, G, P.eo.hot);
+        if (stage) {
+            fj_stage_copy(stage, G, P.eo.hot);
+            fj_stage_copy(stage + P.eo.hot, (const unsigned char *)(P.inst + (size_t)P.env_inst[env] * P.io.stride), P.io.hotw * 4);
+        }
         fj_ctx_init(c, P, env, nullptr, stage);
     }
     const int nobs = P.nobs;
@@ -1590,7 +1633,9 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
         FjStepOut out;
         out.reward = 0.0; out.done = 0;
         int stage = 0;      // 0 nothing, 1 dispatched (run the clock), 2 nothing dispatchable (emit unchanged)
+#ifndef FJ_ONE_BARRIER
         FJ_CTA_SYNC();      // ---- phase A: auto-reset / task_select / machine_select / dispatch
+#endif
         if (!parked) {
             if (c.scal[FJ_S_DONE]) {
                 if (!A.autoreset) {   // a finished env without auto-reset repeats its terminal output
@@ -1638,9 +1683,14 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
                     if (e2 < 0) continue;    // uniform over the CTA
                     {
                         FjCtx c2;
-                        fj_ctx_init(c2, P, e2, nullptr, K.stage_base ? K.stage_base + (size_t)w * P.eo.hot : nullptr);
+                        fj_ctx_init(c2, P, e2, nullptr, K.stage_base ? K.stage_base + (size_t)w * P.stage_stride : nullptr);
                         FjLp L;
-                        fj_lp_carve(L, K.slab, K.slab + (size_t)P.d.Rx * P.d.Rx * 8, P.d);
+                        // scratch in the CTA's shared memory when this LP fits, else on its HBM slab
+                        const size_t Rub = (size_t)(c2.M + 2 * c2.KT - c2.K), Cn = (size_t)FJ_I(c2, hdr)[7] + 1;
+                        if (K.lp_smem && fj_lp_dims_bytes(Rub, Cn, (size_t)c2.KT) <= (size_t)K.lp_smem_bytes)
+                            fj_lp_carve_dims(L, K.lp_smem, K.lp_smem + Rub * Rub * 8, Rub, Cn, (size_t)c2.KT);
+                        else
+                            fj_lp_carve(L, K.slab, K.slab + (size_t)P.d.Rx * P.d.Rx * 8, P.d);
                         int iters = 0;
                         const int rc = fj_lp_solve(K.group, c2, L, K.x, &iters);
                         if (K.group.rank() == 0) { K.meta[0] = iters; K.meta[1] = rc; }
@@ -1654,7 +1704,7 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
                 }
             }
         }
-        FJ_CTA_SYNC();      // ---- phase C: observation, reward, outputs
+        // ---- phase C: observation, reward, outputs (the vote above was the phase barrier)
         if (stage == 1) fj_step_back<VARIANT, SUM_MODE>(c, done, A.reward_policy, A.completion, A.tardiness, A.energy, out);
         else if (stage == 2) {
             out.done = c.scal[FJ_S_DONE];

@@ -105,6 +105,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     // instance offsets (words)
     FjInstOff io;
     int o = 0;
+    // hot head: small arrays every step reads (staged in shared memory by the main kernel)
     io.hdr = o; o += 8;
     io.ntask = o; o += d.Kx;
     io.first = o; o += d.Kx;
@@ -114,20 +115,23 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     io.rjlast = o; o += d.KTx;
     io.elig = o; o += d.KTx;
     io.nelig = o; o += d.KTx;
-    io.mtset = o; o += d.KTx * d.Mx;
-    io.poord = o; o += d.KTx * d.Mx;
-    io.ptime = o; o += d.KTx * d.Mx;
-    io.energy = o; o += d.KTx * d.Mx;
+    io.colbase = o; o += d.KTx;
+    io.mnkt = o; o += d.Mx;
     io.idlep = o; o += d.Mx;
     io.arrive = o; o += d.Sx;
     io.due = o; o += d.Sx;
     io.count = o; o += d.Sx * d.Kx;
     io.cum = o; o += (d.Sx + 1) * d.Kx;
+    o = fj_align(o, 4);
+    io.hotw = o;
+    // per-pair tables and breakdown lists: read through ld.global.nc
+    io.mtset = o; o += d.KTx * d.Mx;
+    io.poord = o; o += d.KTx * d.Mx;
+    io.ptime = o; o += d.KTx * d.Mx;
+    io.energy = o; o += d.KTx * d.Mx;
     io.bdptr = o; o += d.Mx + 1;
     io.bds = o; o += d.NBDx;
     io.bde = o; o += d.NBDx;
-    io.colbase = o; o += d.KTx;
-    io.mnkt = o; o += d.Mx;
     io.stride = fj_align(o, 4);
     t.io = io;
     // env offsets (bytes)

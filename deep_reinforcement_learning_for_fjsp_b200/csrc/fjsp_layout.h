@@ -50,6 +50,7 @@ struct FjInstOff {
     int bde;       // [NBDx]
     int mnkt;      // [Mx] operation types a machine can process (len(kind_task_tuple))
     int colbase;   // [KTx] first LP column of an operation type (prefix of popcount(elig))
+    int hotw;      // words of the record's hot head (everything a step reads except the per-pair tables)
     int stride;    // words per instance
 };
 
@@ -124,6 +125,8 @@ struct FjParams {
     const double *plan_x;       // [n_instances][NPx] cached order-0 LP solution per instance
     const int *plan_meta;       // [n_instances][2]
     const int *plan_ok;         // [n_instances] 1 once cached (null before the first reset)
+    int stage_stride;           // bytes of one warp's shared-memory slab (env hot prefix + instance hot words)
+    int cta_lp_smem;            // bytes of shared-memory LP scratch per CTA of the main kernel (0: none)
     int cta_lp;                 // 1: the main kernel's CTAs solve order-arrival LPs themselves
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory
     int B, variant, sum_mode, nobs;
