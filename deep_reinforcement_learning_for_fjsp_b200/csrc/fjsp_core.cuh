@@ -544,6 +544,12 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
     for (int i = lane; i < KT * Mx; i += FJ_NL) { c.pk[i] = 0; c.slot[i] = 0xFFFF; }
     FJ_NOUNROLL
     for (int m = lane; m < c.M; m += FJ_NL) { c.mD[m] = 0; c.mF[m] = 0.0; }
+    if (lane == 0) {
+        int add = 0;
+        FJ_NOUNROLL
+        for (int r = 0; r < c.K; ++r) add += count[s * Kx + r];
+        c.scal[FJ_S_LEFT] += add;
+    }
     if (c.P->variant == FJSP_SO_FJSSP) {
         // class_FJSSP.py:214-218: every job has its own due date
         //   r_due = round(delivery * len(tasks) / count);  due(n) = round(r_due * n / count)
@@ -816,10 +822,7 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
     const double cro_std = sqrt(fj_div(fj_sum_d(v_fr), (double)KT));
     const double gap_std = sqrt(fj_div(fj_sum_d(v_gr), (double)KT));
     // machines: completion-time spread; MO also the mean / spread of the machines' gap_ave
-    long long tsum_m = 0;
-    FJ_NOUNROLL
-    for (int m = lane; m < M; m += FJ_NL) tsum_m += c.mend[m];
-    tsum_m = fj_sum_ll(tsum_m);
+    const long long tsum_m = fj_get_ll(c.scal, FJ_S_MENDSUM);
     const double ct_ave = fj_div((double)tsum_m, (double)M);
     double v_ct = 0.0;
     FJ_NOUNROLL
@@ -849,14 +852,17 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
         for (int m = lane; m < M; m += FJ_NL) { const double dv = fj_sub(c.gapave[m], gm_ave); v_gm = fj_add(v_gm, fj_mul(dv, dv)); }
         gm_std = sqrt(fj_div(fj_sum_d(v_gm), (double)M));
     }
+    if (lane < 4 || FJ_NL == 1) {   // the four delay rates, one division per lane
+        FJ_NOUNROLL
+        for (int k = (FJ_NL == 1 ? 0 : lane); k < 4; k += (FJ_NL == 1 ? 1 : 4)) {
+            const long long num = k == 0 ? da : k == 1 ? de : k == 2 ? ja : je;
+            const long long den = k < 2 ? tn : jn;
+            c.obs2[(MO ? 11 : 6) + k] = rates_zero ? 0.0 : fj_div((double)num, (double)den);
+        }
+    }
     if (lane == 0) {
         fj_set_ll(c.scal, FJ_S_DELAY_UNPROC, dunp);
         c.scal[FJ_S_NAV] = nav; c.scal[FJ_S_NFAV] = nfav;
-        double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
-        if (!rates_zero) {
-            r0 = fj_div((double)da, (double)tn); r1 = fj_div((double)de, (double)tn);
-            r2 = fj_div((double)ja, (double)jn); r3 = fj_div((double)je, (double)jn);
-        }
         double *o = c.obs2;
         if (MO) {
             uint64_t bits = (uint32_t)FJ_I(c, hdr)[5] | ((uint64_t)(uint32_t)FJ_I(c, hdr)[6] << 32);
@@ -864,10 +870,8 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
             o[0] = ddt; o[1] = (double)M; o[2] = (double)S; o[3] = ct_std;
             o[4] = fj_div((double)nfav, fj_add((double)nav, 1e-08));
             o[5] = cro_ave; o[6] = cro_std; o[7] = gap_ave; o[8] = gap_std; o[9] = gm_ave; o[10] = gm_std;
-            o[11] = r0; o[12] = r1; o[13] = r2; o[14] = r3;
         } else {
             o[0] = (double)M; o[1] = ct_std; o[2] = cro_ave; o[3] = cro_std; o[4] = gap_ave; o[5] = gap_std;
-            o[6] = r0; o[7] = r1; o[8] = r2; o[9] = r3;
         }
     }
     fj_sync();
@@ -1200,6 +1204,7 @@ FJ_FN void fj_reset_begin(FjCtx &c, int fresh)
     fj_sync();
     if (lane == 0) {
         c.scal[FJ_S_NEXTORDER] = 1; c.scal[FJ_S_TIME] = 0; c.scal[FJ_S_STEPS] = 0; c.scal[FJ_S_HASTASK] = 0;
+        c.scal[FJ_S_LEFT] = 0; fj_set_ll(c.scal, FJ_S_MENDSUM, 0);
         c.scal[FJ_S_COMPLETION] = 0; c.scal[FJ_S_COMPLETION_LAST] = 0; c.scal[FJ_S_WASDONE] = was_done;
         fj_set_ll(c.scal, FJ_S_ENERGY, 0); fj_set_ll(c.scal, FJ_S_ENERGY_LAST, 0);
         fj_set_ll(c.scal, FJ_S_DELAY_PROC, 0); fj_set_ll(c.scal, FJ_S_DELAY_LAST, 0);
@@ -1291,6 +1296,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
         const int prev_last = c.mlast[m];
         const unsigned bit = 1u << m;
         const int had = ((unsigned)c.scal[FJ_S_HASTASK] & bit) != 0;
+        fj_set_ll(c.scal, FJ_S_MENDSUM, fj_get_ll(c.scal, FJ_S_MENDSUM) + m_end - c.mend[m]);
         c.mend[m] = m_end; c.mlast[m] = t_end; c.mjob[m] = (q << 16) | n;
         c.scal[FJ_S_BUSY] = (int)((unsigned)c.scal[FJ_S_BUSY] | bit);
         c.scal[FJ_S_HASTASK] = (int)((unsigned)c.scal[FJ_S_HASTASK] | bit);
@@ -1306,6 +1312,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
         }
         if (VARIANT == FJSP_SO_FJSSP) c.unpmask[q * c.P->d.NWx + (n >> 5)] &= ~(1u << (n & 31));
         if (rjlast[q]) {
+            c.scal[FJ_S_LEFT] -= 1;
             long long late = (long long)t_end - (VARIANT == FJSP_SO_FJSSP ? c.duejob[jobbase[r] + n] : due[s]);
             if (late > 0) fj_set_ll(c.scal, FJ_S_DELAY_PROC, fj_get_ll(c.scal, FJ_S_DELAY_PROC) + late);
         }
@@ -1344,10 +1351,13 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
             tmin = fj_min_i(tmin);
             if (tmin == 0x7fffffff) { if (lane == 0) c.scal[FJ_S_ERROR] |= FJ_E_NO_EVENT; break; }
             t = tmin;
-            if (lane == 0) {   // machines release their jobs in ascending machine order
-                FJ_NOUNROLL
-                for (int i = 0; i < M; ++i) {
-                    if (c.mend[i] != t || c.mjob[i] < 0) continue;
+            unsigned rel = 0;   // machines that complete now and hold a job
+            FJ_NOUNROLL
+            for (int i = lane; i < M; i += FJ_NL) if (c.mend[i] == t && c.mjob[i] >= 0) rel |= 1u << i;
+            rel = fj_or_u(rel);
+            if (lane == 0) {   // they release their jobs in ascending machine order
+                while (rel) {
+                    const int i = fj_ffs0(rel); rel &= rel - 1;
                     const int jq = c.mjob[i] >> 16, n = c.mjob[i] & 0xffff;
                     if (rjlast[jq]) continue;
                     const int q2 = jq + 1, r = rjkind[jq];
@@ -1360,11 +1370,7 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
                 }
             }
             fj_sync();
-            left = 0;
-            FJ_NOUNROLL
-            for (int x = lane; x < KT; x += FJ_NL)
-                if (rjlast[x]) for (int s = 0; s < S; ++s) left += c.cntunp[x * Sx + s];
-            left = fj_sum_ll(left);
+            left = c.scal[FJ_S_LEFT];   // maintained at dispatch / arrival
             norder = c.scal[FJ_S_NEXTORDER];
             arr_time = c.scal[FJ_S_ARRTIME];
             fj_sync();

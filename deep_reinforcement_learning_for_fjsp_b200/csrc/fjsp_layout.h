@@ -56,7 +56,7 @@ struct FjInstOff {
 
 // env record: BYTE offsets
 struct FjEnvOff {
-    int scal;      // int32[32] scalars, see FJ_S_* below
+    int scal;      // int32[FJ_S_COUNT] scalars, see FJ_S_* below
     int obs;       // double[16] v(t)
     int obs2;      // double[16] staging for v(t+1)
     int gapave;    // double[Mx] cached machine gap_ave
@@ -101,7 +101,9 @@ enum {
     FJ_S_LPSOLVES = 11, FJ_S_LPITERS = 12, FJ_S_NFL = 13, FJ_S_PHASE = 14, FJ_S_LPSLOT = 15,
     // 64-bit values occupy two slots (even index)
     FJ_S_ENERGY = 16, FJ_S_ENERGY_LAST = 18, FJ_S_DELAY_PROC = 20, FJ_S_DELAY_LAST = 22, FJ_S_DELAY_UNPROC = 24,
-    FJ_S_GAPTIME = 26 /* double */, FJ_S_TT = 28, FJ_S_WASDONE = 29, FJ_S_NAV = 30, FJ_S_NFAV = 31, FJ_S_COUNT = 32
+    FJ_S_GAPTIME = 26 /* double */, FJ_S_TT = 28, FJ_S_WASDONE = 29, FJ_S_NAV = 30, FJ_S_NFAV = 31,
+    FJ_S_LEFT = 32 /* unprocessed last-stage operations = jobs not fully dispatched */,
+    FJ_S_MENDSUM = 34 /* int64: sum of the machines' completion times */, FJ_S_COUNT = 40
 };
 
 // error flags (FJ_S_ERROR), same meaning as the oracle's
