@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_finish_kernel(FjParams P,
 struct fjsp_vec {
     FjTables tb;
     FjParams P;
-    int variant, sum_mode, B, device, grid, step_grid, resume_grid, lp_grid, lp_smem_binv, nstate;
+    int variant, sum_mode, B, device, grid, step_grid, step_threads, resume_grid, lp_grid, lp_smem_binv, nstate;
     size_t lp_smem_bytes, stage_bytes, step_smem_bytes;
     int *d_pend_count, *d_pend_env, *d_lp_meta, *d_rep_env, *d_plan_meta, *d_plan_ok;
     double *d_lp_x, *d_plan_x;
@@ -193,8 +193,15 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (getenv("FJSP_GRID_PER_SM")) cap = prop.multiProcessorCount * atoi(getenv("FJSP_GRID_PER_SM"));
     v->grid = want < cap ? want : cap;
     {
-        const int wpb = FJ_STEP_THREADS / 32;
-        int w2 = (n_envs + wpb - 1) / wpb, c2 = prop.multiProcessorCount * (1024 / FJ_STEP_THREADS);
+        // CTA size at run time: two CTAs per SM; a batch smaller than the resident capacity is
+        // spread evenly (4096 envs on 148 SMs -> 296 CTAs of 14 warps instead of 256 of 16)
+        const int slots = prop.multiProcessorCount * (1024 / FJ_STEP_THREADS);
+        int wpb = (n_envs + slots - 1) / slots;
+        if (wpb > FJ_STEP_THREADS / 32) wpb = FJ_STEP_THREADS / 32;
+        if (wpb < 4) wpb = 4;
+        if (getenv("FJSP_STEP_WARPS")) wpb = atoi(getenv("FJSP_STEP_WARPS"));
+        v->step_threads = wpb * 32;
+        int w2 = (n_envs + wpb - 1) / wpb, c2 = slots;
         v->step_grid = w2 < c2 ? w2 : c2;
     }
     const unsigned long long lp_stride = fj_lp_scratch_bytes(v->tb.d);
@@ -269,13 +276,13 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     // the main kernel stages the hot prefix of its warps' records in shared memory when the
     // slabs of all CTAs resident on an SM fit
     P.stage_stride = v->tb.eo.hot + v->tb.io.hotw * 4;
-    v->stage_bytes = (size_t)(FJ_STEP_THREADS / 32) * P.stage_stride;
+    v->stage_bytes = (size_t)(v->step_threads / 32) * P.stage_stride;
     P.stage = v->stage_bytes * (1024 / FJ_STEP_THREADS) <= 200 * 1024 ? 1 : 0;
     if (getenv("FJSP_NO_STAGE")) P.stage = 0;
     if (!getenv("FJSP_INST_STAGE")) {   // staging the instance head as well measured slightly slower (less L1): opt-in
         v->tb.io.hotw = 0; P.io.hotw = 0;
         P.stage_stride = v->tb.eo.hot;
-        v->stage_bytes = (size_t)(FJ_STEP_THREADS / 32) * P.stage_stride;
+        v->stage_bytes = (size_t)(v->step_threads / 32) * P.stage_stride;
     }
     if (!P.stage) v->stage_bytes = 0;
     P.cta_lp = getenv("FJSP_NO_CTA_LP") ? 0 : 1;   // 0: park order arrivals for the LP / resume kernels
@@ -330,7 +337,7 @@ int fjsp_vec_query(fjsp_vec *v, int64_t *o)
 {
     if (!v || !o) { g_err = "fjsp_vec_query: null argument"; return -1; }
     o[0] = v->B; o[1] = v->nstate; o[2] = v->tb.eo.stride; o[3] = (int64_t)v->tb.io.stride * 4;
-    o[4] = v->step_grid; o[5] = FJ_STEP_THREADS; o[6] = (int64_t)v->P.lp_stride; o[7] = v->launches;
+    o[4] = v->step_grid; o[5] = v->step_threads; o[6] = (int64_t)v->P.lp_stride; o[7] = v->launches;
     return 0;
 }
 
@@ -375,7 +382,7 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     int rc = dispatch(v, [&](auto V, auto SM) {
         constexpr int VV = decltype(V)::value, MM = decltype(SM)::value;
         A.park_count = v->d_pend_count; A.park_env = v->d_pend_env;
-        fjsp_step_kernel<VV, MM><<<v->step_grid, FJ_STEP_THREADS, v->step_smem_bytes, st>>>(v->P, A);
+        fjsp_step_kernel<VV, MM><<<v->step_grid, v->step_threads, v->step_smem_bytes, st>>>(v->P, A);
         // resume rounds: an env can meet a reset and further order arrivals inside one launch; the
         // last round solves whatever is left in line
         for (int r = 0; r < FJ_ROUNDS; ++r) {

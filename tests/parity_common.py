@@ -107,3 +107,53 @@ def schedule_is_feasible(rec, dn, ntask_of_env):
             if dn[t, b]:
                 mach_free, job_end, job_stage = {}, {}, {}
     return True
+
+
+def edge_case_instances():
+    """Smallest and widest shapes the blob format allows in practice."""
+    one = FJSPInstance(machine_count=1, ntask=[3], machine_rj={(0, 0): (0,), (0, 1): (0,), (0, 2): (0,)},
+                       time_rjm={(0, 0): {0: 5}, (0, 1): {0: 7}, (0, 2): {0: 3}}, arrive=[0], due=[9], count=[(1,)],
+                       ddt=1.0, power_rjm={(0, 0): {0: 10}, (0, 1): {0: 20}, (0, 2): {0: 30}}, idle_power=[2],
+                       breakdowns={0: [(6, 8)]}, name="one_machine_one_job")
+    wide = FJSPInstance.generate(77, 1.0, 32, 2, "DA3C", scale=0.08)       # 32 machines: every mask bit used
+    wide.ddt = 1.0
+    late = FJSPInstance.generate(78, 0.5, 3, 4, "HMPSAC", scale=0.3)       # few machines, four orders, tight due dates
+    late.ddt = 0.0
+    return [one, wide, late]
+
+
+def check_edge_cases(make_vec, variant):
+    """Tiny / wide / overloaded instances in ONE batch, run past the end of their episodes twice:
+    first with auto-reset (against the oracle), then without (a finished copy must repeat
+    done=1, reward 0, an empty record and its terminal observation with zero differences)."""
+    insts = edge_case_instances()
+    blobs = [i.to_blob() for i in insts]
+    env_instance = np.array([0, 1, 2, 0, 2], np.int32)       # 5 copies: not a multiple of anything
+    B = len(env_instance)
+    nt, nm = NRULES[variant]
+    vec = make_vec(blobs, env_instance, variant)
+    envs = [oracle_py.OracleEnv(blobs[k], variant) for k in env_instance]
+    assert_states_close(vec.reset_host(), np.stack([e.reset() for e in envs]), "reset")
+    rng = np.random.default_rng(5)
+    T = 40
+    for L in range(3):
+        actions = np.stack([rng.integers(0, nt, (T, B)), rng.integers(0, nm, (T, B))], -1).astype(np.int32)
+        rnd = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
+        st, rw, dn, rec = vec.step_host(actions, rnd, 1, 1.0, 1.0, 1.0, True)
+        ref = oracle_py.batch_rollout(envs, actions, rnd, 1)
+        assert np.array_equal(rec, ref["rec"]) and np.array_equal(rw, ref["reward"]) and np.array_equal(dn, ref["done"])
+        assert_states_close(st, ref["state"], f"edge launch {L}")
+    assert dn.sum() + 1 > 0 and (vec.info()["episodes"][[0, 3]] >= 1).all()     # the 3-operation job finished many times
+    # without auto-reset
+    vec2 = make_vec(blobs, env_instance, variant)
+    vec2.reset_host()
+    T2 = 12
+    actions = np.zeros((T2, B, 2), np.int32)
+    st, rw, dn, rec = vec2.step_host(actions, None, 1, 1.0, 1.0, 1.0, False)
+    for b in (0, 3):                       # the one-job instance is done after its 3 operations
+        assert list(dn[:, b]) == [0, 0, 1] + [1] * (T2 - 3)
+        assert (rw[3:, b] == 0).all() and (rec[3:, b] == -1).all()
+        n = st.shape[-1] // 2
+        assert np.array_equal(st[3:, b, :n], np.broadcast_to(st[2, b, :n], (T2 - 3, n)))
+        assert (st[3:, b, n:] == 0).all()
+    assert (vec2.info()["error"] == 0).all()

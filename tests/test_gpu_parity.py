@@ -195,3 +195,9 @@ def test_large_dynamic_instances():
         assert np.array_equal(rec, ref["rec"]) and np.array_equal(rw, ref["reward"]) and np.array_equal(dn, ref["done"])
         pc.assert_states_close(st, ref["state"], f"launch {L}")
     assert (vec.info()["error"] == 0).all()
+
+
+@pytest.mark.parametrize("variant", ["SO_DFJSP", "MO_DFJSP", "MO_DFJSP_breakdown", "SO_FJSSP"])
+def test_edge_cases(variant):
+    """one machine / one job, 32 machines, overloaded shop; 5 copies; with and without auto-reset"""
+    pc.check_edge_cases(make_vec, variant)

@@ -73,3 +73,8 @@ def test_brandimarte_instances(golden_dir):
         assert np.array_equal(rec, ref["rec"]) and np.array_equal(rw, ref["reward"]) and np.array_equal(dn, ref["done"])
         pc.assert_states_close(st, ref["state"], name)
         assert dn.sum() >= 1
+
+
+@pytest.mark.parametrize("variant", ["SO_DFJSP", "MO_DFJSP", "MO_DFJSP_breakdown", "SO_FJSSP"])
+def test_edge_cases(variant):
+    pc.check_edge_cases(make_vec, variant)
