@@ -128,7 +128,8 @@ struct fjsp_vec {
     unsigned char *d_env, *d_lp;
     long long launches;
     // staging for the host-buffer entry points
-    cudaStream_t stream;
+    cudaStream_t stream, copy_stream;
+    cudaEvent_t chunk_done;
     int stage_T;
     int32_t *d_actions, *d_done, *d_rec;
     uint32_t *d_rnd;
@@ -303,6 +304,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
             return 0;
         })) return -2;
     CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&v->chunk_done, cudaEventDisableTiming));
     v->stage_T = 0;
     v->d_actions = v->d_done = v->d_rec = nullptr; v->d_rnd = nullptr;
     v->d_state64 = v->d_reward = nullptr; v->d_state32 = nullptr;
@@ -328,7 +331,7 @@ int fjsp_vec_destroy(fjsp_vec *v)
     cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
     cudaFree(v->d_rep_env); cudaFree(v->d_plan_x); cudaFree(v->d_plan_meta); cudaFree(v->d_plan_ok);
-    cudaStreamDestroy(v->stream);
+    cudaStreamDestroy(v->stream); cudaStreamDestroy(v->copy_stream); cudaEventDestroy(v->chunk_done);
     delete v;
     return 0;
 }
@@ -425,19 +428,33 @@ int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint3
     int rc = ensure_stage(v, T);
     if (rc) return rc;
     const size_t n = (size_t)T * v->B;
-    cudaStream_t st = v->stream;
+    cudaStream_t st = v->stream, cp = v->copy_stream;
     CK(cudaMemcpyAsync(v->d_actions, h_actions, n * 2 * 4, cudaMemcpyHostToDevice, st));
     if (h_rnd) CK(cudaMemcpyAsync(v->d_rnd, h_rnd, n * 2 * 4, cudaMemcpyHostToDevice, st));
-    rc = fjsp_vec_step(v, st, T, v->d_actions, h_rnd ? v->d_rnd : nullptr, reward_policy, completion, tardiness,
-                       energy, autoreset, h_state64 ? v->d_state64 : nullptr, h_state32 ? v->d_state32 : nullptr,
-                       h_reward ? v->d_reward : nullptr, h_done ? v->d_done : nullptr, h_rec ? v->d_rec : nullptr);
-    if (rc) return rc;
-    if (h_state64) CK(cudaMemcpyAsync(h_state64, v->d_state64, n * v->nstate * 8, cudaMemcpyDeviceToHost, st));
-    if (h_state32) CK(cudaMemcpyAsync(h_state32, v->d_state32, n * v->nstate * 4, cudaMemcpyDeviceToHost, st));
-    if (h_reward) CK(cudaMemcpyAsync(h_reward, v->d_reward, n * 8, cudaMemcpyDeviceToHost, st));
-    if (h_done) CK(cudaMemcpyAsync(h_done, v->d_done, n * 4, cudaMemcpyDeviceToHost, st));
-    if (h_rec) CK(cudaMemcpyAsync(h_rec, v->d_rec, n * 8 * 4, cudaMemcpyDeviceToHost, st));
+    // long rollouts are cut into chunks of 32 steps: the device-to-host copy of one chunk's
+    // outputs (copy stream) overlaps the kernels of the next chunk (compute stream).  Shorter
+    // chunks measured slower (per-launch staging and launch overheads), so T < 64 is one chunk.
+    const int nchunk = T >= 64 ? T / 32 : 1;
+    const size_t B = (size_t)v->B, ns = (size_t)v->nstate;
+    for (int c = 0; c < nchunk; ++c) {
+        const int t0 = (int)((long long)T * c / nchunk), t1 = (int)((long long)T * (c + 1) / nchunk);
+        if (t1 == t0) continue;
+        const size_t o = (size_t)t0 * B, m = (size_t)(t1 - t0) * B;
+        rc = fjsp_vec_step(v, st, t1 - t0, v->d_actions + o * 2, h_rnd ? v->d_rnd + o * 2 : nullptr, reward_policy,
+                           completion, tardiness, energy, autoreset, h_state64 ? v->d_state64 + o * ns : nullptr,
+                           h_state32 ? v->d_state32 + o * ns : nullptr, h_reward ? v->d_reward + o : nullptr,
+                           h_done ? v->d_done + o : nullptr, h_rec ? v->d_rec + o * 8 : nullptr);
+        if (rc) return rc;
+        CK(cudaEventRecord(v->chunk_done, st));
+        CK(cudaStreamWaitEvent(cp, v->chunk_done, 0));
+        if (h_state64) CK(cudaMemcpyAsync(h_state64 + o * ns, v->d_state64 + o * ns, m * ns * 8, cudaMemcpyDeviceToHost, cp));
+        if (h_state32) CK(cudaMemcpyAsync(h_state32 + o * ns, v->d_state32 + o * ns, m * ns * 4, cudaMemcpyDeviceToHost, cp));
+        if (h_reward) CK(cudaMemcpyAsync(h_reward + o, v->d_reward + o, m * 8, cudaMemcpyDeviceToHost, cp));
+        if (h_done) CK(cudaMemcpyAsync(h_done + o, v->d_done + o, m * 4, cudaMemcpyDeviceToHost, cp));
+        if (h_rec) CK(cudaMemcpyAsync(h_rec + o * 8, v->d_rec + o * 8, m * 8 * 4, cudaMemcpyDeviceToHost, cp));
+    }
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(cp));
     return 0;
 }
 

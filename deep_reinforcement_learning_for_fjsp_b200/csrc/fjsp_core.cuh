@@ -32,6 +32,7 @@
 #define FJ_FN_NOINLINE __device__ __noinline__
 #define FJ_OUTLINE __device__ __noinline__
 #define FJ_NOUNROLL _Pragma("unroll 1")
+#define FJ_UNROLL4 _Pragma("unroll 4")
 #define FJ_NL 32
 FJ_FN int fj_lane() { return threadIdx.x & 31; }
 FJ_FN void fj_sync() { __syncwarp(); }
@@ -53,6 +54,7 @@ FJ_FN_NOINLINE double fj_div(double a, double b) { return __ddiv_rn(a, b); }
 #define FJ_FN_NOINLINE static
 #define FJ_OUTLINE static
 #define FJ_NOUNROLL
+#define FJ_UNROLL4
 #define FJ_NL 1
 FJ_FN int fj_lane() { return 0; }
 FJ_FN void fj_sync() {}
@@ -759,6 +761,7 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
                 const double dd = (double)d;
                 if (t > d) { a_cnt += cnt; late_sum += (long long)cnt * (t - d); }
                 double ve = 0.0;
+                FJ_UNROLL4
                 for (int i = 0; i < cnt; ++i) {
                     kd += 1.0;
                     const double est = fj_add(td, fj_mul(f, kd));
