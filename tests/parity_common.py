@@ -59,14 +59,14 @@ def random_batch(seed, variant, n_inst, copies, profile_mix=True, breakdowns=Fal
 
 
 def compare_with_oracle(make_vec, variant, seed, n_inst=6, copies=3, T=48, launches=4, reward_policy=1,
-                        breakdowns=False):
+                        breakdowns=False, sum_mode=1):
     """Random rule actions on a mixed batch with auto-reset; every output of every step must
     agree with the oracle stepping the same instances one by one."""
     insts, env_instance = random_batch(seed, variant, n_inst, copies, breakdowns=breakdowns)
     blobs = [i.to_blob() for i in insts]
     B = len(env_instance)
-    vec = make_vec(blobs, env_instance, variant)
-    envs = [oracle_py.OracleEnv(blobs[k], variant) for k in env_instance]
+    vec = make_vec(blobs, env_instance, variant) if sum_mode == 1 else make_vec(blobs, env_instance, variant, sum_mode)
+    envs = [oracle_py.OracleEnv(blobs[k], variant, sum_mode) for k in env_instance]
     s0 = vec.reset_host()
     o0 = np.stack([e.reset() for e in envs])
     assert_states_close(s0, o0, "reset")

@@ -11,9 +11,9 @@ pytestmark = pytest.mark.gpu
 DEVICE_CASES = golden_cases()
 
 
-def make_vec(blobs, env_instance, variant):
+def make_vec(blobs, env_instance, variant, sum_mode=1):
     from deep_reinforcement_learning_for_fjsp_b200.vec_env import FJSPVecEnv
-    return FJSPVecEnv(None, env_instance, variant, blobs=blobs)
+    return FJSPVecEnv(None, env_instance, variant, blobs=blobs, sum_mode=sum_mode)
 
 
 @pytest.mark.parametrize("case", DEVICE_CASES)
@@ -201,3 +201,7 @@ def test_large_dynamic_instances():
 def test_edge_cases(variant):
     """one machine / one job, 32 machines, overloaded shop; 5 copies; with and without auto-reset"""
     pc.check_edge_cases(make_vec, variant)
+
+
+def test_left_to_right_sum_mode_vs_oracle():
+    pc.compare_with_oracle(make_vec, "SO_DFJSP", 19, n_inst=4, copies=4, T=48, launches=2, sum_mode=0)

@@ -16,8 +16,8 @@ from conftest import golden_cases  # noqa: E402
 DEVICE_CASES = golden_cases()
 
 
-def make_vec(blobs, env_instance, variant):
-    return hostsim.HostSimVec(blobs, env_instance, variant)
+def make_vec(blobs, env_instance, variant, sum_mode=1):
+    return hostsim.HostSimVec(blobs, env_instance, variant, sum_mode)
 
 
 @pytest.mark.parametrize("case", DEVICE_CASES)
@@ -78,3 +78,9 @@ def test_brandimarte_instances(golden_dir):
 @pytest.mark.parametrize("variant", ["SO_DFJSP", "MO_DFJSP", "MO_DFJSP_breakdown", "SO_FJSSP"])
 def test_edge_cases(variant):
     pc.check_edge_cases(make_vec, variant)
+
+
+def test_left_to_right_sum_mode_vs_oracle():
+    """sum_mode 0 (CPython <= 3.11 builtin sum) is a separate template instantiation: it must
+    agree with the oracle run in the same mode."""
+    pc.compare_with_oracle(make_vec, "MO_DFJSP", 9, n_inst=3, copies=2, T=40, launches=2, sum_mode=0)
