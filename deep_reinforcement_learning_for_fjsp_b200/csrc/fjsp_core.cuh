@@ -752,6 +752,14 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
                 }
                 c.mindue[q] = mind;
             } else {
+            // No loop over the operations here.  Inside an order the estimate
+            //   g(k) = fl(t + fl(f * k))  is monotone in the position k, so the count of
+            // estimated-late operations is a suffix found by bisection on the exactly rounded
+            // g, and the order's largest estimated delay is its last term.  The one quantity
+            // that needs every term, the compensated SUM behind the delivery urgency, is a key
+            // of task rules 1, 2 and 4 only and is computed by fj_task_select when such a
+            // rule is actually played (the state is the same then).
+            int kpos = 0;
             FJ_NOUNROLL
             for (int s = 0; s < S; ++s) {
                 const int cnt = c.cntunp[q * Sx + s];
@@ -760,17 +768,23 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
                 const int d = due[s];
                 const double dd = (double)d;
                 if (t > d) { a_cnt += cnt; late_sum += (long long)cnt * (t - d); }
-                double ve = 0.0;
-                FJ_UNROLL4
-                for (int i = 0; i < cnt; ++i) {
-                    kd += 1.0;
-                    const double est = fj_add(td, fj_mul(f, kd));
-                    ve = fj_sub(est, dd);
-                    e_cnt += est > dd;
-                    fj_neumaier<SUM_MODE>(sf, sc, ve);
+                int lo = kpos + 1, hi = kpos + cnt;
+                const double ghi = fj_add(td, fj_mul(f, (double)hi));
+                if (ghi > dd) {
+                    if (fj_add(td, fj_mul(f, (double)lo)) > dd) e_cnt += cnt;
+                    else {   // g(lo) <= dd < g(hi): smallest late position by bisection
+                        FJ_NOUNROLL
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (fj_add(td, fj_mul(f, (double)mid)) > dd) hi = mid; else lo = mid;
+                        }
+                        e_cnt += kpos + cnt - hi + 1;
+                    }
                 }
+                const double ve = fj_sub(ghi, dd);
                 if (first || ve > max_e) max_e = ve;
                 first = false;
+                kpos += cnt;
             }
             }
             p0 += ((long long)residue << 32) + a_cnt;
@@ -782,8 +796,10 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
             s_fr = fj_add(s_fr, fj_div((double)pr, (double)(residue + pr)));
             s_gr = fj_add(s_gr, fj_div(gap, (double)c.fstart[q]));
             if (av) {
-                if (SUM_MODE != 0 && sc != 0.0 && isfinite(sc)) sf = fj_add(sf, sc);
-                c.urg[q] = fj_div(sf, (double)residue);
+                if (VARIANT == FJSP_SO_FJSSP) {
+                    if (SUM_MODE != 0 && sc != 0.0 && isfinite(sc)) sf = fj_add(sf, sc);
+                    c.urg[q] = fj_div(sf, (double)residue);
+                }
                 c.maxe[q] = max_e;
                 dle = e_cnt > 0; dla = a_cnt > 0;
             }
@@ -900,9 +916,35 @@ FJ_FN int fj_mask_any(const uint32_t *mask, int words)
     return v != 0;
 }
 
+// kind_task_delivery_urgency of one operation type (SO_DFJSP.py:139-156): CPython's compensated
+// sum over every unprocessed operation's estimated delay, divided by their number.
+template <int SUM_MODE>
+FJ_FN double fj_urgency(const FjCtx &c, int q, double td)
+{
+    const int S = c.S, Sx = c.Sx;
+    const FjRO due = FJ_I(c, due);
+    const double f = c.tsum[q];
+    double kd = 0.0, sf = 0.0, sc = 0.0;
+    int residue = 0;
+    FJ_NOUNROLL
+    for (int s = 0; s < S; ++s) {
+        const int cnt = c.cntunp[q * Sx + s];
+        if (cnt == 0) continue;
+        residue += cnt;
+        const double dd = (double)due[s];
+        FJ_UNROLL4
+        for (int i = 0; i < cnt; ++i) {
+            kd += 1.0;
+            fj_neumaier<SUM_MODE>(sf, sc, fj_sub(fj_add(td, fj_mul(f, kd)), dd));
+        }
+    }
+    if (SUM_MODE != 0 && sc != 0.0 && isfinite(sc)) sf = fj_add(sf, sc);
+    return fj_div(sf, (double)residue);
+}
+
 // SO_DFJSP.py:270-301 / MO_DFJSP.py:300-352.  Warp-cooperative: lanes own operation types,
 // one argmax/argmin reduction (lowest index on ties = Python's first extremal element).
-template <int VARIANT>
+template <int VARIANT, int SUM_MODE>
 FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
 {
     const int lane = fj_lane();
@@ -946,7 +988,7 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
     for (int q = lane; q < KT; q += FJ_NL) {
         if (!(set[q >> 5] >> (q & 31) & 1u)) continue;
         double k;
-        if (key == 0) k = c.urg[q];
+        if (key == 0) k = (VARIANT == FJSP_SO_FJSSP) ? c.urg[q] : fj_urgency<SUM_MODE>(c, q, (double)t);
         else if (key == 1) k = c.maxe[q];
         else if (key == 2 && VARIANT == FJSP_SO_FJSSP) k = (double)((long long)t - c.mindue[q]);
         else if (key == 4 && VARIANT == FJSP_SO_FJSSP) {   // min due date over the waiting jobs
@@ -1260,7 +1302,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
     const int t = c.scal[FJ_S_TIME];
     // ---- task_select / machine_select on the keys the previous observation left
     const int trule = task_rule0 + 1, mrule = mach_rule0 + 1;
-    int q = fj_task_select<VARIANT>(c, trule, rnd_task), m = -1;
+    int q = fj_task_select<VARIANT, SUM_MODE>(c, trule, rnd_task), m = -1;
     if (q >= 0) m = fj_machine_select<VARIANT, SUM_MODE>(c, mrule, q, rnd_mach);
     q = fj_bcast_i(q, 0); m = fj_bcast_i(m, 0);
     if (q < 0 || m < 0) {
