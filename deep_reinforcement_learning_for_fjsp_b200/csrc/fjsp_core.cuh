@@ -147,6 +147,7 @@ struct FjCtx {
     int32_t *mend, *mlast, *mjob, *mD; double *mF; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
     double *rsum, *tsum; uint16_t *cntunp, *cntnow, *pk, *slot; double *fu, *fa, *ff; uint16_t *next;
     uint32_t *unpmask; int32_t *duejob, *mindue;   // SO_FJSSP only (per-job due dates)
+    uint32_t *h_elig; uint16_t *h_rjinfo; int32_t *h_due;   // hot copies of instance statics
     unsigned char *lp;
 };
 
@@ -168,6 +169,7 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     c.gapave = (double *)(E + o.gapave); c.urg = (double *)(G + o.urg); c.maxe = (double *)(G + o.maxe);
     c.avmask = (uint32_t *)(E + o.avmask); c.favmask = (uint32_t *)(E + o.favmask);
     c.demask = (uint32_t *)(E + o.demask); c.damask = (uint32_t *)(E + o.damask);
+    c.h_elig = (uint32_t *)(E + o.h_elig); c.h_rjinfo = (uint16_t *)(E + o.h_rjinfo); c.h_due = (int32_t *)(E + o.h_due);
     c.mF = (double *)(E + o.mF); c.mD = (int32_t *)(E + o.mD);
     c.mend = (int32_t *)(E + o.mend); c.mlast = (int32_t *)(E + o.mlast); c.mjob = (int32_t *)(E + o.mjob);
     c.qhead = (uint16_t *)(E + o.qhead); c.qtail = (uint16_t *)(E + o.qtail); c.qlen = (uint16_t *)(E + o.qlen);
@@ -206,6 +208,19 @@ FJ_FN FjRO fj_ro_field(const FjCtx &c, int off)
     return r;
 }
 #define FJ_I(c, field) (fj_ro_field((c), (c).P->io.field))
+// the per-operation-type statics every step reads (eligible-machine mask, kind / stage / last
+// flag) and the orders' due dates are copied into the env record's hot prefix at reset(), so
+// the main kernel reads them from shared memory
+struct FjEligRO { const uint32_t *p; FJ_MFN int operator[](int q) const { return (int)p[q]; } };
+struct FjLastRO { const uint16_t *p; FJ_MFN int operator[](int q) const { return p[q] & 1; } };
+struct FjKindRO { const uint16_t *p; FJ_MFN int operator[](int q) const { return p[q] >> 8; } };
+struct FjStageRO { const uint16_t *p; FJ_MFN int operator[](int q) const { return (p[q] >> 1) & 0x7f; } };
+struct FjDueRO { const int32_t *p; FJ_MFN int operator[](int s) const { return p[s]; } };
+FJ_FN FjEligRO fj_elig(const FjCtx &c) { FjEligRO r; r.p = c.h_elig; return r; }
+FJ_FN FjLastRO fj_rjlast(const FjCtx &c) { FjLastRO r; r.p = c.h_rjinfo; return r; }
+FJ_FN FjKindRO fj_rjkind(const FjCtx &c) { FjKindRO r; r.p = c.h_rjinfo; return r; }
+FJ_FN FjStageRO fj_rjstage(const FjCtx &c) { FjStageRO r; r.p = c.h_rjinfo; return r; }
+FJ_FN FjDueRO fj_due(const FjCtx &c) { FjDueRO r; r.p = c.h_due; return r; }
 FJ_FN long long fj_get_ll(const int32_t *scal, int i) { return *(const long long *)(scal + i); }
 FJ_FN void fj_set_ll(int32_t *scal, int i, long long v) { *(long long *)(scal + i) = v; }
 FJ_FN double fj_get_d(const int32_t *scal, int i) { return *(const double *)(scal + i); }
@@ -380,7 +395,7 @@ FJ_FN double fj_lp_colvec_dot(const FjCtx &c, const FjLp &L, const double *brow,
     acc = fj_add(acc, fj_mul(negate ? -b0 : b0, 1.0));
     double b1 = brow[M + q];
     acc = fj_add(acc, fj_mul(negate ? -b1 : b1, L.adem[j]));
-    int stage = FJ_I(c, rjstage)[q];
+    int stage = fj_rjstage(c)[q];
     if (stage > 0 && L.prec[q - 1] >= 0) { double b = brow[L.prec[q - 1]]; acc = fj_add(acc, fj_mul(negate ? -b : b, L.rate[j])); }
     if (L.prec[q] >= 0) { double b = brow[L.prec[q]]; acc = fj_add(acc, fj_mul(negate ? -b : b, -L.rate[j])); }
     return acc;
@@ -393,7 +408,9 @@ FJ_FN int fj_lp_solve(const G &g, FjCtx &c, FjLp &L, double *x_out, int *iters_o
 {
     const int tid = g.rank(), nt = g.size();
     const int M = c.M, KT = c.KT, Mx = c.Mx;
-    const FjRO elig = FJ_I(c, elig), ptime = FJ_I(c, ptime), rjlast = FJ_I(c, rjlast);
+    const FjRO ptime = FJ_I(c, ptime);
+    const FjEligRO elig = fj_elig(c);
+    const FjLastRO rjlast = fj_rjlast(c);
     const FjRO colbase = FJ_I(c, colbase);
     if (tid == 0) {   // precedence rows: sequential numbering
         int nprec = 0;
@@ -525,7 +542,9 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
 {
     const int lane = fj_lane();
     const int KT = c.KT, Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
-    const FjRO rjkind = FJ_I(c, rjkind), rjstage = FJ_I(c, rjstage), count = FJ_I(c, count);
+    const FjRO count = FJ_I(c, count);
+    const FjKindRO rjkind = fj_rjkind(c);
+    const FjStageRO rjstage = fj_rjstage(c);
     FJ_NOUNROLL
     for (int q = lane; q < KT; q += FJ_NL) {
         int cnt = count[s * Kx + rjkind[q]];
@@ -557,7 +576,8 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
         //   r_due = round(delivery * len(tasks) / count);  due(n) = round(r_due * n / count)
         // (Python round() of a float = round-half-even = rint), and the unprocessed sets are
         // kept per job because the due date now varies inside an order
-        const FjRO cum = FJ_I(c, cum), due = FJ_I(c, due), ntask = FJ_I(c, ntask), jobbase = FJ_I(c, jobbase);
+        const FjRO cum = FJ_I(c, cum), ntask = FJ_I(c, ntask), jobbase = FJ_I(c, jobbase);
+        const FjDueRO due = fj_due(c);
         const int NWx = c.P->d.NWx;
         FJ_NOUNROLL
         for (int q = lane; q < KT; q += FJ_NL) {
@@ -583,7 +603,8 @@ FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
 {
     const int lane = fj_lane();
     const int KT = c.KT, Mx = c.Mx;
-    const FjRO elig = FJ_I(c, elig), ptime = FJ_I(c, ptime), poord = FJ_I(c, poord), nelig = FJ_I(c, nelig);
+    const FjRO ptime = FJ_I(c, ptime), poord = FJ_I(c, poord), nelig = FJ_I(c, nelig);
+    const FjEligRO elig = fj_elig(c);
     const FjRO colbase = FJ_I(c, colbase);
     if (lane == 0) {
         c.scal[FJ_S_LPSOLVES] += 1; c.scal[FJ_S_LPITERS] += iters;
@@ -680,7 +701,7 @@ template <int SUM_MODE, int EXACT>
 FJ_OUTLINE double fj_machine_gap_ave(const FjCtx &c, int m, double gt)
 {
     const int KT = c.KT;
-    const FjRO elig = FJ_I(c, elig);
+    const FjEligRO elig = fj_elig(c);
     double f = 0.0, cc = 0.0;
     int n = 0;
     FJ_NOUNROLL
@@ -700,7 +721,9 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
     const int lane = fj_lane();
     const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
     const int M = c.M, KT = c.KT, S = c.S, Sx = c.Sx;
-    const FjRO elig = FJ_I(c, elig), due = FJ_I(c, due), rjlast = FJ_I(c, rjlast);
+    const FjEligRO elig = fj_elig(c);
+    const FjDueRO due = fj_due(c);
+    const FjLastRO rjlast = fj_rjlast(c);
     const int t = c.scal[FJ_S_TIME];
     const double td = (double)t;
     const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
@@ -729,7 +752,7 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
             if (VARIANT == FJSP_SO_FJSSP) {
                 // per-job due dates: walk the set of unprocessed jobs in job-number order
                 const int NWx = c.P->d.NWx;
-                const int r = FJ_I(c, rjkind)[q], jb = FJ_I(c, jobbase)[r];
+                const int r = fj_rjkind(c)[q], jb = FJ_I(c, jobbase)[r];
                 const int arrived = FJ_I(c, cum)[c.scal[FJ_S_NEXTORDER] * c.Kx + r];
                 int mind = 0x7fffffff;
                 FJ_NOUNROLL
@@ -922,7 +945,7 @@ template <int SUM_MODE>
 FJ_FN double fj_urgency(const FjCtx &c, int q, double td)
 {
     const int S = c.S, Sx = c.Sx;
-    const FjRO due = FJ_I(c, due);
+    const FjDueRO due = fj_due(c);
     const double f = c.tsum[q];
     double kd = 0.0, sf = 0.0, sc = 0.0;
     int residue = 0;
@@ -978,7 +1001,8 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
         default: return -1;
         }
     }
-    const FjRO due = FJ_I(c, due), elig = FJ_I(c, elig);
+    const FjDueRO due = fj_due(c);
+    const FjEligRO elig = fj_elig(c);
     const int t = c.scal[FJ_S_TIME];
     const unsigned idle = ~(unsigned)c.scal[FJ_S_BUSY] & c.mmask;
     const double gt = fj_get_d(c.scal, FJ_S_GAPTIME);
@@ -992,9 +1016,9 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
         else if (key == 1) k = c.maxe[q];
         else if (key == 2 && VARIANT == FJSP_SO_FJSSP) k = (double)((long long)t - c.mindue[q]);
         else if (key == 4 && VARIANT == FJSP_SO_FJSSP) {   // min due date over the waiting jobs
-            const int r = FJ_I(c, rjkind)[q], jb = FJ_I(c, jobbase)[r];
+            const int r = fj_rjkind(c)[q], jb = FJ_I(c, jobbase)[r];
             int mind = 0x7fffffff, n;
-            if (FJ_I(c, rjstage)[q] == 0) {
+            if (fj_rjstage(c)[q] == 0) {
                 const int arrived = FJ_I(c, cum)[c.scal[FJ_S_NEXTORDER] * c.Kx + r];
                 FJ_NOUNROLL
                 for (n = arrived - c.qlen[q]; n < arrived; ++n) { const int d = c.duejob[jb + n]; mind = d < mind ? d : mind; }
@@ -1041,20 +1065,23 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
 // 64-bit register (one byte per slot).
 FJ_OUTLINE unsigned fj_small_set_order(unsigned seq, int n)   // seq: members, one byte each, insertion order
 {
-    unsigned long long slots = ~0ull;
+    if (n <= 1) return seq;
+    // slot of every member in the 8-slot table (probe i -> 5i+1; the perturbation is 0 for v < 32)
+    unsigned used = 0, slots = 0;   // slots: 4 bits per member
     FJ_NOUNROLL
     for (int e = 0; e < n; ++e) {
-        const unsigned v = (seq >> (8 * e)) & 0xffu;
-        unsigned i = v & 7u;
-        FJ_NOUNROLL
-        while (((slots >> (8 * i)) & 0xffull) != 0xffull) i = (i * 5u + 1u) & 7u;   // perturb is 0 for v < 32
-        slots = (slots & ~(0xffull << (8 * i))) | ((unsigned long long)v << (8 * i));
+        unsigned i = (seq >> (8 * e)) & 7u;
+        while (used >> i & 1u) i = (i * 5u + 1u) & 7u;
+        used |= 1u << i;
+        slots |= i << (4 * e);
     }
-    unsigned out = 0; int k = 0;
+    // iteration order = ascending slot: a member's rank is the number of members in lower slots
+    unsigned out = 0;
     FJ_NOUNROLL
-    for (int i = 0; i < 8; ++i) {
-        const unsigned bt = (unsigned)((slots >> (8 * i)) & 0xffull);
-        if (bt != 0xffu) out |= bt << (8 * k++);
+    for (int e = 0; e < n; ++e) {
+        const unsigned se = (slots >> (4 * e)) & 7u;
+        const int rank = fj_popc(used & ((1u << se) - 1u));
+        out |= ((seq >> (8 * e)) & 0xffu) << (8 * rank);
     }
     return out;
 }
@@ -1132,7 +1159,7 @@ FJ_FN int fj_machine_select(FjCtx &c, int rule, int q, uint32_t rnd)
         default: return -1;
         }
     }
-    const unsigned em = (unsigned)FJ_I(c, elig)[q], fm = c.flmask[q];
+    const unsigned em = (unsigned)fj_elig(c)[q], fm = c.flmask[q];
     const int ne = FJ_I(c, nelig)[q];
     if ((idle & em) == 0) return -1;
     FjCand cand;
@@ -1226,6 +1253,15 @@ FJ_FN void fj_reset_begin(FjCtx &c, int fresh)
     const int KT = c.KT, Sx = c.Sx, M = c.M;
     int was_done = 0;
     if (fresh) {
+        const FjRO ielig = FJ_I(c, elig), ikind = FJ_I(c, rjkind), istage = FJ_I(c, rjstage), ilast = FJ_I(c, rjlast);
+        const FjRO idue = FJ_I(c, due);
+        FJ_NOUNROLL
+        for (int q = lane; q < KT; q += FJ_NL) {
+            c.h_elig[q] = (uint32_t)ielig[q];
+            c.h_rjinfo[q] = (uint16_t)((ikind[q] << 8) | (istage[q] << 1) | (ilast[q] & 1));
+        }
+        FJ_NOUNROLL
+        for (int k = lane; k < c.S; k += FJ_NL) c.h_due[k] = idue[k];
         FJ_NOUNROLL
         for (int i = lane; i < FJ_S_COUNT; i += FJ_NL) c.scal[i] = 0;
         FJ_NOUNROLL
@@ -1297,8 +1333,11 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
     const int lane = fj_lane();
     const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
     const int Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
-    const FjRO rjkind = FJ_I(c, rjkind), rjstage = FJ_I(c, rjstage), rjlast = FJ_I(c, rjlast);
-    const FjRO due = FJ_I(c, due), cum = FJ_I(c, cum), jobbase = FJ_I(c, jobbase);
+    const FjKindRO rjkind = fj_rjkind(c);
+    const FjStageRO rjstage = fj_rjstage(c);
+    const FjLastRO rjlast = fj_rjlast(c);
+    const FjRO cum = FJ_I(c, cum), jobbase = FJ_I(c, jobbase);
+    const FjDueRO due = fj_due(c);
     const int t = c.scal[FJ_S_TIME];
     // ---- task_select / machine_select on the keys the previous observation left
     const int trule = task_rule0 + 1, mrule = mach_rule0 + 1;
@@ -1376,7 +1415,9 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
 {
     const int lane = fj_lane();
     const int M = c.M, KT = c.KT, S = c.S, Sx = c.Sx;
-    const FjRO rjkind = FJ_I(c, rjkind), rjlast = FJ_I(c, rjlast), elig = FJ_I(c, elig);
+    const FjKindRO rjkind = fj_rjkind(c);
+    const FjLastRO rjlast = fj_rjlast(c);
+    const FjEligRO elig = fj_elig(c);
     const FjRO arrive = FJ_I(c, arrive), jobbase = FJ_I(c, jobbase);
     int t = c.scal[FJ_S_TIME];
     done = 0;
@@ -1620,7 +1661,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
 // step per warp) being re-fetched from L2 by every warp: "no instruction" was the top
 // stall.  Every warp takes every barrier; a warp whose env is finished, parked on an LP or
 // past the batch end just skips the work in between.
-#ifdef FJ_DEVICE_CODE
+#if defined(FJ_DEVICE_CODE) && !defined(FJ_NO_LOCKSTEP)
 #define FJ_CTA_SYNC() __syncthreads()
 #else
 #define FJ_CTA_SYNC()

@@ -161,6 +161,10 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.qlen = b; b += 2 * d.KTx;
     eo.cntunp = b; b += 2 * d.KTx * d.Sx;
     eo.cntnow = b; b += 2 * d.KTx * d.Sx;
+    b = fj_align(b, 4);
+    eo.h_elig = b; b += 4 * d.KTx;
+    eo.h_due = b; b += 4 * d.Sx;
+    eo.h_rjinfo = b; b += 2 * d.KTx;
     b = fj_align(b, 16);
     eo.hot = b;
     // the rest stays in HBM/L2: rule keys of available types, per-pair counters, fluid slots, links
