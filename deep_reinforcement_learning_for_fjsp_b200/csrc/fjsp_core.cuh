@@ -147,7 +147,7 @@ struct FjCtx {
     int32_t *mend, *mlast, *mjob, *mD; double *mF; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
     double *rsum, *tsum; uint16_t *cntunp, *cntnow, *pk, *slot; double *fu, *fa, *ff; uint16_t *next;
     uint32_t *unpmask; int32_t *duejob, *mindue;   // SO_FJSSP only (per-job due dates)
-    uint32_t *h_elig; uint16_t *h_rjinfo; int32_t *h_due;   // hot copies of instance statics
+    uint32_t *h_elig; uint16_t *h_rjinfo; int32_t *h_due, *h_cum, *h_jobbase;   // hot copies of instance statics
     unsigned char *lp;
 };
 
@@ -170,6 +170,7 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     c.avmask = (uint32_t *)(E + o.avmask); c.favmask = (uint32_t *)(E + o.favmask);
     c.demask = (uint32_t *)(E + o.demask); c.damask = (uint32_t *)(E + o.damask);
     c.h_elig = (uint32_t *)(E + o.h_elig); c.h_rjinfo = (uint16_t *)(E + o.h_rjinfo); c.h_due = (int32_t *)(E + o.h_due);
+    c.h_cum = (int32_t *)(E + o.h_cum); c.h_jobbase = (int32_t *)(E + o.h_jobbase);
     c.mF = (double *)(E + o.mF); c.mD = (int32_t *)(E + o.mD);
     c.mend = (int32_t *)(E + o.mend); c.mlast = (int32_t *)(E + o.mlast); c.mjob = (int32_t *)(E + o.mjob);
     c.qhead = (uint16_t *)(E + o.qhead); c.qtail = (uint16_t *)(E + o.qtail); c.qlen = (uint16_t *)(E + o.qlen);
@@ -221,6 +222,8 @@ FJ_FN FjLastRO fj_rjlast(const FjCtx &c) { FjLastRO r; r.p = c.h_rjinfo; return 
 FJ_FN FjKindRO fj_rjkind(const FjCtx &c) { FjKindRO r; r.p = c.h_rjinfo; return r; }
 FJ_FN FjStageRO fj_rjstage(const FjCtx &c) { FjStageRO r; r.p = c.h_rjinfo; return r; }
 FJ_FN FjDueRO fj_due(const FjCtx &c) { FjDueRO r; r.p = c.h_due; return r; }
+FJ_FN FjDueRO fj_cum(const FjCtx &c) { FjDueRO r; r.p = c.h_cum; return r; }          // [(Sx+1)*Kx]
+FJ_FN FjDueRO fj_jobbase(const FjCtx &c) { FjDueRO r; r.p = c.h_jobbase; return r; }  // [Kx]
 FJ_FN long long fj_get_ll(const int32_t *scal, int i) { return *(const long long *)(scal + i); }
 FJ_FN void fj_set_ll(int32_t *scal, int i, long long v) { *(long long *)(scal + i) = v; }
 FJ_FN double fj_get_d(const int32_t *scal, int i) { return *(const double *)(scal + i); }
@@ -244,7 +247,7 @@ FJ_FN int fj_ffs0(unsigned v)   // index of lowest set bit, v != 0
 }
 FJ_OUTLINE int fj_order_of(const FjCtx &c, int r, int n)   // which order job n of kind r came with
 {
-    const FjRO cum = FJ_I(c, cum);
+    const FjDueRO cum = fj_cum(c);
     int s = 0;
     FJ_NOUNROLL
     while (s + 1 < c.S && n >= cum[(s + 1) * c.Kx + r]) ++s;
@@ -576,7 +579,8 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
         //   r_due = round(delivery * len(tasks) / count);  due(n) = round(r_due * n / count)
         // (Python round() of a float = round-half-even = rint), and the unprocessed sets are
         // kept per job because the due date now varies inside an order
-        const FjRO cum = FJ_I(c, cum), ntask = FJ_I(c, ntask), jobbase = FJ_I(c, jobbase);
+        const FjRO ntask = FJ_I(c, ntask);
+        const FjDueRO cum = fj_cum(c), jobbase = fj_jobbase(c);
         const FjDueRO due = fj_due(c);
         const int NWx = c.P->d.NWx;
         FJ_NOUNROLL
@@ -752,8 +756,8 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
             if (VARIANT == FJSP_SO_FJSSP) {
                 // per-job due dates: walk the set of unprocessed jobs in job-number order
                 const int NWx = c.P->d.NWx;
-                const int r = fj_rjkind(c)[q], jb = FJ_I(c, jobbase)[r];
-                const int arrived = FJ_I(c, cum)[c.scal[FJ_S_NEXTORDER] * c.Kx + r];
+                const int r = fj_rjkind(c)[q], jb = fj_jobbase(c)[r];
+                const int arrived = fj_cum(c)[c.scal[FJ_S_NEXTORDER] * c.Kx + r];
                 int mind = 0x7fffffff;
                 FJ_NOUNROLL
                 for (int w = 0; w * 32 < arrived; ++w) {
@@ -1016,10 +1020,10 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
         else if (key == 1) k = c.maxe[q];
         else if (key == 2 && VARIANT == FJSP_SO_FJSSP) k = (double)((long long)t - c.mindue[q]);
         else if (key == 4 && VARIANT == FJSP_SO_FJSSP) {   // min due date over the waiting jobs
-            const int r = fj_rjkind(c)[q], jb = FJ_I(c, jobbase)[r];
+            const int r = fj_rjkind(c)[q], jb = fj_jobbase(c)[r];
             int mind = 0x7fffffff, n;
             if (fj_rjstage(c)[q] == 0) {
-                const int arrived = FJ_I(c, cum)[c.scal[FJ_S_NEXTORDER] * c.Kx + r];
+                const int arrived = fj_cum(c)[c.scal[FJ_S_NEXTORDER] * c.Kx + r];
                 FJ_NOUNROLL
                 for (n = arrived - c.qlen[q]; n < arrived; ++n) { const int d = c.duejob[jb + n]; mind = d < mind ? d : mind; }
             } else {
@@ -1262,6 +1266,13 @@ FJ_FN void fj_reset_begin(FjCtx &c, int fresh)
         }
         FJ_NOUNROLL
         for (int k = lane; k < c.S; k += FJ_NL) c.h_due[k] = idue[k];
+        {
+            const FjRO icum = FJ_I(c, cum), ijb = FJ_I(c, jobbase);
+            FJ_NOUNROLL
+            for (int k = lane; k < (c.Sx + 1) * c.Kx; k += FJ_NL) c.h_cum[k] = icum[k];
+            FJ_NOUNROLL
+            for (int k = lane; k < c.K; k += FJ_NL) c.h_jobbase[k] = ijb[k];
+        }
         FJ_NOUNROLL
         for (int i = lane; i < FJ_S_COUNT; i += FJ_NL) c.scal[i] = 0;
         FJ_NOUNROLL
@@ -1336,7 +1347,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
     const FjKindRO rjkind = fj_rjkind(c);
     const FjStageRO rjstage = fj_rjstage(c);
     const FjLastRO rjlast = fj_rjlast(c);
-    const FjRO cum = FJ_I(c, cum), jobbase = FJ_I(c, jobbase);
+    const FjDueRO cum = fj_cum(c), jobbase = fj_jobbase(c);
     const FjDueRO due = fj_due(c);
     const int t = c.scal[FJ_S_TIME];
     // ---- task_select / machine_select on the keys the previous observation left
@@ -1418,7 +1429,8 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
     const FjKindRO rjkind = fj_rjkind(c);
     const FjLastRO rjlast = fj_rjlast(c);
     const FjEligRO elig = fj_elig(c);
-    const FjRO arrive = FJ_I(c, arrive), jobbase = FJ_I(c, jobbase);
+    const FjRO arrive = FJ_I(c, arrive);
+    const FjDueRO jobbase = fj_jobbase(c);
     int t = c.scal[FJ_S_TIME];
     done = 0;
     FJ_NOUNROLL

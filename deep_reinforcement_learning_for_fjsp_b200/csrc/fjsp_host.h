@@ -164,6 +164,8 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     b = fj_align(b, 4);
     eo.h_elig = b; b += 4 * d.KTx;
     eo.h_due = b; b += 4 * d.Sx;
+    eo.h_cum = b; b += 4 * (d.Sx + 1) * d.Kx;
+    eo.h_jobbase = b; b += 4 * d.Kx;
     eo.h_rjinfo = b; b += 2 * d.KTx;
     b = fj_align(b, 16);
     eo.hot = b;

@@ -71,6 +71,8 @@ struct FjEnvOff {
     int h_elig;    // uint32[KTx] copy of the instance's eligible-machine masks
     int h_rjinfo;  // uint16[KTx] kind << 8 | stage << 1 | last-stage flag
     int h_due;     // int32[Sx]   copy of the orders' due dates
+    int h_cum;     // int32[(Sx+1)*Kx] copy of the cumulative job counts (job number -> order)
+    int h_jobbase; // int32[Kx]
     int mF;        // double[Mx] sum of the machine's fluid rates since the last arrival
     int mD;        // int32[Mx] dispatches on the machine since the last arrival
     int mjob;      // int32[Mx] (rj << 16 | job number) of the job on the machine, -1 none
