@@ -827,7 +827,7 @@ FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
                     if (SUM_MODE != 0 && sc != 0.0 && isfinite(sc)) sf = fj_add(sf, sc);
                     c.urg[q] = fj_div(sf, (double)residue);
                 }
-                c.maxe[q] = max_e;
+                if (VARIANT == FJSP_SO_FJSSP) c.maxe[q] = max_e;   // the D-FJSP classes recompute it on demand
                 dle = e_cnt > 0; dla = a_cnt > 0;
             }
         }
@@ -969,6 +969,26 @@ FJ_FN double fj_urgency(const FjCtx &c, int q, double td)
     return fj_div(sf, (double)residue);
 }
 
+// kind_task_delay_time_e of one operation type (SO_DFJSP.py:152-154): the largest estimated
+// delay over its unprocessed operations = the largest last-of-order term (monotone inside an order)
+FJ_FN double fj_max_est_delay(const FjCtx &c, int q, double td)
+{
+    const int S = c.S, Sx = c.Sx;
+    const FjDueRO due = fj_due(c);
+    const double f = c.tsum[q];
+    int kpos = 0; bool first = true; double mx = 0.0;
+    FJ_NOUNROLL
+    for (int s = 0; s < S; ++s) {
+        const int cnt = c.cntunp[q * Sx + s];
+        if (cnt == 0) continue;
+        kpos += cnt;
+        const double ve = fj_sub(fj_add(td, fj_mul(f, (double)kpos)), (double)due[s]);
+        if (first || ve > mx) mx = ve;
+        first = false;
+    }
+    return mx;
+}
+
 // SO_DFJSP.py:270-301 / MO_DFJSP.py:300-352.  Warp-cooperative: lanes own operation types,
 // one argmax/argmin reduction (lowest index on ties = Python's first extremal element).
 template <int VARIANT, int SUM_MODE>
@@ -1017,7 +1037,7 @@ FJ_FN int fj_task_select(FjCtx &c, int rule, uint32_t rnd)
         if (!(set[q >> 5] >> (q & 31) & 1u)) continue;
         double k;
         if (key == 0) k = (VARIANT == FJSP_SO_FJSSP) ? c.urg[q] : fj_urgency<SUM_MODE>(c, q, (double)t);
-        else if (key == 1) k = c.maxe[q];
+        else if (key == 1) k = (VARIANT == FJSP_SO_FJSSP) ? c.maxe[q] : fj_max_est_delay(c, q, (double)t);
         else if (key == 2 && VARIANT == FJSP_SO_FJSSP) k = (double)((long long)t - c.mindue[q]);
         else if (key == 4 && VARIANT == FJSP_SO_FJSSP) {   // min due date over the waiting jobs
             const int r = fj_rjkind(c)[q], jb = fj_jobbase(c)[r];
