@@ -34,6 +34,7 @@ static thread_local std::string g_err;
 template <int VARIANT, int SUM_MODE>
 __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step_kernel(FjParams P, FjStepArgs A)
 {
+    fj_params_to_shared(P);
     // lockstep phases: every warp of the CTA walks the same number of env groups and steps
     extern __shared__ __align__(16) unsigned char stage_smem[];
     __shared__ int req_env[32], lp_meta[2], red_i[64];
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
 template <int VARIANT, int SUM_MODE, int SUSPEND>
 __global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(FjParams P, FjStepArgs A, const int *count_in, const int *list_in)
 {
+    fj_params_to_shared(P);
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
     unsigned char *lp = P.lp + (size_t)gw * P.lp_stride;
@@ -72,9 +74,12 @@ __global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(FjParams P, FjSte
 
 // LP kernel: one CTA per parked LP, basis inverse in shared memory when it fits
 #define FJ_LP_THREADS 256
+static_assert(FJ_STEP_THREADS / 32 <= FJ_CTX_WARPS && FJ_LP_THREADS / 32 <= FJ_CTX_WARPS && FJ_BLOCK / 32 <= FJ_CTX_WARPS,
+              "fj_sC holds one context per warp of a CTA");
 template <int SMEM_BINV>
 __global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(FjParams P, const int *count_in, const int *list_in)
 {
+    fj_params_to_shared(P);
     extern __shared__ __align__(16) unsigned char smem[];
     int n = *count_in;
     if (n > P.lp_slots) n = P.lp_slots;
@@ -101,6 +106,7 @@ __global__ void fjsp_plan_kernel(FjParams P, const int *rep_env, int n_inst, dou
 
 __global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(FjParams P)
 {
+    fj_params_to_shared(P);
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
     for (int env = gw; env < P.B; env += total) fj_env_reset_begin(P, env);
@@ -110,6 +116,7 @@ __global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(FjParams P)
 template <int VARIANT, int SUM_MODE>
 __global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_finish_kernel(FjParams P, double *state64, float *state32)
 {
+    fj_params_to_shared(P);
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
     unsigned char *lp = P.lp + (size_t)gw * P.lp_stride;
@@ -201,6 +208,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         if (wpb > FJ_STEP_THREADS / 32) wpb = FJ_STEP_THREADS / 32;
         if (wpb < 4) wpb = 4;
         if (getenv("FJSP_STEP_WARPS")) wpb = atoi(getenv("FJSP_STEP_WARPS"));
+        if (wpb > FJ_STEP_THREADS / 32) wpb = FJ_STEP_THREADS / 32;
+        if (wpb < 1) wpb = 1;
         v->step_threads = wpb * 32;
         int w2 = (n_envs + wpb - 1) / wpb, c2 = slots;
         v->step_grid = w2 < c2 ? w2 : c2;

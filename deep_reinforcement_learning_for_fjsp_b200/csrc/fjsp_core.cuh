@@ -151,9 +151,44 @@ struct FjCtx {
     unsigned char *lp;
 };
 
-FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, unsigned char *hot = nullptr)
+// The launch parameters and every warp's context object live in CTA-shared memory (plain
+// statics in the one-lane host build) and are never passed around: each out-of-line function
+// picks its warp's context up with FJ_CTX.  (A 450-byte FjCtx handed by reference to
+// __noinline__ functions lived in the per-thread stack: 1 KB x 896 threads per SM thrashed L1,
+// every `c.field` was an 8-sector local-memory load and half of them missed;
+// profiles/README.md r01_v4.  From shared memory it is one broadcast word.)
+#ifndef FJ_CTX_WARPS
+#define FJ_CTX_WARPS 16   // most warps per CTA of any kernel that uses the contexts
+#endif
+#ifdef __CUDACC__
+static __shared__ FjParams fj_sP;
+static __shared__ FjCtx fj_sC[FJ_CTX_WARPS];
+#define FJ_WIDX (threadIdx.x >> 5)
+// every kernel calls this first (all threads)
+FJ_FN void fj_params_to_shared(const FjParams &P)
 {
-    c.P = &P;
+    const int nw = (int)(sizeof(FjParams) / 4);
+    const int32_t *src = (const int32_t *)&P;
+    int32_t *dst = (int32_t *)&fj_sP;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+FJ_FN const FjParams &fj_params_bind(const FjParams &) { return fj_sP; }
+#else
+static FjParams fj_sP;
+static FjCtx fj_sC[1];
+#define FJ_WIDX 0
+FJ_FN const FjParams &fj_params_bind(const FjParams &P) { fj_sP = P; return fj_sP; }
+#endif
+#define FJ_CTX (fj_sC[FJ_WIDX])
+
+// builds this warp's context for `env` (every lane stores the same words)
+FJ_FN FjCtx &fj_ctx_init(const FjParams &, int env, unsigned char *lp, unsigned char *hot = nullptr)
+{
+    const FjParams &P = fj_sP;
+    FjCtx &c = FJ_CTX;
+    fj_sync();
+    c.P = &fj_sP;
     c.inst = P.env_inst[env];
     c.I = P.inst + (size_t)c.inst * P.io.stride;
     c.IH = hot ? (const int32_t *)(hot + P.eo.hot) : c.I;
@@ -161,7 +196,7 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     const int32_t *h = c.I + P.io.hdr;
     c.M = h[0]; c.K = h[1]; c.KT = h[2]; c.S = h[3];
     c.Mx = P.d.Mx; c.Kx = P.d.Kx; c.Sx = P.d.Sx;
-    c.mmask = c.M >= 32 ? 0xffffffffu : ((1u << c.M) - 1u);
+    c.mmask = h[0] >= 32 ? 0xffffffffu : ((1u << h[0]) - 1u);
     unsigned char *G = P.env + (size_t)env * P.eo.stride;   // record in HBM
     unsigned char *E = hot ? hot : G;                       // hot part, possibly staged in shared memory
     const FjEnvOff &o = P.eo;
@@ -182,6 +217,8 @@ FJ_FN void fj_ctx_init(FjCtx &c, const FjParams &P, int env, unsigned char *lp, 
     c.next = (uint16_t *)(G + o.next);
     c.unpmask = (uint32_t *)(G + o.unpmask); c.duejob = (int32_t *)(G + o.duejob); c.mindue = (int32_t *)(G + o.mindue);
     c.lp = lp;
+    fj_sync();
+    return c;
 }
 
 // read-only instance table.  Cold arrays are loaded through the non-coherent path
@@ -245,12 +282,11 @@ FJ_FN int fj_ffs0(unsigned v)   // index of lowest set bit, v != 0
     return __builtin_ctz(v);
 #endif
 }
-FJ_OUTLINE int fj_order_of(const FjCtx &c, int r, int n)   // which order job n of kind r came with
+FJ_OUTLINE int fj_order_of(const int32_t *cum, int S, int Kx, int r, int n)   // which order job n of kind r came with
 {
-    const FjDueRO cum = fj_cum(c);
     int s = 0;
     FJ_NOUNROLL
-    while (s + 1 < c.S && n >= cum[(s + 1) * c.Kx + r]) ++s;
+    while (s + 1 < S && n >= cum[(s + 1) * Kx + r]) ++s;
     return s;
 }
 
@@ -658,8 +694,9 @@ FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
 
 // in-line arrival: the env's own warp solves the LP on its global scratch slab
 template <int SUM_MODE>
-FJ_FN_NOINLINE void fj_order_arrives_inline(FjCtx &c, int s, int do_begin)
+FJ_FN_NOINLINE void fj_order_arrives_inline(int s, int do_begin)
 {
+    FjCtx &c = FJ_CTX;
     if (do_begin) fj_arrival_begin(c, s);
     FjLp L;
     const FjDims &d = c.P->d;
@@ -692,8 +729,9 @@ template <int SUM_MODE> FJ_FN void fj_neumaier(double &f, double &cc, double x)
     f = t2;
 }
 
-FJ_OUTLINE double fj_gap_mrj(const FjCtx &c, int q, int m, double gt)
+FJ_OUTLINE double fj_gap_mrj(int q, int m, double gt)
 {
+    FjCtx &c = FJ_CTX;
     const int sl = c.slot[q * c.Mx + m];
     if (sl == 0xFFFF) return fj_sub(0.0, (double)c.pk[q * c.Mx + m]);
     return fj_sub(c.fu[sl], fj_sub(c.fa[sl], fj_mul(gt, c.ff[sl])));
@@ -702,8 +740,9 @@ FJ_OUTLINE double fj_gap_mrj(const FjCtx &c, int q, int m, double gt)
 // gap_ave of machine m (class_FJSP.py:156-159).  EXACT: CPython's sum order and compensation
 // (it is a machine-rule key); otherwise a plain running sum (observation feature only).
 template <int SUM_MODE, int EXACT>
-FJ_OUTLINE double fj_machine_gap_ave(const FjCtx &c, int m, double gt)
+FJ_OUTLINE double fj_machine_gap_ave(int m, double gt)
 {
+    FjCtx &c = FJ_CTX;
     const int KT = c.KT;
     const FjEligRO elig = fj_elig(c);
     double f = 0.0, cc = 0.0;
@@ -711,7 +750,7 @@ FJ_OUTLINE double fj_machine_gap_ave(const FjCtx &c, int m, double gt)
     FJ_NOUNROLL
     for (int q = 0; q < KT; ++q) {
         if (!((unsigned)elig[q] >> m & 1u)) continue;
-        const double term = fj_gap_mrj(c, q, m, gt);
+        const double term = fj_gap_mrj(q, m, gt);
         if (EXACT) fj_neumaier<SUM_MODE>(f, cc, term); else f = fj_add(f, term);
         ++n;
     }
@@ -720,8 +759,9 @@ FJ_OUTLINE double fj_machine_gap_ave(const FjCtx &c, int m, double gt)
 }
 
 template <int VARIANT, int SUM_MODE>
-FJ_FN_NOINLINE void fj_observe(FjCtx &c, int rates_zero)
+FJ_FN_NOINLINE void fj_observe(int rates_zero)
 {
+    FjCtx &c = FJ_CTX;
     const int lane = fj_lane();
     const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
     const int M = c.M, KT = c.KT, S = c.S, Sx = c.Sx;
@@ -1205,7 +1245,7 @@ FJ_FN int fj_machine_select(FjCtx &c, int rule, int q, uint32_t rnd)
     if (key_kind == 2) {   // exact gap_ave of the candidates, one lane per machine
         FJ_NOUNROLL
         for (int m = fj_lane(); m < M; m += FJ_NL)
-            if (cand.mask >> m & 1u) c.gapave[m] = fj_machine_gap_ave<SUM_MODE, 1>(c, m, gt);
+            if (cand.mask >> m & 1u) c.gapave[m] = fj_machine_gap_ave<SUM_MODE, 1>(m, gt);
         fj_sync();
     }
     const int n = cand.n;
@@ -1222,7 +1262,7 @@ FJ_FN int fj_machine_select(FjCtx &c, int rule, int q, uint32_t rnd)
         if (n >= 5) { m = fj_ffs0(mk); mk &= mk - 1; } else m = (int)((cand.packed >> (8 * i)) & 0xffu);
         double k;
         switch (key_kind) {
-        case 0: k = fj_gap_mrj(c, q, m, gt); break;
+        case 0: k = fj_gap_mrj(q, m, gt); break;
         case 1: k = (double)FJ_I(c, ptime)[q * Mx + m]; break;
         case 2: k = c.gapave[m]; break;
         case 3: k = (double)FJ_I(c, energy)[q * Mx + m]; break;
@@ -1263,7 +1303,7 @@ FJ_FN void fj_arrival_resume(FjCtx &c, const FjParams &P)
 {
     const int slot = c.scal[FJ_S_LPSLOT];
     if (slot >= 0) fj_arrival_finish<SUM_MODE>(c, P.lp_x + (size_t)slot * P.d.NPx, P.lp_meta[2 * slot], P.lp_meta[2 * slot + 1]);
-    else fj_order_arrives_inline<SUM_MODE>(c, 0, 0);
+    else fj_order_arrives_inline<SUM_MODE>(0, 0);
     if (fj_lane() == 0) c.scal[FJ_S_PHASE] = FJ_PH_RUN;
     fj_sync();
 }
@@ -1331,7 +1371,7 @@ template <int VARIANT, int SUM_MODE>
 FJ_FN void fj_reset_finish(FjCtx &c)
 {
     const int lane = fj_lane();
-    fj_observe<VARIANT, SUM_MODE>(c, c.scal[FJ_S_WASDONE]);
+    fj_observe<VARIANT, SUM_MODE>(c.scal[FJ_S_WASDONE]);
     FJ_NOUNROLL
     for (int i = lane; i < 16; i += FJ_NL) c.obs[i] = c.obs2[i];
     if (lane == 0) c.scal[FJ_S_DONE] = 0;
@@ -1354,13 +1394,12 @@ FJ_FN int fj_reset_from_plan(FjCtx &c, const FjParams &P)
 }
 
 // ---------------------------------------------------------------- step
-struct FjStepOut { double reward; int done; int rec[8]; };
-
-// task_select + machine_select + dispatch; returns 0 when nothing could be dispatched
+// task_select + machine_select + dispatch; returns 0 when nothing could be dispatched.
+// `rec`: this step's row of the dispatch record output (8 int32), or null
 template <int VARIANT, int SUM_MODE>
-FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint32_t rnd_task, uint32_t rnd_mach,
-                                 FjStepOut &out)
+FJ_FN_NOINLINE int fj_step_front(int task_rule0, int mach_rule0, uint32_t rnd_task, uint32_t rnd_mach, int32_t *rec)
 {
+    FjCtx &c = FJ_CTX;
     const int lane = fj_lane();
     const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
     const int Mx = c.Mx, Sx = c.Sx, Kx = c.Kx;
@@ -1377,8 +1416,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
     q = fj_bcast_i(q, 0); m = fj_bcast_i(m, 0);
     if (q < 0 || m < 0) {
         if (lane == 0) c.scal[FJ_S_ERROR] |= (q < 0 ? FJ_E_NO_TASK : FJ_E_NO_MACHINE);
-        FJ_NOUNROLL
-        for (int i = 0; i < 8; ++i) out.rec[i] = -1;
+        if (rec) for (int k = lane; k < 8; k += FJ_NL) rec[k] = -1;
         fj_sync();
         return 0;
     }
@@ -1391,7 +1429,7 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
         else { n = c.qhead[q]; c.qhead[q] = c.next[jobbase[r] + n]; }
         c.qlen[q] = (uint16_t)(c.qlen[q] - 1);
         if (stage > 0 && c.qlen[q] == 0) { c.qhead[q] = 0xFFFF; c.qtail[q] = 0xFFFF; }
-        const int s = fj_order_of(c, r, n);
+        const int s = fj_order_of(c.h_cum, c.S, c.Kx, r, n);
         c.cntunp[q * Sx + s] = (uint16_t)(c.cntunp[q * Sx + s] - 1);
         c.cntnow[q * Sx + s] = (uint16_t)(c.cntnow[q * Sx + s] - 1);
         c.proc[q] += 1;
@@ -1431,19 +1469,24 @@ FJ_FN_NOINLINE int fj_step_front(FjCtx &c, int task_rule0, int mach_rule0, uint3
             long long late = (long long)t_end - (VARIANT == FJSP_SO_FJSSP ? c.duejob[jobbase[r] + n] : due[s]);
             if (late > 0) fj_set_ll(c.scal, FJ_S_DELAY_PROC, fj_get_ll(c.scal, FJ_S_DELAY_PROC) + late);
         }
-        out.rec[0] = q; out.rec[1] = r; out.rec[2] = stage; out.rec[3] = n; out.rec[4] = m;
-        out.rec[5] = t_begin; out.rec[6] = t_end; out.rec[7] = m_end;
+        if (rec) {
+            rec[0] = q; rec[1] = r; rec[2] = stage; rec[3] = n; rec[4] = m;
+            rec[5] = t_begin; rec[6] = t_end; rec[7] = m_end;
+        }
     }
     fj_sync();
     return 1;
 }
 
 // advance the clock while nothing can be dispatched (SO_DFJSP.py:206-253).
-// returns 1 when parked on an order arrival (SUSPEND only); `resume` re-enters right
-// after that arrival.
+// returns FJ_CLK_PARKED when parked on an order arrival (SUSPEND only; `resume` re-enters
+// right after that arrival), FJ_CLK_DONE when the episode finished, else 0.
+enum { FJ_CLK_PARKED = 1, FJ_CLK_DONE = 2 };
 template <int SUM_MODE, int SUSPEND>
-FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
+FJ_FN_NOINLINE int fj_clock(int resume)
 {
+    FjCtx &c = FJ_CTX;
+    int done = 0;
     const int lane = fj_lane();
     const int M = c.M, KT = c.KT, S = c.S, Sx = c.Sx;
     const FjKindRO rjkind = fj_rjkind(c);
@@ -1452,7 +1495,6 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
     const FjRO arrive = FJ_I(c, arrive);
     const FjDueRO jobbase = fj_jobbase(c);
     int t = c.scal[FJ_S_TIME];
-    done = 0;
     FJ_NOUNROLL
     for (;;) {
         long long left = 1;
@@ -1483,7 +1525,7 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
                     else c.next[jobbase[r] + c.qtail[q2]] = (uint16_t)n;
                     c.qtail[q2] = (uint16_t)n;
                     c.qlen[q2] = (uint16_t)(c.qlen[q2] + 1);
-                    const int s = fj_order_of(c, r, n);
+                    const int s = fj_order_of(c.h_cum, c.S, c.Kx, r, n);
                     c.cntnow[q2 * Sx + s] = (uint16_t)(c.cntnow[q2 * Sx + s] + 1);
                 }
             }
@@ -1502,9 +1544,9 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
                 if (SUSPEND) {
                     if (lane == 0) c.scal[FJ_S_TIME] = t;
                     fj_sync();
-                    return 1;
+                    return FJ_CLK_PARKED;
                 } else {
-                    fj_order_arrives_inline<SUM_MODE>(c, norder, 0);
+                    fj_order_arrives_inline<SUM_MODE>(norder, 0);
                     ++norder; left = 1;
                 }
             }
@@ -1526,14 +1568,15 @@ FJ_FN_NOINLINE int fj_clock(FjCtx &c, int resume, int &done)
     }
     if (lane == 0) c.scal[FJ_S_TIME] = t;
     fj_sync();
-    return 0;
+    return done ? FJ_CLK_DONE : 0;
 }
 
-// bookkeeping after the clock loop: new observation, rule cache, reward
+// bookkeeping after the clock loop: new observation, rule cache; returns the reward (lane 0)
 template <int VARIANT, int SUM_MODE>
-FJ_FN_NOINLINE void fj_step_back(FjCtx &c, int done, int reward_policy, double completion_n, double tardiness_n,
-                                 double energy_n, FjStepOut &out)
+FJ_FN_NOINLINE double fj_step_back(int done, int reward_policy, double completion_n, double tardiness_n, double energy_n)
 {
+    FjCtx &c = FJ_CTX;
+    double rew = 0.0;
     const int lane = fj_lane();
     const bool MO = (VARIANT == FJSP_MO_DFJSP || VARIANT == FJSP_MO_BREAKDOWN);
     if (lane == 0) {
@@ -1541,11 +1584,10 @@ FJ_FN_NOINLINE void fj_step_back(FjCtx &c, int done, int reward_policy, double c
         if (done) c.scal[FJ_S_DONE] = 1;
     }
     fj_sync();
-    fj_observe<VARIANT, SUM_MODE>(c, done);
+    fj_observe<VARIANT, SUM_MODE>(done);
     if (lane == 0) {
         const long long dsum = fj_get_ll(c.scal, FJ_S_DELAY_PROC) + fj_get_ll(c.scal, FJ_S_DELAY_UNPROC);
         const long long dlast = fj_get_ll(c.scal, FJ_S_DELAY_LAST);
-        double rew = 0.0;
         if (!MO) rew = -(double)(dsum - dlast);
         else {
             const long long comp = c.scal[FJ_S_COMPLETION], compl_ = c.scal[FJ_S_COMPLETION_LAST];
@@ -1563,10 +1605,9 @@ FJ_FN_NOINLINE void fj_step_back(FjCtx &c, int done, int reward_policy, double c
             fj_set_ll(c.scal, FJ_S_ENERGY_LAST, en);
         }
         fj_set_ll(c.scal, FJ_S_DELAY_LAST, dsum);
-        out.reward = rew;
     }
-    out.done = done;
     fj_sync();
+    return rew;
 }
 
 // ---------------------------------------------------------------- per-env driver
@@ -1594,8 +1635,9 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
 // `stage`: this warp's shared-memory slab (hot part of the env record lives there for the
 // whole launch) or null (work on the record in HBM/L2 directly).
 template <int VARIANT, int SUM_MODE, int SUSPEND>
-FJ_FN void fj_env_rollout(const FjParams &P, const FjStepArgs &A, int env, unsigned char *lp, unsigned char *stage = nullptr)
+FJ_FN void fj_env_rollout(const FjParams &Pin, const FjStepArgs &A, int env, unsigned char *lp, unsigned char *stage = nullptr)
 {
+    const FjParams &P = fj_params_bind(Pin);
     unsigned char *G = P.env + (size_t)env * P.eo.stride;
     if (stage) {
         fj_stage_copy(stage, G, P.eo.hot);
@@ -1609,8 +1651,7 @@ template <int VARIANT, int SUM_MODE, int SUSPEND>
 FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, unsigned char *lp, unsigned char *hot)
 {
     const int lane = fj_lane();
-    FjCtx c;
-    fj_ctx_init(c, P, env, lp, hot);
+    FjCtx &c = fj_ctx_init(P, env, lp, hot);
     const int nobs = P.nobs, ns = 2 * nobs;
     int tt = c.scal[FJ_S_TT];   // this driver only runs parked envs (resume kernel)
     FJ_NOUNROLL
@@ -1636,7 +1677,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
                 fj_sync();
                 if (SUSPEND) { fj_suspend(c, P, A, env, FJ_PH_LP_RESET, tt); return; }
                 else {
-                    fj_order_arrives_inline<SUM_MODE>(c, 0, 0);
+                    fj_order_arrives_inline<SUM_MODE>(0, 0);
                     fj_reset_finish<VARIANT, SUM_MODE>(c);
                 }
             }
@@ -1645,23 +1686,23 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
             fj_reset_finish<VARIANT, SUM_MODE>(c);
             phase = FJ_PH_RUN;
         }
-        FjStepOut out;
-        out.reward = 0.0; out.done = 0;
+        double out_reward = 0.0;
+        int out_done = 0;
         int resume = 0, ok = 1;
         if (phase == FJ_PH_LP_STEP) {
             fj_arrival_resume<SUM_MODE>(c, P);
             resume = 1;
         } else {
-            ok = fj_step_front<VARIANT, SUM_MODE>(c, A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
-                                        A.rnd ? A.rnd[2 * i + 1] : 0u, out);
-            if (A.rec && lane == 0) for (int k = 0; k < 8; ++k) A.rec[i * 8 + k] = out.rec[k];
+            ok = fj_step_front<VARIANT, SUM_MODE>(A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
+                                                  A.rnd ? A.rnd[2 * i + 1] : 0u, A.rec ? A.rec + i * 8 : nullptr);
         }
-        int done = 0;
         if (ok) {
-            if (fj_clock<SUM_MODE, SUSPEND>(c, resume, done)) { fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt); return; }
-            fj_step_back<VARIANT, SUM_MODE>(c, done, A.reward_policy, A.completion, A.tardiness, A.energy, out);
+            const int ck = fj_clock<SUM_MODE, SUSPEND>(resume);
+            if (ck == FJ_CLK_PARKED) { fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt); return; }
+            out_done = ck == FJ_CLK_DONE;
+            out_reward = fj_step_back<VARIANT, SUM_MODE>(out_done, A.reward_policy, A.completion, A.tardiness, A.energy);
         } else {
-            out.done = c.scal[FJ_S_DONE];
+            out_done = c.scal[FJ_S_DONE];
             FJ_NOUNROLL
             for (int k = lane; k < nobs; k += FJ_NL) c.obs2[k] = c.obs[k];
             fj_sync();
@@ -1678,8 +1719,8 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
         FJ_NOUNROLL
         for (int k = lane; k < nobs; k += FJ_NL) c.obs[k] = c.obs2[k];
         if (lane == 0) {
-            if (A.reward) A.reward[i] = out.reward;
-            if (A.done) A.done[i] = out.done;
+            if (A.reward) A.reward[i] = out_reward;
+            if (A.done) A.done[i] = out_done;
         }
         fj_sync();
     }
@@ -1737,25 +1778,26 @@ FJ_FN int fj_cta_sync_or(int pred)
 }
 
 template <int VARIANT, int SUM_MODE>
-FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx &K, int env, int active, unsigned char *stage = nullptr)
+FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaCtx &K, int env, int active, unsigned char *stage = nullptr)
 {
+    const FjParams &P = fj_params_bind(Pin);
     const int lane = fj_lane();
-    FjCtx c;
+    FjCtx &c = FJ_CTX;
     unsigned char *G = P.env + (size_t)env * P.eo.stride;
     if (active) {
         if (stage) {
             fj_stage_copy(stage, G, P.eo.hot);
             fj_stage_copy(stage + P.eo.hot, (const unsigned char *)(P.inst + (size_t)P.env_inst[env] * P.io.stride), P.io.hotw * 4);
         }
-        fj_ctx_init(c, P, env, nullptr, stage);
+        fj_ctx_init(P, env, nullptr, stage);
     }
     const int nobs = P.nobs;
     int parked = !active;
     FJ_NOUNROLL
     for (int tt = 0; tt < A.T; ++tt) {
         const size_t i = (size_t)tt * P.B + env;
-        FjStepOut out;
-        out.reward = 0.0; out.done = 0;
+        double out_reward = 0.0;
+        int out_done = 0;
         int stage = 0;      // 0 nothing, 1 dispatched (run the clock), 2 nothing dispatchable (emit unchanged)
 #ifndef FJ_ONE_BARRIER
         FJ_CTA_SYNC();      // ---- phase A: auto-reset / task_select / machine_select / dispatch
@@ -1776,9 +1818,8 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
                 }
             }
             if (!parked && !c.scal[FJ_S_DONE]) {
-                const int ok = fj_step_front<VARIANT, SUM_MODE>(c, A.actions[2 * i], A.actions[2 * i + 1],
-                                                               A.rnd ? A.rnd[2 * i] : 0u, A.rnd ? A.rnd[2 * i + 1] : 0u, out);
-                if (A.rec && lane == 0) for (int k = 0; k < 8; ++k) A.rec[i * 8 + k] = out.rec[k];
+                const int ok = fj_step_front<VARIANT, SUM_MODE>(A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
+                                                               A.rnd ? A.rnd[2 * i + 1] : 0u, A.rec ? A.rec + i * 8 : nullptr);
                 stage = ok ? 1 : 2;
             }
         }
@@ -1793,7 +1834,8 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
             for (;;) {
                 int want = 0;
                 if (st == 1) {
-                    if (fj_clock<SUM_MODE, 1>(c, resume, done)) { st = 2; want = 1; } else st = 0;
+                    const int ck = fj_clock<SUM_MODE, 1>(resume);
+                    if (ck == FJ_CLK_PARKED) { st = 2; want = 1; } else { st = 0; done = ck == FJ_CLK_DONE; }
                 }
                 if (!K.cta_lp) {             // no CTA service configured: park for the LP / resume kernels
                     if (want) { fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt); parked = 1; stage = 0; }
@@ -1806,8 +1848,7 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
                     const int e2 = K.req_env[w];
                     if (e2 < 0) continue;    // uniform over the CTA
                     {
-                        FjCtx c2;
-                        fj_ctx_init(c2, P, e2, nullptr, K.stage_base ? K.stage_base + (size_t)w * P.stage_stride : nullptr);
+                        FjCtx &c2 = fj_sC[FJ_NL == 1 ? 0 : w];   // the requesting warp's context
                         FjLp L;
                         // scratch in the CTA's shared memory when this LP fits, else on its HBM slab
                         const size_t Rub = (size_t)(c2.M + 2 * c2.KT - c2.K), Cn = (size_t)FJ_I(c2, hdr)[7] + 1;
@@ -1829,9 +1870,11 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
             }
         }
         // ---- phase C: observation, reward, outputs (the vote above was the phase barrier)
-        if (stage == 1) fj_step_back<VARIANT, SUM_MODE>(c, done, A.reward_policy, A.completion, A.tardiness, A.energy, out);
-        else if (stage == 2) {
-            out.done = c.scal[FJ_S_DONE];
+        if (stage == 1) {
+            out_reward = fj_step_back<VARIANT, SUM_MODE>(done, A.reward_policy, A.completion, A.tardiness, A.energy);
+            out_done = done;
+        } else if (stage == 2) {
+            out_done = c.scal[FJ_S_DONE];
             FJ_NOUNROLL
             for (int k = lane; k < nobs; k += FJ_NL) c.obs2[k] = c.obs[k];
             fj_sync();
@@ -1842,8 +1885,8 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
             FJ_NOUNROLL
             for (int k = lane; k < nobs; k += FJ_NL) c.obs[k] = c.obs2[k];
             if (lane == 0) {
-                if (A.reward) A.reward[i] = out.reward;
-                if (A.done) A.done[i] = out.done;
+                if (A.reward) A.reward[i] = out_reward;
+                if (A.done) A.done[i] = out_done;
             }
             fj_sync();
         }
@@ -1852,10 +1895,10 @@ FJ_FN void fj_cta_rollout(const FjParams &P, const FjStepArgs &A, const FjCtaCtx
 }
 
 // reset() entry: phase 1 parks every env on its order-0 LP, phase 2 finishes
-FJ_FN void fj_env_reset_begin(const FjParams &P, int env)
+FJ_FN void fj_env_reset_begin(const FjParams &Pin, int env)
 {
-    FjCtx c;
-    fj_ctx_init(c, P, env, nullptr);
+    const FjParams &P = fj_params_bind(Pin);
+    FjCtx &c = fj_ctx_init(P, env, nullptr);
     fj_reset_begin(c, 1);
     if (fj_lane() == 0) {
         c.scal[FJ_S_PHASE] = FJ_PH_LP_RESET;
@@ -1866,11 +1909,11 @@ FJ_FN void fj_env_reset_begin(const FjParams &P, int env)
 }
 
 template <int VARIANT, int SUM_MODE>
-FJ_FN void fj_env_reset_finish(const FjParams &P, int env, unsigned char *lp, double *state_out, float *state32_out)
+FJ_FN void fj_env_reset_finish(const FjParams &Pin, int env, unsigned char *lp, double *state_out, float *state32_out)
 {
+    const FjParams &P = fj_params_bind(Pin);
     const int lane = fj_lane();
-    FjCtx c;
-    fj_ctx_init(c, P, env, lp);
+    FjCtx &c = fj_ctx_init(P, env, lp);
     fj_arrival_resume<SUM_MODE>(c, P);
     fj_reset_finish<VARIANT, SUM_MODE>(c);
     const int nobs = P.nobs, ns = 2 * nobs;
@@ -1883,11 +1926,11 @@ FJ_FN void fj_env_reset_finish(const FjParams &P, int env, unsigned char *lp, do
 }
 
 // one parked LP, solved by a whole CTA (device) / one thread (host build)
-FJ_FN void fj_lp_service(const FjParams &P, const FjCtaGroup &g, const int *list, int idx, unsigned char *binv, unsigned char *small_)
+FJ_FN void fj_lp_service(const FjParams &Pin, const FjCtaGroup &g, const int *list, int idx, unsigned char *binv, unsigned char *small_)
 {
+    const FjParams &P = fj_params_bind(Pin);
     const int env = list[idx];
-    FjCtx c;
-    fj_ctx_init(c, P, env, nullptr);
+    FjCtx &c = fj_ctx_init(P, env, nullptr);
     FjLp L;
     fj_lp_carve(L, binv, small_, P.d);
     int iters = 0;
