@@ -30,5 +30,13 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """A tuning / diagnostic build next to the product library (select it with FJSP_B200_LIB),
+    e.g. build_variant("trace", ["-DFJ_TRACE"]) for tools/cta_trace.py."""
+    out = os.path.join(HERE, "libfjsp_b200_%s.so" % name)
+    subprocess.check_call([nvcc_path()] + NVCC_FLAGS + list(defines) + ["-o", out, os.path.join(CSRC, "fjsp_api.cu")])
+    return out
+
+
 if __name__ == "__main__":
     print(build_cuda(force=True, verbose=True))

@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
     fj_params_to_shared(P);
     // lockstep phases: every warp of the CTA walks the same number of env groups and steps
     extern __shared__ __align__(16) unsigned char stage_smem[];
-    __shared__ int req_env[32], lp_meta[2], red_i[64];
-    __shared__ double red_d[32];
+    __shared__ int req_env[32], lp_meta[2];
+    __shared__ int4 red4[64];
     const int wpb = blockDim.x >> 5;
     const int total = gridDim.x * wpb;
     unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.stage_stride : nullptr;
@@ -50,13 +50,98 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
     K.meta = lp_meta; K.req_env = req_env;
     K.lp_smem_bytes = P.cta_lp_smem;
     K.lp_smem = P.cta_lp_smem ? stage_smem + (size_t)(P.stage ? wpb * P.stage_stride : 0) : nullptr;
-    K.group.rk = red_d; K.group.ri = red_i; K.group.ra = red_i + 32;
+    K.group.red = red4; K.group.flip = 0;
+    if (P.cta_lp == 2) {
+        // free-running warps: no CTA coupling at all; a warp that reaches an order arrival solves
+        // the fluid LP itself on its own scratch slab
+        unsigned char *lp = P.lp + (size_t)(blockIdx.x * wpb + (threadIdx.x >> 5)) * P.lp_stride;
+        for (int slot = blockIdx.x * wpb + (threadIdx.x >> 5); slot < P.B; slot += total)
+            fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, P.order[slot], lp, stage);
+        return;
+    }
     for (int base = blockIdx.x * wpb; base < P.B; base += total) {
         // envs are visited in order of decreasing static walk length (P.order): the warps that
         // share a CTA's phase barriers then carry similar work, and the longest start first
         const int slot = base + (threadIdx.x >> 5);
         const int env = slot < P.B ? P.order[slot] : 0;
         fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env, slot < P.B, stage);
+    }
+}
+
+// LP-aware packing, run before every step launch.  The warps of a CTA serve each other's fluid
+// LPs, so a CTA's launch time grows with the NUMBER of order arrivals among its envs, and the
+// launch ends with the unluckiest CTA.  Arrivals are predictable (the next order's arrival time
+// is static, the clock's pace per step is roughly steady), so the envs that are likely to meet
+// one in the next T steps are dealt round-robin over the (virtual) CTAs; all other envs fill the
+// remaining warp slots in the static order (similar walk lengths share a CTA).
+// slot = virtual CTA * wpb + warp, virtual CTA = round * gridDim + blockIdx of the step kernel.
+#define FJ_PACK_THREADS 1024
+__device__ __forceinline__ int fj_lp_likely(const FjParams &P, int env, int T)
+{
+    // Measured on the bench workload: the later orders arrive early in an episode (arrival times
+    // of a few hundred against makespans of tens of thousands), so an episode meets all its
+    // order-arrival LPs within its first few dozen steps, usually inside one launch.  Likely =
+    // an order is still to come, or the episode ends (and restarts) within the next T steps.
+    const int32_t *s = (const int32_t *)(P.env + (size_t)env * P.eo.stride + P.eo.scal);
+    if (s[FJ_S_DONE]) return 1;
+    const int32_t *I = P.inst + (size_t)P.env_inst[env] * P.io.stride;
+    if (s[FJ_S_NEXTORDER] < I[P.io.hdr + 3]) return 1;
+    return I[P.io.hdr + 8] - s[FJ_S_STEPS] <= T - 8; // operations left: the restart needs ~10 steps to reach an arrival
+}
+__global__ void fjsp_flag_kernel(FjParams P, const int32_t *static_order, unsigned char *flags, int T)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.B) flags[i] = (unsigned char)fj_lp_likely(P, static_order[i], T);
+}
+__global__ void __launch_bounds__(FJ_PACK_THREADS) fjsp_pack_kernel(FjParams P, const int32_t *static_order, const unsigned char *flags, int32_t *order_out, int wpb)
+{
+    __shared__ int wsum[32];
+    __shared__ int s_total;
+    const int B = P.B, tid = threadIdx.x, nt = blockDim.x;
+    const int V = (B + wpb - 1) / wpb, last = B - (V - 1) * wpb;
+    const int VA = last == wpb ? V : V - 1;          // virtual CTAs that take likely envs
+    const int per = (B + nt - 1) / nt, lo = tid * per, hi = lo + per < B ? lo + per : B;
+    if (VA <= 0) { for (int i = lo; i < hi; ++i) order_out[i] = static_order[i]; return; }
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) cnt += flags[i];
+    // exclusive scan of the per-thread counts
+    int inc = cnt;
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if ((tid & 31) >= d) inc += o; }
+    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+    __syncthreads();
+    if (tid < 32) {
+        int v = tid < (nt >> 5) ? wsum[tid] : 0, w = v;
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, d); if (tid >= d) w += o; }
+        wsum[tid] = w - v;
+        if (tid == 31) s_total = w;
+    }
+    __syncthreads();
+    int rA = wsum[tid >> 5] + inc - cnt;             // likely envs before this thread's chunk
+    const int nA = min(s_total, VA * (wpb / 2 > 0 ? wpb / 2 : 1));   // beyond that spreading buys nothing
+    const int qa = nA / VA, ra = nA % VA;
+    for (int i = lo; i < hi; ++i) {
+        const int env = static_order[i];
+        const int f = flags[i];
+        int slot;
+        if (f && rA < nA) {
+            slot = (rA % VA) * wpb + rA / VA;
+        } else {
+            const int rB = i - min(rA, nA);          // unlikely envs before this one
+            // free slots of the virtual CTAs before v: v * wpb - (likely envs dealt to them)
+            int a = 0, b = V - 1;                    // largest v with free(v) <= rB
+            while (a < b) {
+                const int m = (a + b + 1) >> 1;
+                const int mm = m < VA ? m : VA;
+                const int fr = m * wpb - (mm * qa + (mm < ra ? mm : ra));
+                if (fr <= rB) a = m; else b = m - 1;
+            }
+            const int am = a < VA ? a : VA;
+            const int fr = a * wpb - (am * qa + (am < ra ? am : ra));
+            const int av = a < VA ? qa + (a < ra) : 0;
+            slot = a * wpb + av + (rB - fr);
+        }
+        order_out[slot] = env;
+        rA += f;
     }
 }
 
@@ -86,9 +171,9 @@ __global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(FjParams P, cons
     const size_t binv_bytes = (size_t)P.d.Rx * P.d.Rx * 8;
     unsigned char *binv = SMEM_BINV ? smem : P.lp + (size_t)blockIdx.x * P.lp_stride;
     unsigned char *small_ = SMEM_BINV ? smem + binv_bytes : smem;
-    unsigned char *red = small_ + (fj_lp_small_bytes(P.d) + 7) / 8 * 8;
+    unsigned char *red = smem + ((SMEM_BINV ? binv_bytes : 0) + fj_lp_small_bytes(P.d) + 15) / 16 * 16;   // 16-byte aligned
     FjCtaGroup g;
-    g.rk = (double *)red; g.ri = (int *)(red + 32 * 8); g.ra = g.ri + 32;
+    g.red = (int4 *)red; g.flip = 0;
     for (int i = blockIdx.x; i < n; i += gridDim.x) fj_lp_service(P, g, list_in, i, binv, small_);
 }
 
@@ -131,7 +216,9 @@ struct fjsp_vec {
     int *d_pend_count, *d_pend_env, *d_lp_meta, *d_rep_env, *d_plan_meta, *d_plan_ok;
     double *d_lp_x, *d_plan_x;
     int n_inst, plan_ready;
-    int32_t *d_inst, *d_env_inst, *d_order;
+    int32_t *d_inst, *d_env_inst, *d_order, *d_order_dyn;
+    unsigned char *d_flags;
+    int pack;
     unsigned char *d_env, *d_lp;
     long long launches;
     // staging for the host-buffer entry points
@@ -142,6 +229,7 @@ struct fjsp_vec {
     uint32_t *d_rnd;
     double *d_state64, *d_reward;
     float *d_state32;
+    long long *d_trace;          // FJ_TRACE builds only
 };
 
 static void launch_lp(fjsp_vec *v, cudaStream_t st, int round)
@@ -219,7 +307,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     int rcap = prop.multiProcessorCount * 4;
     v->resume_grid = want < rcap ? want : rcap;
     v->lp_grid = prop.multiProcessorCount * 2;
-    const size_t small_b = (fj_lp_small_bytes_host(v->tb.d) + 7) / 8 * 8 + 32 * 16;
+    const size_t small_b = fj_lp_small_bytes_host(v->tb.d) + 16 + 64 * 16;   // + alignment slack + reduction scratch
     const size_t binv_b = (size_t)v->tb.d.Rx * v->tb.d.Rx * 8;
     v->lp_smem_binv = (binv_b + small_b <= 200 * 1024) ? 1 : 0;
     v->lp_smem_bytes = v->lp_smem_binv ? binv_b + small_b : small_b;
@@ -228,11 +316,14 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     int slabs = v->resume_grid * FJ_WARPS_PER_BLOCK;
     if (v->lp_grid > slabs) slabs = v->lp_grid;
     if (v->step_grid > slabs) slabs = v->step_grid;   // one slab per CTA of the main kernel (in-CTA LP service)
+    if (getenv("FJSP_FREE_RUN") && v->step_grid * (v->step_threads / 32) > slabs) slabs = v->step_grid * (v->step_threads / 32);
     const size_t lp_bytes = (size_t)lp_stride * slabs;
     const size_t env_bytes = (size_t)n_envs * v->tb.eo.stride;
     CK(cudaMalloc(&v->d_inst, v->tb.inst.size() * 4));
     CK(cudaMalloc(&v->d_env_inst, (size_t)n_envs * 4));
     CK(cudaMalloc(&v->d_order, (size_t)n_envs * 4));
+    CK(cudaMalloc(&v->d_order_dyn, (size_t)n_envs * 4));
+    CK(cudaMalloc(&v->d_flags, (size_t)n_envs));
     {
         // static walk length of an env: jobs of its largest kind x warp rounds over its operation types
         std::vector<long long> key(n_instances);
@@ -244,6 +335,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         for (int e = 0; e < n_envs; ++e) order[e] = e;
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[env_instance[x]] > key[env_instance[y]]; });
         CK(cudaMemcpy(v->d_order, order.data(), (size_t)n_envs * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(v->d_order_dyn, order.data(), (size_t)n_envs * 4, cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&v->d_env, env_bytes));
     CK(cudaMalloc(&v->d_lp, lp_bytes));
@@ -275,12 +367,18 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaFuncSetAttribute(fjsp_lp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->lp_smem_bytes));
     FjParams &P = v->P;
     P.d = v->tb.d; P.io = v->tb.io; P.eo = v->tb.eo;
-    P.order = v->d_order;
+    P.order = v->d_order_dyn;   // rewritten before every step launch by fjsp_pack_kernel
     P.inst = v->d_inst; P.env_inst = v->d_env_inst; P.env = v->d_env; P.lp = v->d_lp; P.lp_stride = lp_stride;
     P.B = n_envs; P.variant = variant; P.sum_mode = v->sum_mode; P.nobs = v->nstate / 2;
     P.pend_count = v->d_pend_count; P.pend_env = v->d_pend_env; P.lp_x = v->d_lp_x; P.lp_meta = v->d_lp_meta;
     P.lp_slots = (int)slots;
     P.plan_x = v->d_plan_x; P.plan_meta = v->d_plan_meta; P.plan_ok = nullptr;
+    P.trace = nullptr; v->d_trace = nullptr;
+#ifdef FJ_TRACE
+    CK(cudaMalloc(&v->d_trace, (size_t)v->step_grid * 16 * 8 * 8));
+    CK(cudaMemset(v->d_trace, 0, (size_t)v->step_grid * 16 * 8 * 8));
+    P.trace = v->d_trace;
+#endif
     // hot part of the env records staged in shared memory for the whole launch when four
     // warps' worth fits with at least two CTAs per SM
     // the main kernel stages the hot prefix of its warps' records in shared memory when the
@@ -296,6 +394,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     }
     if (!P.stage) v->stage_bytes = 0;
     P.cta_lp = getenv("FJSP_NO_CTA_LP") ? 0 : 1;   // 0: park order arrivals for the LP / resume kernels
+    if (getenv("FJSP_FREE_RUN")) P.cta_lp = 2;
+    v->pack = (P.cta_lp == 1 && !getenv("FJSP_NO_PACK")) ? 1 : 0;
     {   // shared-memory scratch for the in-CTA LP: what is left of the SM's 200 KB per resident CTA
         const size_t per_cta = (size_t)200 * 1024 / (1024 / FJ_STEP_THREADS);
         size_t left = per_cta > v->stage_bytes + 1024 ? per_cta - v->stage_bytes - 1024 : 0;
@@ -336,9 +436,10 @@ int fjsp_vec_destroy(fjsp_vec *v)
     if (!v) return 0;
     cudaSetDevice(v->device);
     free_stage(v);
-    cudaFree(v->d_order);
+    cudaFree(v->d_order); cudaFree(v->d_order_dyn); cudaFree(v->d_flags);
     cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
+    cudaFree(v->d_trace);
     cudaFree(v->d_rep_env); cudaFree(v->d_plan_x); cudaFree(v->d_plan_meta); cudaFree(v->d_plan_ok);
     cudaStreamDestroy(v->stream); cudaStreamDestroy(v->copy_stream); cudaEventDestroy(v->chunk_done);
     delete v;
@@ -394,6 +495,10 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     int rc = dispatch(v, [&](auto V, auto SM) {
         constexpr int VV = decltype(V)::value, MM = decltype(SM)::value;
         A.park_count = v->d_pend_count; A.park_env = v->d_pend_env;
+        if (v->pack) {
+            fjsp_flag_kernel<<<(v->B + 255) / 256, 256, 0, st>>>(v->P, v->d_order, v->d_flags, T);
+            fjsp_pack_kernel<<<1, FJ_PACK_THREADS, 0, st>>>(v->P, v->d_order, v->d_flags, v->d_order_dyn, v->step_threads / 32);
+        }
         fjsp_step_kernel<VV, MM><<<v->step_grid, v->step_threads, v->step_smem_bytes, st>>>(v->P, A);
         // resume rounds: an env can meet a reset and further order arrivals inside one launch; the
         // last round solves whatever is left in line
@@ -407,7 +512,7 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
         return 0;
     });
     if (rc) return rc;
-    v->launches += 1 + 2 * FJ_ROUNDS;
+    v->launches += 1 + 2 * FJ_ROUNDS + 2 * v->pack;
     CK(cudaGetLastError());
     return 0;
 }
@@ -480,6 +585,18 @@ int fjsp_vec_reset_host(fjsp_vec *v, double *h_state64, float *h_state32)
     if (h_state64) CK(cudaMemcpyAsync(h_state64, v->d_state64, n * 8, cudaMemcpyDeviceToHost, st));
     if (h_state32) CK(cudaMemcpyAsync(h_state32, v->d_state32, n * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int fjsp_vec_trace(fjsp_vec *v, int64_t *h_out, int clear)
+{
+    if (!v) { g_err = "fjsp_vec_trace: null handle"; return -1; }
+    if (!v->d_trace) { g_err = "fjsp_vec_trace: not a trace build (compile with -DFJ_TRACE)"; return -6; }
+    CK(cudaSetDevice(v->device));
+    CK(cudaDeviceSynchronize());
+    const size_t bytes = (size_t)v->step_grid * 16 * 8 * 8;
+    if (h_out) CK(cudaMemcpy(h_out, v->d_trace, bytes, cudaMemcpyDeviceToHost));
+    if (clear) CK(cudaMemset(v->d_trace, 0, bytes));
     return 0;
 }
 

@@ -300,6 +300,50 @@ FJ_OUTLINE int fj_order_of(const int32_t *cum, int S, int Kx, int r, int n)   //
 #define FJ_LP_EPS_PIV 1e-9
 #define FJ_LP_EPS_ZERO 1e-9
 
+// Group reductions.  argmin() is the lexicographic minimum of (key, idx) over the group's
+// candidates (idx 0x7fffffff = none; candidate idx values are distinct), `aux` travels with the
+// winner; every member gets the result, and the call orders the group's earlier memory writes
+// before its later reads (it contains a group barrier).  On the device the pair is reduced with
+// three redux.sync minima over an order-preserving integer image of the double (keys are never
+// NaN or -0.0 here): the first version's shuffle butterfly plus a serial scan of the per-warp
+// partials by every thread was a third of all LP instructions (profiles/README.md r01_v5).
+#define FJ_EMPTY 0x7fffffff
+#ifdef __CUDACC__
+FJ_FN unsigned long long fj_ord_enc(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+FJ_FN double fj_ord_dec(unsigned hi, unsigned lo)
+{
+    const unsigned long long u = ((unsigned long long)hi << 32) | lo;
+    return __longlong_as_double((long long)((u >> 63) ? (u ^ 0x8000000000000000ull) : ~u));
+}
+// (hi, lo, id): id = idx << 12 | aux, 0xffffffff = none.  All lanes return the minimum.
+FJ_FN void fj_warp_lexmin(unsigned &hi, unsigned &lo, unsigned &id)
+{
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    lo = hi == mh ? lo : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
+    id = (hi == mh && lo == ml) ? id : 0xffffffffu;
+    id = __reduce_min_sync(0xffffffffu, id);
+    hi = mh; lo = ml;
+}
+FJ_FN void fj_lex_pack(double key, int idx, int aux, unsigned &hi, unsigned &lo, unsigned &id)
+{
+    const unsigned long long u = fj_ord_enc(key);
+    const bool none = idx == FJ_EMPTY;
+    hi = none ? 0xffffffffu : (unsigned)(u >> 32);
+    lo = none ? 0xffffffffu : (unsigned)u;
+    id = none ? 0xffffffffu : (((unsigned)idx << 12) | (unsigned)aux);
+}
+FJ_FN void fj_lex_unpack(unsigned hi, unsigned lo, unsigned id, double &key, int &idx, int &aux)
+{
+    if (id == 0xffffffffu) { idx = FJ_EMPTY; return; }
+    key = fj_ord_dec(hi, lo); idx = (int)(id >> 12); aux = (int)(id & 0xfffu);
+}
+#endif
+
 struct FjWarpGroup {
     FJ_MFN int rank() const { return fj_lane(); }
     FJ_MFN int size() const { return FJ_NL; }
@@ -307,64 +351,68 @@ struct FjWarpGroup {
     FJ_MFN int warp() const { return 0; }
     FJ_MFN int nwarps() const { return 1; }
     FJ_MFN void sync() const { fj_sync(); }
-    FJ_MFN int min_i(int v) const { return fj_min_i(v); }
-    // lexicographic (key, idx) minimum, idx 0x7fffffff = empty; `aux` travels with the winner
-    FJ_MFN void argmin(double &key, int &idx, int &aux) const
+    FJ_MFN int min_i(int v) { fj_sync(); return fj_min_i(v); }
+    FJ_MFN void argmin(double &key, int &idx, int &aux)
     {
-        for (int m = FJ_NL / 2; m > 0; m >>= 1) {
-            double ok = fj_xor_d(key, m); int oi = fj_xor_i(idx, m); int oa = fj_xor_i(aux, m);
-            if (oi == 0x7fffffff) continue;
-            if (idx == 0x7fffffff || ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; aux = oa; }
-        }
+        fj_sync();
+#ifdef FJ_DEVICE_CODE
+        unsigned hi, lo, id;
+        fj_lex_pack(key, idx, aux, hi, lo, id);
+        fj_warp_lexmin(hi, lo, id);
+        fj_lex_unpack(hi, lo, id, key, idx, aux);
+#endif
     }
 };
 
 #ifdef __CUDACC__
 struct FjCtaGroup {
-    double *rk; int *ri, *ra;    // shared scratch: one entry per warp (<= 32)
+    int4 *red;    // shared scratch: two buffers of one entry per warp (<= 32 warps)
+    int flip;     // which buffer the next reduction uses (same value in every thread)
     FJ_MFN int rank() const { return threadIdx.x; }
     FJ_MFN int size() const { return blockDim.x; }
     FJ_MFN int lane() const { return threadIdx.x & 31; }
     FJ_MFN int warp() const { return threadIdx.x >> 5; }
     FJ_MFN int nwarps() const { return blockDim.x >> 5; }
     FJ_MFN void sync() const { __syncthreads(); }
-    FJ_MFN int min_i(int v) const
+    // one barrier per reduction: the partials of consecutive reductions alternate between two
+    // buffers, so a buffer is rewritten only after every thread has passed the next barrier
+    FJ_MFN int min_i(int v)
     {
-        v = fj_min_i(v);
-        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        v = (int)__reduce_min_sync(0xffffffffu, (unsigned)v);   // callers pass non-negative values
+        int4 *buf = red + flip * 32; flip ^= 1;
+        if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5].x = v;
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) ri[w] = v;
-        __syncthreads();
-        int r = ri[0];
-        for (int i = 1; i < nw; ++i) r = ri[i] < r ? ri[i] : r;
-        return r;
+        const int l = threadIdx.x & 31;
+        const unsigned o = l < (int)(blockDim.x >> 5) ? (unsigned)buf[l].x : 0xffffffffu;
+        return (int)__reduce_min_sync(0xffffffffu, o);
     }
-    FJ_MFN void argmin(double &key, int &idx, int &aux) const
+    FJ_MFN void argmin(double &key, int &idx, int &aux)
     {
-        FjWarpGroup wg; wg.argmin(key, idx, aux);
-        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        unsigned hi, lo, id;
+        fj_lex_pack(key, idx, aux, hi, lo, id);
+        fj_warp_lexmin(hi, lo, id);
+        int4 *buf = red + flip * 32; flip ^= 1;
+        if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = make_int4((int)hi, (int)lo, (int)id, 0);
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) { rk[w] = key; ri[w] = idx; ra[w] = aux; }
-        __syncthreads();
-        key = rk[0]; idx = ri[0]; aux = ra[0];
-        for (int i = 1; i < nw; ++i) {
-            const double ok = rk[i]; const int oi = ri[i];
-            if (oi == 0x7fffffff) continue;
-            if (idx == 0x7fffffff || ok < key || (ok == key && oi < idx)) { key = ok; idx = oi; aux = ra[i]; }
-        }
+        const int l = threadIdx.x & 31;
+        hi = lo = id = 0xffffffffu;
+        if (l < (int)(blockDim.x >> 5)) { const int4 e = buf[l]; hi = (unsigned)e.x; lo = (unsigned)e.y; id = (unsigned)e.z; }
+        fj_warp_lexmin(hi, lo, id);
+        fj_lex_unpack(hi, lo, id, key, idx, aux);
     }
 };
 #else
+struct int4 { int x, y, z, w; };
 struct FjCtaGroup {   // host simulation: one thread
-    double *rk; int *ri, *ra;
+    int4 *red; int flip;
     FJ_MFN int rank() const { return 0; }
     FJ_MFN int size() const { return 1; }
     FJ_MFN int lane() const { return 0; }
     FJ_MFN int warp() const { return 0; }
     FJ_MFN int nwarps() const { return 1; }
     FJ_MFN void sync() const {}
-    FJ_MFN int min_i(int v) const { return v; }
-    FJ_MFN void argmin(double &, int &, int &) const {}
+    FJ_MFN int min_i(int v) { return v; }
+    FJ_MFN void argmin(double &, int &, int &) {}
 };
 #endif
 
@@ -440,17 +488,35 @@ FJ_FN double fj_lp_colvec_dot(const FjCtx &c, const FjLp &L, const double *brow,
     return acc;
 }
 
+#if defined(FJ_TRACE) && defined(FJ_DEVICE_CODE)
+// per-phase cycles of the CTA-group LP, accumulated by thread 0 in registers and added to trace
+// row 15 of its CTA when the LP ends: setup, pricing, entering argmin, w + ratios, leaving
+// argmin, xB / pivot row, rank-1 update, iterations
+#define FJ_LPT_DECL long long lt_ = clock64(), la_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define FJ_LPT(k) do { const long long n_ = clock64(); la_[k] += n_ - lt_; lt_ = n_; } while (0)
+#define FJ_LPT_ITER() (la_[7] += 1)
+#define FJ_LPT_FLUSH() do { if (g.rank() == 0 && g.size() > FJ_NL && c.P->trace) { \
+    for (int k_ = 0; k_ < 8; ++k_) c.P->trace[((size_t)blockIdx.x * 16 + 15) * 8 + k_] += la_[k_]; } } while (0)
+#else
+#define FJ_LPT_DECL
+#define FJ_LPT(k)
+#define FJ_LPT_ITER()
+#define FJ_LPT_FLUSH()
+#endif
+
 // Builds the canonical LP from the env record (after fj_arrival_begin) and solves it.
 // On return x[0..NP) holds the structural solution (values < 1e-9 flushed to 0).
 template <class G>
-FJ_FN int fj_lp_solve(const G &g, FjCtx &c, FjLp &L, double *x_out, int *iters_out)
+FJ_FN int fj_lp_solve(const G &g_in, FjCtx &c, FjLp &L, double *x_out, int *iters_out)
 {
+    G g = g_in;
     const int tid = g.rank(), nt = g.size();
     const int M = c.M, KT = c.KT, Mx = c.Mx;
     const FjRO ptime = FJ_I(c, ptime);
     const FjEligRO elig = fj_elig(c);
     const FjLastRO rjlast = fj_rjlast(c);
     const FjRO colbase = FJ_I(c, colbase);
+    FJ_LPT_DECL;
     if (tid == 0) {   // precedence rows: sequential numbering
         int nprec = 0;
         for (int q = 0; q < KT; ++q) {
@@ -482,14 +548,19 @@ FJ_FN int fj_lp_solve(const G &g, FjCtx &c, FjLp &L, double *x_out, int *iters_o
     g.sync();
     const int dantzig_iters = 20 * R + 100, hard_iters = 200 * R + 1000;
     const int nvar = C + R, t_col = NP;
+    // rank-1 update: warps own contiguous row blocks (four rows in flight), lanes own columns
+    const int rpw = (R + g.nwarps() - 1) / g.nwarps();
+    const int row_lo = g.warp() * rpw, row_hi = row_lo + rpw < R ? row_lo + rpw : R;
     int it = 0, rc = 0;
+    FJ_LPT(0);
     for (;; ++it) {
+        FJ_LPT_ITER();
         if (it >= hard_iters) { rc = 2; break; }
         const int pt = L.pos[t_col];
         const double *yrow = L.Binv + (size_t)(pt >= 0 ? pt : 0) * R;
         const int bland = it >= dantzig_iters;
         // pricing: most negative reduced cost (lowest column on ties) / Bland: lowest column
-        double ek = 0.0; int ei = 0x7fffffff, ea = 0;
+        double ek = 0.0; int ei = FJ_EMPTY, ea = 0;
         for (int j = tid; j < nvar; j += nt) {
             if (L.pos[j] >= 0) continue;
             double d;
@@ -500,48 +571,54 @@ FJ_FN int fj_lp_solve(const G &g, FjCtx &c, FjLp &L, double *x_out, int *iters_o
                 d = pt >= 0 ? -(-yrow[j - C]) : -0.0;
             }
             if (d < -FJ_LP_EPS_D) {
-                if (bland) { if (ei == 0x7fffffff) { ek = d; ei = j; } }
-                else if (ei == 0x7fffffff || d < ek) { ek = d; ei = j; }
+                if (bland) { if (ei == FJ_EMPTY) { ek = d; ei = j; } }
+                else if (ei == FJ_EMPTY || d < ek) { ek = d; ei = j; }
             }
         }
+        FJ_LPT(1);
         if (bland) ei = g.min_i(ei); else g.argmin(ek, ei, ea);
+        FJ_LPT(2);
         const int qin = ei;
-        if (qin == 0x7fffffff) break;   // optimal
-        // w = Binv * A_q
+        if (qin == FJ_EMPTY) break;   // optimal
+        // w = Binv * A_q and, by the same thread, the row's ratio  max(xB,0)/w  (w > eps);
+        // ties -> lowest basic variable
+        double rk = 0.0; int ri = FJ_EMPTY, rrow = 0;
         for (int i = tid; i < R; i += nt) {
             const double *brow = L.Binv + (size_t)i * R;
-            L.w[i] = qin < C ? fj_lp_colvec_dot(c, L, brow, qin, 0) : brow[qin - C];
-        }
-        g.sync();
-        // ratio test: min max(xB,0)/w over w > eps, ties -> lowest basic variable
-        double rk = 0.0; int ri = 0x7fffffff, rrow = -1;
-        for (int i = tid; i < R; i += nt) {
-            double wi = L.w[i];
+            const double wi = qin < C ? fj_lp_colvec_dot(c, L, brow, qin, 0) : brow[qin - C];
+            L.w[i] = wi;
             if (wi > FJ_LP_EPS_PIV) {
-                double xb = L.xB[i] > 0.0 ? L.xB[i] : 0.0;
-                double r = fj_div(xb, wi);
-                int bi = L.basis[i];
-                if (ri == 0x7fffffff || r < rk || (r == rk && bi < ri)) { rk = r; ri = bi; rrow = i; }
+                const double xb = L.xB[i] > 0.0 ? L.xB[i] : 0.0;
+                const double r = fj_div(xb, wi);
+                const int bi = L.basis[i];
+                if (ri == FJ_EMPTY || r < rk || (r == rk && bi < ri)) { rk = r; ri = bi; rrow = i; }
             }
         }
-        g.argmin(rk, ri, rrow);
-        if (ri == 0x7fffffff) { rc = 3; break; }
+        FJ_LPT(3);
+        g.argmin(rk, ri, rrow);    // also publishes w
+        FJ_LPT(4);
+        if (ri == FJ_EMPTY) { rc = 3; break; }
         const int p = rrow;
         const double theta = rk, wp = L.w[p];
         for (int i = tid; i < R; i += nt)
             L.xB[i] = (i == p) ? theta : fj_sub(L.xB[i], fj_mul(theta, L.w[i]));
         double *rowp = L.Binv + (size_t)p * R;
         for (int k = tid; k < R; k += nt) rowp[k] = fj_div(rowp[k], wp);
+        if (tid == 0) {
+            L.pos[L.basis[p]] = -1;
+            L.basis[p] = qin;
+            L.pos[qin] = p;
+        }
         g.sync();
-        // rank-1 update of every other row: warps own rows (four at a time, so that the four
-        // loads of a column are in flight together), lanes own columns.  Per element it is
-        // still  B[i][k] - w[i] * B[p][k]  with separately rounded multiply and subtract.
-        for (int i0 = g.warp() * 4; i0 < R; i0 += g.nwarps() * 4) {
+        FJ_LPT(5);
+        // every other row:  B[i][k] - w[i] * B[p][k]  with separately rounded multiply and
+        // subtract; rows with w[i] == 0 are left alone
+        for (int i0 = row_lo; i0 < row_hi; i0 += 4) {
             double wv0 = 0.0, wv1 = 0.0, wv2 = 0.0, wv3 = 0.0;
-            if (i0 + 0 < R && i0 + 0 != p) wv0 = L.w[i0 + 0];
-            if (i0 + 1 < R && i0 + 1 != p) wv1 = L.w[i0 + 1];
-            if (i0 + 2 < R && i0 + 2 != p) wv2 = L.w[i0 + 2];
-            if (i0 + 3 < R && i0 + 3 != p) wv3 = L.w[i0 + 3];
+            if (i0 + 0 < row_hi && i0 + 0 != p) wv0 = L.w[i0 + 0];
+            if (i0 + 1 < row_hi && i0 + 1 != p) wv1 = L.w[i0 + 1];
+            if (i0 + 2 < row_hi && i0 + 2 != p) wv2 = L.w[i0 + 2];
+            if (i0 + 3 < row_hi && i0 + 3 != p) wv3 = L.w[i0 + 3];
             if (wv0 == 0.0 && wv1 == 0.0 && wv2 == 0.0 && wv3 == 0.0) continue;
             double *r0 = L.Binv + (size_t)(i0 + 0) * R, *r1 = L.Binv + (size_t)(i0 + 1) * R;
             double *r2 = L.Binv + (size_t)(i0 + 2) * R, *r3 = L.Binv + (size_t)(i0 + 3) * R;
@@ -558,12 +635,8 @@ FJ_FN int fj_lp_solve(const G &g, FjCtx &c, FjLp &L, double *x_out, int *iters_o
                 if (wv3 != 0.0) r3[k] = fj_sub(e3, fj_mul(wv3, pk_));
             }
         }
-        if (tid == 0) {
-            L.pos[L.basis[p]] = -1;
-            L.basis[p] = qin;
-            L.pos[qin] = p;
-        }
         g.sync();
+        FJ_LPT(6);
     }
     for (int j = tid; j < NP; j += nt) {
         double x = L.pos[j] >= 0 ? L.xB[L.pos[j]] : 0.0;
@@ -571,6 +644,7 @@ FJ_FN int fj_lp_solve(const G &g, FjCtx &c, FjLp &L, double *x_out, int *iters_o
         x_out[j] = x;
     }
     g.sync();
+    FJ_LPT_FLUSH();
     if (iters_out) *iters_out = it;
     return rc;
 }
@@ -1653,7 +1727,7 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
     const int lane = fj_lane();
     FjCtx &c = fj_ctx_init(P, env, lp, hot);
     const int nobs = P.nobs, ns = 2 * nobs;
-    int tt = c.scal[FJ_S_TT];   // this driver only runs parked envs (resume kernel)
+    int tt = c.scal[FJ_S_PHASE] == FJ_PH_RUN ? 0 : c.scal[FJ_S_TT];   // a parked env continues at the step it parked in
     FJ_NOUNROLL
     for (; tt < A.T; ++tt) {
         const size_t i = (size_t)tt * P.B + env;
@@ -1777,6 +1851,24 @@ FJ_FN int fj_cta_sync_or(int pred)
 #endif
 }
 
+// FJ_TRACE builds (tools/cta_trace.py): every warp accumulates the cycles it spends in each
+// phase of a step (barrier waits excluded) so that CTA / SM imbalance can be read off.
+#if defined(FJ_TRACE) && defined(FJ_DEVICE_CODE)
+#define FJ_TR_DECL long long tr_[6] = {0, 0, 0, 0, 0, 0}; long long tr_t_ = clock64(); const long long tr_begin_ = tr_t_
+#define FJ_TR_MARK() (tr_t_ = clock64())
+#define FJ_TR_ACC(k) do { const long long n_ = clock64(); tr_[k] += n_ - tr_t_; tr_t_ = n_; } while (0)
+#define FJ_TR_COUNT(k) (tr_[k] += 1)
+#define FJ_TR_FLUSH(P, K) do { if ((P).trace && fj_lane() == 0) { long long *o_ = (P).trace + ((size_t)blockIdx.x * 16 + (K).warp) * 8; \
+    unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); \
+    o_[0] += clock64() - tr_begin_; for (int k_ = 0; k_ < 6; ++k_) o_[1 + k_] += tr_[k_]; o_[7] = sm_; } } while (0)
+#else
+#define FJ_TR_DECL
+#define FJ_TR_MARK()
+#define FJ_TR_ACC(k)
+#define FJ_TR_COUNT(k)
+#define FJ_TR_FLUSH(P, K)
+#endif
+
 template <int VARIANT, int SUM_MODE>
 FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaCtx &K, int env, int active, unsigned char *stage = nullptr)
 {
@@ -1793,6 +1885,7 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
     }
     const int nobs = P.nobs;
     int parked = !active;
+    FJ_TR_DECL;
     FJ_NOUNROLL
     for (int tt = 0; tt < A.T; ++tt) {
         const size_t i = (size_t)tt * P.B + env;
@@ -1802,6 +1895,7 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
 #ifndef FJ_ONE_BARRIER
         FJ_CTA_SYNC();      // ---- phase A: auto-reset / task_select / machine_select / dispatch
 #endif
+        FJ_TR_MARK();
         if (!parked) {
             if (c.scal[FJ_S_DONE]) {
                 if (!A.autoreset) {   // a finished env without auto-reset repeats its terminal output
@@ -1823,6 +1917,7 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
                 stage = ok ? 1 : 2;
             }
         }
+        FJ_TR_ACC(0);
         // ---- phase B: discrete-event clock.  A warp whose clock reaches an order arrival asks
         // the CTA for the fluid LP: at the phase barrier all warps of the CTA solve it together
         // (FjCtaGroup, basis inverse on the CTA's scratch slab), the owner applies it and
@@ -1833,20 +1928,24 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
             int resume = 0;
             for (;;) {
                 int want = 0;
+                FJ_TR_MARK();
                 if (st == 1) {
                     const int ck = fj_clock<SUM_MODE, 1>(resume);
                     if (ck == FJ_CLK_PARKED) { st = 2; want = 1; } else { st = 0; done = ck == FJ_CLK_DONE; }
                 }
+                FJ_TR_ACC(1);
                 if (!K.cta_lp) {             // no CTA service configured: park for the LP / resume kernels
                     if (want) { fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt); parked = 1; stage = 0; }
                     break;
                 }
                 if (lane == 0) K.req_env[K.warp] = want ? env : -1;
                 if (!fj_cta_sync_or(want)) break;
+                FJ_TR_MARK();
                 FJ_NOUNROLL
                 for (int w = 0; w < K.nwarps; ++w) {
                     const int e2 = K.req_env[w];
                     if (e2 < 0) continue;    // uniform over the CTA
+                    FJ_TR_COUNT(4);
                     {
                         FjCtx &c2 = fj_sC[FJ_NL == 1 ? 0 : w];   // the requesting warp's context
                         FjLp L;
@@ -1867,8 +1966,10 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
                     }
                     K.group.sync();
                 }
+                FJ_TR_ACC(2);
             }
         }
+        FJ_TR_MARK();
         // ---- phase C: observation, reward, outputs (the vote above was the phase barrier)
         if (stage == 1) {
             out_reward = fj_step_back<VARIANT, SUM_MODE>(done, A.reward_policy, A.completion, A.tardiness, A.energy);
@@ -1890,8 +1991,10 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
             }
             fj_sync();
         }
+        FJ_TR_ACC(3);
     }
     if (active && stage) fj_stage_copy(G, stage, P.eo.hot);
+    FJ_TR_FLUSH(P, K);
 }
 
 // reset() entry: phase 1 parks every env on its order-0 LP, phase 2 finishes

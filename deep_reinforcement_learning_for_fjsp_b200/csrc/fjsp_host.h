@@ -106,7 +106,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     FjInstOff io;
     int o = 0;
     // hot head: small arrays every step reads (staged in shared memory by the main kernel)
-    io.hdr = o; o += 8;
+    io.hdr = o; o += 12;
     io.ntask = o; o += d.Kx;
     io.first = o; o += d.Kx;
     io.jobbase = o; o += d.Kx;
@@ -192,6 +192,11 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
         int32_t *w = t.inst.data() + (size_t)i * io.stride;
         int32_t *h = w + io.hdr;
         h[0] = v.M; h[1] = v.K; h[2] = v.KT; h[3] = v.S; h[4] = v.NJ; h[5] = v.ddt_lo; h[6] = v.ddt_hi; h[7] = v.NP;
+        {   // h[8]: operations of one episode (every step dispatches one)
+            long long ops = 0;
+            for (int r = 0; r < v.K; ++r) { long long c = 0; for (int s = 0; s < v.S; ++s) c += v.count[s * v.K + r]; ops += c * v.ntask[r]; }
+            h[8] = (int32_t)(ops > 0x7fffffff ? 0x7fffffff : ops);
+        }
         int acc = 0, jb = 0;
         for (int r = 0; r < v.K; ++r) {
             w[io.ntask + r] = v.ntask[r];

@@ -27,7 +27,7 @@ struct FjDims {
 
 // instance record: word (int32) offsets
 struct FjInstOff {
-    int hdr;       // [8]: M, K, KT, S, NJ, ddt_lo, ddt_hi, NP
+    int hdr;       // [12]: M, K, KT, S, NJ, ddt_lo, ddt_hi, NP, operations per episode, 0, 0, 0
     int ntask;     // [Kx]
     int first;     // [Kx]  first operation type of a kind
     int jobbase;   // [Kx]  offset of a kind's jobs in the per-env link array
@@ -137,6 +137,7 @@ struct FjParams {
     int cta_lp;                 // 1: the main kernel's CTAs solve order-arrival LPs themselves
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory
     int B, variant, sum_mode, nobs;
+    long long *trace;           // FJ_TRACE builds: [grid][16 warps][8] per-warp cycle counters (null otherwise)
 };
 
 struct FjStepArgs {

@@ -81,6 +81,11 @@ int fjsp_vec_reset_host(fjsp_vec *v, double *h_state64, float *h_state32);
  * delay_time_sum_unprocessed.  Host buffer [n_envs][12]. */
 int fjsp_vec_info(fjsp_vec *v, int64_t *h_out);
 
+/* Diagnostic (builds with -DFJ_TRACE only, otherwise returns -6): per warp of the step
+ * kernel's grid 8 int64 [grid][16][8] = cycles in the rollout, in dispatch, clock loop, CTA LP
+ * service, observation/outputs, LPs served by the CTA, spare, SM id.  clear != 0 zeroes them. */
+int fjsp_vec_trace(fjsp_vec *v, int64_t *h_out, int clear);
+
 #ifdef __cplusplus
 }
 #endif

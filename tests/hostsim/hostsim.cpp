@@ -31,7 +31,7 @@ static void run_lp_service(HostVec *h, int round = 0)
     const FjDims &d = h->tb.d;
     unsigned char *binv = h->lp.data();
     unsigned char *small_ = h->lp.data() + (size_t)d.Rx * d.Rx * 8;
-    FjCtaGroup g; g.rk = nullptr; g.ri = nullptr; g.ra = nullptr;
+    FjCtaGroup g; g.red = nullptr; g.flip = 0;
     int n = h->pend_count < h->P.lp_slots ? h->pend_count : h->P.lp_slots;
     for (int i = 0; i < n; ++i) fj_lp_service(h->P, g, list, i, binv, small_);
 }
@@ -77,7 +77,7 @@ static void run_step(HostVec *h, const FjStepArgs &A)
     const char *lps = getenv("FJSP_HOSTSIM_LP_SMEM");   // bytes of emulated shared-memory LP scratch
     lpsm.assign(lps ? atoi(lps) : 0, 0);
     K.lp_smem = lpsm.empty() ? nullptr : lpsm.data(); K.lp_smem_bytes = (int)lpsm.size();
-    K.meta = meta; K.req_env = req_env; K.group.rk = nullptr; K.group.ri = nullptr; K.group.ra = nullptr;
+    K.meta = meta; K.req_env = req_env; K.group.red = nullptr; K.group.flip = 0;
     for (int e = 0; e < h->P.B; ++e) fj_cta_rollout<V, SM>(h->P, B_, K, e, 1, stage);               // main kernel
     for (int r = 0; r < FJ_ROUNDS; ++r) {
         run_lp_service(h, r);                                                                       // LP kernel
