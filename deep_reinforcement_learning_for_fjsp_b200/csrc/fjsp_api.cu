@@ -26,7 +26,8 @@ static thread_local std::string g_err;
 
 // main step kernel: every env; parks an env on the first fluid LP it needs
 #ifndef FJ_STEP_THREADS
-#define FJ_STEP_THREADS 512      // 16 warps in lockstep phases, two CTAs per SM at 64 registers (measured best of 128..1024)
+#define FJ_STEP_THREADS 1024     // up to 32 warps in lockstep phases, one CTA per SM at 64 registers: one instruction
+                                 // stream per SM and every thread of the SM on a CTA-served LP (71.0 M vs 69.1 M at 2 x 512)
 #endif
 #ifndef FJ_STEP_MIN_BLOCKS
 #define FJ_STEP_MIN_BLOCKS (1024 / FJ_STEP_THREADS)
@@ -51,97 +52,121 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
     K.lp_smem_bytes = P.cta_lp_smem;
     K.lp_smem = P.cta_lp_smem ? stage_smem + (size_t)(P.stage ? wpb * P.stage_stride : 0) : nullptr;
     K.group.red = red4; K.group.flip = 0;
+    // P.order maps warp slots to envs: slot = virtual CTA * wpb + warp, -1 = empty.  CTA b plays
+    // the virtual CTAs b, b + gridDim, ...
     if (P.cta_lp == 2) {
         // free-running warps: no CTA coupling at all; a warp that reaches an order arrival solves
         // the fluid LP itself on its own scratch slab
         unsigned char *lp = P.lp + (size_t)(blockIdx.x * wpb + (threadIdx.x >> 5)) * P.lp_stride;
-        for (int slot = blockIdx.x * wpb + (threadIdx.x >> 5); slot < P.B; slot += total)
-            fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, P.order[slot], lp, stage);
+        for (int slot = blockIdx.x * wpb + (threadIdx.x >> 5); slot < P.n_slots; slot += total) {
+            const int env = P.order[slot];
+            if (env >= 0) fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, env, lp, stage);
+        }
         return;
     }
-    for (int base = blockIdx.x * wpb; base < P.B; base += total) {
-        // envs are visited in order of decreasing static walk length (P.order): the warps that
-        // share a CTA's phase barriers then carry similar work, and the longest start first
-        const int slot = base + (threadIdx.x >> 5);
-        const int env = slot < P.B ? P.order[slot] : 0;
-        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env, slot < P.B, stage);
+    for (int base = blockIdx.x * wpb; base < P.n_slots; base += total) {
+        const int env = P.order[base + (threadIdx.x >> 5)];
+        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env < 0 ? 0 : env, env >= 0, stage);
     }
 }
 
 // LP-aware packing, run before every step launch.  The warps of a CTA serve each other's fluid
-// LPs, so a CTA's launch time grows with the NUMBER of order arrivals among its envs, and the
-// launch ends with the unluckiest CTA.  Arrivals are predictable (the next order's arrival time
-// is static, the clock's pace per step is roughly steady), so the envs that are likely to meet
-// one in the next T steps are dealt round-robin over the (virtual) CTAs; all other envs fill the
-// remaining warp slots in the static order (similar walk lengths share a CTA).
-// slot = virtual CTA * wpb + warp, virtual CTA = round * gridDim + blockIdx of the step kernel.
+// LPs in lockstep, so a CTA's launch time is  (lockstep steps of its envs) + (its LPs), and the
+// launch ends with the slowest CTA.  Measured (profiles/README.md r01_v5): an episode meets all
+// its order-arrival LPs within its first few dozen steps, an LP costs 0.15 M (small instances) to
+// 0.9 M cycles (R ~ 110 rows) against 2.2 M cycles for 32 lockstep steps of a full CTA, and a
+// warp alone (no CTA-mates to wait for) needs only 1.45 M for its 32 steps.  So the envs that
+// are about to meet an LP get a virtual CTA of their own whose remaining warp slots are filled
+// the less the heavier the instance's LP is; every other env fills the remaining virtual CTAs
+// in the static order (similar walk lengths share a CTA).
+//   slot = virtual CTA * wpb + warp;  the step kernel's CTA b plays virtual CTAs b, b + grid, ...
 #define FJ_PACK_THREADS 1024
-__device__ __forceinline__ int fj_lp_likely(const FjParams &P, int env, int T)
+__device__ __forceinline__ int fj_lp_class(const FjParams &P, int env, int T, int r_heavy, int r_medium)
 {
-    // Measured on the bench workload: the later orders arrive early in an episode (arrival times
-    // of a few hundred against makespans of tens of thousands), so an episode meets all its
-    // order-arrival LPs within its first few dozen steps, usually inside one launch.  Likely =
-    // an order is still to come, or the episode ends (and restarts) within the next T steps.
+    // 0: no LP expected in the next T steps; 1 / 2 / 3: expected, heavy / medium / light LP
     const int32_t *s = (const int32_t *)(P.env + (size_t)env * P.eo.stride + P.eo.scal);
-    if (s[FJ_S_DONE]) return 1;
     const int32_t *I = P.inst + (size_t)P.env_inst[env] * P.io.stride;
-    if (s[FJ_S_NEXTORDER] < I[P.io.hdr + 3]) return 1;
-    return I[P.io.hdr + 8] - s[FJ_S_STEPS] <= T - 8; // operations left: the restart needs ~10 steps to reach an arrival
+    const int32_t *h = I + P.io.hdr;
+    // likely = an order is still to come (they all arrive early in an episode), or the episode ends
+    // and restarts within the launch (the restart needs ~10 steps to reach the first arrival)
+    const int likely = s[FJ_S_DONE] || s[FJ_S_NEXTORDER] < h[3] || h[8] - s[FJ_S_STEPS] <= T - 8;
+    if (!likely) return 0;
+    const int rub = h[0] + 2 * h[2] - h[1];          // upper bound of the LP's rows: M + 2 KT - K
+    return rub >= r_heavy ? 1 : rub >= r_medium ? 2 : 3;
 }
-__global__ void fjsp_flag_kernel(FjParams P, const int32_t *static_order, unsigned char *flags, int T)
+__global__ void fjsp_flag_kernel(FjParams P, const int32_t *static_order, unsigned char *flags, int T, int r_heavy, int r_medium)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.B) flags[i] = (unsigned char)fj_lp_likely(P, static_order[i], T);
+    if (i < P.B) flags[i] = (unsigned char)fj_lp_class(P, static_order[i], T, r_heavy, r_medium);
 }
-__global__ void __launch_bounds__(FJ_PACK_THREADS) fjsp_pack_kernel(FjParams P, const int32_t *static_order, const unsigned char *flags, int32_t *order_out, int wpb)
+struct FjPackPlan { int e1, e2, e3, f1, f2, f3; };   // virtual CTAs per class, free slots per CTA of the class
+__device__ __forceinline__ int fj_pack_free(const FjPackPlan &p, int wpb, int m)   // free slots of virtual CTAs < m
 {
-    __shared__ int wsum[32];
-    __shared__ int s_total;
+    int f = 0, x = m;
+    int n = x < p.e1 ? x : p.e1; f += n * p.f1; x -= n;
+    n = x < p.e2 ? x : p.e2; f += n * p.f2; x -= n;
+    n = x < p.e3 ? x : p.e3; f += n * p.f3; x -= n;
+    return f + x * wpb;
+}
+__global__ void __launch_bounds__(FJ_PACK_THREADS) fjsp_pack_kernel(FjParams P, const int32_t *static_order, const unsigned char *flags,
+                                                                    int32_t *order_out, int wpb, int cap1, int cap2, int cap3)
+{
+    __shared__ unsigned long long wsum[32];
+    __shared__ FjPackPlan s_plan;
     const int B = P.B, tid = threadIdx.x, nt = blockDim.x;
-    const int V = (B + wpb - 1) / wpb, last = B - (V - 1) * wpb;
-    const int VA = last == wpb ? V : V - 1;          // virtual CTAs that take likely envs
-    const int per = (B + nt - 1) / nt, lo = tid * per, hi = lo + per < B ? lo + per : B;
-    if (VA <= 0) { for (int i = lo; i < hi; ++i) order_out[i] = static_order[i]; return; }
-    int cnt = 0;
-    for (int i = lo; i < hi; ++i) cnt += flags[i];
-    // exclusive scan of the per-thread counts
-    int inc = cnt;
-    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if ((tid & 31) >= d) inc += o; }
+    const int V = P.n_slots / wpb;
+    for (int i = tid; i < P.n_slots; i += nt) order_out[i] = -1;
+    const int per = (B + nt - 1) / nt, lo = tid * per < B ? tid * per : B, hi = lo + per < B ? lo + per : B;
+    // per-class counts, 21 bits each, scanned together
+    unsigned long long cnt = 0;
+    for (int i = lo; i < hi; ++i) { const int c = flags[i]; if (c) cnt += 1ull << (21 * (c - 1)); }
+    unsigned long long inc = cnt;
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d); if ((tid & 31) >= d) inc += o; }
     if ((tid & 31) == 31) wsum[tid >> 5] = inc;
     __syncthreads();
     if (tid < 32) {
-        int v = tid < (nt >> 5) ? wsum[tid] : 0, w = v;
-        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, d); if (tid >= d) w += o; }
+        const unsigned long long v = tid < (nt >> 5) ? wsum[tid] : 0;
+        unsigned long long w = v;
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, w, d); if (tid >= d) w += o; }
         wsum[tid] = w - v;
-        if (tid == 31) s_total = w;
+        if (tid == 31) {
+            const int n1 = (int)(w & 0x1fffff), n2 = (int)((w >> 21) & 0x1fffff), n3 = (int)((w >> 42) & 0x1fffff);
+            FjPackPlan p;
+            p.e1 = n1 < V ? n1 : V; p.e2 = n2 < V - p.e1 ? n2 : V - p.e1; p.e3 = n3 < V - p.e1 - p.e2 ? n3 : V - p.e1 - p.e2;
+            int c1 = cap1 < wpb ? cap1 : wpb, c2 = cap2 < wpb ? cap2 : wpb, c3 = cap3 < wpb ? cap3 : wpb;
+            if (c1 < 1) c1 = 1; if (c2 < c1) c2 = c1; if (c3 < c2) c3 = c2;
+            // every env needs a slot: widen the light, then the medium, then the heavy CTAs until they do
+            for (;;) {
+                const long long capacity = (long long)p.e1 * c1 + (long long)p.e2 * c2 + (long long)p.e3 * c3 + (long long)(V - p.e1 - p.e2 - p.e3) * wpb;
+                if (capacity >= B) break;
+                if (c3 < wpb) ++c3; else if (c2 < wpb) ++c2; else ++c1;
+            }
+            p.f1 = c1 - 1; p.f2 = c2 - 1; p.f3 = c3 - 1;
+            s_plan = p;
+        }
     }
     __syncthreads();
-    int rA = wsum[tid >> 5] + inc - cnt;             // likely envs before this thread's chunk
-    const int nA = min(s_total, VA * (wpb / 2 > 0 ? wpb / 2 : 1));   // beyond that spreading buys nothing
-    const int qa = nA / VA, ra = nA % VA;
+    const FjPackPlan p = s_plan;
+    unsigned long long before = wsum[tid >> 5] + inc - cnt;   // per-class likely envs before this thread's chunk
+    int r1 = (int)(before & 0x1fffff), r2 = (int)((before >> 21) & 0x1fffff), r3 = (int)((before >> 42) & 0x1fffff);
     for (int i = lo; i < hi; ++i) {
-        const int env = static_order[i];
-        const int f = flags[i];
-        int slot;
-        if (f && rA < nA) {
-            slot = (rA % VA) * wpb + rA / VA;
-        } else {
-            const int rB = i - min(rA, nA);          // unlikely envs before this one
-            // free slots of the virtual CTAs before v: v * wpb - (likely envs dealt to them)
+        const int env = static_order[i], c = flags[i];
+        int slot = -1;
+        if (c == 1 && r1 < p.e1) slot = r1 * wpb;
+        else if (c == 2 && r2 < p.e2) slot = (p.e1 + r2) * wpb;
+        else if (c == 3 && r3 < p.e3) slot = (p.e1 + p.e2 + r3) * wpb;
+        if (slot < 0) {
+            // rank among the envs that do not own a virtual CTA, then the CTA whose free slots hold it
+            const int rB = i - ((r1 < p.e1 ? r1 : p.e1) + (r2 < p.e2 ? r2 : p.e2) + (r3 < p.e3 ? r3 : p.e3));
             int a = 0, b = V - 1;                    // largest v with free(v) <= rB
             while (a < b) {
                 const int m = (a + b + 1) >> 1;
-                const int mm = m < VA ? m : VA;
-                const int fr = m * wpb - (mm * qa + (mm < ra ? mm : ra));
-                if (fr <= rB) a = m; else b = m - 1;
+                if (fj_pack_free(p, wpb, m) <= rB) a = m; else b = m - 1;
             }
-            const int am = a < VA ? a : VA;
-            const int fr = a * wpb - (am * qa + (am < ra ? am : ra));
-            const int av = a < VA ? qa + (a < ra) : 0;
-            slot = a * wpb + av + (rB - fr);
+            slot = a * wpb + (a < p.e1 + p.e2 + p.e3 ? 1 : 0) + (rB - fj_pack_free(p, wpb, a));
         }
         order_out[slot] = env;
-        rA += f;
+        r1 += c == 1; r2 += c == 2; r3 += c == 3;
     }
 }
 
@@ -174,7 +199,7 @@ __global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(FjParams P, cons
     unsigned char *red = smem + ((SMEM_BINV ? binv_bytes : 0) + fj_lp_small_bytes(P.d) + 15) / 16 * 16;   // 16-byte aligned
     FjCtaGroup g;
     g.red = (int4 *)red; g.flip = 0;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) fj_lp_service(P, g, list_in, i, binv, small_);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) fj_lp_service(P, g, list_in, i, binv, small_, P.lp + (size_t)blockIdx.x * P.lp_stride);
 }
 
 // after the first reset(): copy each instance's order-0 LP solution from its representative env
@@ -217,6 +242,7 @@ struct fjsp_vec {
     double *d_lp_x, *d_plan_x;
     int n_inst, plan_ready;
     int32_t *d_inst, *d_env_inst, *d_order, *d_order_dyn;
+    int n_slots, pack_cap[3], pack_rows[2], multi_round;
     unsigned char *d_flags;
     int pack;
     unsigned char *d_env, *d_lp;
@@ -289,18 +315,28 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (getenv("FJSP_GRID_PER_SM")) cap = prop.multiProcessorCount * atoi(getenv("FJSP_GRID_PER_SM"));
     v->grid = want < cap ? want : cap;
     {
-        // CTA size at run time: two CTAs per SM; a batch smaller than the resident capacity is
-        // spread evenly (4096 envs on 148 SMs -> 296 CTAs of 14 warps instead of 256 of 16)
-        const int slots = prop.multiProcessorCount * (1024 / FJ_STEP_THREADS);
-        int wpb = (n_envs + slots - 1) / slots;
-        if (wpb > FJ_STEP_THREADS / 32) wpb = FJ_STEP_THREADS / 32;
+        // CTA size at run time.  The batch gets ~15 % more warp slots than envs: the spare slots are
+        // what lets the packing kernel give the envs that are about to solve an LP lightly
+        // loaded CTAs.  Slots = rounds x grid x wpb, grid <= resident CTAs.
+        const int per_sm = 1024 / FJ_STEP_THREADS, gmax = prop.multiProcessorCount * per_sm, wmax = FJ_STEP_THREADS / 32;
+        const int spare_pct = getenv("FJSP_SPARE") ? atoi(getenv("FJSP_SPARE")) : 15;
+        long long want_slots = (long long)n_envs + (n_envs * (long long)spare_pct + 99) / 100;
+        if (getenv("FJSP_NO_PACK") || getenv("FJSP_FREE_RUN") || getenv("FJSP_NO_CTA_LP")) want_slots = n_envs;
+        // a batch that needs several rounds of CTAs averages its LPs out by itself: no spare slots
+        // (measured at 65 536 copies: 99 M env-steps/s with 15 % spare, 110 M without)
+        v->multi_round = (long long)n_envs > (long long)gmax * wmax;
+        if (v->multi_round && !getenv("FJSP_SPARE")) want_slots = n_envs;
+        int wpb = (int)((want_slots + gmax - 1) / gmax);
+        if (wpb > wmax) wpb = wmax;
         if (wpb < 4) wpb = 4;
         if (getenv("FJSP_STEP_WARPS")) wpb = atoi(getenv("FJSP_STEP_WARPS"));
-        if (wpb > FJ_STEP_THREADS / 32) wpb = FJ_STEP_THREADS / 32;
+        if (wpb > wmax) wpb = wmax;
         if (wpb < 1) wpb = 1;
         v->step_threads = wpb * 32;
-        int w2 = (n_envs + wpb - 1) / wpb, c2 = slots;
-        v->step_grid = w2 < c2 ? w2 : c2;
+        long long ctas = (want_slots + wpb - 1) / wpb;              // virtual CTAs
+        v->step_grid = (int)(ctas < gmax ? ctas : gmax);
+        const long long rounds = (ctas + v->step_grid - 1) / v->step_grid;
+        v->n_slots = (int)(rounds * v->step_grid * wpb);
     }
     const unsigned long long lp_stride = fj_lp_scratch_bytes(v->tb.d);
     // the resume kernel (in-line LP fallback) and the LP kernel (global Binv fallback) share the slabs
@@ -322,7 +358,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaMalloc(&v->d_inst, v->tb.inst.size() * 4));
     CK(cudaMalloc(&v->d_env_inst, (size_t)n_envs * 4));
     CK(cudaMalloc(&v->d_order, (size_t)n_envs * 4));
-    CK(cudaMalloc(&v->d_order_dyn, (size_t)n_envs * 4));
+    CK(cudaMalloc(&v->d_order_dyn, (size_t)v->n_slots * 4));
     CK(cudaMalloc(&v->d_flags, (size_t)n_envs));
     {
         // static walk length of an env: jobs of its largest kind x warp rounds over its operation types
@@ -335,7 +371,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         for (int e = 0; e < n_envs; ++e) order[e] = e;
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[env_instance[x]] > key[env_instance[y]]; });
         CK(cudaMemcpy(v->d_order, order.data(), (size_t)n_envs * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(v->d_order_dyn, order.data(), (size_t)n_envs * 4, cudaMemcpyHostToDevice));
+        order.resize(v->n_slots, -1);   // without packing: the static order, spare slots empty
+        CK(cudaMemcpy(v->d_order_dyn, order.data(), (size_t)v->n_slots * 4, cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&v->d_env, env_bytes));
     CK(cudaMalloc(&v->d_lp, lp_bytes));
@@ -368,6 +405,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     FjParams &P = v->P;
     P.d = v->tb.d; P.io = v->tb.io; P.eo = v->tb.eo;
     P.order = v->d_order_dyn;   // rewritten before every step launch by fjsp_pack_kernel
+    P.n_slots = v->n_slots;
     P.inst = v->d_inst; P.env_inst = v->d_env_inst; P.env = v->d_env; P.lp = v->d_lp; P.lp_stride = lp_stride;
     P.B = n_envs; P.variant = variant; P.sum_mode = v->sum_mode; P.nobs = v->nstate / 2;
     P.pend_count = v->d_pend_count; P.pend_env = v->d_pend_env; P.lp_x = v->d_lp_x; P.lp_meta = v->d_lp_meta;
@@ -375,8 +413,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     P.plan_x = v->d_plan_x; P.plan_meta = v->d_plan_meta; P.plan_ok = nullptr;
     P.trace = nullptr; v->d_trace = nullptr;
 #ifdef FJ_TRACE
-    CK(cudaMalloc(&v->d_trace, (size_t)v->step_grid * 16 * 8 * 8));
-    CK(cudaMemset(v->d_trace, 0, (size_t)v->step_grid * 16 * 8 * 8));
+    CK(cudaMalloc(&v->d_trace, (size_t)v->step_grid * FJ_TRACE_ROWS * 8 * 8));
+    CK(cudaMemset(v->d_trace, 0, (size_t)v->step_grid * FJ_TRACE_ROWS * 8 * 8));
     P.trace = v->d_trace;
 #endif
     // hot part of the env records staged in shared memory for the whole launch when four
@@ -396,6 +434,14 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     P.cta_lp = getenv("FJSP_NO_CTA_LP") ? 0 : 1;   // 0: park order arrivals for the LP / resume kernels
     if (getenv("FJSP_FREE_RUN")) P.cta_lp = 2;
     v->pack = (P.cta_lp == 1 && !getenv("FJSP_NO_PACK")) ? 1 : 0;
+    {   // warp slots of a virtual CTA that holds an env with a heavy / medium / light LP ahead, and the
+        // row bounds (M + 2 KT - K) of the classes; FJSP_PACK="cap1,cap2,cap3,rows_heavy,rows_medium"
+        const int w = v->step_threads / 32;
+        v->pack_cap[0] = 1; v->pack_cap[1] = w / 8 > 1 ? w / 8 : 1; v->pack_cap[2] = w / 2 > 1 ? w / 2 : 1;
+        v->pack_rows[0] = 70; v->pack_rows[1] = 45;
+        if (v->multi_round) v->pack_cap[0] = v->pack_cap[1] = v->pack_cap[2] = w;   // spread the LP envs over the CTAs, nothing else
+        if (getenv("FJSP_PACK")) sscanf(getenv("FJSP_PACK"), "%d,%d,%d,%d,%d", &v->pack_cap[0], &v->pack_cap[1], &v->pack_cap[2], &v->pack_rows[0], &v->pack_rows[1]);
+    }
     {   // shared-memory scratch for the in-CTA LP: what is left of the SM's 200 KB per resident CTA
         const size_t per_cta = (size_t)200 * 1024 / (1024 / FJ_STEP_THREADS);
         size_t left = per_cta > v->stage_bytes + 1024 ? per_cta - v->stage_bytes - 1024 : 0;
@@ -496,8 +542,9 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
         constexpr int VV = decltype(V)::value, MM = decltype(SM)::value;
         A.park_count = v->d_pend_count; A.park_env = v->d_pend_env;
         if (v->pack) {
-            fjsp_flag_kernel<<<(v->B + 255) / 256, 256, 0, st>>>(v->P, v->d_order, v->d_flags, T);
-            fjsp_pack_kernel<<<1, FJ_PACK_THREADS, 0, st>>>(v->P, v->d_order, v->d_flags, v->d_order_dyn, v->step_threads / 32);
+            fjsp_flag_kernel<<<(v->B + 255) / 256, 256, 0, st>>>(v->P, v->d_order, v->d_flags, T, v->pack_rows[0], v->pack_rows[1]);
+            fjsp_pack_kernel<<<1, FJ_PACK_THREADS, 0, st>>>(v->P, v->d_order, v->d_flags, v->d_order_dyn, v->step_threads / 32,
+                                                            v->pack_cap[0], v->pack_cap[1], v->pack_cap[2]);
         }
         fjsp_step_kernel<VV, MM><<<v->step_grid, v->step_threads, v->step_smem_bytes, st>>>(v->P, A);
         // resume rounds: an env can meet a reset and further order arrivals inside one launch; the
@@ -588,13 +635,24 @@ int fjsp_vec_reset_host(fjsp_vec *v, double *h_state64, float *h_state32)
     return 0;
 }
 
+int fjsp_vec_slots(fjsp_vec *v, int32_t *h_out, int capacity)
+{
+    if (!v) { g_err = "fjsp_vec_slots: null handle"; return -1; }
+    if (!h_out) return v->n_slots;
+    if (capacity < v->n_slots) { g_err = "fjsp_vec_slots: buffer too small"; return -1; }
+    CK(cudaSetDevice(v->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h_out, v->d_order_dyn, (size_t)v->n_slots * 4, cudaMemcpyDeviceToHost));
+    return v->n_slots;
+}
+
 int fjsp_vec_trace(fjsp_vec *v, int64_t *h_out, int clear)
 {
     if (!v) { g_err = "fjsp_vec_trace: null handle"; return -1; }
     if (!v->d_trace) { g_err = "fjsp_vec_trace: not a trace build (compile with -DFJ_TRACE)"; return -6; }
     CK(cudaSetDevice(v->device));
     CK(cudaDeviceSynchronize());
-    const size_t bytes = (size_t)v->step_grid * 16 * 8 * 8;
+    const size_t bytes = (size_t)v->step_grid * FJ_TRACE_ROWS * 8 * 8;
     if (h_out) CK(cudaMemcpy(h_out, v->d_trace, bytes, cudaMemcpyDeviceToHost));
     if (clear) CK(cudaMemset(v->d_trace, 0, bytes));
     return 0;

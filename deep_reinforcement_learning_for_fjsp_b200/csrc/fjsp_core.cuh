@@ -157,8 +157,9 @@ struct FjCtx {
 // __noinline__ functions lived in the per-thread stack: 1 KB x 896 threads per SM thrashed L1,
 // every `c.field` was an 8-sector local-memory load and half of them missed;
 // profiles/README.md r01_v4.  From shared memory it is one broadcast word.)
+#define FJ_TRACE_ROWS 33   // trace rows per CTA: one per warp (<= 32) + one for the CTA's LP phases
 #ifndef FJ_CTX_WARPS
-#define FJ_CTX_WARPS 16   // most warps per CTA of any kernel that uses the contexts
+#define FJ_CTX_WARPS 32   // most warps per CTA of any kernel that uses the contexts
 #endif
 #ifdef __CUDACC__
 static __shared__ FjParams fj_sP;
@@ -496,7 +497,7 @@ FJ_FN double fj_lp_colvec_dot(const FjCtx &c, const FjLp &L, const double *brow,
 #define FJ_LPT(k) do { const long long n_ = clock64(); la_[k] += n_ - lt_; lt_ = n_; } while (0)
 #define FJ_LPT_ITER() (la_[7] += 1)
 #define FJ_LPT_FLUSH() do { if (g.rank() == 0 && g.size() > FJ_NL && c.P->trace) { \
-    for (int k_ = 0; k_ < 8; ++k_) c.P->trace[((size_t)blockIdx.x * 16 + 15) * 8 + k_] += la_[k_]; } } while (0)
+    for (int k_ = 0; k_ < 8; ++k_) c.P->trace[((size_t)blockIdx.x * FJ_TRACE_ROWS + FJ_TRACE_ROWS - 1) * 8 + k_] += la_[k_]; } } while (0)
 #else
 #define FJ_LPT_DECL
 #define FJ_LPT(k)
@@ -648,6 +649,215 @@ FJ_FN int fj_lp_solve(const G &g_in, FjCtx &c, FjLp &L, double *x_out, int *iter
     if (iters_out) *iters_out = it;
     return rc;
 }
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- CTA fast path of the LP
+// The same pivoting rules and the same floating-point operations as fj_lp_solve (results are
+// bit-identical; tests/test_gpu_parity.py compares both with the oracle), organised for latency:
+// an LP iteration is a chain of short dependent phases, and a warp here retires one
+// instruction per ~15-20 cycles, so what counts is the number of instructions on the chain.
+//   * every structural column carries a descriptor: its four row indices (machine row,
+//     demand row, the two precedence rows; a missing row points at a padding column of B^-1
+//     that is always 0, which adds +-0 and leaves the accumulator unchanged) and its two
+//     coefficients.  A reduced cost or an entry of w is 4 loads, 4 multiplies, 4 adds, no branch;
+//   * the basis inverse rows have stride R + 1 (the padding column);
+//   * x_B, the basis and w of row i stay in registers of thread i;
+//   * the t row of B^-1 (the pricing vector y) is mirrored in shared memory and updated by
+//     the threads that scale the pivot row, so the pricing of the next iteration overlaps the
+//     rank-1 update of this one: three CTA barriers per iteration (two of them inside the
+//     reductions) instead of seven.
+#define FJ_LPF_RMAX 192
+struct FjLpFastSmem {
+    double w[FJ_LPF_RMAX];
+    double y[2][FJ_LPF_RMAX + 2];
+    short prec[FJSP_MAX_KT];
+    int nprec;
+};
+static __shared__ FjLpFastSmem fj_sLpf;
+
+FJ_FN double fj_lpf_dot(const double *row, uint2 ix, double a, double r, bool negate)
+{
+    const double b0 = row[ix.x & 0xffffu], b1 = row[ix.x >> 16], b2 = row[ix.y & 0xffffu], b3 = row[ix.y >> 16];
+    double acc = fj_add(0.0, fj_mul(negate ? -b0 : b0, 1.0));
+    acc = fj_add(acc, fj_mul(negate ? -b1 : b1, a));
+    acc = fj_add(acc, fj_mul(negate ? -b2 : b2, r));
+    acc = fj_add(acc, fj_mul(negate ? -b3 : b3, -r));
+    return acc;
+}
+
+// returns -1 when the LP does not fit the fast path (the caller then runs fj_lp_solve)
+FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab, double *x_out, int *iters_out)
+{
+    FjCtaGroup g = g_in;
+    FjLpFastSmem &S = fj_sLpf;
+    const int tid = g.rank(), nt = g.size();
+    const int M = c.M, KT = c.KT, Mx = c.Mx;
+    const FjRO ptime = FJ_I(c, ptime);
+    const FjEligRO elig = fj_elig(c);
+    const FjLastRO rjlast = fj_rjlast(c);
+    const FjStageRO rjstage = fj_rjstage(c);
+    const FjRO colbase = FJ_I(c, colbase);
+    FJ_LPT_DECL;
+    if (tid < 32) {   // precedence rows, numbered in ascending operation-type order
+        int base = 0;
+        for (int q0 = 0; q0 < KT; q0 += 32) {
+            const int q = q0 + tid;
+            const int f = q < KT && !rjlast[q] && c.qlen[q + 1] == 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (q < KT) S.prec[q] = (short)(f ? M + KT + base + __popc(bal & ((1u << tid) - 1u)) : -1);
+            base += __popc(bal);
+        }
+        if (tid == 0) S.nprec = base;
+    }
+    __syncthreads();
+    const int NP = FJ_I(c, hdr)[7], R = M + KT + S.nprec, C = NP + 1, Rs = (R + 2) & ~1;   // even stride: 16-byte rows, >= 1 padding column
+    if (R > FJ_LPF_RMAX || R > nt || R >= 0xffff) { __syncthreads(); return -1; }
+    // carve the slab: B^-1 [R][Rs], column descriptors, positions, final x_B
+    double *Binv = (double *)slab;
+    double2 *coef = (double2 *)(slab + ((size_t)R * Rs * 8 + 15) / 16 * 16);
+    uint2 *cidx = (uint2 *)(coef + C);
+    int *pos = (int *)(cidx + C);
+    double *xBm = (double *)(pos + ((C + R + 1) & ~1));
+    for (int q = tid; q < KT; q += nt) {
+        unsigned em = (unsigned)elig[q];
+        int col = colbase[q];
+        const double fs = (double)c.fstart[q];
+        const int p_prev = (rjstage[q] > 0 && S.prec[q - 1] >= 0) ? S.prec[q - 1] : R;
+        const int p_own = S.prec[q] >= 0 ? S.prec[q] : R;
+        while (em) {
+            const int m = fj_ffs0(em); em &= em - 1;
+            const double rate = fj_div(1.0, (double)ptime[q * Mx + m]);
+            coef[col] = make_double2(-fj_div(rate, fs), rate);
+            cidx[col] = make_uint2((unsigned)m | ((unsigned)(M + q) << 16), (unsigned)p_prev | ((unsigned)p_own << 16));
+            ++col;
+        }
+    }
+    for (int j = tid; j < C + R; j += nt) pos[j] = j >= C ? j - C : -1;
+    for (int e = tid; e < R * Rs; e += nt) { const int i = e / Rs, k = e - i * Rs; Binv[e] = i == k ? 1.0 : 0.0; }
+    for (int k = tid; k < R + 2; k += nt) { S.y[0][k] = 0.0; S.y[1][k] = 0.0; }
+    double xb = tid < M ? 1.0 : 0.0;        // x_B of row tid (tid < R)
+    int bvar = C + tid;                     // basic variable of row tid
+    __syncthreads();
+    const int dantzig_iters = 20 * R + 100, hard_iters = 200 * R + 1000;
+    const int nvar = C + R, t_col = NP;
+    // warps 0 .. npw-1 hold the columns that are priced; in a large CTA they leave the rank-1
+    // update to the other warps, so that pricing and update run side by side
+    const int nw = nt >> 5, npw = (nvar + 31) >> 5;
+    const bool split = nw - npw >= 8 && nw >= 2 * npw;
+    const int uw = split ? (tid >> 5) - npw : (tid >> 5), nuw = split ? nw - npw : nw;
+    const int rpw = (R + nuw - 1) / nuw;
+    const int row_lo = uw < 0 ? R : (uw * rpw < R ? uw * rpw : R), row_hi = row_lo + rpw < R ? row_lo + rpw : R;
+    const int lane = tid & 31;
+    int it = 0, rc = 0, cur = 0, pt = -1, p_last = -1;
+    FJ_LPT(0);
+    for (;; ++it) {
+        FJ_LPT_ITER();
+        if (it >= hard_iters) { rc = 2; break; }
+        // ---- pricing on the mirrored t row: most negative reduced cost (lowest column on
+        // ties) / Bland: lowest column
+        const double *y = S.y[cur];
+        const int bland = it >= dantzig_iters;
+        double ek = 0.0; int ei = FJ_EMPTY, ea = 0;
+        for (int j = tid; j < nvar; j += nt) {
+            if (pos[j] >= 0) continue;
+            double d;
+            if (j < NP) {
+                const double2 cf = coef[j];
+                d = fj_sub(0.0, pt >= 0 ? fj_lpf_dot(y, cidx[j], cf.x, cf.y, true) : 0.0);
+            } else if (j == NP) {
+                double acc = 0.0;
+                if (pt >= 0) for (int q = 0; q < KT; ++q) acc = fj_add(acc, fj_mul(-y[M + q], 1.0));
+                d = fj_sub(-1.0, acc);
+            } else {
+                d = pt >= 0 ? -(-y[j - C]) : -0.0;
+            }
+            if (d < -FJ_LP_EPS_D) {
+                if (bland) { if (ei == FJ_EMPTY) { ek = d; ei = j; } }
+                else if (ei == FJ_EMPTY || d < ek) { ek = d; ei = j; }
+            }
+        }
+        FJ_LPT(1);
+        // ---- rank-1 update of the previous pivot (rows != p_last); the pricing above did not
+        // need it.  Warps own row blocks (four rows in flight), a lane owns two adjacent columns.
+        if (p_last >= 0) {
+            const double2 *rowp = (const double2 *)(Binv + (size_t)p_last * Rs);
+            const int R2 = (R + 1) >> 1;   // column pairs; the pair that covers column R updates a zero with a zero
+            for (int i0 = row_lo; i0 < row_hi; i0 += 4) {
+                double wv0 = 0.0, wv1 = 0.0, wv2 = 0.0, wv3 = 0.0;
+                if (i0 + 0 < row_hi && i0 + 0 != p_last) wv0 = S.w[i0 + 0];
+                if (i0 + 1 < row_hi && i0 + 1 != p_last) wv1 = S.w[i0 + 1];
+                if (i0 + 2 < row_hi && i0 + 2 != p_last) wv2 = S.w[i0 + 2];
+                if (i0 + 3 < row_hi && i0 + 3 != p_last) wv3 = S.w[i0 + 3];
+                if (wv0 == 0.0 && wv1 == 0.0 && wv2 == 0.0 && wv3 == 0.0) continue;
+                double2 *r0 = (double2 *)(Binv + (size_t)(i0 + 0) * Rs), *r1 = r0 + (Rs >> 1), *r2 = r1 + (Rs >> 1), *r3 = r2 + (Rs >> 1);
+                for (int k = lane; k < R2; k += 32) {
+                    const double2 pk_ = rowp[k];
+                    double2 e0, e1, e2, e3;
+                    if (wv0 != 0.0) e0 = r0[k];
+                    if (wv1 != 0.0) e1 = r1[k];
+                    if (wv2 != 0.0) e2 = r2[k];
+                    if (wv3 != 0.0) e3 = r3[k];
+                    if (wv0 != 0.0) r0[k] = make_double2(fj_sub(e0.x, fj_mul(wv0, pk_.x)), fj_sub(e0.y, fj_mul(wv0, pk_.y)));
+                    if (wv1 != 0.0) r1[k] = make_double2(fj_sub(e1.x, fj_mul(wv1, pk_.x)), fj_sub(e1.y, fj_mul(wv1, pk_.y)));
+                    if (wv2 != 0.0) r2[k] = make_double2(fj_sub(e2.x, fj_mul(wv2, pk_.x)), fj_sub(e2.y, fj_mul(wv2, pk_.y)));
+                    if (wv3 != 0.0) r3[k] = make_double2(fj_sub(e3.x, fj_mul(wv3, pk_.x)), fj_sub(e3.y, fj_mul(wv3, pk_.y)));
+                }
+            }
+        }
+        FJ_LPT(6);
+        if (bland) ei = g.min_i(ei); else g.argmin(ek, ei, ea);   // barrier: the rank-1 update is complete
+        FJ_LPT(2);
+        const int qin = ei;
+        if (qin == FJ_EMPTY) break;   // optimal
+        // ---- w = B^-1 A_q and the ratio test, row tid
+        double wi = 0.0, rk = 0.0; int ri = FJ_EMPTY, rrow = 0;
+        if (tid < R) {
+            const double *brow = Binv + (size_t)tid * Rs;
+            if (qin < NP) { const double2 cf = coef[qin]; wi = fj_lpf_dot(brow, cidx[qin], cf.x, cf.y, false); }
+            else if (qin == NP) { double acc = 0.0; for (int q = 0; q < KT; ++q) acc = fj_add(acc, fj_mul(brow[M + q], 1.0)); wi = acc; }
+            else wi = brow[qin - C];
+            S.w[tid] = wi;
+            if (wi > FJ_LP_EPS_PIV) { rk = fj_div(xb > 0.0 ? xb : 0.0, wi); ri = bvar; rrow = tid; }
+        }
+        FJ_LPT(3);
+        g.argmin(rk, ri, rrow);       // barrier: publishes w
+        FJ_LPT(4);
+        if (ri == FJ_EMPTY) { rc = 3; break; }
+        const int p = rrow;
+        const double theta = rk, wp = S.w[p];
+        if (tid < R) {
+            if (tid == p) { xb = theta; bvar = qin; }
+            else xb = fj_sub(xb, fj_mul(theta, wi));
+            // pivot row, and the new t row of B^-1 for the next pricing
+            double *rowp = Binv + (size_t)p * Rs;
+            const double pr = fj_div(rowp[tid], wp);
+            rowp[tid] = pr;
+            const int pt_new = qin == t_col ? p : (ri == t_col ? -1 : pt);
+            double yn = 0.0;
+            if (pt_new == p) yn = pr;
+            else if (pt_new >= 0) { const double wt = S.w[pt_new], yo = S.y[cur][tid]; yn = wt != 0.0 ? fj_sub(yo, fj_mul(wt, pr)) : yo; }
+            S.y[cur ^ 1][tid] = yn;
+        }
+        if (tid == 0) { pos[ri] = -1; pos[qin] = p; }
+        pt = qin == t_col ? p : (ri == t_col ? -1 : pt);
+        p_last = p; cur ^= 1;
+        __syncthreads();
+        FJ_LPT(5);
+    }
+    // the update of the last pivot was folded into the pricing pass that found no entering column
+    if (tid < R) xBm[tid] = xb;
+    __syncthreads();
+    for (int j = tid; j < NP; j += nt) {
+        double x = pos[j] >= 0 ? xBm[pos[j]] : 0.0;
+        if (x < FJ_LP_EPS_ZERO) x = 0.0;
+        x_out[j] = x;
+    }
+    __syncthreads();
+    FJ_LPT_FLUSH();
+    if (iters_out) *iters_out = it;
+    return rc;
+}
+#endif
 
 // class_FJSP.py:218-248 reset_object_add up to the LP: the new order's jobs join the
 // counters, fluid start counts are taken, per-pair fluid bookkeeping is cleared.
@@ -1858,7 +2068,7 @@ FJ_FN int fj_cta_sync_or(int pred)
 #define FJ_TR_MARK() (tr_t_ = clock64())
 #define FJ_TR_ACC(k) do { const long long n_ = clock64(); tr_[k] += n_ - tr_t_; tr_t_ = n_; } while (0)
 #define FJ_TR_COUNT(k) (tr_[k] += 1)
-#define FJ_TR_FLUSH(P, K) do { if ((P).trace && fj_lane() == 0) { long long *o_ = (P).trace + ((size_t)blockIdx.x * 16 + (K).warp) * 8; \
+#define FJ_TR_FLUSH(P, K) do { if ((P).trace && fj_lane() == 0) { long long *o_ = (P).trace + ((size_t)blockIdx.x * FJ_TRACE_ROWS + (K).warp) * 8; \
     unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); \
     o_[0] += clock64() - tr_begin_; for (int k_ = 0; k_ < 6; ++k_) o_[1 + k_] += tr_[k_]; o_[7] = sm_; } } while (0)
 #else
@@ -1956,7 +2166,11 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
                         else
                             fj_lp_carve(L, K.slab, K.slab + (size_t)P.d.Rx * P.d.Rx * 8, P.d);
                         int iters = 0;
-                        const int rc = fj_lp_solve(K.group, c2, L, K.x, &iters);
+                        int rc = -1;
+#ifdef FJ_DEVICE_CODE
+                        if (!K.lp_smem) rc = fj_lp_solve_fast(K.group, c2, K.slab, K.x, &iters);
+#endif
+                        if (rc < 0) rc = fj_lp_solve(K.group, c2, L, K.x, &iters);
                         if (K.group.rank() == 0) { K.meta[0] = iters; K.meta[1] = rc; }
                         K.group.sync();
                     }
@@ -2029,7 +2243,7 @@ FJ_FN void fj_env_reset_finish(const FjParams &Pin, int env, unsigned char *lp, 
 }
 
 // one parked LP, solved by a whole CTA (device) / one thread (host build)
-FJ_FN void fj_lp_service(const FjParams &Pin, const FjCtaGroup &g, const int *list, int idx, unsigned char *binv, unsigned char *small_)
+FJ_FN void fj_lp_service(const FjParams &Pin, const FjCtaGroup &g, const int *list, int idx, unsigned char *binv, unsigned char *small_, unsigned char *fast_slab = nullptr)
 {
     const FjParams &P = fj_params_bind(Pin);
     const int env = list[idx];
@@ -2037,7 +2251,11 @@ FJ_FN void fj_lp_service(const FjParams &Pin, const FjCtaGroup &g, const int *li
     FjLp L;
     fj_lp_carve(L, binv, small_, P.d);
     int iters = 0;
-    const int rc = fj_lp_solve(g, c, L, P.lp_x + (size_t)idx * P.d.NPx, &iters);
+    int rc = -1;
+#ifdef FJ_DEVICE_CODE
+    if (fast_slab) rc = fj_lp_solve_fast(g, c, fast_slab, P.lp_x + (size_t)idx * P.d.NPx, &iters);
+#endif
+    if (rc < 0) rc = fj_lp_solve(g, c, L, P.lp_x + (size_t)idx * P.d.NPx, &iters);
     if (g.rank() == 0) { P.lp_meta[2 * idx] = iters; P.lp_meta[2 * idx + 1] = rc; }
     g.sync();
 }

@@ -120,7 +120,8 @@ struct FjParams {
     FjEnvOff eo;
     const int32_t *inst;        // instance table
     const int32_t *env_inst;    // [B] instance index of each env
-    const int32_t *order;       // [B] envs by decreasing static walk length (main kernel's visiting order)
+    const int32_t *order;       // [n_slots] env of every warp slot of the main kernel (slot = virtual CTA * warps + warp), -1 = empty
+    int n_slots;
     unsigned char *env;         // env table
     unsigned char *lp;          // LP scratch, one slab per resident warp
     unsigned long long lp_stride;

@@ -81,9 +81,16 @@ int fjsp_vec_reset_host(fjsp_vec *v, double *h_state64, float *h_state32);
  * delay_time_sum_unprocessed.  Host buffer [n_envs][12]. */
 int fjsp_vec_info(fjsp_vec *v, int64_t *h_out);
 
+/* Diagnostic: the warp-slot map of the last step launch (environment of every warp slot of the
+ * step kernel, slot = virtual CTA * warps per CTA + warp, -1 = empty; written before every launch
+ * by the LP-aware packing).  h_out == NULL returns the number of slots, else fills h_out
+ * (capacity entries) and returns the number of slots; negative on error. */
+int fjsp_vec_slots(fjsp_vec *v, int32_t *h_out, int capacity);
+
 /* Diagnostic (builds with -DFJ_TRACE only, otherwise returns -6): per warp of the step
- * kernel's grid 8 int64 [grid][16][8] = cycles in the rollout, in dispatch, clock loop, CTA LP
- * service, observation/outputs, LPs served by the CTA, spare, SM id.  clear != 0 zeroes them. */
+ * kernel's grid 8 int64 [grid][33][8] = cycles in the rollout, in dispatch, clock loop, CTA LP
+ * service, observation/outputs, LPs served by the CTA, spare, SM id (row 32 of a CTA: cycles per
+ * phase of its LPs).  clear != 0 zeroes them. */
 int fjsp_vec_trace(fjsp_vec *v, int64_t *h_out, int clear);
 
 #ifdef __cplusplus

@@ -44,23 +44,55 @@ def main():
         vec.rollout(sets[i % 4][0], sets[(i + 1) % 4][1], reward_policy=1, out=out, state_dtype=torch.float32)
     q = vec.query()
     grid = q["grid"]
-    tr = np.zeros((grid, 16, 8), dtype=np.int64)
+    inf = vec.info()
+    ops = np.array([x.total_operations for x in insts]); rub = np.array([x.machine_count + 2 * sum(x.ntask) - x.kind_count for x in insts])
+    likely = (inf["done"] != 0) | (inf["next_order"] < 3) | (ops - inf["step_count"] <= T - 8)
+    print("predicted LP envs: %d of %d (done %d, young %d, ending %d); heavy %d medium %d light %d" % (
+        likely.sum(), B, (inf["done"] != 0).sum(), (inf["next_order"] < 3).sum(), (ops - inf["step_count"] <= T - 8).sum(),
+        (likely & (rub >= 85)).sum(), (likely & (rub >= 55) & (rub < 85)).sum(), (likely & (rub < 55)).sum()))
+    tr = np.zeros((grid, 33, 8), dtype=np.int64)
     L = _lib.load()
     _lib.check(L.fjsp_vec_trace(vec._h, tr.ctypes.data, 1))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    acc = np.zeros_like(tr)
+    ms = 0.0
     for i in range(a.launches):
+        ev0.record()
         vec.rollout(sets[i % 4][0], sets[(i + 1) % 4][1], reward_policy=1, out=out, state_dtype=torch.float32)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / a.launches
-    _lib.check(L.fjsp_vec_trace(vec._h, tr.ctypes.data, 0))
+        ev1.record()
+        torch.cuda.synchronize()
+        ms_i = ev0.elapsed_time(ev1)
+        ms += ms_i / a.launches
+        _lib.check(L.fjsp_vec_trace(vec._h, tr.ctypes.data, 1))
+        nwi = q["block"] // 32
+        ct = tr[:, :nwi, 0].max(1)
+        nl = tr[:, 0, 5]
+        act = (tr[:, :nwi, 1] > 100000).sum(1)
+        top = np.argsort(-ct)[:4]
+        print("launch %d: %.3f ms = %.2f M cycles @1.965 GHz | median CTA %.2f M, CTAs with LPs %d, LPs %d | slowest CTAs: %s" % (
+            i, ms_i, ms_i * 1.965, np.median(ct) / 1e6, (nl > 0).sum(), nl.sum(),
+            "; ".join("#%d %.2f M (%d envs, %d LPs %.2f M, busy %.2f M)" % (b, ct[b] / 1e6, act[b], nl[b], tr[b, 0, 3] / 1e6,
+                                                                  (tr[b, :nwi, 1] + tr[b, :nwi, 2] + tr[b, :nwi, 4]).max() / 1e6) for b in top)))
+        ones = np.where(act == 1)[0]
+        if len(ones):
+            print("   single-env CTAs: %d, total mean %.2f M max %.2f M, LP mean %.2f M, LPs mean %.1f" % (
+                len(ones), ct[ones].mean() / 1e6, ct[ones].max() / 1e6, tr[ones, 0, 3].mean() / 1e6, nl[ones].mean()))
+        acc += tr
+        if i == 0:
+            ns = L.fjsp_vec_slots(vec._h, None, 0)
+            sl = np.zeros(ns, dtype=np.int32)
+            L.fjsp_vec_slots(vec._h, sl.ctypes.data, ns)
+            sl = sl.reshape(-1, nwi)
+            occ = (sl >= 0).sum(1)
+            print("   slot map: %d virtual CTAs x %d; envs placed %d (distinct %d); occupancy histogram %s; first CTAs %s" % (
+                sl.shape[0], nwi, (sl >= 0).sum(), len(set(sl[sl >= 0].tolist())), np.bincount(occ, minlength=nwi + 1).tolist(), occ[:24].tolist()))
+    tr = acc
     tr = tr.astype(np.float64) / a.launches
     nw = q["block"] // 32
-    if nw < 16:
-        lpt = tr[:, 15, :].sum(0) * a.launches
+    if True:
+        lpt = tr[:, 32, :].sum(0) * a.launches
         solves = tr[:, 0, 5].sum() * a.launches
-        names = ["setup", "pricing", "argmin-in", "w", "ratio+argmin", "xB/pivot-row", "rank-1 update"]
+        names = ["setup", "pricing", "argmin-in", "w+ratio", "argmin-out", "xB/pivot-row", "rank-1 update"]
         print("LP phases (cycles per iteration): " + ", ".join("%s %.0f" % (n, lpt[k] / max(lpt[7], 1)) for k, n in enumerate(names) if k)
               + "; setup per LP %.0f; iterations per LP %.1f; LPs %d" % (lpt[0] / max(solves, 1), lpt[7] / max(solves, 1), solves))
     tr = tr[:, :nw]
