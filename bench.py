@@ -49,6 +49,7 @@ def parse():
                     help="also time this many copies (the same instances, replicated) for a few launches; 0 = skip")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the T=1 / T=128 rollout-length lines")
     return ap.parse_args()
 
 
@@ -246,6 +247,29 @@ def main():
         e2e_call(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    # ---- other rollout lengths on the same batch (not the headline): T = 1 is one reference
+    # step() per launch, T = 128 a PPO-style rollout
+    sweep = []
+    if args.sweep:
+        for T2, n2 in ((1, 64), (128, max(3, K // 4))):
+            a2 = [torch.from_numpy(make_actions(rng, T2, B, args.variant)[0]).to(dev) for _ in range(2)]
+            r2 = [torch.from_numpy(make_actions(rng, T2, B, args.variant)[1].view(np.int32)).to(dev) for _ in range(2)]
+            o2 = {"state": torch.empty((T2, B, vec.state_size), dtype=torch.float32, device=dev),
+                  "reward": torch.empty((T2, B), dtype=torch.float64, device=dev),
+                  "done": torch.empty((T2, B), dtype=torch.int32, device=dev)}
+            for i in range(3):
+                vec.rollout(a2[i % 2], r2[(i + 1) % 2], reward_policy=1, out=o2, state_dtype=torch.float32)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            e0.record(stream)
+            for i in range(n2):
+                vec.rollout(a2[i % 2], r2[(i + 1) % 2], reward_policy=1, out=o2, state_dtype=torch.float32)
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms2 = e0.elapsed_time(e1)
+            sweep.append({"env_steps_per_launch": T2, "launches": n2, "value": B * T2 * n2 / (ms2 / 1e3), "unit": UNIT,
+                          "ms_per_launch": ms2 / n2})
+            del a2, r2, o2
     # ---- the same kernels with enough copies to fill the machine (not the headline)
     large = None
     if args.large_envs and args.large_envs > B:
@@ -305,7 +329,7 @@ def main():
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "envs_per_gpu": B, "env_steps_per_step": T,
                            "machines": args.machines, "orders": args.orders, "variant": args.variant,
-                           "l2": "flushed between timed launches (256 MiB fill)", "kernels_per_step": "step kernel (in-CTA LP service) + empty LP/resume fallback launches", "parallelism": f"shard{world}",
+                           "l2": "flushed between timed launches (256 MiB fill)", "kernels_per_step": "flag + pack kernels (LP-aware env-to-CTA map), step kernel (in-CTA LP service)", "parallelism": f"shard{world}",
                            "env_record_bytes": q["env_record_bytes"], "grid": q["grid"], "block": q["block"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "fjsp_vec_step_host (C ABI, pinned host buffers, float32 state out)"},
@@ -319,7 +343,8 @@ def main():
                 "wall_s_timed_region": wall, "env_errors": errors,
                 "timed_region_events": {"fluid_lp_solves": lp_solves, "episodes_finished": episodes,
                                         "burnin_env_steps_per_copy": args.burnin},
-                "launch_ms_min_max": [min(per_launch_ms), max(per_launch_ms)], "large_batch": large}
+                "launch_ms_min_max": [min(per_launch_ms), max(per_launch_ms)], "large_batch": large,
+                "rollout_sweep": sweep}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_port_throughput(insts[:64], args.variant, args.cpu_seconds, T, args.seed)
         print(json.dumps(line), flush=True)

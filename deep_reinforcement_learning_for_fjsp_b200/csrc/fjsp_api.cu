@@ -240,7 +240,7 @@ struct fjsp_vec {
     size_t lp_smem_bytes, stage_bytes, step_smem_bytes;
     int *d_pend_count, *d_pend_env, *d_lp_meta, *d_rep_env, *d_plan_meta, *d_plan_ok;
     double *d_lp_x, *d_plan_x;
-    int n_inst, plan_ready;
+    int n_inst, plan_ready, plan_all;   // plan_all: every instance's order-0 LP solution gets cached by the first reset
     int32_t *d_inst, *d_env_inst, *d_order, *d_order_dyn;
     int n_slots, pack_cap[3], pack_rows[2], multi_round;
     unsigned char *d_flags;
@@ -393,6 +393,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         std::vector<int> rep(n_instances, -1);
         for (int e = n_envs - 1; e >= 0; --e) rep[env_instance[e]] = e;
         v->n_inst = n_instances; v->plan_ready = 0;
+        v->plan_all = 1;
+        for (int i2 = 0; i2 < n_instances; ++i2) if (rep[i2] < 0 || (size_t)rep[i2] >= slots) v->plan_all = 0;
         CK(cudaMalloc(&v->d_rep_env, (size_t)n_instances * 4));
         CK(cudaMalloc(&v->d_plan_x, (size_t)n_instances * per_slot));
         CK(cudaMalloc(&v->d_plan_meta, (size_t)n_instances * 8));
@@ -549,7 +551,10 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
         fjsp_step_kernel<VV, MM><<<v->step_grid, v->step_threads, v->step_smem_bytes, st>>>(v->P, A);
         // resume rounds: an env can meet a reset and further order arrivals inside one launch; the
         // last round solves whatever is left in line
-        for (int r = 0; r < FJ_ROUNDS; ++r) {
+        // With the CTA-served LP and every instance's order-0 solution cached nothing can park
+        // (an env parks only for a reset that finds no cached solution): skip the fallback rounds.
+        const bool can_park = !(v->P.cta_lp == 1 && v->plan_ready && v->plan_all);
+        for (int r = 0; can_park && r < FJ_ROUNDS; ++r) {
             launch_lp(v, st, r);
             const int *cnt = v->d_pend_count + r, *lst = v->d_pend_env + (size_t)(r & 1) * v->B;
             A.park_count = v->d_pend_count + r + 1; A.park_env = v->d_pend_env + (size_t)((r + 1) & 1) * v->B;
@@ -559,7 +564,7 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
         return 0;
     });
     if (rc) return rc;
-    v->launches += 1 + 2 * FJ_ROUNDS + 2 * v->pack;
+    v->launches += 1 + ((v->P.cta_lp == 1 && v->plan_ready && v->plan_all) ? 0 : 2 * FJ_ROUNDS) + 2 * v->pack;
     CK(cudaGetLastError());
     return 0;
 }

@@ -146,6 +146,17 @@ class FJSPVecEnv:
         _lib.check(self._L.fjsp_vec_info(self._h, a.ctypes.data))
         return {k: a[:, i] for i, k in enumerate(INFO_KEYS)}
 
+    def slots(self):
+        """Diagnostic: environment of every warp slot of the last step launch (-1 = empty),
+        shaped [virtual CTAs, warps per CTA] (the LP-aware packing rewrites it before every launch)."""
+        n = self._L.fjsp_vec_slots(self._h, None, 0)
+        if n < 0:
+            _lib.check(n)
+        a = np.zeros(n, np.int32)
+        if self._L.fjsp_vec_slots(self._h, a.ctypes.data, n) < 0:
+            _lib.check(-1)
+        return a.reshape(-1, self.query()["block"] // 32)
+
     def query(self):
         a = np.zeros(8, np.int64)
         _lib.check(self._L.fjsp_vec_query(self._h, a.ctypes.data))

@@ -205,3 +205,33 @@ def test_edge_cases(variant):
 
 def test_left_to_right_sum_mode_vs_oracle():
     pc.compare_with_oracle(make_vec, "SO_DFJSP", 19, n_inst=4, copies=4, T=48, launches=2, sum_mode=0)
+
+
+@pytest.mark.parametrize("n_inst,copies", [(3, 1), (5, 7), (16, 40), (8, 600)])
+def test_lp_aware_packing_places_every_env_once(n_inst, copies):
+    """The warp-slot map the packing kernel writes before each launch holds every environment
+    exactly once, whatever the batch size (one partial CTA, several CTAs, more than one round of
+    CTAs), and the launch that used it agrees with the oracle on a sample of environments."""
+    import oracle_py
+    insts, env_instance = pc.random_batch(77 + n_inst, "MO_DFJSP", n_inst, copies)
+    blobs = [i.to_blob() for i in insts]
+    vec = make_vec(blobs, env_instance, "MO_DFJSP")
+    B, T = len(env_instance), 48
+    rng = np.random.default_rng(5)
+    vec.reset_host()
+    sample = list(range(0, B, max(1, B // 12)))
+    envs = [oracle_py.OracleEnv(blobs[env_instance[e]], "MO_DFJSP") for e in sample]
+    for e in envs:
+        e.reset()
+    for launch in range(6):
+        actions = np.stack([rng.integers(0, 12, (T, B)), rng.integers(0, 10, (T, B))], -1).astype(np.int32)
+        rnd = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
+        st, rw, dn, rec = vec.step_host(actions, rnd, 1)
+        sl = vec.slots()
+        placed = sl[sl >= 0]
+        assert placed.size == B and np.array_equal(np.sort(placed), np.arange(B))
+        ref = oracle_py.batch_rollout(envs, actions[:, sample], rnd[:, sample], 1)
+        assert np.array_equal(rec[:, sample], ref["rec"]) and np.array_equal(dn[:, sample], ref["done"])
+        assert np.array_equal(rw[:, sample], ref["reward"])
+        assert np.allclose(st[:, sample], ref["state"], rtol=1e-9, atol=1e-12)
+    assert (vec.info()["error"] == 0).all()
