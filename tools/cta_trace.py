@@ -67,7 +67,10 @@ def main():
         nwi = q["block"] // 32
         ct = tr[:, :nwi, 0].max(1)
         nl = tr[:, 0, 5]
-        act = (tr[:, :nwi, 1] > 100000).sum(1)
+        ns = L.fjsp_vec_slots(vec._h, None, 0)
+        slm = np.zeros(ns, dtype=np.int32)
+        L.fjsp_vec_slots(vec._h, slm.ctypes.data, ns)
+        act = (slm.reshape(-1, nwi)[:grid] >= 0).sum(1)
         top = np.argsort(-ct)[:4]
         print("launch %d: %.3f ms = %.2f M cycles @1.965 GHz | median CTA %.2f M, CTAs with LPs %d, LPs %d | slowest CTAs: %s" % (
             i, ms_i, ms_i * 1.965, np.median(ct) / 1e6, (nl > 0).sum(), nl.sum(),

@@ -5,7 +5,7 @@ TAG=${1:-x}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/tests_$TAG.log
 cat gpurun_out/tests_$TAG.log
-python bench.py --steps 10 --warmup 3 --cpu-seconds 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+python bench.py --steps 20 --warmup 3 --cpu-seconds 10 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_$TAG.json"))
