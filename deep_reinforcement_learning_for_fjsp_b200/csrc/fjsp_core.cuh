@@ -2011,8 +2011,8 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
 }
 
 // ---------------------------------------------------------------- main kernel driver
-// The main step kernel runs the warps of a CTA in LOCKSTEP PHASES (dispatch + clock /
-// observation, one CTA barrier each): all warps then execute the same few KB of straight-line code at
+// The main step kernel runs the warps of a CTA in LOCKSTEP (one CTA barrier per step, after the
+// clock loop: it is also the vote on fluid-LP requests): all warps then execute the same few KB of straight-line code at
 // the same time and share its instruction-cache lines.  Profiling the free-running
 // version (profiles/README.md) showed the per-step code (tens of KB, executed once per
 // step per warp) being re-fetched from L2 by every warp: "no instruction" was the top
@@ -2102,8 +2102,11 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
         double out_reward = 0.0;
         int out_done = 0;
         int stage = 0;      // 0 nothing, 1 dispatched (run the clock), 2 nothing dispatchable (emit unchanged)
-#ifndef FJ_ONE_BARRIER
-        FJ_CTA_SYNC();      // ---- phase A: auto-reset / task_select / machine_select / dispatch
+        // ---- phase A: auto-reset / task_select / machine_select / dispatch.  The step's one CTA
+        // barrier is the LP vote after the clock loop (a second barrier here measured 3 % slower
+        // with one CTA per SM: 66.1 M vs 68.1 M env-steps/s; FJ_TWO_BARRIERS brings it back).
+#ifdef FJ_TWO_BARRIERS
+        FJ_CTA_SYNC();
 #endif
         FJ_TR_MARK();
         if (!parked) {
