@@ -73,31 +73,64 @@ FJ_FN double fj_div(double a, double b) { return a / b; }
 #endif
 
 // ---------------------------------------------------------------- warp reductions
-FJ_OUTLINE long long fj_sum_ll(long long v)
+// Integer reductions are single redux.sync instructions on the device (the shuffle butterflies
+// they replace were ~250 instructions on every step's serial chain).
+#ifdef FJ_DEVICE_CODE
+FJ_FN int fj_min_i(int v) { return __reduce_min_sync(0xffffffffu, v); }
+FJ_FN unsigned fj_or_u(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
+// sum of non-negative 64-bit values: three 22-bit limbs, each summed exactly in 32 bits
+FJ_FN long long fj_sum_ll(long long v)
 {
-    for (int m = FJ_NL / 2; m > 0; m >>= 1) v += fj_xor_ll(v, m);
-    return v;
+    const unsigned long long u = (unsigned long long)v;
+    const unsigned long long s0 = __reduce_add_sync(0xffffffffu, (unsigned)(u & 0x3fffffu));
+    const unsigned long long s1 = __reduce_add_sync(0xffffffffu, (unsigned)((u >> 22) & 0x3fffffu));
+    const unsigned long long s2 = __reduce_add_sync(0xffffffffu, (unsigned)(u >> 44));
+    return (long long)(s0 + (s1 << 22) + (s2 << 44));
 }
-FJ_OUTLINE int fj_sum_i(int v)
+// sum of two packed non-negative 32-bit counters (hi << 32 | lo), each total below 2^32
+FJ_FN long long fj_sum_pair(long long v)
 {
-    for (int m = FJ_NL / 2; m > 0; m >>= 1) v += fj_xor_i(v, m);
-    return v;
+    const unsigned long long lo = __reduce_add_sync(0xffffffffu, (unsigned)v);
+    const unsigned long long hi = __reduce_add_sync(0xffffffffu, (unsigned)((unsigned long long)v >> 32));
+    return (long long)((hi << 32) | lo);
 }
-FJ_OUTLINE int fj_min_i(int v)
-{
-    for (int m = FJ_NL / 2; m > 0; m >>= 1) { int o = fj_xor_i(v, m); v = o < v ? o : v; }
-    return v;
-}
-FJ_OUTLINE unsigned fj_or_u(unsigned v)
-{
-    for (int m = FJ_NL / 2; m > 0; m >>= 1) v |= (unsigned)fj_xor_i((int)v, m);
-    return v;
-}
+#else
+FJ_FN long long fj_sum_ll(long long v) { return v; }
+FJ_FN long long fj_sum_pair(long long v) { return v; }
+FJ_FN int fj_min_i(int v) { return v; }
+FJ_FN unsigned fj_or_u(unsigned v) { return v; }
+#endif
 FJ_OUTLINE double fj_sum_d(double v)   // observation-only sums (fixed butterfly order)
 {
     for (int m = FJ_NL / 2; m > 0; m >>= 1) v = fj_add(v, fj_xor_d(v, m));
     return v;
 }
+
+// Lexicographic minimum of (key, id) over the warp on an order-preserving integer image of the
+// double key (keys are never NaN; -0.0 is canonicalised by the callers): three redux.sync minima.
+#define FJ_EMPTY 0x7fffffff
+#ifdef __CUDACC__
+FJ_FN unsigned long long fj_ord_enc(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+FJ_FN double fj_ord_dec(unsigned hi, unsigned lo)
+{
+    const unsigned long long u = ((unsigned long long)hi << 32) | lo;
+    return __longlong_as_double((long long)((u >> 63) ? (u ^ 0x8000000000000000ull) : ~u));
+}
+// (hi, lo, id), 0xffffffff everywhere = none.  All lanes return the minimum.
+FJ_FN void fj_warp_lexmin(unsigned &hi, unsigned &lo, unsigned &id)
+{
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    lo = hi == mh ? lo : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
+    id = (hi == mh && lo == ml) ? id : 0xffffffffu;
+    id = __reduce_min_sync(0xffffffffu, id);
+    hi = mh; lo = ml;
+}
+#endif
 
 // running "first extremal element" of Python's max()/min() over a list in index order
 struct FjBest {
@@ -107,15 +140,20 @@ FJ_FN void fj_best_init(FjBest &b) { b.key = 0.0; b.idx = 0x7fffffff; }
 // local update; candidates arrive in ascending idx on a lane, so strict comparison keeps the first
 FJ_FN void fj_best_max(FjBest &b, double key, int idx) { if (b.idx == 0x7fffffff || key > b.key) { b.key = key; b.idx = idx; } }
 FJ_FN void fj_best_min(FjBest &b, double key, int idx) { if (b.idx == 0x7fffffff || key < b.key) { b.key = key; b.idx = idx; } }
-FJ_OUTLINE void fj_best_reduce(FjBest &b, int want_max)
+// warp-wide winner: extremal key, lowest index on ties (only idx is meaningful afterwards)
+FJ_FN void fj_best_reduce(FjBest &b, int want_max)
 {
-    for (int m = FJ_NL / 2; m > 0; m >>= 1) {
-        double ok = fj_xor_d(b.key, m);
-        int oi = fj_xor_i(b.idx, m);
-        if (oi == 0x7fffffff) continue;
-        bool better = (b.idx == 0x7fffffff) || (want_max ? ok > b.key : ok < b.key) || (ok == b.key && oi < b.idx);
-        if (better) { b.key = ok; b.idx = oi; }
-    }
+#ifdef FJ_DEVICE_CODE
+    const bool none = b.idx == 0x7fffffff;
+    unsigned long long u = fj_ord_enc(fj_add(b.key, 0.0));   // -0.0 -> +0.0: equal keys, equal images
+    if (want_max) u = ~u;
+    unsigned hi = none ? 0xffffffffu : (unsigned)(u >> 32), lo = none ? 0xffffffffu : (unsigned)u;
+    unsigned id = none ? 0xffffffffu : (unsigned)b.idx;
+    fj_warp_lexmin(hi, lo, id);
+    b.idx = id == 0xffffffffu ? 0x7fffffff : (int)id;
+#else
+    (void)b; (void)want_max;
+#endif
 }
 
 // ---------------------------------------------------------------- CPython sum()
@@ -308,28 +346,7 @@ FJ_OUTLINE int fj_order_of(const int32_t *cum, int S, int Kx, int r, int n)   //
 // three redux.sync minima over an order-preserving integer image of the double (keys are never
 // NaN or -0.0 here): the first version's shuffle butterfly plus a serial scan of the per-warp
 // partials by every thread was a third of all LP instructions (profiles/README.md r01_v5).
-#define FJ_EMPTY 0x7fffffff
 #ifdef __CUDACC__
-FJ_FN unsigned long long fj_ord_enc(double v)
-{
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-FJ_FN double fj_ord_dec(unsigned hi, unsigned lo)
-{
-    const unsigned long long u = ((unsigned long long)hi << 32) | lo;
-    return __longlong_as_double((long long)((u >> 63) ? (u ^ 0x8000000000000000ull) : ~u));
-}
-// (hi, lo, id): id = idx << 12 | aux, 0xffffffff = none.  All lanes return the minimum.
-FJ_FN void fj_warp_lexmin(unsigned &hi, unsigned &lo, unsigned &id)
-{
-    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
-    lo = hi == mh ? lo : 0xffffffffu;
-    const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
-    id = (hi == mh && lo == ml) ? id : 0xffffffffu;
-    id = __reduce_min_sync(0xffffffffu, id);
-    hi = mh; lo = ml;
-}
 FJ_FN void fj_lex_pack(double key, int idx, int aux, unsigned &hi, unsigned &lo, unsigned &id)
 {
     const unsigned long long u = fj_ord_enc(key);
@@ -1060,6 +1077,7 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
     long long p0 = 0, p1 = 0, p2 = 0, dunp = 0;
     int nav = 0, nfav = 0;
     double s_fr = 0.0, s_gr = 0.0;
+    double fr_keep = 0.0, gr_keep = 0.0;   // this lane's two rates when every operation type has its own lane
     const int rounds = (KT + FJ_NL - 1) / FJ_NL;
     FJ_NOUNROLL
     for (int rd = 0; rd < rounds; ++rd) {
@@ -1144,8 +1162,10 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
             const double fluid_unp = fj_sub((double)c.fstart[q], fj_mul(c.rsum[q], gt));
             const double gap = fj_sub((double)residue, fluid_unp);
             const int pr = c.proc[q];
-            s_fr = fj_add(s_fr, fj_div((double)pr, (double)(residue + pr)));
-            s_gr = fj_add(s_gr, fj_div(gap, (double)c.fstart[q]));
+            fr_keep = fj_div((double)pr, (double)(residue + pr));
+            gr_keep = fj_div(gap, (double)c.fstart[q]);
+            s_fr = fj_add(s_fr, fr_keep);
+            s_gr = fj_add(s_gr, gr_keep);
             if (av) {
                 if (VARIANT == FJSP_SO_FJSSP) {
                     if (SUM_MODE != 0 && sc != 0.0 && isfinite(sc)) sf = fj_add(sf, sc);
@@ -1170,13 +1190,16 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
         nav += av; nfav += fav;
 #endif
     }
-    p0 = fj_sum_ll(p0); p1 = fj_sum_ll(p1); p2 = fj_sum_ll(p2); dunp = fj_sum_ll(dunp);
+    p0 = fj_sum_pair(p0); p1 = fj_sum_pair(p1); p2 = fj_sum_pair(p2); dunp = fj_sum_ll(dunp);
     const long long tn = p0 >> 32, da = p0 & 0xffffffffll, de = p1 >> 32, jn = p1 & 0xffffffffll;
     const long long ja = p2 >> 32, je = p2 & 0xffffffffll;
     const double cro_ave = fj_div(fj_sum_d(s_fr), (double)KT);
     const double gap_ave = fj_div(fj_sum_d(s_gr), (double)KT);
     // second pass: variances (observation only)
     double v_fr = 0.0, v_gr = 0.0;
+    if (rounds == 1) {
+        if (lane < KT) { v_fr = fj_mul(fr_keep - cro_ave, fr_keep - cro_ave); v_gr = fj_mul(gr_keep - gap_ave, gr_keep - gap_ave); }
+    } else
     FJ_NOUNROLL
     for (int q = lane; q < KT; q += FJ_NL) {
         int residue = 0;
