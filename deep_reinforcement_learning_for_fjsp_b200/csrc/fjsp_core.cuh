@@ -106,6 +106,11 @@ FJ_OUTLINE double fj_sum_d(double v)   // observation-only sums (fixed butterfly
     return v;
 }
 
+FJ_FN void fj_sum_d2(double &a, double &b)   // two observation-only sums in one butterfly (same order per value)
+{
+    for (int m = FJ_NL / 2; m > 0; m >>= 1) { const double oa = fj_xor_d(a, m), ob = fj_xor_d(b, m); a = fj_add(a, oa); b = fj_add(b, ob); }
+}
+
 // Lexicographic minimum of (key, id) over the warp on an order-preserving integer image of the
 // double key (keys are never NaN; -0.0 is canonicalised by the callers): three redux.sync minima.
 #define FJ_EMPTY 0x7fffffff
@@ -182,7 +187,7 @@ struct FjCtx {
     int M, K, KT, S, Mx, Kx, Sx;
     unsigned mmask;
     int32_t *scal; double *obs, *obs2, *gapave, *urg, *maxe; uint32_t *avmask, *favmask, *demask, *damask;
-    int32_t *mend, *mlast, *mjob, *mD; double *mF; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
+    int32_t *mend, *mlast, *mjob, *mD; double *mF, *invnkt; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
     double *rsum, *tsum; uint16_t *cntunp, *cntnow, *pk, *slot; double *fu, *fa, *ff; uint16_t *next;
     uint32_t *unpmask; int32_t *duejob, *mindue;   // SO_FJSSP only (per-job due dates)
     uint32_t *h_elig; uint16_t *h_rjinfo; int32_t *h_due, *h_cum, *h_jobbase;   // hot copies of instance statics
@@ -245,7 +250,7 @@ FJ_FN FjCtx &fj_ctx_init(const FjParams &, int env, unsigned char *lp, unsigned 
     c.demask = (uint32_t *)(E + o.demask); c.damask = (uint32_t *)(E + o.damask);
     c.h_elig = (uint32_t *)(E + o.h_elig); c.h_rjinfo = (uint16_t *)(E + o.h_rjinfo); c.h_due = (int32_t *)(E + o.h_due);
     c.h_cum = (int32_t *)(E + o.h_cum); c.h_jobbase = (int32_t *)(E + o.h_jobbase);
-    c.mF = (double *)(E + o.mF); c.mD = (int32_t *)(E + o.mD);
+    c.mF = (double *)(E + o.mF); c.mD = (int32_t *)(E + o.mD); c.invnkt = (double *)(E + o.invnkt);
     c.mend = (int32_t *)(E + o.mend); c.mlast = (int32_t *)(E + o.mlast); c.mjob = (int32_t *)(E + o.mjob);
     c.qhead = (uint16_t *)(E + o.qhead); c.qtail = (uint16_t *)(E + o.qtail); c.qlen = (uint16_t *)(E + o.qlen);
     c.proc = (int32_t *)(E + o.proc); c.fstart = (int32_t *)(E + o.fstart); c.flmask = (uint32_t *)(E + o.flmask);
@@ -1193,9 +1198,13 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
     p0 = fj_sum_pair(p0); p1 = fj_sum_pair(p1); p2 = fj_sum_pair(p2); dunp = fj_sum_ll(dunp);
     const long long tn = p0 >> 32, da = p0 & 0xffffffffll, de = p1 >> 32, jn = p1 & 0xffffffffll;
     const long long ja = p2 >> 32, je = p2 & 0xffffffffll;
-    const double cro_ave = fj_div(fj_sum_d(s_fr), (double)KT);
-    const double gap_ave = fj_div(fj_sum_d(s_gr), (double)KT);
-    // second pass: variances (observation only)
+    // observation-only moments: warp-tree sums; spreads and the machines' gap_ave use the stored reciprocals
+    const double inv_kt = fj_get_d(c.scal, FJ_S_INV_KT), inv_m = fj_get_d(c.scal, FJ_S_INV_M);
+    fj_sum_d2(s_fr, s_gr);
+    // (the means feed differences, so they stay true divisions; the spreads use the reciprocals)
+    const double cro_ave = fj_div(s_fr, (double)KT);
+    const double gap_ave = fj_div(s_gr, (double)KT);
+    // second pass: variances
     double v_fr = 0.0, v_gr = 0.0;
     if (rounds == 1) {
         if (lane < KT) { v_fr = fj_mul(fr_keep - cro_ave, fr_keep - cro_ave); v_gr = fj_mul(gr_keep - gap_ave, gr_keep - gap_ave); }
@@ -1212,38 +1221,35 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
         v_fr = fj_add(v_fr, fj_mul(fr - cro_ave, fr - cro_ave));
         v_gr = fj_add(v_gr, fj_mul(gr - gap_ave, gr - gap_ave));
     }
-    const double cro_std = sqrt(fj_div(fj_sum_d(v_fr), (double)KT));
-    const double gap_std = sqrt(fj_div(fj_sum_d(v_gr), (double)KT));
-    // machines: completion-time spread; MO also the mean / spread of the machines' gap_ave
+    // machines: completion-time spread; MO also the mean / spread of the machines' gap_ave.  Summed
+    // over a machine's operation types, unprocessed - fluid_unprocessed telescopes to
+    // (gap_time * sum of its fluid rates) - (dispatches on it since the last arrival); the exact
+    // CPython-ordered value is only needed as the key of machine rule 4 and is computed there.
     const long long tsum_m = fj_get_ll(c.scal, FJ_S_MENDSUM);
     const double ct_ave = fj_div((double)tsum_m, (double)M);
-    double v_ct = 0.0;
+    double v_ct = 0.0, s_gm = 0.0, ga_l = 0.0;
     FJ_NOUNROLL
     for (int m = lane; m < M; m += FJ_NL) {
         const double dv = fj_sub((double)c.mend[m], ct_ave);
         v_ct = fj_add(v_ct, fj_mul(dv, dv));
-    }
-    const double ct_std = sqrt(fj_div(fj_sum_d(v_ct), (double)M));
-    double gm_ave = 0.0, gm_std = 0.0;
-    if (MO) {
-        // gap_ave of every machine as an observation feature.  Summed over a machine's
-        // operation types, unprocessed - fluid_unprocessed telescopes to
-        // (gap_time * sum of its fluid rates) - (dispatches on it since the last arrival);
-        // the exact CPython-ordered value is only needed as the key of machine rule 4 and is
-        // computed there.
-        const FjRO nkt = FJ_I(c, mnkt);
-        double s_gm = 0.0, ga_l = 0.0;
-        FJ_NOUNROLL
-        for (int m = lane; m < M; m += FJ_NL) {
-            ga_l = fj_div(fj_sub(fj_mul(gt, c.mF[m]), (double)c.mD[m]), (double)nkt[m]);
+        if (MO) {
+            ga_l = fj_mul(fj_sub(fj_mul(gt, c.mF[m]), (double)c.mD[m]), c.invnkt[m]);
             c.gapave[m] = ga_l;      // same lane reads it back below
             s_gm = fj_add(s_gm, ga_l);
         }
-        gm_ave = fj_div(fj_sum_d(s_gm), (double)M);
+    }
+    fj_sum_d2(v_fr, v_gr);
+    fj_sum_d2(v_ct, s_gm);
+    const double cro_std = sqrt(fj_mul(v_fr, inv_kt));
+    const double gap_std = sqrt(fj_mul(v_gr, inv_kt));
+    const double ct_std = sqrt(fj_mul(v_ct, inv_m));
+    double gm_ave = 0.0, gm_std = 0.0;
+    if (MO) {
+        gm_ave = fj_div(s_gm, (double)M);
         double v_gm = 0.0;
         FJ_NOUNROLL
         for (int m = lane; m < M; m += FJ_NL) { const double dv = fj_sub(c.gapave[m], gm_ave); v_gm = fj_add(v_gm, fj_mul(dv, dv)); }
-        gm_std = sqrt(fj_div(fj_sum_d(v_gm), (double)M));
+        gm_std = sqrt(fj_mul(fj_sum_d(v_gm), inv_m));
     }
     if (lane < 4 || FJ_NL == 1) {   // the four delay rates, one division per lane
         FJ_NOUNROLL
@@ -1644,6 +1650,13 @@ FJ_FN void fj_reset_begin(FjCtx &c, int fresh)
         for (int i = lane; i < FJ_S_COUNT; i += FJ_NL) c.scal[i] = 0;
         FJ_NOUNROLL
         for (int i = lane; i < 16; i += FJ_NL) c.obs[i] = 0.0;
+        fj_sync();
+        {   // reciprocals of the static divisors of the observation-only means (x * (1/n) instead of x / n)
+            const FjRO inkt = FJ_I(c, mnkt);
+            FJ_NOUNROLL
+            for (int m = lane; m < M; m += FJ_NL) c.invnkt[m] = fj_div(1.0, (double)inkt[m]);
+            if (lane == 0) { fj_set_d(c.scal, FJ_S_INV_KT, fj_div(1.0, (double)KT)); fj_set_d(c.scal, FJ_S_INV_M, fj_div(1.0, (double)M)); }
+        }
         fj_sync();
     } else {
         was_done = c.scal[FJ_S_DONE];

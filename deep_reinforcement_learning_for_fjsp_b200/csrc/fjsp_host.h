@@ -143,6 +143,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.obs2 = b; b += 8 * 16;
     eo.gapave = b; b += 8 * d.Mx;
     eo.mF = b; b += 8 * d.Mx;
+    eo.invnkt = b; b += 8 * d.Mx;
     eo.rsum = b; b += 8 * d.KTx;
     eo.tsum = b; b += 8 * d.KTx;
     eo.avmask = b; b += 4 * d.KTW;

@@ -74,6 +74,7 @@ struct FjEnvOff {
     int h_cum;     // int32[(Sx+1)*Kx] copy of the cumulative job counts (job number -> order)
     int h_jobbase; // int32[Kx]
     int mF;        // double[Mx] sum of the machine's fluid rates since the last arrival
+    int invnkt;    // double[Mx] 1 / (operation types the machine can process): observation features only
     int mD;        // int32[Mx] dispatches on the machine since the last arrival
     int mjob;      // int32[Mx] (rj << 16 | job number) of the job on the machine, -1 none
     int qhead;     // uint16[KTx] stage>0 waiting queue (linked through `next`)
@@ -108,7 +109,8 @@ enum {
     FJ_S_ENERGY = 16, FJ_S_ENERGY_LAST = 18, FJ_S_DELAY_PROC = 20, FJ_S_DELAY_LAST = 22, FJ_S_DELAY_UNPROC = 24,
     FJ_S_GAPTIME = 26 /* double */, FJ_S_TT = 28, FJ_S_WASDONE = 29, FJ_S_NAV = 30, FJ_S_NFAV = 31,
     FJ_S_LEFT = 32 /* unprocessed last-stage operations = jobs not fully dispatched */,
-    FJ_S_MENDSUM = 34 /* int64: sum of the machines' completion times */, FJ_S_COUNT = 40
+    FJ_S_MENDSUM = 34 /* int64: sum of the machines' completion times */,
+    FJ_S_INV_KT = 36 /* double 1/KT */, FJ_S_INV_M = 38 /* double 1/M: divisors of observation-only means */, FJ_S_COUNT = 40
 };
 
 // error flags (FJ_S_ERROR), same meaning as the oracle's
