@@ -423,15 +423,10 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     // warps' worth fits with at least two CTAs per SM
     // the main kernel stages the hot prefix of its warps' records in shared memory when the
     // slabs of all CTAs resident on an SM fit
-    P.stage_stride = v->tb.eo.hot + v->tb.io.hotw * 4;
+    P.stage_stride = v->tb.eo.hot;
     v->stage_bytes = (size_t)(v->step_threads / 32) * P.stage_stride;
     P.stage = v->stage_bytes * (1024 / FJ_STEP_THREADS) <= 200 * 1024 ? 1 : 0;
     if (getenv("FJSP_NO_STAGE")) P.stage = 0;
-    if (!getenv("FJSP_INST_STAGE")) {   // staging the instance head as well measured slightly slower (less L1): opt-in
-        v->tb.io.hotw = 0; P.io.hotw = 0;
-        P.stage_stride = v->tb.eo.hot;
-        v->stage_bytes = (size_t)(v->step_threads / 32) * P.stage_stride;
-    }
     if (!P.stage) v->stage_bytes = 0;
     P.cta_lp = getenv("FJSP_NO_CTA_LP") ? 0 : 1;   // 0: park order arrivals for the LP / resume kernels
     if (getenv("FJSP_FREE_RUN")) P.cta_lp = 2;

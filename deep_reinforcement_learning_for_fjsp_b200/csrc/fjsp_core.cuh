@@ -181,8 +181,7 @@ template <int MODE> FJ_FN double fj_pysum_result(const FjPySum &s)
 // ---------------------------------------------------------------- per-env context
 struct FjCtx {
     const FjParams *P;
-    const int32_t *I, *IH;   // instance record in HBM; staged copy of its hot words (or null)
-    int ihotw;
+    const int32_t *I;        // instance record in HBM (read-only path)
     int inst;
     int M, K, KT, S, Mx, Kx, Sx;
     unsigned mmask;
@@ -235,8 +234,6 @@ FJ_FN FjCtx &fj_ctx_init(const FjParams &, int env, unsigned char *lp, unsigned 
     c.P = &fj_sP;
     c.inst = P.env_inst[env];
     c.I = P.inst + (size_t)c.inst * P.io.stride;
-    c.IH = hot ? (const int32_t *)(hot + P.eo.hot) : c.I;
-    c.ihotw = hot ? P.io.hotw : 0;
     const int32_t *h = c.I + P.io.hdr;
     c.M = h[0]; c.K = h[1]; c.KT = h[2]; c.S = h[3];
     c.Mx = P.d.Mx; c.Kx = P.d.Kx; c.Sx = P.d.Sx;
@@ -265,30 +262,24 @@ FJ_FN FjCtx &fj_ctx_init(const FjParams &, int env, unsigned char *lp, unsigned 
     return c;
 }
 
-// read-only instance table.  Cold arrays are loaded through the non-coherent path
-// (ld.global.nc: L1-cached, never invalidated by the env-state stores); the small arrays every
-// step touches (the record's first io.hotw words) are read from the warp's shared-memory copy
-// when the main kernel staged one.
+// read-only instance table: loaded through the non-coherent path (ld.global.nc: L1-cached, never
+// invalidated by the env-state stores).  (Staging its small arrays in shared memory next to the
+// env record was measured slower -- it takes L1 away -- and is gone; the per-operation-type
+// statics every step reads are copied into the env record's hot prefix at reset() instead.)
 struct FjRO {
     const int32_t *p;
-    int plain;
     FJ_MFN int operator[](int i) const
     {
 #ifdef FJ_DEVICE_CODE
-        return plain ? p[i] : __ldg(p + i);
+        return __ldg(p + i);
 #else
         return p[i];
 #endif
     }
-    FJ_MFN FjRO operator+(int o) const { FjRO r; r.p = p + o; r.plain = plain; return r; }
+    FJ_MFN FjRO operator+(int o) const { FjRO r; r.p = p + o; return r; }
 };
-FJ_FN FjRO fj_ro(const int32_t *p) { FjRO r; r.p = p; r.plain = 0; return r; }
-FJ_FN FjRO fj_ro_field(const FjCtx &c, int off)
-{
-    FjRO r;
-    if (off < c.ihotw) { r.p = c.IH + off; r.plain = 1; } else { r.p = c.I + off; r.plain = 0; }
-    return r;
-}
+FJ_FN FjRO fj_ro(const int32_t *p) { FjRO r; r.p = p; return r; }
+FJ_FN FjRO fj_ro_field(const FjCtx &c, int off) { FjRO r; r.p = c.I + off; return r; }
 #define FJ_I(c, field) (fj_ro_field((c), (c).P->io.field))
 // the per-operation-type statics every step reads (eligible-machine mask, kind / stage / last
 // flag) and the orders' due dates are copied into the env record's hot prefix at reset(), so
@@ -1961,7 +1952,6 @@ FJ_FN void fj_env_rollout(const FjParams &Pin, const FjStepArgs &A, int env, uns
     unsigned char *G = P.env + (size_t)env * P.eo.stride;
     if (stage) {
         fj_stage_copy(stage, G, P.eo.hot);
-        fj_stage_copy(stage + P.eo.hot, (const unsigned char *)(P.inst + (size_t)P.env_inst[env] * P.io.stride), P.io.hotw * 4);
     }
     fj_env_rollout_body<VARIANT, SUM_MODE, SUSPEND>(P, A, env, lp, stage);
     if (stage) fj_stage_copy(G, stage, P.eo.hot);
@@ -2125,7 +2115,6 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
     if (active) {
         if (stage) {
             fj_stage_copy(stage, G, P.eo.hot);
-            fj_stage_copy(stage + P.eo.hot, (const unsigned char *)(P.inst + (size_t)P.env_inst[env] * P.io.stride), P.io.hotw * 4);
         }
         fj_ctx_init(P, env, nullptr, stage);
     }

@@ -63,7 +63,7 @@ static void run_step(HostVec *h, const FjStepArgs &A)
 {
     // FJSP_HOSTSIM_STAGE=1: run on a staged copy of the record's hot part (the shared-memory path)
     static std::vector<unsigned char> slab;
-    slab.assign(h->tb.eo.hot + h->tb.io.hotw * 4 + 16, 0);
+    slab.assign(h->tb.eo.hot + 16, 0);
     unsigned char *stage = getenv("FJSP_HOSTSIM_STAGE") ? slab.data() : nullptr;
     for (int r = 0; r <= FJ_ROUNDS; ++r) h->pend_counts[r] = 0;
     FjStepArgs B_ = A;
@@ -129,7 +129,7 @@ int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst
     P.lp_slots = ov ? atoi(ov) : n_envs;
     h->lp_x.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * h->tb.d.NPx, 0.0);
     h->lp_meta.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * 2, 0);
-    P.stage = 0; P.cta_lp_smem = 0; P.stage_stride = h->tb.eo.hot + h->tb.io.hotw * 4;
+    P.stage = 0; P.cta_lp_smem = 0; P.stage_stride = h->tb.eo.hot;
     P.cta_lp = getenv("FJSP_HOSTSIM_NO_CTA_LP") ? 0 : 1;
     P.plan_x = nullptr; P.plan_meta = nullptr; P.plan_ok = nullptr;
     h->pend_count = 0;
