@@ -33,7 +33,7 @@ static thread_local std::string g_err;
 #define FJ_STEP_MIN_BLOCKS (1024 / FJ_STEP_THREADS)
 #endif
 template <int VARIANT, int SUM_MODE>
-__global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step_kernel(FjParams P, FjStepArgs A)
+__global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step_kernel(const __grid_constant__ FjParams P, const __grid_constant__ FjStepArgs A)
 {
     fj_params_to_shared(P);
     // lockstep phases: every warp of the CTA walks the same number of env groups and steps
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(FJ_PACK_THREADS) fjsp_pack_kernel(FjParams P, 
 
 // resume kernel: parked envs only; picks up the LP solution, finishes the launch
 template <int VARIANT, int SUM_MODE, int SUSPEND>
-__global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(FjParams P, FjStepArgs A, const int *count_in, const int *list_in)
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(const __grid_constant__ FjParams P, FjStepArgs A, const int *count_in, const int *list_in)
 {
     fj_params_to_shared(P);
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(FjParams P, FjSte
 static_assert(FJ_STEP_THREADS / 32 <= FJ_CTX_WARPS && FJ_LP_THREADS / 32 <= FJ_CTX_WARPS && FJ_BLOCK / 32 <= FJ_CTX_WARPS,
               "fj_sC holds one context per warp of a CTA");
 template <int SMEM_BINV>
-__global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(FjParams P, const int *count_in, const int *list_in)
+__global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(const __grid_constant__ FjParams P, const int *count_in, const int *list_in)
 {
     fj_params_to_shared(P);
     extern __shared__ __align__(16) unsigned char smem[];
@@ -214,7 +214,7 @@ __global__ void fjsp_plan_kernel(FjParams P, const int *rep_env, int n_inst, dou
     if (threadIdx.x == 0) { plan_meta[2 * ii] = P.lp_meta[2 * env]; plan_meta[2 * ii + 1] = P.lp_meta[2 * env + 1]; plan_ok[ii] = 1; }
 }
 
-__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(FjParams P)
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(const __grid_constant__ FjParams P)
 {
     fj_params_to_shared(P);
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(FjParams P)
 }
 
 template <int VARIANT, int SUM_MODE>
-__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_finish_kernel(FjParams P, double *state64, float *state32)
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_finish_kernel(const __grid_constant__ FjParams P, double *state64, float *state32)
 {
     fj_params_to_shared(P);
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);

@@ -1231,16 +1231,22 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
     }
     fj_sum_d2(v_fr, v_gr);
     fj_sum_d2(v_ct, s_gm);
-    const double cro_std = sqrt(fj_mul(v_fr, inv_kt));
-    const double gap_std = sqrt(fj_mul(v_gr, inv_kt));
-    const double ct_std = sqrt(fj_mul(v_ct, inv_m));
-    double gm_ave = 0.0, gm_std = 0.0;
+    double gm_ave = 0.0, v_gm = 0.0;
     if (MO) {
         gm_ave = fj_div(s_gm, (double)M);
-        double v_gm = 0.0;
         FJ_NOUNROLL
         for (int m = lane; m < M; m += FJ_NL) { const double dv = fj_sub(c.gapave[m], gm_ave); v_gm = fj_add(v_gm, fj_mul(dv, dv)); }
-        gm_std = sqrt(fj_mul(fj_sum_d(v_gm), inv_m));
+        v_gm = fj_sum_d(v_gm);
+    }
+    // the four spreads: one square root per lane (lanes 0..3), written straight to the observation
+    double cro_std = 0.0, gap_std = 0.0, ct_std = 0.0, gm_std = 0.0;
+    if (FJ_NL == 1) {
+        cro_std = sqrt(fj_mul(v_fr, inv_kt)); gap_std = sqrt(fj_mul(v_gr, inv_kt)); ct_std = sqrt(fj_mul(v_ct, inv_m));
+        if (MO) gm_std = sqrt(fj_mul(v_gm, inv_m));
+    } else if (lane < 4) {
+        const double sd = sqrt(fj_mul(lane == 0 ? v_fr : lane == 1 ? v_gr : lane == 2 ? v_ct : v_gm, lane < 2 ? inv_kt : inv_m));
+        if (MO) c.obs2[lane == 0 ? 6 : lane == 1 ? 8 : lane == 2 ? 3 : 10] = sd;
+        else if (lane < 3) c.obs2[lane == 0 ? 3 : lane == 1 ? 5 : 1] = sd;
     }
     if (lane < 4 || FJ_NL == 1) {   // the four delay rates, one division per lane
         FJ_NOUNROLL
@@ -1257,11 +1263,13 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
         if (MO) {
             uint64_t bits = (uint32_t)FJ_I(c, hdr)[5] | ((uint64_t)(uint32_t)FJ_I(c, hdr)[6] << 32);
             double ddt; memcpy(&ddt, &bits, 8);
-            o[0] = ddt; o[1] = (double)M; o[2] = (double)S; o[3] = ct_std;
+            o[0] = ddt; o[1] = (double)M; o[2] = (double)S;
             o[4] = fj_div((double)nfav, fj_add((double)nav, 1e-08));
-            o[5] = cro_ave; o[6] = cro_std; o[7] = gap_ave; o[8] = gap_std; o[9] = gm_ave; o[10] = gm_std;
+            o[5] = cro_ave; o[7] = gap_ave; o[9] = gm_ave;
+            if (FJ_NL == 1) { o[3] = ct_std; o[6] = cro_std; o[8] = gap_std; o[10] = gm_std; }
         } else {
-            o[0] = (double)M; o[1] = ct_std; o[2] = cro_ave; o[3] = cro_std; o[4] = gap_ave; o[5] = gap_std;
+            o[0] = (double)M; o[2] = cro_ave; o[4] = gap_ave;
+            if (FJ_NL == 1) { o[1] = ct_std; o[3] = cro_std; o[5] = gap_std; }
         }
     }
     fj_sync();
