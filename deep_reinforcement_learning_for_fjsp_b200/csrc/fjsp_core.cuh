@@ -1193,8 +1193,15 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
     const double inv_kt = fj_get_d(c.scal, FJ_S_INV_KT), inv_m = fj_get_d(c.scal, FJ_S_INV_M);
     fj_sum_d2(s_fr, s_gr);
     // (the means feed differences, so they stay true divisions; the spreads use the reciprocals)
-    const double cro_ave = fj_div(s_fr, (double)KT);
-    const double gap_ave = fj_div(s_gr, (double)KT);
+    // the three means that need no further reduction: one division on lanes 0..2, then broadcast
+    const long long tsum_m = fj_get_ll(c.scal, FJ_S_MENDSUM);
+    double cro_ave, gap_ave, ct_ave;
+    if (FJ_NL == 1) {
+        cro_ave = fj_div(s_fr, (double)KT); gap_ave = fj_div(s_gr, (double)KT); ct_ave = fj_div((double)tsum_m, (double)M);
+    } else {
+        const double mean = fj_div(lane == 0 ? s_fr : lane == 1 ? s_gr : (double)tsum_m, lane < 2 ? (double)KT : (double)M);
+        cro_ave = fj_bcast_d(mean, 0); gap_ave = fj_bcast_d(mean, 1 % FJ_NL); ct_ave = fj_bcast_d(mean, 2 % FJ_NL);
+    }
     // second pass: variances
     double v_fr = 0.0, v_gr = 0.0;
     if (rounds == 1) {
@@ -1216,8 +1223,6 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
     // over a machine's operation types, unprocessed - fluid_unprocessed telescopes to
     // (gap_time * sum of its fluid rates) - (dispatches on it since the last arrival); the exact
     // CPython-ordered value is only needed as the key of machine rule 4 and is computed there.
-    const long long tsum_m = fj_get_ll(c.scal, FJ_S_MENDSUM);
-    const double ct_ave = fj_div((double)tsum_m, (double)M);
     double v_ct = 0.0, s_gm = 0.0, ga_l = 0.0;
     FJ_NOUNROLL
     for (int m = lane; m < M; m += FJ_NL) {
@@ -1248,12 +1253,13 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
         if (MO) c.obs2[lane == 0 ? 6 : lane == 1 ? 8 : lane == 2 ? 3 : 10] = sd;
         else if (lane < 3) c.obs2[lane == 0 ? 3 : lane == 1 ? 5 : 1] = sd;
     }
-    if (lane < 4 || FJ_NL == 1) {   // the four delay rates, one division per lane
+    if (lane < 5 || FJ_NL == 1) {   // the four delay rates and MO's fluid-available ratio: one division per lane
         FJ_NOUNROLL
-        for (int k = (FJ_NL == 1 ? 0 : lane); k < 4; k += (FJ_NL == 1 ? 1 : 4)) {
-            const long long num = k == 0 ? da : k == 1 ? de : k == 2 ? ja : je;
-            const long long den = k < 2 ? tn : jn;
-            c.obs2[(MO ? 11 : 6) + k] = rates_zero ? 0.0 : fj_div((double)num, (double)den);
+        for (int k = (FJ_NL == 1 ? 0 : lane); k < (MO ? 5 : 4); k += (FJ_NL == 1 ? 1 : 5)) {
+            const long long num = k == 0 ? da : k == 1 ? de : k == 2 ? ja : k == 3 ? je : (long long)nfav;
+            const double den = k < 2 ? (double)tn : k < 4 ? (double)jn : fj_add((double)nav, 1e-08);
+            const double r = fj_div((double)num, den);
+            if (k < 4) c.obs2[(MO ? 11 : 6) + k] = rates_zero ? 0.0 : r; else c.obs2[4] = r;
         }
     }
     if (lane == 0) {
@@ -1264,7 +1270,6 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
             uint64_t bits = (uint32_t)FJ_I(c, hdr)[5] | ((uint64_t)(uint32_t)FJ_I(c, hdr)[6] << 32);
             double ddt; memcpy(&ddt, &bits, 8);
             o[0] = ddt; o[1] = (double)M; o[2] = (double)S;
-            o[4] = fj_div((double)nfav, fj_add((double)nav, 1e-08));
             o[5] = cro_ave; o[7] = gap_ave; o[9] = gm_ave;
             if (FJ_NL == 1) { o[3] = ct_std; o[6] = cro_std; o[8] = gap_std; o[10] = gm_std; }
         } else {
