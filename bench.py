@@ -286,7 +286,7 @@ def main():
                 "done": torch.empty((T, BL), dtype=torch.int32, device=dev)}
         for i in range(min(args.burnin, 1024) // T + 3):
             vecL.rollout(aL[i % 2], rL[(i + 1) % 2], reward_policy=1, out=outL, state_dtype=torch.float32)
-        torch.cuda.synchronize(dev)
+        barrier()
         KL = max(3, K // 4)
         evL = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KL)]
         for i in range(KL):
@@ -295,7 +295,11 @@ def main():
             evL[i][1].record(stream)
         torch.cuda.synchronize(dev)
         msL = sum(a.elapsed_time(b) for a, b in evL)
-        large = {"envs_per_gpu": BL, "value": BL * T * KL / (msL / 1e3), "unit": UNIT, "launches": KL,
+        if world > 1:   # whole-job number: every rank ran its own copies at the same time; max over ranks
+            tL = torch.tensor([msL], dtype=torch.float64, device=dev)
+            dist.all_reduce(tL, op=dist.ReduceOp.MAX)
+            msL = float(tL[0])
+        large = {"envs_per_gpu": BL, "value": world * BL * T * KL / (msL / 1e3), "unit": UNIT, "launches": KL,
                  "ms_per_launch": msL / KL, "env_errors": int((vecL.info()["error"] != 0).sum()),
                  "note": "instances replicated 16x; state 0.8 GB > L2, no flush needed"}
         del vecL, outL, aL, rL
