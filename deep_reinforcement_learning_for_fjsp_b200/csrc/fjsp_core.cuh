@@ -111,6 +111,14 @@ FJ_FN void fj_sum_d2(double &a, double &b)   // two observation-only sums in one
     for (int m = FJ_NL / 2; m > 0; m >>= 1) { const double oa = fj_xor_d(a, m), ob = fj_xor_d(b, m); a = fj_add(a, oa); b = fj_add(b, ob); }
 }
 
+FJ_FN void fj_sum_d4(double &a, double &b, double &c, double &d)
+{
+    for (int m = FJ_NL / 2; m > 0; m >>= 1) {
+        const double oa = fj_xor_d(a, m), ob = fj_xor_d(b, m), oc = fj_xor_d(c, m), od = fj_xor_d(d, m);
+        a = fj_add(a, oa); b = fj_add(b, ob); c = fj_add(c, oc); d = fj_add(d, od);
+    }
+}
+
 // Lexicographic minimum of (key, id) over the warp on an order-preserving integer image of the
 // double key (keys are never NaN; -0.0 is canonicalised by the callers): three redux.sync minima.
 #define FJ_EMPTY 0x7fffffff
@@ -1162,6 +1170,9 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
             gr_keep = fj_div(gap, (double)c.fstart[q]);
             s_fr = fj_add(s_fr, fr_keep);
             s_gr = fj_add(s_gr, gr_keep);
+            // more operation types than lanes: park the two rates for the variance pass (the D-FJSP
+            // classes do not use the urg / maxe arrays of the record otherwise)
+            if (VARIANT != FJSP_SO_FJSSP && rounds > 1) { c.urg[q] = fr_keep; c.maxe[q] = gr_keep; }
             if (av) {
                 if (VARIANT == FJSP_SO_FJSSP) {
                     if (SUM_MODE != 0 && sc != 0.0 && isfinite(sc)) sf = fj_add(sf, sc);
@@ -1209,13 +1220,17 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
     } else
     FJ_NOUNROLL
     for (int q = lane; q < KT; q += FJ_NL) {
-        int residue = 0;
-        FJ_NOUNROLL
-        for (int s = 0; s < S; ++s) residue += c.cntunp[q * Sx + s];
-        const int pr = c.proc[q];
-        const double fr = fj_div((double)pr, (double)(residue + pr));
-        const double fluid_unp = fj_sub((double)c.fstart[q], fj_mul(c.rsum[q], gt));
-        const double gr = fj_div(fj_sub((double)residue, fluid_unp), (double)c.fstart[q]);
+        double fr, gr;
+        if (VARIANT != FJSP_SO_FJSSP) { fr = c.urg[q]; gr = c.maxe[q]; }   // written by this lane above
+        else {
+            int residue = 0;
+            FJ_NOUNROLL
+            for (int s = 0; s < S; ++s) residue += c.cntunp[q * Sx + s];
+            const int pr = c.proc[q];
+            fr = fj_div((double)pr, (double)(residue + pr));
+            const double fluid_unp = fj_sub((double)c.fstart[q], fj_mul(c.rsum[q], gt));
+            gr = fj_div(fj_sub((double)residue, fluid_unp), (double)c.fstart[q]);
+        }
         v_fr = fj_add(v_fr, fj_mul(fr - cro_ave, fr - cro_ave));
         v_gr = fj_add(v_gr, fj_mul(gr - gap_ave, gr - gap_ave));
     }
@@ -1234,8 +1249,7 @@ FJ_FN_NOINLINE void fj_observe(int rates_zero)
             s_gm = fj_add(s_gm, ga_l);
         }
     }
-    fj_sum_d2(v_fr, v_gr);
-    fj_sum_d2(v_ct, s_gm);
+    fj_sum_d4(v_fr, v_gr, v_ct, s_gm);
     double gm_ave = 0.0, v_gm = 0.0;
     if (MO) {
         gm_ave = fj_div(s_gm, (double)M);
