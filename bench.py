@@ -346,7 +346,7 @@ def main():
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "kernel": "fjsp_step_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                              "launch_ms": launch_s * 1e3,
-                             "note": "latency-bound discrete-event kernel (3.7k warp instructions per env step, 37% issue utilisation, 44% of warp time at CTA barriers), not HBM-bound; see DESIGN.md section 4"},
+                             "note": "latency-bound discrete-event kernel (3.5k warp instructions per env step, 36% issue utilisation, 45% of warp time at CTA barriers), not HBM-bound; see DESIGN.md section 4"},
                 "wall_s_timed_region": wall, "env_errors": errors,
                 "timed_region_events": {"fluid_lp_solves": lp_solves, "episodes_finished": episodes,
                                         "burnin_env_steps_per_copy": args.burnin},
