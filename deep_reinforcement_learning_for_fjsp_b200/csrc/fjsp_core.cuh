@@ -197,7 +197,7 @@ struct FjCtx {
     int32_t *mend, *mlast, *mjob, *mD; double *mF, *invnkt; uint16_t *qhead, *qtail, *qlen; int32_t *proc, *fstart; uint32_t *flmask;
     double *rsum, *tsum; uint16_t *cntunp, *cntnow, *pk, *slot; double *fu, *fa, *ff; uint16_t *next;
     uint32_t *unpmask; int32_t *duejob, *mindue;   // SO_FJSSP only (per-job due dates)
-    uint32_t *h_elig; uint16_t *h_rjinfo; int32_t *h_due, *h_cum, *h_jobbase;   // hot copies of instance statics
+    uint32_t *h_elig, *h_mtpack, *h_fo; uint16_t *h_rjinfo; int32_t *h_due, *h_cum, *h_jobbase;   // hot copies of instance statics
     unsigned char *lp;
 };
 
@@ -253,7 +253,7 @@ FJ_FN FjCtx &fj_ctx_init(const FjParams &, int env, unsigned char *lp, unsigned 
     c.gapave = (double *)(E + o.gapave); c.urg = (double *)(G + o.urg); c.maxe = (double *)(G + o.maxe);
     c.avmask = (uint32_t *)(E + o.avmask); c.favmask = (uint32_t *)(E + o.favmask);
     c.demask = (uint32_t *)(E + o.demask); c.damask = (uint32_t *)(E + o.damask);
-    c.h_elig = (uint32_t *)(E + o.h_elig); c.h_rjinfo = (uint16_t *)(E + o.h_rjinfo); c.h_due = (int32_t *)(E + o.h_due);
+    c.h_elig = (uint32_t *)(E + o.h_elig); c.h_mtpack = (uint32_t *)(E + o.h_mtpack); c.h_fo = (uint32_t *)(E + o.h_fo); c.h_rjinfo = (uint16_t *)(E + o.h_rjinfo); c.h_due = (int32_t *)(E + o.h_due);
     c.h_cum = (int32_t *)(E + o.h_cum); c.h_jobbase = (int32_t *)(E + o.h_jobbase);
     c.mF = (double *)(E + o.mF); c.mD = (int32_t *)(E + o.mD); c.invnkt = (double *)(E + o.invnkt);
     c.mend = (int32_t *)(E + o.mend); c.mlast = (int32_t *)(E + o.mlast); c.mjob = (int32_t *)(E + o.mjob);
@@ -942,6 +942,8 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
     fj_sync();
 }
 
+FJ_OUTLINE unsigned fj_small_set_order(unsigned seq, int n);
+
 // class_FJSP.py:292-316 update_fluid_parameter from the LP solution x (canonical columns)
 template <int SUM_MODE>
 FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
@@ -957,7 +959,8 @@ FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
     }
     FJ_NOUNROLL
     for (int q = lane; q < KT; q += FJ_NL) {
-        unsigned em = (unsigned)elig[q], fm = 0;
+        unsigned em = (unsigned)elig[q], fm = 0, fseq = 0;
+        int nfq = 0;
         FjPySum ps; fj_pysum_init(ps);
         FJ_NOUNROLL
         for (int k = 0; k < nelig[q]; ++k) {
@@ -966,8 +969,11 @@ FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
             double xv = x[col];
             double fr = fj_mul(xv, fj_div(1.0, (double)ptime[q * Mx + m]));
             fj_pysum_add<SUM_MODE>(ps, fr);
-            if (xv != 0.0) fm |= 1u << m;
+            if (xv != 0.0) { fm |= 1u << m; if (nfq < 4) fseq |= (unsigned)m << (8 * nfq); ++nfq; }
         }
+        // set(fluid_machine_list) is built from x.items() order: its iteration order (what machine_select
+        // walks) is fixed until the next arrival
+        c.h_fo[q] = nfq < 5 ? fj_small_set_order(fseq, nfq) : 0u;
         double rs = fj_pysum_result<SUM_MODE>(ps);
         c.rsum[q] = rs;
         c.tsum[q] = fj_div(1.0, rs);
@@ -1483,10 +1489,9 @@ FJ_OUTLINE unsigned fj_small_set_order(unsigned seq, int n)   // seq: members, o
 
 struct FjCand { unsigned mask; unsigned packed; int n; };   // n >= 5: ascending over mask; else packed order
 
-// list(set(idle) & set(other)); other given by its mask, its size and a functor-free walk:
-// `ord` = iteration order of set(other) as an int32 array (static), or, when ord_packed_n >= 0,
-// as packed bytes.
-FJ_OUTLINE FjCand fj_selectable(unsigned idle, unsigned omask, int nother, FjRO ord, unsigned ord_packed, int use_packed)
+// list(set(idle) & set(other)); other given by its mask, its size and, when it has at most four
+// members, its iteration order packed one byte per member (five or more iterate ascending)
+FJ_OUTLINE FjCand fj_selectable(unsigned idle, unsigned omask, int nother, unsigned ord_packed)
 {
     FjCand r;
     r.mask = idle & omask; r.n = fj_popc(r.mask); r.packed = 0;
@@ -1504,16 +1509,8 @@ FJ_OUTLINE FjCand fj_selectable(unsigned idle, unsigned omask, int nother, FjRO 
             for (int i = 0; i < na; ++i) { const unsigned v = (ao >> (8 * i)) & 0xffu; if (omask >> v & 1u) seq |= v << (8 * k++); }
         }
     } else {             // iterate set(other)
-        if (nother >= 5 && !use_packed) {
-            // set(other) has >= 5 members: ascending
-            unsigned mk = r.mask; while (mk) { seq |= (unsigned)fj_ffs0(mk) << (8 * k++); mk &= mk - 1; }
-        } else if (use_packed) {
-            if (nother >= 5) { unsigned mk = r.mask; while (mk) { seq |= (unsigned)fj_ffs0(mk) << (8 * k++); mk &= mk - 1; } }
-            else for (int i = 0; i < nother; ++i) { const unsigned v = (ord_packed >> (8 * i)) & 0xffu; if (idle >> v & 1u) seq |= v << (8 * k++); }
-        } else {
-            FJ_NOUNROLL
-            for (int i = 0; i < nother; ++i) { const unsigned v = (unsigned)ord[i]; if (idle >> v & 1u) seq |= v << (8 * k++); }
-        }
+        if (nother >= 5) { unsigned mk = r.mask; while (mk) { seq |= (unsigned)fj_ffs0(mk) << (8 * k++); mk &= mk - 1; } }
+        else for (int i = 0; i < nother; ++i) { const unsigned v = (ord_packed >> (8 * i)) & 0xffu; if (idle >> v & 1u) seq |= v << (8 * k++); }
     }
     r.packed = fj_small_set_order(seq, r.n);
     return r;
@@ -1555,24 +1552,12 @@ FJ_FN int fj_machine_select(FjCtx &c, int rule, int q, uint32_t rnd)
         }
     }
     const unsigned em = (unsigned)fj_elig(c)[q], fm = c.flmask[q];
-    const int ne = FJ_I(c, nelig)[q];
     if ((idle & em) == 0) return -1;
     FjCand cand;
-    if (use_f && (idle & fm) != 0) {
-        // set(fluid_machine_list): members in x.items() order
-        const int nf = fj_popc(fm);
-        unsigned fo = 0;
-        if (nf < 5) {
-            const FjRO poord = FJ_I(c, poord) + q * Mx;
-            unsigned seq = 0; int k = 0;
-            FJ_NOUNROLL
-            for (int i = 0; i < ne; ++i) { const unsigned v = (unsigned)poord[i]; if (fm >> v & 1u) seq |= v << (8 * k++); }
-            fo = fj_small_set_order(seq, nf);
-        }
-        cand = fj_selectable(idle, fm, nf, fj_ro(nullptr), fo, 1);
-    } else {
-        cand = fj_selectable(idle, em, ne, FJ_I(c, mtset) + q * Mx, 0, 0);
-    }
+    // set(fluid_machine_list) (members in x.items() order) or set(machine_tuple): both iteration
+    // orders are kept packed in the record's hot prefix
+    if (use_f && (idle & fm) != 0) cand = fj_selectable(idle, fm, fj_popc(fm), c.h_fo[q]);
+    else cand = fj_selectable(idle, em, fj_popc(em), c.h_mtpack[q]);
     if (key_kind == 2) {   // exact gap_ave of the candidates, one lane per machine
         FJ_NOUNROLL
         for (int m = fj_lane(); m < M; m += FJ_NL)
@@ -1653,6 +1638,8 @@ FJ_FN void fj_reset_begin(FjCtx &c, int fresh)
         FJ_NOUNROLL
         for (int q = lane; q < KT; q += FJ_NL) {
             c.h_elig[q] = (uint32_t)ielig[q];
+            c.h_mtpack[q] = (uint32_t)FJ_I(c, mtpack)[q];
+            c.h_fo[q] = 0;
             c.h_rjinfo[q] = (uint16_t)((ikind[q] << 8) | (istage[q] << 1) | (ilast[q] & 1));
         }
         FJ_NOUNROLL

@@ -126,6 +126,7 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     io.hotw = o;
     // per-pair tables and breakdown lists: read through ld.global.nc
     io.mtset = o; o += d.KTx * d.Mx;
+    io.mtpack = o; o += d.KTx;
     io.poord = o; o += d.KTx * d.Mx;
     io.ptime = o; o += d.KTx * d.Mx;
     io.energy = o; o += d.KTx * d.Mx;
@@ -164,6 +165,8 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     eo.cntnow = b; b += 2 * d.KTx * d.Sx;
     b = fj_align(b, 4);
     eo.h_elig = b; b += 4 * d.KTx;
+    eo.h_mtpack = b; b += 4 * d.KTx;
+    eo.h_fo = b; b += 4 * d.KTx;
     eo.h_due = b; b += 4 * d.Sx;
     eo.h_cum = b; b += 4 * (d.Sx + 1) * d.Kx;
     eo.h_jobbase = b; b += 4 * d.Kx;
@@ -227,6 +230,11 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
             w[io.elig + q] = (int32_t)mask;
             int n = fj_pyset_order(seq, v.nelig[q], ord);
             for (int k = 0; k < d.Mx; ++k) w[io.mtset + q * d.Mx + k] = k < n ? ord[k] : -1;
+            {
+                unsigned pk = 0;
+                if (n <= 4) for (int k = 0; k < n; ++k) pk |= (unsigned)ord[k] << (8 * k);
+                w[io.mtpack + q] = (int32_t)pk;
+            }
             // machines of q sorted by pair rank
             int cnt = 0;
             for (int m = 0; m < v.M; ++m) if (mask >> m & 1) {

@@ -37,6 +37,7 @@ struct FjInstOff {
     int elig;      // [KTx] machine bit mask
     int nelig;     // [KTx]
     int mtset;     // [KTx*Mx] iteration order of set(machine_tuple) (CPython slot order)
+    int mtpack;    // [KTx] the same order packed one byte per member when the type has at most 4 machines (else 0)
     int poord;     // [KTx*Mx] machines of the type in x.items() (pair) order
     int ptime;     // [KTx*Mx]
     int energy;    // [KTx*Mx] power * time
@@ -70,6 +71,8 @@ struct FjEnvOff {
     int mlast;     // int32[Mx] end time of the machine's previous operation
     int h_elig;    // uint32[KTx] copy of the instance's eligible-machine masks
     int h_rjinfo;  // uint16[KTx] kind << 8 | stage << 1 | last-stage flag
+    int h_mtpack;  // uint32[KTx] copy of the instance's packed set(machine_tuple) orders
+    int h_fo;      // uint32[KTx] iteration order of set(fluid machines of the type), packed (at most 4 members), set at order arrival
     int h_due;     // int32[Sx]   copy of the orders' due dates
     int h_cum;     // int32[(Sx+1)*Kx] copy of the cumulative job counts (job number -> order)
     int h_jobbase; // int32[Kx]

@@ -191,7 +191,9 @@ int fjsp_hostsim_selectable(unsigned idle, const int *other_ord, int nother, int
 {
     unsigned omask = 0;
     for (int i = 0; i < nother; ++i) omask |= 1u << other_ord[i];
-    FjCand cand = fj_selectable(idle, omask, nother, fj_ro(other_ord), 0, 0);
+    unsigned packed = 0;   // other_ord: iteration order of set(other); packed when it has at most 4 members
+    if (nother <= 4) for (int i = 0; i < nother; ++i) packed |= (unsigned)other_ord[i] << (8 * i);
+    FjCand cand = fj_selectable(idle, omask, nother, packed);
     unsigned mk = cand.mask;
     for (int i = 0; i < cand.n; ++i) {
         if (cand.n >= 5) { out[i] = __builtin_ctz(mk); mk &= mk - 1; }
