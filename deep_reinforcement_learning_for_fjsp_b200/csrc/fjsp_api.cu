@@ -419,10 +419,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaMemset(v->d_trace, 0, (size_t)v->step_grid * FJ_TRACE_ROWS * 8 * 8));
     P.trace = v->d_trace;
 #endif
-    // hot part of the env records staged in shared memory for the whole launch when four
-    // warps' worth fits with at least two CTAs per SM
-    // the main kernel stages the hot prefix of its warps' records in shared memory when the
-    // slabs of all CTAs resident on an SM fit
+    // the main kernel stages the hot prefix of its warps' records in shared memory for the whole
+    // launch when the slabs of all CTAs resident on an SM fit
     P.stage_stride = v->tb.eo.hot;
     v->stage_bytes = (size_t)(v->step_threads / 32) * P.stage_stride;
     P.stage = v->stage_bytes * (1024 / FJ_STEP_THREADS) <= 200 * 1024 ? 1 : 0;

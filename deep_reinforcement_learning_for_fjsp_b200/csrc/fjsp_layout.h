@@ -143,7 +143,7 @@ struct FjParams {
     int cta_lp;                 // 1: the main kernel's CTAs solve order-arrival LPs themselves
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory
     int B, variant, sum_mode, nobs;
-    long long *trace;           // FJ_TRACE builds: [grid][16 warps][8] per-warp cycle counters (null otherwise)
+    long long *trace;           // FJ_TRACE builds: [grid][33][8] per-warp cycle counters + one row of LP phase cycles per CTA (null otherwise)
 };
 
 struct FjStepArgs {
