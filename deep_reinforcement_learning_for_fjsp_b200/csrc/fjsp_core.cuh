@@ -2135,9 +2135,10 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
     const int nobs = P.nobs;
     int parked = !active;
     FJ_TR_DECL;
+    const size_t batch = (size_t)P.B;
+    size_t i = (size_t)env;             // row of this env in the [T][B] inputs / outputs of step tt
     FJ_NOUNROLL
-    for (int tt = 0; tt < A.T; ++tt) {
-        const size_t i = (size_t)tt * P.B + env;
+    for (int tt = 0; tt < A.T; ++tt, i += batch) {
         double out_reward = 0.0;
         int out_done = 0;
         int stage = 0;      // 0 nothing, 1 dispatched (run the clock), 2 nothing dispatchable (emit unchanged)
