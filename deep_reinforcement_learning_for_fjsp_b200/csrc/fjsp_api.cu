@@ -451,6 +451,9 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (dispatch(v, [&](auto V, auto SM) {
             cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->step_smem_bytes);
+            if (getenv("FJSP_CARVEOUT"))   // percent of the unified L1 / shared memory given to shared memory
+                cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,
+                                     cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("FJSP_CARVEOUT")));
             return 0;
         })) return -2;
     CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
