@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """FJSP env-steps/sec benchmark (BASELINE.json metric) for the B200 vector environment.
 
-Workload (BASELINE.json configs[1]): MO_DFJSP, 4096 generated instances per GPU
-(Instance_generate.py distributions: 10 machines, 3 orders), random composite-rule
-actions (task rule 0..11, machine rule 0..9, with the random rules' draws), auto-reset.
-One bench "step" = ONE launch of the step kernel = `--rollout` env steps for every
-environment copy.  `value` is device-timed (CUDA events on the launching stream, inputs
-resident in HBM, L2 flushed between timed launches); `e2e` goes through the host-buffer
-C-ABI call with pinned host buffers, H2D of actions/draws and D2H of state/reward/done
-inside the timed region.
+  python bench.py [--config NAME] [--gpus N --steps K --warmup W]   (N > 1: launched under torchrun)
+  python bench.py --impl reference [--config NAME] ...              (the CPU port of the reference env)
 
-  python bench.py [--gpus N --steps K --warmup W]      (N > 1: launched under torchrun)
-  python bench.py --impl reference ...                 (the CPU port of the reference env)
+Configs (BASELINE.json `configs`, one JSON line each; the default is the one the metric is quoted on):
+  so_single        [0] SO_DFJSP, one generated instance (10 machines, 3 orders), one step() per launch
+  mo_4096          [1] MO_DFJSP, 4096 generated instances per GPU, random composite-rule actions   (default)
+  breakdown_65536  [2] MO_DFJSP_breakdown, 65 536 copies per GPU (4096 generated instances with machine
+                       breakdown / repair intervals x 16), 32-step rollouts (MPPPO-style)
+  brandimarte_1m   [3] SO_DFJSP on Brandimarte mk01-mk10, 131 072 copies per GPU (1 M over 8 GPUs)
+  large_m20        [4] MO_DFJSP, 20 machines, 5 orders (HMPSAC generator profile), 4096 instances per GPU
+
+One bench "step" = ONE launch of the step kernel = `T` env steps for every environment copy of the
+rank (so_single: 64 launches of one step).  `value` is device-timed (CUDA events on the launching
+stream, inputs resident in HBM, L2 flushed between timed launches); `e2e` goes through the host-buffer
+C-ABI call with pinned host buffers, H2D of actions/draws and D2H of state/reward/done inside the timed
+region.  After the timed region a sample of environments of that very batch is replayed on the CPU
+oracle from reset() through every launch and compared (`parity_sample`).
 """
 import argparse
 import json
@@ -28,7 +34,20 @@ sys.path.insert(0, ROOT)
 
 METRIC = "fjsp_env_steps_per_sec"
 UNIT = "env_steps/s"
-WORKLOAD = "MO_DFJSP_4096_generated_instances_random_rules"
+
+CONFIGS = {
+    "so_single": dict(variant="SO_DFJSP", envs=1, T=1, launches_per_step=64, machines=10, orders=3, profile="DA3C",
+                      workload="SO_DFJSP_single_generated_instance_M10_S3_one_step_per_launch", large=0, burnin=256),
+    "mo_4096": dict(variant="MO_DFJSP", envs=4096, T=32, machines=10, orders=3, profile="DA3C",
+                    workload="MO_DFJSP_4096_generated_instances_random_rules", large=65536, burnin=2048),
+    "breakdown_65536": dict(variant="MO_DFJSP_breakdown", envs=65536, distinct=4096, T=32, machines=10, orders=3,
+                            profile="DA3C", breakdowns=True, large=0, burnin=1024,
+                            workload="MO_DFJSP_breakdown_65536_copies_of_4096_generated_instances_32_step_rollouts"),
+    "brandimarte_1m": dict(variant="SO_DFJSP", envs=131072, brandimarte=True, T=32, large=0, burnin=512,
+                           workload="SO_DFJSP_Brandimarte_mk01_mk10_131072_copies_per_gpu"),
+    "large_m20": dict(variant="MO_DFJSP", envs=4096, T=32, machines=20, orders=5, profile="HMPSAC", large=0,
+                      burnin=1024, workload="MO_DFJSP_4096_generated_instances_M20_S5_HMPSAC_profile"),
+}
 
 
 def parse():
@@ -37,33 +56,53 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="environment copies per GPU")
-    ap.add_argument("--rollout", type=int, default=32, help="env steps per kernel launch")
-    ap.add_argument("--variant", default="MO_DFJSP")
-    ap.add_argument("--machines", type=int, default=10)
-    ap.add_argument("--orders", type=int, default=3)
+    ap.add_argument("--config", default="mo_4096", choices=sorted(CONFIGS))
+    ap.add_argument("--envs", type=int, default=None, help="environment copies per GPU (default: the config's)")
+    ap.add_argument("--rollout", type=int, default=None, help="env steps per kernel launch (default: the config's)")
     ap.add_argument("--seed", type=int, default=2026)
-    ap.add_argument("--burnin", type=int, default=2048,
+    ap.add_argument("--burnin", type=int, default=None,
                     help="untimed env steps per copy before timing, so episodes (order arrivals, resets) desynchronise")
-    ap.add_argument("--large-envs", type=int, default=65536,
+    ap.add_argument("--large-envs", type=int, default=None,
                     help="also time this many copies (the same instances, replicated) for a few launches; 0 = skip")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the T=1 / T=128 rollout-length lines")
-    return ap.parse_args()
+    ap.add_argument("--no-policy", dest="policy", action="store_false", help="skip the policy-in-the-loop lines")
+    ap.add_argument("--parity-envs", type=int, default=16, help="environments replayed on the CPU oracle after timing")
+    a = ap.parse_args()
+    cfg = dict(CONFIGS[a.config])
+    if a.envs is not None:
+        cfg["envs"] = a.envs
+    if a.rollout is not None:
+        cfg["T"] = a.rollout
+    if a.burnin is not None:
+        cfg["burnin"] = a.burnin
+    if a.large_envs is not None:
+        cfg["large"] = a.large_envs
+    cfg.setdefault("launches_per_step", 1)
+    return a, cfg
 
 
-def make_instances(n, seed, M, S):
+def make_instances(n, seed, M, S, profile="DA3C", breakdowns=False):
     from deep_reinforcement_learning_for_fjsp_b200.instance import FJSPInstance
-    insts = []
-    for i in range(n):
-        inst = FJSPInstance.generate(seed * 100003 + i, [0.5, 1.0, 1.5][i % 3], M, S, "DA3C")
-        insts.append(inst)
-    return insts
+    return [FJSPInstance.generate(seed * 100003 + i, [0.5, 1.0, 1.5][i % 3], M, S, profile, breakdowns=breakdowns)
+            for i in range(n)]
+
+
+def config_blobs(cfg, seed, rank=0):
+    """(instance blobs, env -> instance map) of one rank's shard."""
+    B = cfg["envs"]
+    if cfg.get("brandimarte"):
+        z = np.load(os.path.join(ROOT, "tests", "golden", "brandimarte_blobs.npz"))   # the reference's data/benchmark/Brandimarte_Data
+        blobs = [z["Mk%02d" % k] for k in range(1, 11)]
+        return blobs, (np.arange(B) % 10).astype(np.int32)
+    n = min(B, cfg.get("distinct", B))
+    insts = make_instances(n, seed + 7919 * rank, cfg["machines"], cfg["orders"], cfg["profile"], cfg.get("breakdowns", False))
+    return [i.to_blob() for i in insts], (np.arange(B) % n).astype(np.int32)
 
 
 def make_actions(rng, T, B, variant):
-    nt, nm = (6, 5) if variant == "SO_DFJSP" else (12, 10)
+    nt, nm = (6, 5) if variant in ("SO_DFJSP", "SO_FJSSP") else (12, 10)
     a = np.stack([rng.integers(0, nt, (T, B)), rng.integers(0, nm, (T, B))], -1).astype(np.int32)
     r = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
     return a, r
@@ -102,76 +141,170 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_port_throughput(insts, variant, seconds, rollout, seed):
-    """The oracle (C port of the reference env) on the host cores, a bounded sample of the
-    same workload: as many environments as threads, `rollout`-step chunks until the budget."""
+def oracle_mod():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
+    return oracle_py
+
+
+def cpu_port_throughput(blobs, variant, seconds, T, seed):
+    """The oracle (C port of the reference env) on the host cores, a bounded sample of the
+    same workload: two environments per thread, `T`-step chunks until the budget."""
+    oracle_py = oracle_mod()
     threads = oracle_py.lib().fjsp_oracle_max_threads()
     B = max(threads * 2, 8)
-    envs = [oracle_py.OracleEnv(insts[i % len(insts)].to_blob(), variant) for i in range(B)]
+    Tc = max(T, 32)
+    envs = [oracle_py.OracleEnv(blobs[i % len(blobs)], variant) for i in range(B)]
     for e in envs:
         e.reset()
     rng = np.random.default_rng(seed)
-    a, r = make_actions(rng, rollout, B, variant)
+    a, r = make_actions(rng, Tc, B, variant)
     oracle_py.batch_rollout(envs, a, r, 1, want_state=True, want_rec=False, threads=threads)  # warm-up
     steps, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
-        a, r = make_actions(rng, rollout, B, variant)
+        a, r = make_actions(rng, Tc, B, variant)
         oracle_py.batch_rollout(envs, a, r, 1, want_state=True, want_rec=False, threads=threads)
-        steps += rollout * B
+        steps += Tc * B
     dt = time.perf_counter() - t0
     return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{B} envs x {steps // B} steps of the same workload in {dt:.1f}s on {threads} host threads "
                       f"(oracle/fjsp_oracle.c, the C port pinned bit-exact to the Python reference)"}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, cfg, rank):
+    """--impl reference: the reference's CPU implementation of the path (its C port, oracle/: the Python
+    reference needs CPLEX and cannot travel) on ALL host threads, on this config's own workload: the same
+    instances, T and action distribution; a step = T env steps of up to 4096 of the config's copies."""
     if rank != 0:
         return
-    insts = make_instances(64, args.seed, args.machines, args.orders)
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py
+    oracle_py = oracle_mod()
     threads = oracle_py.lib().fjsp_oracle_max_threads()
-    B = max(threads * 2, 8)
-    envs = [oracle_py.OracleEnv(insts[i % len(insts)].to_blob(), args.variant) for i in range(B)]
+    variant, T, lps = cfg["variant"], cfg["T"], cfg["launches_per_step"]
+    blobs, env_inst = config_blobs(cfg, args.seed, 0)
+    B = min(cfg["envs"], 4096)
+    envs = [oracle_py.OracleEnv(blobs[env_inst[i]], variant) for i in range(B)]
     for e in envs:
         e.reset()
     rng = np.random.default_rng(args.seed)
-    T = args.rollout
-    for _ in range(args.warmup):
-        a, r = make_actions(rng, T, B, args.variant)
+    Tc = T * lps
+
+    def one():
+        a, r = make_actions(rng, Tc, B, variant)
         oracle_py.batch_rollout(envs, a, r, 1, want_rec=False, threads=threads)
+    for _ in range(args.warmup):
+        one()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        a, r = make_actions(rng, T, B, args.variant)
-        oracle_py.batch_rollout(envs, a, r, 1, want_rec=False, threads=threads)
+        one()
     dt = time.perf_counter() - t0
-    value = args.steps * T * B / dt
-    sample = f"{B} envs x {args.steps * T} steps on {threads} host threads (C port of the reference env; the Python " \
-             f"reference itself needs CPLEX and runs ~20-200 steps/s, see BASELINE.md)"
+    value = args.steps * Tc * B / dt
+    sample = (f"{B} of the config's {cfg['envs']} environment copies x {args.steps * Tc} steps in {dt:.1f}s on {threads} host "
+              f"threads (C port of the reference env, oracle/fjsp_oracle.c; the Python reference itself needs CPLEX and runs "
+              f"~20-200 steps/s on one core, see BASELINE.md)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_sampled": B, "env_steps_per_step": T,
-                       "machines": args.machines, "orders": args.orders},
+            "config": {"workload": cfg["workload"], "envs_per_gpu": cfg["envs"], "envs_sampled": B, "env_steps_per_step": Tc,
+                       "variant": variant, "machines": cfg.get("machines"), "orders": cfg.get("orders")},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def parity_sample(vec, blobs, env_inst, variant, history, sample, dev, rng):
+    """Replays `sample` environments of the timed batch on the CPU oracle from reset() through every
+    launch the GPU ran (`history`: per launch the [T, len(sample), 2] actions / draws they were fed), then
+    runs ONE more launch on both with the schedule records requested and compares everything."""
+    import torch
+    oracle_py = oracle_mod()
+    envs = [oracle_py.OracleEnv(blobs[env_inst[e]], variant) for e in sample]
+    for e in envs:
+        e.reset()
+    steps = 0
+    for a, r in history:
+        oracle_py.batch_rollout(envs, a, r, 1, want_state=False, want_rec=False)
+        steps += a.shape[0]
+    T, B = history[-1][0].shape[0], vec.n_envs
+    a, r = make_actions(rng, T, B, variant)
+    o = vec.rollout(torch.from_numpy(a).to(dev), torch.from_numpy(r.view(np.int32)).to(dev), reward_policy=1, want_rec=True)
+    torch.cuda.synchronize(dev)
+    ref = oracle_py.batch_rollout(envs, a[:, sample], r[:, sample], 1)
+    st = o["state"][:, sample].cpu().numpy()
+    rec_eq = bool(np.array_equal(o["rec"][:, sample].cpu().numpy(), ref["rec"]))
+    rew_eq = bool(np.array_equal(o["reward"][:, sample].cpu().numpy(), ref["reward"]))
+    done_eq = bool(np.array_equal(o["done"][:, sample].cpu().numpy(), ref["done"]))
+    rel = float(np.max(np.abs(st - ref["state"]) / np.maximum(np.abs(ref["state"]), 1e-300) * (ref["state"] != 0)
+                       + np.abs(st - ref["state"]) * (ref["state"] == 0)))
+    info = vec.info()
+    oi = [e.info() for e in envs]
+    time_eq = bool(np.array_equal(info["step_time"][sample], [x["step_time"] for x in oi]))
+    return {"envs": len(sample), "env_steps_replayed_per_env": steps + T, "schedule_records_equal": rec_eq,
+            "rewards_equal": rew_eq, "dones_equal": done_eq, "clock_equal": time_eq, "state_max_rel_err": rel,
+            "ok": rec_eq and rew_eq and done_eq and time_eq and rel <= 1e-5,
+            "how": "oracle/fjsp_oracle.c replayed from reset() through the burn-in, warm-up and timed launches, "
+                   "then one more launch compared output for output (float64 states; bar 1e-5 relative)"}
+
+
+def policy_in_loop(blobs, env_inst, variant, local_rank, world, n_steps=200, seed=0):
+    """One policy.forward + one step() per environment step (the loop every reference agent runs),
+    device-timed: `PolicyRollout` replays policy MLP + Gumbel-max sampling + packing + step kernel as
+    one CUDA graph.  Also the agent-side NCCL use: a PPO-shaped gradient all-reduce of the policy."""
+    import torch
+    import torch.distributed as dist
+    from deep_reinforcement_learning_for_fjsp_b200.vec_env import FJSPVecEnv
+    from deep_reinforcement_learning_for_fjsp_b200.agent_loop import PolicyRollout, make_mlp
+    from deep_reinforcement_learning_for_fjsp_b200 import sharding
+    dev = torch.device("cuda", local_rank)
+    vec = FJSPVecEnv(None, env_inst, variant, device=local_rank, blobs=blobs)
+    nt, nm = vec.actions_size
+    net = make_mlp(vec.state_size, nt * nm, device=dev, seed=seed)       # same weights on every rank
+    res = {"envs_per_gpu": vec.n_envs, "policy": f"MLP {vec.state_size}-200-200-200-{nt * nm} (DDQN ActorNet shape), fp32"}
+    for graph in (True, False):
+        pr = PolicyRollout(vec, net, reward_policy=1, use_graph=graph)
+        pr.run(64)                                                       # warm-up / desynchronise a little
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = n_steps if graph else max(20, n_steps // 4)
+        e0.record(torch.cuda.current_stream(dev))
+        pr.run(n)
+        e1.record(torch.cuda.current_stream(dev))
+        torch.cuda.synchronize(dev)
+        ms, total = sharding.reduce_timing(e0.elapsed_time(e1), vec.n_envs * n, dev)
+        res["cuda_graph" if graph else "eager_launches"] = {"value": total / (ms / 1e3), "unit": UNIT, "steps": n,
+                                                            "ms_per_step": ms / n}
+        if graph:
+            # a PPO-shaped update on the last step's batch: loss -> backward -> gradient all-reduce (NCCL)
+            st = pr.state.clone()
+            logits = net(st)
+            loss = -(torch.log_softmax(logits, -1).max(-1).values * pr.out["reward"][0].float()).mean()
+            loss.backward()
+            torch.cuda.synchronize(dev)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(torch.cuda.current_stream(dev))
+            nel = sharding.allreduce_gradients(net.parameters())
+            g1.record(torch.cuda.current_stream(dev))
+            torch.cuda.synchronize(dev)
+            res["gradient_allreduce"] = {"elements": int(nel), "ms": g0.elapsed_time(g1),
+                                         "backend": dist.get_backend() if world > 1 else "single rank (no collective)"}
+            net.zero_grad(set_to_none=True)
+        res["env_errors"] = int((vec.info()["error"] != 0).sum())
+    vec.close()
+    return res
+
+
 def main():
-    args = parse()
+    args, cfg = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, cfg, rank)
         return
     import torch
     import torch.distributed as dist
     from deep_reinforcement_learning_for_fjsp_b200.vec_env import FJSPVecEnv
+    from deep_reinforcement_learning_for_fjsp_b200 import _lib, sharding
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
@@ -181,19 +314,25 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
-    B, T, K, W = args.envs, args.rollout, args.steps, max(args.warmup, 3)
-    # every rank plays its own shard of distinct instances: no data-path collective
-    insts = make_instances(B, args.seed + 7919 * rank, args.machines, args.orders)
-    vec = FJSPVecEnv(insts, np.arange(B), args.variant, device=local_rank)
+    variant, B, T, LPS = cfg["variant"], cfg["envs"], cfg["T"], cfg["launches_per_step"]
+    K, W = args.steps, max(args.warmup, 3)
+    # every rank plays its own shard: no data-path collective
+    blobs, env_inst = config_blobs(cfg, args.seed, rank)
+    vec = FJSPVecEnv(None, env_inst, variant, device=local_rank, blobs=blobs)
     q = vec.query()
     vec.reset()
     rng = np.random.default_rng(args.seed + rank)
-    # inputs for every launch, resident in HBM before the timed region
-    acts, rnds = [], []
-    for _ in range(W + K):
-        a, r = make_actions(rng, T, B, args.variant)
+    sample = np.unique(np.linspace(0, B - 1, min(args.parity_envs, B)).astype(np.int64))
+    history = []                                    # what the sample environments were fed, launch by launch
+    # inputs for every launch, resident in HBM before the timed region (a pool that the burn-in cycles through)
+    NP_ = min(W + K, 8) if B * T > 2_000_000 else W + K
+    acts, rnds, acts_h, rnds_h = [], [], [], []
+    for _ in range(NP_):
+        a, r = make_actions(rng, T, B, variant)
         acts.append(torch.from_numpy(a).to(dev))
         rnds.append(torch.from_numpy(r.view(np.int32)).to(dev))
+        acts_h.append(a[:, sample].copy())
+        rnds_h.append(r[:, sample].copy())
     out = {"state": torch.empty((T, B, vec.state_size), dtype=torch.float32, device=dev),
            "reward": torch.empty((T, B), dtype=torch.float64, device=dev),
            "done": torch.empty((T, B), dtype=torch.int32, device=dev)}
@@ -205,10 +344,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range((args.burnin + T - 1) // T):      # untimed burn-in: reach the steady mix of episode phases
-        vec.rollout(acts[i % (W + K)], rnds[(i * 7 + 3) % (W + K)], reward_policy=1, out=out, state_dtype=torch.float32)
-    for i in range(W):
-        vec.rollout(acts[i], rnds[i], reward_policy=1, out=out, state_dtype=torch.float32)
+    def launch(ia, ir):
+        vec.rollout(acts[ia], rnds[ir], reward_policy=1, out=out, state_dtype=torch.float32)
+        history.append((acts_h[ia], rnds_h[ir]))
+
+    for i in range((cfg["burnin"] + T - 1) // T):   # untimed burn-in: reach the steady mix of episode phases
+        launch(i % NP_, (i * 7 + 3) % NP_)
+    for i in range(W * LPS):
+        launch(i % NP_, i % NP_)
     barrier()
     info0 = vec.info()
     sampler = ClockSampler(local_rank)
@@ -217,31 +360,41 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     t_wall0 = time.perf_counter()
     for i in range(K):
-        flush.fill_(i & 0xff)                       # evict L2 between timed launches (not timed)
+        flush.fill_(i & 0xff)                       # evict L2 between timed steps (not timed)
         ev[i][0].record(stream)
-        vec.rollout(acts[W + i], rnds[W + i], reward_policy=1, out=out, state_dtype=torch.float32)
+        for j in range(LPS):
+            launch((W + i * LPS + j) % NP_, (W + i * LPS + j) % NP_)
         ev[i][1].record(stream)
     barrier()
     wall = time.perf_counter() - t_wall0
-    per_launch_ms = [a.elapsed_time(b) for a, b in ev]
-    dev_ms = float(sum(per_launch_ms))
+    per_step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = float(sum(per_step_ms))
     launches = vec.query()["launches"] - launches0
     info1 = vec.info()
     errors = int((info1["error"] != 0).sum())
     lp_solves = int((info1["lp_solves"] - info0["lp_solves"]).sum())
     episodes = int((info1["episodes"] - info0["episodes"]).sum())
+    # ---- parity of the timed batch itself: a sample of its environments against the CPU oracle
+    parity = parity_sample(vec, blobs, env_inst, variant, history, sample, dev, rng) if len(sample) else None
     # ---- e2e: the host-buffer C-ABI call, pinned host buffers, copies inside the timed region
-    ha = [torch.from_numpy(make_actions(rng, T, B, args.variant)[0]).pin_memory() for _ in range(2)]
-    hr = [torch.from_numpy(make_actions(rng, T, B, args.variant)[1].view(np.int32)).pin_memory() for _ in range(2)]
-    hs = torch.empty((T, B, vec.state_size), dtype=torch.float32).pin_memory()
-    hrw = torch.empty((T, B), dtype=torch.float64).pin_memory()
-    hdn = torch.empty((T, B), dtype=torch.int32).pin_memory()
+    Te = T * LPS
+    ha = [torch.from_numpy(make_actions(rng, Te, B, variant)[0]).pin_memory() for _ in range(2)]
+    hr = [torch.from_numpy(make_actions(rng, Te, B, variant)[1].view(np.int32)).pin_memory() for _ in range(2)]
+    hs = torch.empty((Te, B, vec.state_size), dtype=torch.float32).pin_memory()
+    hrw = torch.empty((Te, B), dtype=torch.float64).pin_memory()
+    hdn = torch.empty((Te, B), dtype=torch.int32).pin_memory()
     L = vec._L
-    from deep_reinforcement_learning_for_fjsp_b200 import _lib
 
     def e2e_call(i):
-        _lib.check(L.fjsp_vec_step_host(vec._h, T, ha[i % 2].data_ptr(), hr[i % 2].data_ptr(), 1, 1.0, 1.0, 1.0, 1,
-                                        None, hs.data_ptr(), hrw.data_ptr(), hdn.data_ptr(), None))
+        if LPS == 1:
+            _lib.check(L.fjsp_vec_step_host(vec._h, T, ha[i % 2].data_ptr(), hr[i % 2].data_ptr(), 1, 1.0, 1.0, 1.0, 1,
+                                            None, hs.data_ptr(), hrw.data_ptr(), hdn.data_ptr(), None))
+        else:   # one step() per call, as a single-environment agent loop makes them
+            for j in range(LPS):
+                o = j * B
+                _lib.check(L.fjsp_vec_step_host(vec._h, 1, ha[i % 2].data_ptr() + o * 8, hr[i % 2].data_ptr() + o * 8, 1, 1.0, 1.0,
+                                                1.0, 1, None, hs.data_ptr() + o * vec.state_size * 4, hrw.data_ptr() + o * 8,
+                                                hdn.data_ptr() + o * 4, None))
     for i in range(W):
         e2e_call(i)
     barrier()
@@ -250,41 +403,47 @@ def main():
         e2e_call(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    h2d = ha[0].numel() * 4 + hr[0].numel() * 4
+    d2h = hs.numel() * 4 + hrw.numel() * 8 + hdn.numel() * 4
+    del ha, hr, hs, hrw, hdn
     # ---- other rollout lengths on the same batch (not the headline): T = 1 is one reference
     # step() per launch, T = 128 a PPO-style rollout
     sweep = []
-    if args.sweep:
+    if args.sweep and B * 128 <= 4096 * 128 * 4:
         for T2, n2 in ((1, 64), (128, max(3, K // 4))):
-            a2 = [torch.from_numpy(make_actions(rng, T2, B, args.variant)[0]).to(dev) for _ in range(2)]
-            r2 = [torch.from_numpy(make_actions(rng, T2, B, args.variant)[1].view(np.int32)).to(dev) for _ in range(2)]
+            if T2 == T:
+                continue
+            a2 = [torch.from_numpy(make_actions(rng, T2, B, variant)[0]).to(dev) for _ in range(4)]
+            r2 = [torch.from_numpy(make_actions(rng, T2, B, variant)[1].view(np.int32)).to(dev) for _ in range(4)]
             o2 = {"state": torch.empty((T2, B, vec.state_size), dtype=torch.float32, device=dev),
                   "reward": torch.empty((T2, B), dtype=torch.float64, device=dev),
                   "done": torch.empty((T2, B), dtype=torch.int32, device=dev)}
             for i in range(3):
-                vec.rollout(a2[i % 2], r2[(i + 1) % 2], reward_policy=1, out=o2, state_dtype=torch.float32)
+                vec.rollout(a2[i % 4], r2[(i + 1) % 4], reward_policy=1, out=o2, state_dtype=torch.float32)
+            lp_a = int(vec.info()["lp_solves"].sum())
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(dev)
             e0.record(stream)
             for i in range(n2):
-                vec.rollout(a2[i % 2], r2[(i + 1) % 2], reward_policy=1, out=o2, state_dtype=torch.float32)
+                vec.rollout(a2[i % 4], r2[(i + 1) % 4], reward_policy=1, out=o2, state_dtype=torch.float32)
             e1.record(stream)
             torch.cuda.synchronize(dev)
             ms2 = e0.elapsed_time(e1)
             sweep.append({"env_steps_per_launch": T2, "launches": n2, "value": B * T2 * n2 / (ms2 / 1e3), "unit": UNIT,
-                          "ms_per_launch": ms2 / n2})
+                          "ms_per_launch": ms2 / n2, "fluid_lp_solves": int(vec.info()["lp_solves"].sum()) - lp_a})
             del a2, r2, o2
     # ---- the same kernels with enough copies to fill the machine (not the headline)
     large = None
-    if args.large_envs and args.large_envs > B:
-        BL = args.large_envs
-        vecL = FJSPVecEnv(insts, np.arange(BL) % B, args.variant, device=local_rank)
+    if cfg["large"] and cfg["large"] > B:
+        BL = cfg["large"]
+        vecL = FJSPVecEnv(None, np.arange(BL) % len(blobs), variant, device=local_rank, blobs=blobs)
         vecL.reset()
-        aL = [torch.from_numpy(make_actions(rng, T, BL, args.variant)[0]).to(dev) for _ in range(2)]
-        rL = [torch.from_numpy(make_actions(rng, T, BL, args.variant)[1].view(np.int32)).to(dev) for _ in range(2)]
+        aL = [torch.from_numpy(make_actions(rng, T, BL, variant)[0]).to(dev) for _ in range(2)]
+        rL = [torch.from_numpy(make_actions(rng, T, BL, variant)[1].view(np.int32)).to(dev) for _ in range(2)]
         outL = {"state": torch.empty((T, BL, vec.state_size), dtype=torch.float32, device=dev),
                 "reward": torch.empty((T, BL), dtype=torch.float64, device=dev),
                 "done": torch.empty((T, BL), dtype=torch.int32, device=dev)}
-        for i in range(min(args.burnin, 1024) // T + 3):
+        for i in range(min(cfg["burnin"], 1024) // T + 3):
             vecL.rollout(aL[i % 2], rL[(i + 1) % 2], reward_policy=1, out=outL, state_dtype=torch.float32)
         barrier()
         KL = max(3, K // 4)
@@ -294,24 +453,28 @@ def main():
             vecL.rollout(aL[i % 2], rL[(i + 1) % 2], reward_policy=1, out=outL, state_dtype=torch.float32)
             evL[i][1].record(stream)
         torch.cuda.synchronize(dev)
-        msL = sum(a.elapsed_time(b) for a, b in evL)
-        if world > 1:   # whole-job number: every rank ran its own copies at the same time; max over ranks
-            tL = torch.tensor([msL], dtype=torch.float64, device=dev)
-            dist.all_reduce(tL, op=dist.ReduceOp.MAX)
-            msL = float(tL[0])
-        large = {"envs_per_gpu": BL, "value": world * BL * T * KL / (msL / 1e3), "unit": UNIT, "launches": KL,
+        msL, stepsL = sharding.reduce_timing(sum(a.elapsed_time(b) for a, b in evL), BL * T * KL, dev)
+        large = {"envs_per_gpu": BL, "value": stepsL / (msL / 1e3), "unit": UNIT, "launches": KL,
                  "ms_per_launch": msL / KL, "env_errors": int((vecL.info()["error"] != 0).sum()),
-                 "note": "instances replicated 16x; state 0.8 GB > L2, no flush needed"}
+                 "note": "instances replicated; env table > L2, no flush needed"}
+        vecL.close()
         del vecL, outL, aL, rL
+    # ---- the agent loop: one policy forward + one step() per env step, CUDA-graphed (not the headline)
+    pol = []
+    if args.policy and B >= 64:
+        for Bp in sorted({min(B, 4096), cfg["large"] or B, B} - {0}):
+            try:
+                pol.append(policy_in_loop(blobs, (np.arange(Bp) % len(blobs)).astype(np.int32), variant, local_rank, world,
+                                          seed=args.seed))
+            except Exception as e:   # the headline must survive a failure of a side line
+                pol.append({"envs_per_gpu": Bp, "error": repr(e)[:300]})
     clocks = sampler.summary()
-    h2d = ha[0].numel() * 4 + hr[0].numel() * 4
-    d2h = hs.numel() * 4 + hrw.numel() * 8 + hdn.numel() * 4
+    # ---- rollout statistics of every copy, gathered over the ranks (NCCL at N > 1; the only collectives
+    # besides the timing reduction: there is none on the data path)
+    stats = sharding.gather_episode_stats(info1["completion_time"], info1["delay_time_sum"], info1["energy_consumption"], dev)
     # ---- max over ranks
-    tm = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = float(tm[0]), float(tm[1])
-    total_steps = world * B * T * K
+    dev_ms_max, total_steps = sharding.reduce_timing(dev_ms, B * T * LPS * K, dev)
+    e2e_ms_max, _ = sharding.reduce_timing(e2e_s * 1e3, 0, dev)
     value = total_steps / (dev_ms_max / 1e3)
     e2e_value = total_steps / (e2e_ms_max / 1e3)
     if rank == 0:
@@ -325,35 +488,48 @@ def main():
         # outputs (float32 state, float64 reward, int32 done)
         per_env_step_io = 16 + vec.state_size * 4 + 8 + 4
         algo_bytes = B * (2 * q["env_record_bytes"] + T * per_env_step_io)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and B == 4096 and T == 32:
-            traffic = json.load(open(tpath))["dram_bytes_per_launch"]   # from the committed ncu --set full capture
-        launch_s = (dev_ms / K) / 1e3
+        ncu = {}
+        npath = os.path.join(ROOT, "profiles", "r02_ncu_summary.json")
+        if os.path.exists(npath):
+            ncu = json.load(open(npath)).get(args.config, {}) if (B, T) == (CONFIGS[args.config]["envs"], CONFIGS[args.config]["T"]) else {}
+        launch_s = (dev_ms / (K * LPS)) / 1e3
         achieved = algo_bytes / launch_s / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "envs_per_gpu": B, "env_steps_per_step": T,
-                           "machines": args.machines, "orders": args.orders, "variant": args.variant,
-                           "l2": "flushed between timed launches (256 MiB fill)", "kernels_per_step": "flag + pack kernels (LP-aware env-to-CTA map), step kernel (in-CTA LP service)", "parallelism": f"shard{world}",
-                           "env_record_bytes": q["env_record_bytes"], "grid": q["grid"], "block": q["block"]},
+                "dtype": "f64", "state_out_dtype": "f32 (timed launches and e2e write the observation as float32; clocks and counters are int32/int64, rule keys and features float64)",
+                "data": "synthetic",
+                "config": {"workload": cfg["workload"], "name": args.config, "envs_per_gpu": B, "env_steps_per_step": T * LPS,
+                           "launches_per_step": LPS, "machines": cfg.get("machines"), "orders": cfg.get("orders"), "variant": variant,
+                           "distinct_instances_per_gpu": len(blobs),
+                           "l2": "flushed between timed steps (256 MiB fill)",
+                           "kernels_per_step": "flag + pack kernels (LP-aware env-to-warp map), step kernel (lockstep env warps + LP team)",
+                           "parallelism": f"shard{world}", "env_record_bytes": q["env_record_bytes"], "grid": q["grid"],
+                           "block": q["block"], "env_warps": q["env_warps"], "lp_team_warps": q["team_warps"],
+                           "step_kernel_dynamic_smem": q["step_smem_bytes"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "link_gbs": (h2d + d2h) * K / e2e_s / 1e9,
                         "api": "fjsp_vec_step_host (C ABI, pinned host buffers, float32 state out)"},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": ncu.get("dram_bytes_per_launch"), "peak_source": peak_src,
                              "kernel": "fjsp_step_kernel", "algorithmic_bytes_per_launch": algo_bytes,
                              "launch_ms": launch_s * 1e3,
-                             "note": "latency-bound discrete-event kernel (3.5k warp instructions per env step, 36% issue utilisation, 45% of warp time at CTA barriers), not HBM-bound; see DESIGN.md section 4"},
+                             "note": "latency-bound discrete-event kernel, not HBM-bound (see roofline_issue and DESIGN.md section 4)"},
+                "roofline_issue": {"bound": "warp-instruction issue", "inst_per_env_step": ncu.get("warp_inst_per_env_step"),
+                                   "issue_pct_of_peak": ncu.get("inst_executed_pct_of_peak"),
+                                   "source": ncu.get("source", "no ncu capture committed for this config")},
+                "parity_sample": parity,
                 "wall_s_timed_region": wall, "env_errors": errors,
                 "timed_region_events": {"fluid_lp_solves": lp_solves, "episodes_finished": episodes,
-                                        "burnin_env_steps_per_copy": args.burnin},
-                "launch_ms_min_max": [min(per_launch_ms), max(per_launch_ms)], "large_batch": large,
-                "rollout_sweep": sweep}
+                                        "burnin_env_steps_per_copy": cfg["burnin"]},
+                "episode_stats_all_ranks": {"copies": int(stats.shape[0]), "mean_completion_time": float(stats[:, 0].mean()),
+                                            "mean_delay_time_sum": float(stats[:, 1].mean()),
+                                            "gathered_with": "sharding.gather_episode_stats (" + (dist.get_backend() if world > 1 else "single rank") + ")"},
+                "step_ms_min_max": [min(per_step_ms), max(per_step_ms)], "large_batch": large,
+                "rollout_sweep": sweep, "policy_in_loop": pol}
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_port_throughput(insts[:64], args.variant, args.cpu_seconds, T, args.seed)
+            line["cpu_baseline"] = cpu_port_throughput(blobs[:64], variant, args.cpu_seconds, T, args.seed)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

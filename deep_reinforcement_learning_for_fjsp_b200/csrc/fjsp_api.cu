@@ -36,38 +36,58 @@ template <int VARIANT, int SUM_MODE>
 __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step_kernel(const __grid_constant__ FjParams P, const __grid_constant__ FjStepArgs A)
 {
     fj_params_to_shared(P);
-    // lockstep phases: every warp of the CTA walks the same number of env groups and steps
     extern __shared__ __align__(16) unsigned char stage_smem[];
-    __shared__ int req_env[32], lp_meta[2];
+    __shared__ FjLpBoard board;
     __shared__ int4 red4[64];
-    const int wpb = blockDim.x >> 5;
-    const int total = gridDim.x * wpb;
-    unsigned char *stage = P.stage ? stage_smem + (size_t)(threadIdx.x >> 5) * P.stage_stride : nullptr;
+    const int warp = threadIdx.x >> 5;
+    const int nenv = P.env_warps;                 // env warps of the CTA (= warp slots of a virtual CTA)
+    const int nteam = (blockDim.x >> 5) - nenv;   // LP team: the CTA's last warps (0 in the free-running / parking modes)
+    for (int k = threadIdx.x; k < 32; k += blockDim.x) {
+        board.req[k] = -1; board.resp[k] = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fj_smem_addr(&board.mbar[k])) : "memory");
+    }
+    if (threadIdx.x == 0) { board.quit = 0; board.cur[0] = board.cur[1] = -1; }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    unsigned char *hotbuf = P.stage && warp < nenv ? stage_smem + (size_t)warp * P.stage_stride : nullptr;
     FjCtaCtx K;
-    K.warp = threadIdx.x >> 5; K.nwarps = wpb; K.cta_lp = P.cta_lp;
-    K.stage_base = P.stage ? stage_smem : nullptr;
+    K.warp = warp; K.nwarps = nenv; K.cta_lp = P.cta_lp == 1 && nteam > 0;
     K.slab = P.lp + (size_t)blockIdx.x * P.lp_stride;
-    K.x = (double *)(K.slab + (size_t)P.d.Rx * P.d.Rx * 8 + (fj_lp_small_bytes(P.d) + 7) / 8 * 8);
-    K.meta = lp_meta; K.req_env = req_env;
-    K.lp_smem_bytes = P.cta_lp_smem;
-    K.lp_smem = P.cta_lp_smem ? stage_smem + (size_t)(P.stage ? wpb * P.stage_stride : 0) : nullptr;
-    K.group.red = red4; K.group.flip = 0;
-    // P.order maps warp slots to envs: slot = virtual CTA * wpb + warp, -1 = empty.  CTA b plays
+    K.xbuf = P.cta_x + (size_t)blockIdx.x * nenv * P.d.NPx;
+    K.team_smem = P.team_smem ? stage_smem + (P.stage ? (size_t)nenv * P.stage_stride : 0) : nullptr;
+    K.board = &board;
+    K.group.red = red4; K.group.flip = 0; K.group.base = nenv * 32; K.group.nthr = nteam * 32; K.group.bar = FJ_BAR_TEAM;
+    const int total = gridDim.x * nenv;
+    // P.order maps warp slots to envs: slot = virtual CTA * nenv + warp, -1 = empty.  CTA b plays
     // the virtual CTAs b, b + gridDim, ...
     if (P.cta_lp == 2) {
         // free-running warps: no CTA coupling at all; a warp that reaches an order arrival solves
-        // the fluid LP itself on its own scratch slab
-        unsigned char *lp = P.lp + (size_t)(blockIdx.x * wpb + (threadIdx.x >> 5)) * P.lp_stride;
-        for (int slot = blockIdx.x * wpb + (threadIdx.x >> 5); slot < P.n_slots; slot += total) {
+        // the fluid LP itself on its own scratch slab (diagnostic mode, FJSP_FREE_RUN)
+        unsigned char *lp = P.lp + (size_t)(blockIdx.x * nenv + warp) * P.lp_stride;
+        for (int slot = blockIdx.x * nenv + warp; slot < P.n_slots; slot += total) {
             const int env = P.order[slot];
-            if (env >= 0) fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, env, lp, stage);
+            if (env >= 0) fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, env, lp, nullptr);
         }
         return;
     }
-    for (int base = blockIdx.x * wpb; base < P.n_slots; base += total) {
-        const int env = P.order[base + (threadIdx.x >> 5)];
-        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env < 0 ? 0 : env, env >= 0, stage);
+    if (warp >= nenv) { fj_lp_team_loop(P, K); return; }
+    unsigned uses = 0;
+    for (int base = blockIdx.x * nenv; base < P.n_slots; base += total) {
+        const int raw = P.order[base + warp];
+        const int env = raw < 0 ? -1 : raw & (FJ_SLOT_DETACHED - 1);
+        const int detached = raw >= 0 && (raw & FJ_SLOT_DETACHED);
+        int next_env = base + total < P.n_slots ? P.order[base + total + warp] : -1;
+        if (next_env >= 0) next_env &= FJ_SLOT_DETACHED - 1;
+        // the round's lockstep group: env warps that hold an env which is not expected to meet an LP or
+        // a reset (those free-run: their long steps would stall every mate at the slot barrier)
+        const int lock_threads = fj_env_count(env >= 0 && !detached, nenv * 32);
+        if (env < 0) continue;
+        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env, 1, hotbuf, next_env, uses & 1u, detached ? 0 : lock_threads);
+        if (hotbuf) ++uses;
     }
+    // every env warp (the free-running ones included) has finished its last round: release the LP team
+    fj_env_count(0, nenv * 32);
+    if (threadIdx.x == 0) *(volatile int *)&board.quit = 1;
 }
 
 // LP-aware packing, run before every step launch.  The warps of a CTA serve each other's fluid
@@ -109,7 +129,7 @@ __device__ __forceinline__ int fj_pack_free(const FjPackPlan &p, int wpb, int m)
     return f + x * wpb;
 }
 __global__ void __launch_bounds__(FJ_PACK_THREADS) fjsp_pack_kernel(FjParams P, const int32_t *static_order, const unsigned char *flags,
-                                                                    int32_t *order_out, int wpb, int cap1, int cap2, int cap3)
+                                                                    int32_t *order_out, int wpb, int cap1, int cap2, int cap3, int detach)
 {
     __shared__ unsigned long long wsum[32];
     __shared__ FjPackPlan s_plan;
@@ -165,7 +185,7 @@ __global__ void __launch_bounds__(FJ_PACK_THREADS) fjsp_pack_kernel(FjParams P, 
             }
             slot = a * wpb + (a < p.e1 + p.e2 + p.e3 ? 1 : 0) + (rB - fj_pack_free(p, wpb, a));
         }
-        order_out[slot] = env;
+        order_out[slot] = c && detach ? (env | FJ_SLOT_DETACHED) : env;
         r1 += c == 1; r2 += c == 2; r3 += c == 3;
     }
 }
@@ -198,7 +218,7 @@ __global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(const __grid_con
     unsigned char *small_ = SMEM_BINV ? smem + binv_bytes : smem;
     unsigned char *red = smem + ((SMEM_BINV ? binv_bytes : 0) + fj_lp_small_bytes(P.d) + 15) / 16 * 16;   // 16-byte aligned
     FjCtaGroup g;
-    g.red = (int4 *)red; g.flip = 0;
+    g.red = (int4 *)red; g.flip = 0; g.whole_cta();
     for (int i = blockIdx.x; i < n; i += gridDim.x) fj_lp_service(P, g, list_in, i, binv, small_, P.lp + (size_t)blockIdx.x * P.lp_stride);
 }
 
@@ -242,7 +262,8 @@ struct fjsp_vec {
     double *d_lp_x, *d_plan_x;
     int n_inst, plan_ready, plan_all;   // plan_all: every instance's order-0 LP solution gets cached by the first reset
     int32_t *d_inst, *d_env_inst, *d_order, *d_order_dyn;
-    int n_slots, pack_cap[3], pack_rows[2], multi_round;
+    int n_slots, pack_cap[3], pack_rows[2], multi_round, env_warps, team_warps, detach;
+    double *d_cta_x;
     unsigned char *d_flags;
     int pack;
     unsigned char *d_env, *d_lp;
@@ -284,7 +305,7 @@ template <typename F> static int dispatch(fjsp_vec *v, F f)
 extern "C" {
 
 const char *fjsp_last_error(void) { return g_err.c_str(); }
-int fjsp_abi_version(void) { return 1; }
+int fjsp_abi_version(void) { return 2; }
 
 int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_instances,
                     const int32_t *env_instance, int n_envs, int variant, int sum_mode, int device,
@@ -314,25 +335,26 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     int cap = prop.multiProcessorCount * 8;
     if (getenv("FJSP_GRID_PER_SM")) cap = prop.multiProcessorCount * atoi(getenv("FJSP_GRID_PER_SM"));
     v->grid = want < cap ? want : cap;
+    const int lp_mode = getenv("FJSP_FREE_RUN") ? 2 : getenv("FJSP_NO_CTA_LP") ? 0 : 1;
     {
-        // CTA size at run time.  The batch gets ~15 % more warp slots than envs: the spare slots are
-        // what lets the packing kernel give the envs that are about to solve an LP lightly
-        // loaded CTAs.  Slots = rounds x grid x wpb, grid <= resident CTAs.
-        const int per_sm = 1024 / FJ_STEP_THREADS, gmax = prop.multiProcessorCount * per_sm, wmax = FJ_STEP_THREADS / 32;
-        const int spare_pct = getenv("FJSP_SPARE") ? atoi(getenv("FJSP_SPARE")) : 15;
-        long long want_slots = (long long)n_envs + (n_envs * (long long)spare_pct + 99) / 100;
-        if (getenv("FJSP_NO_PACK") || getenv("FJSP_FREE_RUN") || getenv("FJSP_NO_CTA_LP")) want_slots = n_envs;
-        // a batch that needs several rounds of CTAs averages its LPs out by itself: no spare slots
-        // (measured at 65 536 copies: 99 M env-steps/s with 15 % spare, 110 M without)
-        v->multi_round = (long long)n_envs > (long long)gmax * wmax;
-        if (v->multi_round && !getenv("FJSP_SPARE")) want_slots = n_envs;
+        // CTA shape at run time: `env_warps` env warps (one environment copy each, lockstep slots) plus
+        // an LP team of 4 warps (8 when an LP can have more than 128 rows).  One CTA per SM; a batch
+        // larger than grid x env_warps is played in rounds.
+        const int gmax = prop.multiProcessorCount, wmax = FJ_STEP_THREADS / 32;
+        int team = lp_mode == 1 ? (v->tb.d.Rx > 128 ? 8 : 4) : 0;
+        if (getenv("FJSP_LP_TEAM") && lp_mode == 1) team = atoi(getenv("FJSP_LP_TEAM"));
+        if (team < 1 && lp_mode == 1) team = 1;
+        if (team > wmax / 2) team = wmax / 2;
+        const long long want_slots = (long long)n_envs + (getenv("FJSP_SPARE") ? n_envs * (long long)atoi(getenv("FJSP_SPARE")) / 100 : 0);
+        v->multi_round = (long long)n_envs > (long long)gmax * (wmax - team);
         int wpb = (int)((want_slots + gmax - 1) / gmax);
-        if (wpb > wmax) wpb = wmax;
+        if (wpb > wmax - team) wpb = wmax - team;
         if (wpb < 4) wpb = 4;
         if (getenv("FJSP_STEP_WARPS")) wpb = atoi(getenv("FJSP_STEP_WARPS"));
-        if (wpb > wmax) wpb = wmax;
+        if (wpb > wmax - team) wpb = wmax - team;
         if (wpb < 1) wpb = 1;
-        v->step_threads = wpb * 32;
+        v->env_warps = wpb; v->team_warps = team;
+        v->step_threads = (wpb + team) * 32;
         long long ctas = (want_slots + wpb - 1) / wpb;              // virtual CTAs
         v->step_grid = (int)(ctas < gmax ? ctas : gmax);
         const long long rounds = (ctas + v->step_grid - 1) / v->step_grid;
@@ -352,7 +374,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     int slabs = v->resume_grid * FJ_WARPS_PER_BLOCK;
     if (v->lp_grid > slabs) slabs = v->lp_grid;
     if (v->step_grid > slabs) slabs = v->step_grid;   // one slab per CTA of the main kernel (in-CTA LP service)
-    if (getenv("FJSP_FREE_RUN") && v->step_grid * (v->step_threads / 32) > slabs) slabs = v->step_grid * (v->step_threads / 32);
+    if (lp_mode == 2 && v->step_grid * v->env_warps > slabs) slabs = v->step_grid * v->env_warps;
     const size_t lp_bytes = (size_t)lp_stride * slabs;
     const size_t env_bytes = (size_t)n_envs * v->tb.eo.stride;
     CK(cudaMalloc(&v->d_inst, v->tb.inst.size() * 4));
@@ -376,6 +398,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     }
     CK(cudaMalloc(&v->d_env, env_bytes));
     CK(cudaMalloc(&v->d_lp, lp_bytes));
+    CK(cudaMalloc(&v->d_cta_x, (size_t)v->step_grid * v->env_warps * v->tb.d.NPx * 8 + 16));
     CK(cudaMemcpy(v->d_inst, v->tb.inst.data(), v->tb.inst.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(v->d_env_inst, env_instance, (size_t)n_envs * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(v->d_env, 0, env_bytes));
@@ -410,6 +433,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     P.n_slots = v->n_slots;
     P.inst = v->d_inst; P.env_inst = v->d_env_inst; P.env = v->d_env; P.lp = v->d_lp; P.lp_stride = lp_stride;
     P.B = n_envs; P.variant = variant; P.sum_mode = v->sum_mode; P.nobs = v->nstate / 2;
+    P.cta_x = v->d_cta_x; P.env_warps = v->env_warps;
     P.pend_count = v->d_pend_count; P.pend_env = v->d_pend_env; P.lp_x = v->d_lp_x; P.lp_meta = v->d_lp_meta;
     P.lp_slots = (int)slots;
     P.plan_x = v->d_plan_x; P.plan_meta = v->d_plan_meta; P.plan_ok = nullptr;
@@ -419,35 +443,41 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaMemset(v->d_trace, 0, (size_t)v->step_grid * FJ_TRACE_ROWS * 8 * 8));
     P.trace = v->d_trace;
 #endif
-    // the main kernel stages the hot prefix of its warps' records in shared memory for the whole
-    // launch when the slabs of all CTAs resident on an SM fit
+    // the main kernel stages the hot prefix of its env warps' records in shared memory for the whole
+    // launch (TMA bulk copies) when the slabs fit next to the static shared memory
     P.stage_stride = v->tb.eo.hot;
-    v->stage_bytes = (size_t)(v->step_threads / 32) * P.stage_stride;
-    P.stage = v->stage_bytes * (1024 / FJ_STEP_THREADS) <= 200 * 1024 ? 1 : 0;
+    v->stage_bytes = (size_t)v->env_warps * P.stage_stride;
+    P.stage = v->stage_bytes <= 200 * 1024 ? 1 : 0;
     if (getenv("FJSP_NO_STAGE")) P.stage = 0;
     if (!P.stage) v->stage_bytes = 0;
-    P.cta_lp = getenv("FJSP_NO_CTA_LP") ? 0 : 1;   // 0: park order arrivals for the LP / resume kernels
-    if (getenv("FJSP_FREE_RUN")) P.cta_lp = 2;
+    P.cta_lp = lp_mode;
     v->pack = (P.cta_lp == 1 && !getenv("FJSP_NO_PACK")) ? 1 : 0;
-    {   // warp slots of a virtual CTA that holds an env with a heavy / medium / light LP ahead, and the
-        // row bounds (M + 2 KT - K) of the classes; FJSP_PACK="cap1,cap2,cap3,rows_heavy,rows_medium"
-        const int w = v->step_threads / 32;
-        v->pack_cap[0] = 1; v->pack_cap[1] = w / 8 > 1 ? w / 8 : 1; v->pack_cap[2] = w / 2 > 1 ? w / 2 : 1;
+    {   // The packing kernel deals the envs that will meet an LP in this launch one per virtual CTA first
+        // (one LP team per CTA serves them one at a time) and fills the rest in the static order.
+        // FJSP_PACK="cap1,cap2,cap3,rows_heavy,rows_medium" limits the env warps of a virtual CTA that
+        // holds an env with a heavy / medium / light LP ahead (needs spare slots, FJSP_SPARE).
+        const int w = v->env_warps;
+        v->pack_cap[0] = v->pack_cap[1] = v->pack_cap[2] = w;
         v->pack_rows[0] = 70; v->pack_rows[1] = 45;
-        if (v->multi_round) v->pack_cap[0] = v->pack_cap[1] = v->pack_cap[2] = w;   // spread the LP envs over the CTAs, nothing else
         if (getenv("FJSP_PACK")) sscanf(getenv("FJSP_PACK"), "%d,%d,%d,%d,%d", &v->pack_cap[0], &v->pack_cap[1], &v->pack_cap[2], &v->pack_rows[0], &v->pack_rows[1]);
     }
-    {   // shared-memory scratch for the in-CTA LP: what is left of the SM's 200 KB per resident CTA
-        const size_t per_cta = (size_t)200 * 1024 / (1024 / FJ_STEP_THREADS);
-        size_t left = per_cta > v->stage_bytes + 1024 ? per_cta - v->stage_bytes - 1024 : 0;
-        const size_t want_lp = ((size_t)v->tb.d.Rx * v->tb.d.Rx * 8 + fj_lp_small_bytes_host(v->tb.d) + 15) / 16 * 16;
-        if (left > want_lp) left = want_lp;
-        left = left / 16 * 16;
-        // measured (profiles/README.md): the extra shared memory costs more L1 than the faster pivots win,
-        // so the shared-memory LP scratch is opt-in
-        P.cta_lp_smem = (P.cta_lp && getenv("FJSP_LP_SMEM") && left >= 8 * 1024) ? (int)left : 0;
-        v->step_smem_bytes = v->stage_bytes + (size_t)P.cta_lp_smem;
+    {   // LP team scratch in shared memory: column descriptors, positions and B^-1 of the largest LP the
+        // batch can meet (rows <= M + 2 KT - K), capped by what the SM has left
+        // (FJSP_TEAM_SMEM_KB overrides the cap; 0 keeps the LP scratch in HBM/L2)
+        size_t rub = 1;
+        for (int i = 0; i < n_instances; ++i) { const int32_t *b = blobs + blob_offsets[i]; const size_t r = (size_t)b[2] + 2 * b[4] - b[3]; if (r > rub) rub = r; }
+        const size_t C = (size_t)v->tb.d.NPx + 1;
+        const size_t small_b = (C * 24 + ((C + rub + 1) & ~(size_t)1) * 4 + rub * 8 + 15) / 16 * 16;
+        const size_t want = small_b + ((rub + 1) * (rub | 1) * 8 + 15) / 16 * 16;
+        size_t cap = (size_t)(getenv("FJSP_TEAM_SMEM_KB") ? atoi(getenv("FJSP_TEAM_SMEM_KB")) : 64) * 1024;
+        const size_t room = (size_t)200 * 1024 > v->stage_bytes ? (size_t)200 * 1024 - v->stage_bytes : 0;
+        if (cap > room) cap = room;
+        size_t give = want <= cap ? want : (small_b <= cap ? cap : 0);
+        if (P.cta_lp != 1) give = 0;
+        P.team_smem = (int)(give / 16 * 16);
     }
+    v->step_smem_bytes = v->stage_bytes + (size_t)P.team_smem;
+    v->detach = getenv("FJSP_NO_DETACH") ? 0 : 1;
     if (dispatch(v, [&](auto V, auto SM) {
             cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->step_smem_bytes);
@@ -483,7 +513,7 @@ int fjsp_vec_destroy(fjsp_vec *v)
     cudaFree(v->d_order); cudaFree(v->d_order_dyn); cudaFree(v->d_flags);
     cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
-    cudaFree(v->d_trace);
+    cudaFree(v->d_trace); cudaFree(v->d_cta_x);
     cudaFree(v->d_rep_env); cudaFree(v->d_plan_x); cudaFree(v->d_plan_meta); cudaFree(v->d_plan_ok);
     cudaStreamDestroy(v->stream); cudaStreamDestroy(v->copy_stream); cudaEventDestroy(v->chunk_done);
     delete v;
@@ -495,6 +525,7 @@ int fjsp_vec_query(fjsp_vec *v, int64_t *o)
     if (!v || !o) { g_err = "fjsp_vec_query: null argument"; return -1; }
     o[0] = v->B; o[1] = v->nstate; o[2] = v->tb.eo.stride; o[3] = (int64_t)v->tb.io.stride * 4;
     o[4] = v->step_grid; o[5] = v->step_threads; o[6] = (int64_t)v->P.lp_stride; o[7] = v->launches;
+    o[8] = v->env_warps; o[9] = v->team_warps; o[10] = v->n_slots; o[11] = (int64_t)v->step_smem_bytes;
     return 0;
 }
 
@@ -511,7 +542,8 @@ int fjsp_vec_reset(fjsp_vec *v, void *stream, double *d_state64, float *d_state3
         v->P.plan_ok = v->d_plan_ok;   // later launches may reset from the cache
     }
     int rc = dispatch(v, [&](auto V, auto SM) {
-        fjsp_reset_finish_kernel<decltype(V)::value, decltype(SM)::value><<<v->grid, FJ_BLOCK, 0, st>>>(v->P, d_state64, d_state32);
+        // one LP slab per warp (the in-line fallback of an env without a solution slot writes it): the resume kernel's grid
+        fjsp_reset_finish_kernel<decltype(V)::value, decltype(SM)::value><<<v->resume_grid, FJ_BLOCK, 0, st>>>(v->P, d_state64, d_state32);
         return 0;
     });
     if (rc) return rc;
@@ -541,8 +573,8 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
         A.park_count = v->d_pend_count; A.park_env = v->d_pend_env;
         if (v->pack) {
             fjsp_flag_kernel<<<(v->B + 255) / 256, 256, 0, st>>>(v->P, v->d_order, v->d_flags, T, v->pack_rows[0], v->pack_rows[1]);
-            fjsp_pack_kernel<<<1, FJ_PACK_THREADS, 0, st>>>(v->P, v->d_order, v->d_flags, v->d_order_dyn, v->step_threads / 32,
-                                                            v->pack_cap[0], v->pack_cap[1], v->pack_cap[2]);
+            fjsp_pack_kernel<<<1, FJ_PACK_THREADS, 0, st>>>(v->P, v->d_order, v->d_flags, v->d_order_dyn, v->env_warps,
+                                                            v->pack_cap[0], v->pack_cap[1], v->pack_cap[2], v->detach);
         }
         fjsp_step_kernel<VV, MM><<<v->step_grid, v->step_threads, v->step_smem_bytes, st>>>(v->P, A);
         // resume rounds: an env can meet a reset and further order arrivals inside one launch; the
@@ -644,6 +676,7 @@ int fjsp_vec_slots(fjsp_vec *v, int32_t *h_out, int capacity)
     CK(cudaSetDevice(v->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h_out, v->d_order_dyn, (size_t)v->n_slots * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < v->n_slots; ++i) if (h_out[i] >= 0) h_out[i] &= FJ_SLOT_DETACHED - 1;   // bit 30: the env free-runs in that launch
     return v->n_slots;
 }
 

@@ -387,25 +387,30 @@ struct FjWarpGroup {
 };
 
 #ifdef __CUDACC__
+// A group of whole warps of one CTA that synchronises on its own named barrier: the whole CTA
+// (base 0, blockDim.x threads, barrier 0 = __syncthreads) in the LP kernel, or the LP team of the
+// step kernel (the CTA's last warps, barrier FJ_BAR_TEAM) while the env warps keep stepping.
 struct FjCtaGroup {
     int4 *red;    // shared scratch: two buffers of one entry per warp (<= 32 warps)
     int flip;     // which buffer the next reduction uses (same value in every thread)
-    FJ_MFN int rank() const { return threadIdx.x; }
-    FJ_MFN int size() const { return blockDim.x; }
+    int base, nthr, bar;   // first thread, threads (multiple of 32), hardware barrier id
+    FJ_MFN void whole_cta() { base = 0; nthr = (int)blockDim.x; bar = 0; }
+    FJ_MFN int rank() const { return (int)threadIdx.x - base; }
+    FJ_MFN int size() const { return nthr; }
     FJ_MFN int lane() const { return threadIdx.x & 31; }
-    FJ_MFN int warp() const { return threadIdx.x >> 5; }
-    FJ_MFN int nwarps() const { return blockDim.x >> 5; }
-    FJ_MFN void sync() const { __syncthreads(); }
+    FJ_MFN int warp() const { return ((int)threadIdx.x - base) >> 5; }
+    FJ_MFN int nwarps() const { return nthr >> 5; }
+    FJ_MFN void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthr) : "memory"); }
     // one barrier per reduction: the partials of consecutive reductions alternate between two
     // buffers, so a buffer is rewritten only after every thread has passed the next barrier
     FJ_MFN int min_i(int v)
     {
         v = (int)__reduce_min_sync(0xffffffffu, (unsigned)v);   // callers pass non-negative values
         int4 *buf = red + flip * 32; flip ^= 1;
-        if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5].x = v;
-        __syncthreads();
-        const int l = threadIdx.x & 31;
-        const unsigned o = l < (int)(blockDim.x >> 5) ? (unsigned)buf[l].x : 0xffffffffu;
+        if (lane() == 0) buf[warp()].x = v;
+        sync();
+        const int l = lane();
+        const unsigned o = l < nwarps() ? (unsigned)buf[l].x : 0xffffffffu;
         return (int)__reduce_min_sync(0xffffffffu, o);
     }
     FJ_MFN void argmin(double &key, int &idx, int &aux)
@@ -413,12 +418,13 @@ struct FjCtaGroup {
         unsigned hi, lo, id;
         fj_lex_pack(key, idx, aux, hi, lo, id);
         fj_warp_lexmin(hi, lo, id);
+        if (nthr == 32) { fj_lex_unpack(hi, lo, id, key, idx, aux); sync(); return; }
         int4 *buf = red + flip * 32; flip ^= 1;
-        if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = make_int4((int)hi, (int)lo, (int)id, 0);
-        __syncthreads();
-        const int l = threadIdx.x & 31;
+        if (lane() == 0) buf[warp()] = make_int4((int)hi, (int)lo, (int)id, 0);
+        sync();
+        const int l = lane();
         hi = lo = id = 0xffffffffu;
-        if (l < (int)(blockDim.x >> 5)) { const int4 e = buf[l]; hi = (unsigned)e.x; lo = (unsigned)e.y; id = (unsigned)e.z; }
+        if (l < nwarps()) { const int4 e = buf[l]; hi = (unsigned)e.x; lo = (unsigned)e.y; id = (unsigned)e.z; }
         fj_warp_lexmin(hi, lo, id);
         fj_lex_unpack(hi, lo, id, key, idx, aux);
     }
@@ -426,7 +432,8 @@ struct FjCtaGroup {
 #else
 struct int4 { int x, y, z, w; };
 struct FjCtaGroup {   // host simulation: one thread
-    int4 *red; int flip;
+    int4 *red; int flip; int base, nthr, bar;
+    FJ_MFN void whole_cta() { base = 0; nthr = 1; bar = 0; }
     FJ_MFN int rank() const { return 0; }
     FJ_MFN int size() const { return 1; }
     FJ_MFN int lane() const { return 0; }
@@ -672,33 +679,42 @@ FJ_FN int fj_lp_solve(const G &g_in, FjCtx &c, FjLp &L, double *x_out, int *iter
 }
 
 #ifdef __CUDACC__
-// ---------------------------------------------------------------- CTA fast path of the LP
+// ---------------------------------------------------------------- group fast path of the LP
 // The same pivoting rules and the same floating-point operations as fj_lp_solve (results are
-// bit-identical; tests/test_gpu_parity.py compares both with the oracle), organised for latency:
-// an LP iteration is a chain of short dependent phases, and a warp here retires one
-// instruction per ~15-20 cycles, so what counts is the number of instructions on the chain.
-//   * every structural column carries a descriptor: its four row indices (machine row,
-//     demand row, the two precedence rows; a missing row points at a padding column of B^-1
-//     that is always 0, which adds +-0 and leaves the accumulator unchanged) and its two
-//     coefficients.  A reduced cost or an entry of w is 4 loads, 4 multiplies, 4 adds, no branch;
-//   * the basis inverse rows have stride R + 1 (the padding column);
-//   * x_B, the basis and w of row i stay in registers of thread i;
-//   * the t row of B^-1 (the pricing vector y) is mirrored in shared memory and updated by
-//     the threads that scale the pivot row, so the pricing of the next iteration overlaps the
-//     rank-1 update of this one: three CTA barriers per iteration (two of them inside the
-//     reductions) instead of seven.
-#define FJ_LPF_RMAX 192
+// bit-identical; tests/test_gpu_parity.py compares both with the oracle), organised for a SMALL
+// group (the step kernel's 4- or 8-warp LP team, the LP kernel's 8-warp CTA).  An LP iteration is
+// a chain of short dependent phases and a warp retires one instruction per 10-25 cycles, so what
+// counts is the number of instructions every warp executes per iteration:
+//   * every structural column carries a descriptor: its four row indices (machine row, demand
+//     row, the two precedence rows; a missing row points at a padding column of B^-1 that is
+//     always 0, which adds +-0 and leaves the accumulator unchanged) and its two coefficients:
+//     a reduced cost or an entry of w is 4 loads, 4 multiplies, 4 adds, no branch;
+//   * thread i owns ROW i of B^-1 (x_B, the basic variable and w of the row stay in its
+//     registers) and B^-1 is stored COLUMN-major with an odd column stride: "thread i reads
+//     B^-1[i][k]" is a conflict-free shared-memory access (coalesced when the scratch is global),
+//     and so is "thread k reads B^-1[p][k]" of the pivot-row scaling;
+//   * the rank-1 update is flat: a warp owns 32 rows and a chunk of the columns, a thread runs
+//     B^-1[i][k] -= w_i * pr[k] over its chunk with pr broadcast from shared memory -- 5
+//     instructions per element (round 1's row-block version spent 30 instructions of set-up per row
+//     on one inner iteration: 68 % of all LP instructions);
+//   * the t row of B^-1 (the pricing vector y) is mirrored in shared memory and updated by the
+//     threads that scale the pivot row, so the rank-1 update of pivot n runs after the pricing
+//     of iteration n+1 without a barrier in between: three group barriers per iteration.
+#define FJ_LPF_RMAX 256
 struct FjLpFastSmem {
     double w[FJ_LPF_RMAX];
+    double pr[FJ_LPF_RMAX];
     double y[2][FJ_LPF_RMAX + 2];
     short prec[FJSP_MAX_KT];
     int nprec;
 };
 static __shared__ FjLpFastSmem fj_sLpf;
 
-FJ_FN double fj_lpf_dot(const double *row, uint2 ix, double a, double r, bool negate)
+// sum over the column's four rows of  (negate ? -v[row] : v[row]) * coefficient,  v = a vector indexed by row
+// (stride 1: the pricing vector) or row i of the column-major B^-1 (stride = column stride)
+FJ_FN double fj_lpf_dot(const double *v, int stride, uint2 ix, double a, double r, bool negate)
 {
-    const double b0 = row[ix.x & 0xffffu], b1 = row[ix.x >> 16], b2 = row[ix.y & 0xffffu], b3 = row[ix.y >> 16];
+    const double b0 = v[(ix.x & 0xffffu) * stride], b1 = v[(ix.x >> 16) * stride], b2 = v[(ix.y & 0xffffu) * stride], b3 = v[(ix.y >> 16) * stride];
     double acc = fj_add(0.0, fj_mul(negate ? -b0 : b0, 1.0));
     acc = fj_add(acc, fj_mul(negate ? -b1 : b1, a));
     acc = fj_add(acc, fj_mul(negate ? -b2 : b2, r));
@@ -706,8 +722,12 @@ FJ_FN double fj_lpf_dot(const double *row, uint2 ix, double a, double r, bool ne
     return acc;
 }
 
-// returns -1 when the LP does not fit the fast path (the caller then runs fj_lp_solve)
-FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab, double *x_out, int *iters_out)
+// returns -1 when the LP does not fit the fast path (the caller then runs fj_lp_solve).
+// `smem` / `smem_bytes`: shared-memory scratch of the calling group (the step kernel's LP team).  The
+// column descriptors and positions go there when they fit, and B^-1 too when it still fits; the
+// rest lives on `slab` (HBM/L2).
+FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab, double *x_out, int *iters_out,
+                           unsigned char *smem = nullptr, int smem_bytes = 0)
 {
     FjCtaGroup g = g_in;
     FjLpFastSmem &S = fj_sLpf;
@@ -730,12 +750,17 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab
         }
         if (tid == 0) S.nprec = base;
     }
-    __syncthreads();
-    const int NP = FJ_I(c, hdr)[7], R = M + KT + S.nprec, C = NP + 1, Rs = (R + 2) & ~1;   // even stride: 16-byte rows, >= 1 padding column
-    if (R > FJ_LPF_RMAX || R > nt || R >= 0xffff) { __syncthreads(); return -1; }
-    // carve the slab: B^-1 [R][Rs], column descriptors, positions, final x_B
-    double *Binv = (double *)slab;
-    double2 *coef = (double2 *)(slab + ((size_t)R * Rs * 8 + 15) / 16 * 16);
+    g.sync();
+    const int NP = FJ_I(c, hdr)[7], R = M + KT + S.nprec, C = NP + 1, Rs = R | 1;   // odd column stride
+    if (R > FJ_LPF_RMAX || R > nt || R >= 0xffff) { g.sync(); return -1; }
+    // carve: B^-1 (R + 1 columns of Rs entries: column R is the all-zero padding), column descriptors,
+    // positions, final x_B
+    const size_t binv_bytes = ((size_t)(R + 1) * Rs * 8 + 15) / 16 * 16;
+    const size_t small_bytes = (size_t)C * 24 + (size_t)((C + R + 1) & ~1) * 4 + (size_t)R * 8;
+    const bool small_sm = smem && (size_t)smem_bytes >= small_bytes;
+    const bool binv_sm = small_sm && (size_t)smem_bytes >= ((small_bytes + 15) / 16 * 16) + binv_bytes;
+    double *BT = (double *)(binv_sm ? smem + (small_bytes + 15) / 16 * 16 : slab);
+    double2 *coef = (double2 *)(small_sm ? smem : slab + binv_bytes);
     uint2 *cidx = (uint2 *)(coef + C);
     int *pos = (int *)(cidx + C);
     double *xBm = (double *)(pos + ((C + R + 1) & ~1));
@@ -754,21 +779,23 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab
         }
     }
     for (int j = tid; j < C + R; j += nt) pos[j] = j >= C ? j - C : -1;
-    for (int e = tid; e < R * Rs; e += nt) { const int i = e / Rs, k = e - i * Rs; Binv[e] = i == k ? 1.0 : 0.0; }
+    for (int e = tid; e < (R + 1) * Rs; e += nt) BT[e] = 0.0;
     for (int k = tid; k < R + 2; k += nt) { S.y[0][k] = 0.0; S.y[1][k] = 0.0; }
     double xb = tid < M ? 1.0 : 0.0;        // x_B of row tid (tid < R)
     int bvar = C + tid;                     // basic variable of row tid
-    __syncthreads();
+    g.sync();
+    if (tid < R) BT[(size_t)tid * Rs + tid] = 1.0;
+    g.sync();
     const int dantzig_iters = 20 * R + 100, hard_iters = 200 * R + 1000;
     const int nvar = C + R, t_col = NP;
-    // warps 0 .. npw-1 hold the columns that are priced; in a large CTA they leave the rank-1
-    // update to the other warps, so that pricing and update run side by side
-    const int nw = nt >> 5, npw = (nvar + 31) >> 5;
-    const bool split = nw - npw >= 8 && nw >= 2 * npw;
-    const int uw = split ? (tid >> 5) - npw : (tid >> 5), nuw = split ? nw - npw : nw;
-    const int rpw = (R + nuw - 1) / nuw;
-    const int row_lo = uw < 0 ? R : (uw * rpw < R ? uw * rpw : R), row_hi = row_lo + rpw < R ? row_lo + rpw : R;
-    const int lane = tid & 31;
+    // rank-1 update: a warp owns a group of 32 rows and one chunk of the columns
+    const int lane = tid & 31, nw = nt >> 5, ngrp = (R + 31) >> 5;
+    const int nchunk = nw >= ngrp ? nw / ngrp : 1;                 // column chunks per row group
+    const int csize = (R + nchunk - 1) / nchunk;
+    const int my_grp0 = nw >= ngrp ? (tid >> 5) % ngrp : (tid >> 5);   // first row group of this warp
+    const int grp_step = nw >= ngrp ? ngrp : nw;                       // (a warp loops over groups only when there are more groups than warps)
+    const int my_chunk = nw >= ngrp ? (tid >> 5) / ngrp : 0;
+    const int k_lo = my_chunk < nchunk ? my_chunk * csize : R, k_hi = k_lo + csize < R ? k_lo + csize : R;
     int it = 0, rc = 0, cur = 0, pt = -1, p_last = -1;
     FJ_LPT(0);
     for (;; ++it) {
@@ -784,7 +811,7 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab
             double d;
             if (j < NP) {
                 const double2 cf = coef[j];
-                d = fj_sub(0.0, pt >= 0 ? fj_lpf_dot(y, cidx[j], cf.x, cf.y, true) : 0.0);
+                d = fj_sub(0.0, pt >= 0 ? fj_lpf_dot(y, 1, cidx[j], cf.x, cf.y, true) : 0.0);
             } else if (j == NP) {
                 double acc = 0.0;
                 if (pt >= 0) for (int q = 0; q < KT; ++q) acc = fj_add(acc, fj_mul(-y[M + q], 1.0));
@@ -798,30 +825,25 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab
             }
         }
         FJ_LPT(1);
-        // ---- rank-1 update of the previous pivot (rows != p_last); the pricing above did not
-        // need it.  Warps own row blocks (four rows in flight), a lane owns two adjacent columns.
+        // ---- rank-1 update of the previous pivot (rows != p_last; rows with w == 0 are left alone);
+        // the pricing above did not need it
         if (p_last >= 0) {
-            const double2 *rowp = (const double2 *)(Binv + (size_t)p_last * Rs);
-            const int R2 = (R + 1) >> 1;   // column pairs; the pair that covers column R updates a zero with a zero
-            for (int i0 = row_lo; i0 < row_hi; i0 += 4) {
-                double wv0 = 0.0, wv1 = 0.0, wv2 = 0.0, wv3 = 0.0;
-                if (i0 + 0 < row_hi && i0 + 0 != p_last) wv0 = S.w[i0 + 0];
-                if (i0 + 1 < row_hi && i0 + 1 != p_last) wv1 = S.w[i0 + 1];
-                if (i0 + 2 < row_hi && i0 + 2 != p_last) wv2 = S.w[i0 + 2];
-                if (i0 + 3 < row_hi && i0 + 3 != p_last) wv3 = S.w[i0 + 3];
-                if (wv0 == 0.0 && wv1 == 0.0 && wv2 == 0.0 && wv3 == 0.0) continue;
-                double2 *r0 = (double2 *)(Binv + (size_t)(i0 + 0) * Rs), *r1 = r0 + (Rs >> 1), *r2 = r1 + (Rs >> 1), *r3 = r2 + (Rs >> 1);
-                for (int k = lane; k < R2; k += 32) {
-                    const double2 pk_ = rowp[k];
-                    double2 e0, e1, e2, e3;
-                    if (wv0 != 0.0) e0 = r0[k];
-                    if (wv1 != 0.0) e1 = r1[k];
-                    if (wv2 != 0.0) e2 = r2[k];
-                    if (wv3 != 0.0) e3 = r3[k];
-                    if (wv0 != 0.0) r0[k] = make_double2(fj_sub(e0.x, fj_mul(wv0, pk_.x)), fj_sub(e0.y, fj_mul(wv0, pk_.y)));
-                    if (wv1 != 0.0) r1[k] = make_double2(fj_sub(e1.x, fj_mul(wv1, pk_.x)), fj_sub(e1.y, fj_mul(wv1, pk_.y)));
-                    if (wv2 != 0.0) r2[k] = make_double2(fj_sub(e2.x, fj_mul(wv2, pk_.x)), fj_sub(e2.y, fj_mul(wv2, pk_.y)));
-                    if (wv3 != 0.0) r3[k] = make_double2(fj_sub(e3.x, fj_mul(wv3, pk_.x)), fj_sub(e3.y, fj_mul(wv3, pk_.y)));
+            for (int grp = my_grp0; grp < ngrp; grp += grp_step) {
+                const int i = grp * 32 + lane;
+                const double wv = i < R && i != p_last ? S.w[i] : 0.0;
+                if (wv != 0.0) {
+                    double *b = BT + i + k_lo * Rs;       // entry (i, k) of the column-major inverse, k = k_lo ..
+                    const double *pv = S.pr + k_lo;
+                    int n = k_hi - k_lo;
+                    for (; n >= 4; n -= 4, b += 4 * Rs, pv += 4) {
+                        const double p0 = pv[0], p1 = pv[1], p2 = pv[2], p3 = pv[3];
+                        const double e0 = b[0], e1 = b[Rs], e2 = b[2 * Rs], e3 = b[3 * Rs];
+                        b[0] = fj_sub(e0, fj_mul(wv, p0));
+                        b[Rs] = fj_sub(e1, fj_mul(wv, p1));
+                        b[2 * Rs] = fj_sub(e2, fj_mul(wv, p2));
+                        b[3 * Rs] = fj_sub(e3, fj_mul(wv, p3));
+                    }
+                    for (; n > 0; --n, b += Rs, ++pv) b[0] = fj_sub(b[0], fj_mul(wv, pv[0]));
                 }
             }
         }
@@ -833,10 +855,10 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab
         // ---- w = B^-1 A_q and the ratio test, row tid
         double wi = 0.0, rk = 0.0; int ri = FJ_EMPTY, rrow = 0;
         if (tid < R) {
-            const double *brow = Binv + (size_t)tid * Rs;
-            if (qin < NP) { const double2 cf = coef[qin]; wi = fj_lpf_dot(brow, cidx[qin], cf.x, cf.y, false); }
-            else if (qin == NP) { double acc = 0.0; for (int q = 0; q < KT; ++q) acc = fj_add(acc, fj_mul(brow[M + q], 1.0)); wi = acc; }
-            else wi = brow[qin - C];
+            const double *brow = BT + tid;      // row tid: entry k at brow[k * Rs]
+            if (qin < NP) { const double2 cf = coef[qin]; wi = fj_lpf_dot(brow, Rs, cidx[qin], cf.x, cf.y, false); }
+            else if (qin == NP) { double acc = 0.0; for (int q = 0; q < KT; ++q) acc = fj_add(acc, fj_mul(brow[(size_t)(M + q) * Rs], 1.0)); wi = acc; }
+            else wi = brow[(size_t)(qin - C) * Rs];
             S.w[tid] = wi;
             if (wi > FJ_LP_EPS_PIV) { rk = fj_div(xb > 0.0 ? xb : 0.0, wi); ri = bvar; rrow = tid; }
         }
@@ -849,10 +871,10 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab
         if (tid < R) {
             if (tid == p) { xb = theta; bvar = qin; }
             else xb = fj_sub(xb, fj_mul(theta, wi));
-            // pivot row, and the new t row of B^-1 for the next pricing
-            double *rowp = Binv + (size_t)p * Rs;
-            const double pr = fj_div(rowp[tid], wp);
-            rowp[tid] = pr;
+            // pivot row (entry tid of it), and the new t row of B^-1 for the next pricing
+            const double pr = fj_div(BT[(size_t)tid * Rs + p], wp);
+            BT[(size_t)tid * Rs + p] = pr;
+            S.pr[tid] = pr;
             const int pt_new = qin == t_col ? p : (ri == t_col ? -1 : pt);
             double yn = 0.0;
             if (pt_new == p) yn = pr;
@@ -862,18 +884,18 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab
         if (tid == 0) { pos[ri] = -1; pos[qin] = p; }
         pt = qin == t_col ? p : (ri == t_col ? -1 : pt);
         p_last = p; cur ^= 1;
-        __syncthreads();
+        g.sync();
         FJ_LPT(5);
     }
     // the update of the last pivot was folded into the pricing pass that found no entering column
     if (tid < R) xBm[tid] = xb;
-    __syncthreads();
+    g.sync();
     for (int j = tid; j < NP; j += nt) {
         double x = pos[j] >= 0 ? xBm[pos[j]] : 0.0;
         if (x < FJ_LP_EPS_ZERO) x = 0.0;
         x_out[j] = x;
     }
-    __syncthreads();
+    g.sync();
     FJ_LPT_FLUSH();
     if (iters_out) *iters_out = it;
     return rc;
@@ -2051,18 +2073,21 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
 }
 
 // ---------------------------------------------------------------- main kernel driver
-// The main step kernel runs the warps of a CTA in LOCKSTEP (one CTA barrier per step, after the
-// clock loop: it is also the vote on fluid-LP requests): all warps then execute the same few KB of straight-line code at
-// the same time and share its instruction-cache lines.  Profiling the free-running
-// version (profiles/README.md) showed the per-step code (tens of KB, executed once per
-// step per warp) being re-fetched from L2 by every warp: "no instruction" was the top
-// stall.  Every warp takes every barrier; a warp whose env is finished, parked on an LP or
-// past the batch end just skips the work in between.
-#if defined(FJ_DEVICE_CODE) && !defined(FJ_NO_LOCKSTEP)
-#define FJ_CTA_SYNC() __syncthreads()
-#else
-#define FJ_CTA_SYNC()
-#endif
+// The step kernel's CTA has two roles.
+//   * ENV warps (one environment copy each) run in LOCKSTEP slots, one named barrier per slot:
+//     all of them execute the same few KB of straight-line code at the same time and share its
+//     instruction-cache lines (free-running warps re-fetched the per-step code from L2: "no
+//     instruction" was the top stall, profiles/README.md).  A slot is one env step.
+//   * the LP TEAM (the CTA's last 4 or 8 warps, own named barrier) serves fluid LPs.  An env warp
+//     whose clock reaches an order arrival posts a request on the CTA's board and keeps taking the
+//     slot barriers WITHOUT working until the solution is there; its CTA-mates keep stepping.
+//     Every env warp counts its own steps, the CTA leaves the loop when all have done T.
+//     (Round 1 stopped the whole CTA for every LP: 45 % of all warp stalls were that barrier and
+//     the two 1024-thread argmin reductions were 2.5 k of an iteration's 6.4 k cycles.)
+#define FJ_BAR_ENV 1
+#define FJ_BAR_TEAM 2
+#define FJ_BAR_ROUND 3
+#define FJ_SLOT_DETACHED 0x40000000   // P.order flag: the env free-runs (it is expected to meet a fluid LP or a reset in this launch)
 
 FJ_FN void fj_emit_state(const FjCtx &c, const FjStepArgs &A, size_t i, int nobs, int terminal)
 {
@@ -2078,28 +2103,78 @@ FJ_FN void fj_emit_state(const FjCtx &c, const FjStepArgs &A, size_t i, int nobs
     }
 }
 
-// per-CTA context of the main kernel: which warp this is, the staging slabs of all warps and
-// the CTA's LP service (scratch slab in global memory, solution vector, request board)
-struct FjCtaCtx {
-    int warp, nwarps, cta_lp;
-    unsigned char *stage_base;   // shared-memory staging slabs of the CTA's warps, or null
-    unsigned char *slab;         // LP scratch in HBM: Binv, small arrays
-    unsigned char *lp_smem;      // LP scratch in shared memory (used when an LP fits), or null
-    int lp_smem_bytes;
-    double *x;                   // LP solution
-    int *meta;                   // iterations, return code
-    int *req_env;                // [nwarps] env each warp wants an LP for, -1 none
-    FjCtaGroup group;
+// the CTA's LP request board (shared memory)
+struct FjLpBoard {
+    int req[32];      // env a warp wants an LP for, -1 none (written by the owner, cleared by the team)
+    int resp[32];     // 1: the warp's solution is ready (set by the team, cleared by the owner)
+    int meta[64];     // per warp: iterations, return code
+    int cur[2];       // the team leader's pick for this team iteration (double-buffered)
+    int quit;         // set by the env warps after their last round
+    int pad;
+    unsigned long long mbar[32];   // one mbarrier per env warp: TMA stage-in of its record's hot prefix
 };
 
-FJ_FN int fj_cta_sync_or(int pred)
+// per-CTA context of the main kernel
+struct FjCtaCtx {
+    int warp, nwarps, cta_lp;    // env warp index, env warps of the CTA
+    unsigned char *slab;         // the CTA's LP scratch in HBM/L2: B^-1 and the small arrays
+    unsigned char *team_smem;    // the LP team's shared-memory scratch (P.team_smem bytes), or null
+    double *xbuf;                // [nwarps][NPx] LP solutions, one per env warp
+    FjLpBoard *board;
+    FjCtaGroup group;            // the LP team (device) / one thread (host build)
+};
+
+#ifdef __CUDACC__
+FJ_FN int fj_env_vote(int pred, int nthreads)   // barrier of the lockstep group + number of its threads with pred
 {
-#ifdef FJ_DEVICE_CODE
-    return __syncthreads_or(pred);
-#else
-    return pred;
-#endif
+    unsigned r;
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %1, 0;\n bar.red.popc.u32 %0, %2, %3, q;\n}"
+                 : "=r"(r) : "r"(pred), "n"(FJ_BAR_ENV), "r"(nthreads) : "memory");
+    return (int)r;
 }
+FJ_FN int fj_env_count(int pred, int nthreads)   // barrier of ALL env warps + number of threads with pred
+{
+    unsigned r;
+    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %1, 0;\n bar.red.popc.u32 %0, %2, %3, q;\n}"
+                 : "=r"(r) : "r"(pred), "n"(FJ_BAR_ROUND), "r"(nthreads) : "memory");
+    return (int)r;
+}
+FJ_FN unsigned fj_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// TMA bulk copies of a record's hot prefix (16-byte aligned, multiple of 16 bytes): global ->
+// shared completes on the warp's mbarrier, shared -> global is a bulk group of the issuing lane
+FJ_FN void fj_tma_load(unsigned char *dst, const unsigned char *src, unsigned bytes, unsigned long long *mbar, unsigned parity)
+{
+    // the slab was last touched through the generic proxy (previous round) and read by the bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const unsigned bar = fj_smem_addr(mbar);
+    if (fj_lane() == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(fj_smem_addr(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+FJ_FN void fj_tma_store(unsigned char *dst, const unsigned char *src, unsigned bytes)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // every lane's writes, then the issuing lane
+    __syncwarp();
+    if (fj_lane() == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(fj_smem_addr(src)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+}
+FJ_FN void fj_tma_prefetch_l2(const unsigned char *src, unsigned bytes)   // one lane
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+#endif
 
 // FJ_TRACE builds (tools/cta_trace.py): every warp accumulates the cycles it spends in each
 // phase of a step (barrier waits excluded) so that CTA / SM imbalance can be read off.
@@ -2119,138 +2194,216 @@ FJ_FN int fj_cta_sync_or(int pred)
 #define FJ_TR_FLUSH(P, K)
 #endif
 
+// one LP for the env whose context is c2, solved by group g on `slab`; x and (iterations, rc) out
+FJ_FN void fj_lp_for_ctx(const FjParams &P, const FjCtaGroup &g, FjCtx &c2, unsigned char *slab, double *x, int *meta,
+                         unsigned char *smem = nullptr, int smem_bytes = 0)
+{
+    FjLp L;
+    fj_lp_carve(L, slab, slab + (size_t)P.d.Rx * P.d.Rx * 8, P.d);
+    int iters = 0, rc = -1;
+#ifdef FJ_DEVICE_CODE
+    rc = fj_lp_solve_fast(g, c2, slab, x, &iters, smem, smem_bytes);
+#endif
+    (void)smem; (void)smem_bytes;
+    if (rc < 0) rc = fj_lp_solve(g, c2, L, x, &iters);
+    if (g.rank() == 0) { meta[0] = iters; meta[1] = rc; }
+    g.sync();
+}
+
+#ifdef __CUDACC__
+// The LP team's loop: the leader warp scans the request board, the team solves the picked LP
+// into the owner's solution buffer and flags it ready.  Leaves when the env warps set `quit`.
+FJ_FN void fj_lp_team_loop(const FjParams &Pin, const FjCtaCtx &K)
+{
+    const FjParams &P = fj_params_bind(Pin);
+    FjLpBoard &bd = *K.board;
+    const FjCtaGroup &g = K.group;
+    volatile int *req = bd.req, *resp = bd.resp, *cur = bd.cur, *quit = &bd.quit;
+    for (int it = 0;; ++it) {
+        if (g.rank() < 32) {
+            const int l = g.rank();
+            const int r = l < K.nwarps ? req[l] : -1;
+            const unsigned b = __ballot_sync(0xffffffffu, r >= 0);
+            int w = -1;
+            if (b) w = __ffs((int)b) - 1;
+            else if (*quit) w = -2;
+            else __nanosleep(64);
+            if (l == 0) cur[it & 1] = w;
+        }
+        g.sync();
+        const int w = cur[it & 1];
+        if (w == -2) break;
+        if (w < 0) continue;
+        __threadfence_block();
+        fj_lp_for_ctx(P, g, fj_sC[w], K.slab, K.xbuf + (size_t)w * P.d.NPx, bd.meta + 2 * w, K.team_smem, P.team_smem);
+        if (g.rank() == 0) {
+            __threadfence_block();
+            req[w] = -1;
+            __threadfence_block();
+            resp[w] = 1;
+        }
+    }
+}
+#endif
+
+enum { FJ_ST_IDLE = 0, FJ_ST_FRONT = 1, FJ_ST_WAIT = 2 };
+
+// One round of a CTA's env warps: this warp plays `env` for A.T steps (or just keeps the slot
+// barriers when it has no env).  `hotbuf`: the warp's shared-memory slab for the record's hot
+// prefix (staged by TMA for the whole launch) or null (work on the record in HBM/L2 directly).
+// `next_env`: the env this warp plays in the CTA's next round (-1 none): its record is
+// prefetched into L2 while this round runs.
 template <int VARIANT, int SUM_MODE>
-FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaCtx &K, int env, int active, unsigned char *stage = nullptr)
+FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaCtx &K, int env, int active, unsigned char *hotbuf = nullptr,
+                          int next_env = -1, unsigned parity = 0, int lock_threads = 0)
 {
     const FjParams &P = fj_params_bind(Pin);
     const int lane = fj_lane();
     FjCtx &c = FJ_CTX;
     unsigned char *G = P.env + (size_t)env * P.eo.stride;
     if (active) {
-        if (stage) {
-            fj_stage_copy(stage, G, P.eo.hot);
+        if (hotbuf) {
+#ifdef FJ_DEVICE_CODE
+            fj_tma_load(hotbuf, G, (unsigned)P.eo.hot, &K.board->mbar[K.warp], parity);
+            if (next_env >= 0 && lane == 0) fj_tma_prefetch_l2(P.env + (size_t)next_env * P.eo.stride, (unsigned)P.eo.stride);
+#else
+            fj_stage_copy(hotbuf, G, P.eo.hot);
+#endif
         }
-        fj_ctx_init(P, env, nullptr, stage);
+        fj_ctx_init(P, env, nullptr, hotbuf);
     }
+    (void)next_env; (void)parity;
     const int nobs = P.nobs;
-    int parked = !active;
     FJ_TR_DECL;
     const size_t batch = (size_t)P.B;
-    size_t i = (size_t)env;             // row of this env in the [T][B] inputs / outputs of step tt
-    FJ_NOUNROLL
-    for (int tt = 0; tt < A.T; ++tt, i += batch) {
-        double out_reward = 0.0;
-        int out_done = 0;
-        int stage = 0;      // 0 nothing, 1 dispatched (run the clock), 2 nothing dispatchable (emit unchanged)
-        // ---- phase A: auto-reset / task_select / machine_select / dispatch.  The step's one CTA
-        // barrier is the LP vote after the clock loop (a second barrier here measured 3 % slower
-        // with one CTA per SM: 66.1 M vs 68.1 M env-steps/s; FJ_TWO_BARRIERS brings it back).
-#ifdef FJ_TWO_BARRIERS
-        FJ_CTA_SYNC();
+    size_t i = (size_t)env;             // row of this env in the [T][B] inputs / outputs of its step tt
+    int tt = 0;
+    int st = active && A.T > 0 ? FJ_ST_FRONT : FJ_ST_IDLE;
+#ifdef FJ_DEVICE_CODE
+    // lock_threads: threads of this round's lockstep group (this warp is one of them), 0: this warp
+    // free-runs (no slot barrier; it polls for its LP solutions)
+    volatile int *req = K.board->req, *resp = K.board->resp;
 #endif
-        FJ_TR_MARK();
-        if (!parked) {
-            if (c.scal[FJ_S_DONE]) {
-                if (!A.autoreset) {   // a finished env without auto-reset repeats its terminal output
-                    if (A.done && lane == 0) A.done[i] = 1;
-                    if (A.reward && lane == 0) A.reward[i] = 0.0;
-                    fj_emit_state(c, A, i, nobs, 1);
-                    if (A.rec) for (int k = lane; k < 8; k += FJ_NL) A.rec[i * 8 + k] = -1;
-                } else if (!fj_reset_from_plan<VARIANT, SUM_MODE>(c, P)) {
-                    fj_reset_begin(c, 0);
-                    if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
-                    fj_sync();
-                    fj_suspend(c, P, A, env, FJ_PH_LP_RESET, tt);
-                    parked = 1;
-                }
-            }
-            if (!parked && !c.scal[FJ_S_DONE]) {
-                const int ok = fj_step_front<VARIANT, SUM_MODE>(A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
-                                                               A.rnd ? A.rnd[2 * i + 1] : 0u, A.rec ? A.rec + i * 8 : nullptr);
-                stage = ok ? 1 : 2;
-            }
-        }
-        FJ_TR_ACC(0);
-        // ---- phase B: discrete-event clock.  A warp whose clock reaches an order arrival asks
-        // the CTA for the fluid LP: at the phase barrier all warps of the CTA solve it together
-        // (FjCtaGroup, basis inverse on the CTA's scratch slab), the owner applies it and
-        // re-enters its clock loop.  No kernel boundary, no parked tail.
-        int done = 0;
-        {
-            int st = stage == 1 ? 1 : 0;     // 1 clock to run, 2 waiting for an LP, 0 nothing / finished
+    for (;;) {
+        if (st != FJ_ST_IDLE) {
+            int kind = 0;       // 0 nothing to emit, 1 dispatched (clock, observation), 2 nothing dispatchable (emit unchanged)
             int resume = 0;
-            for (;;) {
-                int want = 0;
-                FJ_TR_MARK();
-                if (st == 1) {
+            FJ_TR_MARK();
+#ifdef FJ_DEVICE_CODE
+            if (st == FJ_ST_WAIT) {
+                int ready = lane == 0 ? resp[K.warp] : 0;
+                ready = fj_bcast_i(ready, 0);
+                if (!ready) { __nanosleep(lock_threads ? 200 : 100); FJ_TR_ACC(2); goto vote; }
+                __threadfence_block();
+                fj_arrival_finish<SUM_MODE>(c, K.xbuf + (size_t)K.warp * P.d.NPx, K.board->meta[2 * K.warp], K.board->meta[2 * K.warp + 1]);
+                if (lane == 0) resp[K.warp] = 0;
+                resume = 1; kind = 1; st = FJ_ST_FRONT;
+                FJ_TR_ACC(2);
+            } else
+#endif
+            {
+                // ---- auto-reset / task_select / machine_select / dispatch
+                if (c.scal[FJ_S_DONE]) {
+                    if (!A.autoreset) {   // a finished env without auto-reset repeats its terminal output
+                        if (A.done && lane == 0) A.done[i] = 1;
+                        if (A.reward && lane == 0) A.reward[i] = 0.0;
+                        fj_emit_state(c, A, i, nobs, 1);
+                        if (A.rec) for (int k = lane; k < 8; k += FJ_NL) A.rec[i * 8 + k] = -1;
+                    } else if (!fj_reset_from_plan<VARIANT, SUM_MODE>(c, P)) {
+                        // no cached order-0 solution: the LP / resume kernels finish this env's launch
+                        fj_reset_begin(c, 0);
+                        if (lane == 0) c.scal[FJ_S_EPISODES] += 1;
+                        fj_sync();
+                        fj_suspend(c, P, A, env, FJ_PH_LP_RESET, tt);
+                        st = FJ_ST_IDLE;
+                        FJ_TR_ACC(0);
+                        goto vote;
+                    }
+                }
+                if (!c.scal[FJ_S_DONE]) {
+                    const int ok = fj_step_front<VARIANT, SUM_MODE>(A.actions[2 * i], A.actions[2 * i + 1], A.rnd ? A.rnd[2 * i] : 0u,
+                                                                   A.rnd ? A.rnd[2 * i + 1] : 0u, A.rec ? A.rec + i * 8 : nullptr);
+                    kind = ok ? 1 : 2;
+                }
+                FJ_TR_ACC(0);
+            }
+            // ---- discrete-event clock.  At an order arrival the env needs the fluid LP of its
+            // new state: the CTA's LP team solves it (device) / it is solved in line (host build)
+            int done = 0;
+            if (kind == 1) {
+                for (;;) {
                     const int ck = fj_clock<SUM_MODE, 1>(resume);
-                    if (ck == FJ_CLK_PARKED) { st = 2; want = 1; } else { st = 0; done = ck == FJ_CLK_DONE; }
+                    if (ck != FJ_CLK_PARKED) { done = ck == FJ_CLK_DONE; break; }
+                    if (!K.cta_lp) {             // no in-CTA service configured: park for the LP / resume kernels
+                        fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt);
+                        st = FJ_ST_IDLE; kind = 0;
+                        break;
+                    }
+#ifdef FJ_DEVICE_CODE
+                    FJ_TR_COUNT(4);
+                    __threadfence_block();
+                    fj_sync();
+                    if (lane == 0) req[K.warp] = env;
+                    st = FJ_ST_WAIT; kind = 0;
+                    break;
+#else
+                    fj_lp_for_ctx(P, K.group, c, K.slab, K.xbuf, K.board->meta);
+                    fj_arrival_finish<SUM_MODE>(c, K.xbuf, K.board->meta[0], K.board->meta[1]);
+                    resume = 1;
+#endif
                 }
                 FJ_TR_ACC(1);
-                if (!K.cta_lp) {             // no CTA service configured: park for the LP / resume kernels
-                    if (want) { fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt); parked = 1; stage = 0; }
-                    break;
+                if (st != FJ_ST_FRONT) goto vote;
+            }
+            // ---- observation, reward, outputs
+            if (kind) {
+                double out_reward = 0.0;
+                int out_done;
+                if (kind == 1) {
+                    out_reward = fj_step_back<VARIANT, SUM_MODE>(done, A.reward_policy, A.completion, A.tardiness, A.energy);
+                    out_done = done;
+                } else {
+                    out_done = c.scal[FJ_S_DONE];
+                    FJ_NOUNROLL
+                    for (int k = lane; k < nobs; k += FJ_NL) c.obs2[k] = c.obs[k];
+                    fj_sync();
                 }
-                if (lane == 0) K.req_env[K.warp] = want ? env : -1;
-                if (!fj_cta_sync_or(want)) break;
-                FJ_TR_MARK();
+                fj_emit_state(c, A, i, nobs, 0);
+                fj_sync();
                 FJ_NOUNROLL
-                for (int w = 0; w < K.nwarps; ++w) {
-                    const int e2 = K.req_env[w];
-                    if (e2 < 0) continue;    // uniform over the CTA
-                    FJ_TR_COUNT(4);
-                    {
-                        FjCtx &c2 = fj_sC[FJ_NL == 1 ? 0 : w];   // the requesting warp's context
-                        FjLp L;
-                        // scratch in the CTA's shared memory when this LP fits, else on its HBM slab
-                        const size_t Rub = (size_t)(c2.M + 2 * c2.KT - c2.K), Cn = (size_t)FJ_I(c2, hdr)[7] + 1;
-                        if (K.lp_smem && fj_lp_dims_bytes(Rub, Cn, (size_t)c2.KT) <= (size_t)K.lp_smem_bytes)
-                            fj_lp_carve_dims(L, K.lp_smem, K.lp_smem + Rub * Rub * 8, Rub, Cn, (size_t)c2.KT);
-                        else
-                            fj_lp_carve(L, K.slab, K.slab + (size_t)P.d.Rx * P.d.Rx * 8, P.d);
-                        int iters = 0;
-                        int rc = -1;
-#ifdef FJ_DEVICE_CODE
-                        if (!K.lp_smem) rc = fj_lp_solve_fast(K.group, c2, K.slab, K.x, &iters);
-#endif
-                        if (rc < 0) rc = fj_lp_solve(K.group, c2, L, K.x, &iters);
-                        if (K.group.rank() == 0) { K.meta[0] = iters; K.meta[1] = rc; }
-                        K.group.sync();
-                    }
-                    if (w == K.warp) {
-                        fj_arrival_finish<SUM_MODE>(c, K.x, K.meta[0], K.meta[1]);
-                        resume = 1; st = 1;
-                    }
-                    K.group.sync();
+                for (int k = lane; k < nobs; k += FJ_NL) c.obs[k] = c.obs2[k];
+                if (lane == 0) {
+                    if (A.reward) A.reward[i] = out_reward;
+                    if (A.done) A.done[i] = out_done;
                 }
-                FJ_TR_ACC(2);
+                fj_sync();
             }
+            FJ_TR_ACC(3);
+            ++tt; i += batch;
+            if (tt >= A.T) st = FJ_ST_IDLE;
         }
-        FJ_TR_MARK();
-        // ---- phase C: observation, reward, outputs (the vote above was the phase barrier)
-        if (stage == 1) {
-            out_reward = fj_step_back<VARIANT, SUM_MODE>(done, A.reward_policy, A.completion, A.tardiness, A.energy);
-            out_done = done;
-        } else if (stage == 2) {
-            out_done = c.scal[FJ_S_DONE];
-            FJ_NOUNROLL
-            for (int k = lane; k < nobs; k += FJ_NL) c.obs2[k] = c.obs[k];
-            fj_sync();
+    vote:
+#ifdef FJ_DEVICE_CODE
+        // slot barrier of the lockstep group.  A warp stays in the group only while it steps: one that
+        // has done its T steps leaves, and so does one that waits for an LP (it free-runs from here
+        // on: its mates must not slip a slot per poll); the vote tells the others the new group size.
+        if (lock_threads) {
+            const int stay = st == FJ_ST_FRONT;
+            const int n = fj_env_vote(stay, lock_threads);
+            lock_threads = stay ? n : 0;
         }
-        if (stage) {
-            fj_emit_state(c, A, i, nobs, 0);
-            fj_sync();
-            FJ_NOUNROLL
-            for (int k = lane; k < nobs; k += FJ_NL) c.obs[k] = c.obs2[k];
-            if (lane == 0) {
-                if (A.reward) A.reward[i] = out_reward;
-                if (A.done) A.done[i] = out_done;
-            }
-            fj_sync();
-        }
-        FJ_TR_ACC(3);
+        if (st == FJ_ST_IDLE) break;
+#else
+        if (st == FJ_ST_IDLE) break;
+#endif
     }
-    if (active && stage) fj_stage_copy(G, stage, P.eo.hot);
+    if (active && hotbuf) {
+#ifdef FJ_DEVICE_CODE
+        fj_tma_store(G, hotbuf, (unsigned)P.eo.hot);
+#else
+        fj_stage_copy(G, hotbuf, P.eo.hot);
+#endif
+    }
     FJ_TR_FLUSH(P, K);
 }
 

@@ -128,7 +128,7 @@ struct FjParams {
     const int32_t *order;       // [n_slots] env of every warp slot of the main kernel (slot = virtual CTA * warps + warp), -1 = empty
     int n_slots;
     unsigned char *env;         // env table
-    unsigned char *lp;          // LP scratch, one slab per resident warp
+    unsigned char *lp;          // LP scratch slabs (one per CTA of the main kernel / per warp of the resume kernel)
     unsigned long long lp_stride;
     int *pend_count;            // [FJ_ROUNDS + 1] parked LPs per resume round of the current launch
     int *pend_env;              // [2][B] env of each parked LP (ping-pong between rounds)
@@ -139,8 +139,10 @@ struct FjParams {
     const int *plan_meta;       // [n_instances][2]
     const int *plan_ok;         // [n_instances] 1 once cached (null before the first reset)
     int stage_stride;           // bytes of one warp's shared-memory slab (env hot prefix + instance hot words)
-    int cta_lp_smem;            // bytes of shared-memory LP scratch per CTA of the main kernel (0: none)
-    int cta_lp;                 // 1: the main kernel's CTAs solve order-arrival LPs themselves
+    int env_warps;              // env warps per CTA of the main kernel (= warp slots of a virtual CTA); the CTA's other warps are its LP team
+    int cta_lp;                 // 1: the LP team of an env's CTA solves its order-arrival LPs; 0: park for the LP / resume kernels; 2: free-running warps
+    int team_smem;              // bytes of shared-memory LP scratch of the CTA's LP team (after the env warps' slabs)
+    double *cta_x;              // [step grid][env_warps][NPx] LP solutions of the in-CTA service, one buffer per env warp
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory
     int B, variant, sum_mode, nobs;
     long long *trace;           // FJ_TRACE builds: [grid][33][8] per-warp cycle counters + one row of LP phase cycles per CTA (null otherwise)

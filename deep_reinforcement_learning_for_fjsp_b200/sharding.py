@@ -48,3 +48,29 @@ def gather_episode_stats(completion, tardiness, energy, device=None):
     parts = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad)
     return torch.cat([p[: int(s[0])] for p, s in zip(parts, sizes)], 0).cpu().numpy()
+
+
+def allreduce_gradients(parameters, average=True):
+    """Data-parallel gradient reduction for the agents' PPO / SAC / DQN updates: every rank
+    computes its loss on its own shard of environment copies, the gradients are summed over the
+    ranks in ONE flat bucket (NCCL on GPUs, gloo in the CPU tests) and averaged.  The reference
+    trains single-process (agents/MPPPO/MPPPO.py:221-250 computes the loss of one episode and
+    steps Adam); with the batch sharded over GPUs this call sits between loss.backward() and
+    optimizer.step().  Returns the number of gradient elements reduced."""
+    import torch
+    import torch.distributed as dist
+    params = [p for p in parameters if p.grad is not None]
+    if not params:
+        return 0
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return sum(p.grad.numel() for p in params)
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if average:
+        flat /= dist.get_world_size()
+    o = 0
+    for p in params:
+        n = p.grad.numel()
+        p.grad.copy_(flat[o:o + n].view_as(p.grad))
+        o += n
+    return o

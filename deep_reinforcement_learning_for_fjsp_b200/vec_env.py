@@ -148,20 +148,20 @@ class FJSPVecEnv:
 
     def slots(self):
         """Diagnostic: environment of every warp slot of the last step launch (-1 = empty),
-        shaped [virtual CTAs, warps per CTA] (the LP-aware packing rewrites it before every launch)."""
+        shaped [virtual CTAs, env warps per CTA] (the LP-aware packing rewrites it before every launch)."""
         n = self._L.fjsp_vec_slots(self._h, None, 0)
         if n < 0:
             _lib.check(n)
         a = np.zeros(n, np.int32)
         if self._L.fjsp_vec_slots(self._h, a.ctypes.data, n) < 0:
             _lib.check(-1)
-        return a.reshape(-1, self.query()["block"] // 32)
+        return a.reshape(-1, self.query()["env_warps"])
 
     def query(self):
-        a = np.zeros(8, np.int64)
+        a = np.zeros(12, np.int64)
         _lib.check(self._L.fjsp_vec_query(self._h, a.ctypes.data))
         keys = ["n_envs", "state_size", "env_record_bytes", "instance_record_bytes", "grid", "block",
-                "lp_scratch_bytes_per_warp", "launches"]
+                "lp_scratch_bytes_per_slab", "launches", "env_warps", "team_warps", "n_slots", "step_smem_bytes"]
         return dict(zip(keys, (int(x) for x in a)))
 
 

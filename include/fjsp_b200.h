@@ -47,9 +47,11 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
                     fjsp_vec **out);
 int fjsp_vec_destroy(fjsp_vec *v);
 
-/* out[0..7] = n_envs, state_size (20 SO / 30 MO), env record bytes, instance record bytes,
- * grid blocks, threads per block, LP scratch bytes per warp, kernel launches so far */
-int fjsp_vec_query(fjsp_vec *v, int64_t *out8);
+/* out[0..11] = n_envs, state_size (20 SO / 30 MO), env record bytes, instance record bytes,
+ * grid blocks, threads per block, LP scratch bytes per slab, kernel launches so far,
+ * env warps per block (= warp slots of a virtual CTA), LP-team warps per block, warp slots,
+ * dynamic shared memory bytes per block of the step kernel */
+int fjsp_vec_query(fjsp_vec *v, int64_t *out12);
 
 /* reset() of every environment (SO_DFJSP.py:54-79, MO_DFJSP.py:58-89).  d_state64 /
  * d_state32: DEVICE buffers [n_envs][state_size] (either may be null).  stream: a

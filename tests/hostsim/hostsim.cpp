@@ -31,7 +31,7 @@ static void run_lp_service(HostVec *h, int round = 0)
     const FjDims &d = h->tb.d;
     unsigned char *binv = h->lp.data();
     unsigned char *small_ = h->lp.data() + (size_t)d.Rx * d.Rx * 8;
-    FjCtaGroup g; g.red = nullptr; g.flip = 0;
+    FjCtaGroup g; g.red = nullptr; g.flip = 0; g.whole_cta();
     int n = h->pend_count < h->P.lp_slots ? h->pend_count : h->P.lp_slots;
     for (int i = 0; i < n; ++i) fj_lp_service(h->P, g, list, i, binv, small_);
 }
@@ -69,15 +69,11 @@ static void run_step(HostVec *h, const FjStepArgs &A)
     FjStepArgs B_ = A;
     B_.park_count = &h->pend_counts[0]; B_.park_env = h->pend_env.data();
     FjCtaCtx K;
-    static int req_env[1], meta[2];
-    K.warp = 0; K.nwarps = 1; K.cta_lp = h->P.cta_lp; K.stage_base = stage;
-    K.slab = h->lp.data();
-    K.x = (double *)(K.slab + (size_t)h->tb.d.Rx * h->tb.d.Rx * 8 + (fj_lp_small_bytes(h->tb.d) + 7) / 8 * 8);
-    static std::vector<unsigned char> lpsm;
-    const char *lps = getenv("FJSP_HOSTSIM_LP_SMEM");   // bytes of emulated shared-memory LP scratch
-    lpsm.assign(lps ? atoi(lps) : 0, 0);
-    K.lp_smem = lpsm.empty() ? nullptr : lpsm.data(); K.lp_smem_bytes = (int)lpsm.size();
-    K.meta = meta; K.req_env = req_env; K.group.red = nullptr; K.group.flip = 0;
+    static FjLpBoard board;
+    K.warp = 0; K.nwarps = 1; K.cta_lp = h->P.cta_lp;
+    K.slab = h->lp.data(); K.team_smem = nullptr;
+    K.xbuf = (double *)(K.slab + (size_t)h->tb.d.Rx * h->tb.d.Rx * 8 + (fj_lp_small_bytes(h->tb.d) + 7) / 8 * 8);
+    K.board = &board; K.group.red = nullptr; K.group.flip = 0; K.group.whole_cta();
     for (int e = 0; e < h->P.B; ++e) fj_cta_rollout<V, SM>(h->P, B_, K, e, 1, stage);               // main kernel
     for (int r = 0; r < FJ_ROUNDS; ++r) {
         run_lp_service(h, r);                                                                       // LP kernel
@@ -129,7 +125,7 @@ int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst
     P.lp_slots = ov ? atoi(ov) : n_envs;
     h->lp_x.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * h->tb.d.NPx, 0.0);
     h->lp_meta.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * 2, 0);
-    P.stage = 0; P.cta_lp_smem = 0; P.stage_stride = h->tb.eo.hot;
+    P.stage = 0; P.env_warps = 1; P.cta_x = nullptr; P.team_smem = 0; P.stage_stride = h->tb.eo.hot;
     P.cta_lp = getenv("FJSP_HOSTSIM_NO_CTA_LP") ? 0 : 1;
     P.plan_x = nullptr; P.plan_meta = nullptr; P.plan_ok = nullptr;
     h->pend_count = 0;

@@ -31,7 +31,7 @@ def test_header_functions_are_exported(lib):
             "fjsp_abi_version"} <= set(names)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/fjsp_b200.h but not exported"
-    assert lib.fjsp_abi_version() == 1
+    assert lib.fjsp_abi_version() == 2
 
 
 def test_create_argument_errors(lib):

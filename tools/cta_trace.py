@@ -64,9 +64,9 @@ def main():
         ms_i = ev0.elapsed_time(ev1)
         ms += ms_i / a.launches
         _lib.check(L.fjsp_vec_trace(vec._h, tr.ctypes.data, 1))
-        nwi = q["block"] // 32
+        nwi = q["env_warps"]
         ct = tr[:, :nwi, 0].max(1)
-        nl = tr[:, 0, 5]
+        nl = tr[:, :nwi, 5].sum(1)
         ns = L.fjsp_vec_slots(vec._h, None, 0)
         slm = np.zeros(ns, dtype=np.int32)
         L.fjsp_vec_slots(vec._h, slm.ctypes.data, ns)
@@ -74,12 +74,12 @@ def main():
         top = np.argsort(-ct)[:4]
         print("launch %d: %.3f ms = %.2f M cycles @1.965 GHz | median CTA %.2f M, CTAs with LPs %d, LPs %d | slowest CTAs: %s" % (
             i, ms_i, ms_i * 1.965, np.median(ct) / 1e6, (nl > 0).sum(), nl.sum(),
-            "; ".join("#%d %.2f M (%d envs, %d LPs %.2f M, busy %.2f M)" % (b, ct[b] / 1e6, act[b], nl[b], tr[b, 0, 3] / 1e6,
+            "; ".join("#%d %.2f M (%d envs, %d LPs, longest LP wait %.2f M, busy %.2f M)" % (b, ct[b] / 1e6, act[b], nl[b], tr[b, :nwi, 3].max() / 1e6,
                                                                   (tr[b, :nwi, 1] + tr[b, :nwi, 2] + tr[b, :nwi, 4]).max() / 1e6) for b in top)))
         ones = np.where(act == 1)[0]
         if len(ones):
             print("   single-env CTAs: %d, total mean %.2f M max %.2f M, LP mean %.2f M, LPs mean %.1f" % (
-                len(ones), ct[ones].mean() / 1e6, ct[ones].max() / 1e6, tr[ones, 0, 3].mean() / 1e6, nl[ones].mean()))
+                len(ones), ct[ones].mean() / 1e6, ct[ones].max() / 1e6, tr[ones, :nwi, 3].max(1).mean() / 1e6, nl[ones].mean()))
         acc += tr
         if i == 0:
             ns = L.fjsp_vec_slots(vec._h, None, 0)
@@ -91,10 +91,10 @@ def main():
                 sl.shape[0], nwi, (sl >= 0).sum(), len(set(sl[sl >= 0].tolist())), np.bincount(occ, minlength=nwi + 1).tolist(), occ[:24].tolist()))
     tr = acc
     tr = tr.astype(np.float64) / a.launches
-    nw = q["block"] // 32
+    nw = q["env_warps"]
     if True:
         lpt = tr[:, 32, :].sum(0) * a.launches
-        solves = tr[:, 0, 5].sum() * a.launches
+        solves = tr[:, :nw, 5].sum() * a.launches
         names = ["setup", "pricing", "argmin-in", "w+ratio", "argmin-out", "xB/pivot-row", "rank-1 update"]
         print("LP phases (cycles per iteration): " + ", ".join("%s %.0f" % (n, lpt[k] / max(lpt[7], 1)) for k, n in enumerate(names) if k)
               + "; setup per LP %.0f; iterations per LP %.1f; LPs %d" % (lpt[0] / max(solves, 1), lpt[7] / max(solves, 1), solves))
@@ -107,8 +107,8 @@ def main():
     print(f"CTA total cycles: min {cta_tot.min():.0f} mean {cta_tot.mean():.0f} max {cta_tot.max():.0f}")
     print("per-warp mean cycles: total %.0f busy %.0f (front %.0f clock %.0f lp %.0f back %.0f) barrier-wait %.0f" % (
         tot.mean(), busy.mean(), front.mean(), clock.mean(), lp.mean(), back.mean(), (tot - busy).mean()))
-    print("LPs per CTA per launch: mean %.2f max %.2f; lp cycles per CTA mean %.0f max %.0f" % (
-        nlp[:, 0].mean(), nlp[:, 0].max(), lp[:, 0].mean(), lp[:, 0].max()))
+    print("LPs per CTA per launch: mean %.2f max %.2f; cycles its slowest warp waited for LPs: mean %.0f max %.0f" % (
+        nlp.sum(1).mean(), nlp.sum(1).max(), lp.max(1).mean(), lp.max(1).max()))
     # deciles of CTAs by index (CTA index = rank in decreasing static walk length)
     for lo in range(0, grid, max(1, grid // 10)):
         hi = min(grid, lo + max(1, grid // 10))
