@@ -131,26 +131,34 @@ __device__ __forceinline__ int fj_pack_free(const FjPackPlan &p, int wpb, int m)
 __global__ void __launch_bounds__(FJ_PACK_THREADS) fjsp_pack_kernel(FjParams P, const int32_t *static_order, const unsigned char *flags,
                                                                     int32_t *order_out, int wpb, int cap1, int cap2, int cap3, int detach)
 {
-    __shared__ unsigned long long wsum[32];
+    __shared__ int wsum[3][32];
     __shared__ FjPackPlan s_plan;
     const int B = P.B, tid = threadIdx.x, nt = blockDim.x;
     const int V = P.n_slots / wpb;
     for (int i = tid; i < P.n_slots; i += nt) order_out[i] = -1;
     const int per = (B + nt - 1) / nt, lo = tid * per < B ? tid * per : B, hi = lo + per < B ? lo + per : B;
-    // per-class counts, 21 bits each, scanned together
-    unsigned long long cnt = 0;
-    for (int i = lo; i < hi; ++i) { const int c = flags[i]; if (c) cnt += 1ull << (21 * (c - 1)); }
-    unsigned long long inc = cnt;
-    for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d); if ((tid & 31) >= d) inc += o; }
-    if ((tid & 31) == 31) wsum[tid >> 5] = inc;
+    // per-class counts of this thread's chunk, scanned over the block (three 32-bit scans: any batch size)
+    int cnt[3] = {0, 0, 0};
+    for (int i = lo; i < hi; ++i) { const int c = flags[i]; if (c) ++cnt[c - 1]; }
+    int inc[3];
+    for (int k = 0; k < 3; ++k) {
+        int v = cnt[k];
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, v, d); if ((tid & 31) >= d) v += o; }
+        inc[k] = v;
+        if ((tid & 31) == 31) wsum[k][tid >> 5] = v;
+    }
     __syncthreads();
     if (tid < 32) {
-        const unsigned long long v = tid < (nt >> 5) ? wsum[tid] : 0;
-        unsigned long long w = v;
-        for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, w, d); if (tid >= d) w += o; }
-        wsum[tid] = w - v;
+        int tot[3];
+        for (int k = 0; k < 3; ++k) {
+            const int v = tid < (nt >> 5) ? wsum[k][tid] : 0;
+            int w = v;
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, w, d); if (tid >= d) w += o; }
+            wsum[k][tid] = w - v;
+            tot[k] = w;
+        }
         if (tid == 31) {
-            const int n1 = (int)(w & 0x1fffff), n2 = (int)((w >> 21) & 0x1fffff), n3 = (int)((w >> 42) & 0x1fffff);
+            const int n1 = tot[0], n2 = tot[1], n3 = tot[2];
             FjPackPlan p;
             p.e1 = n1 < V ? n1 : V; p.e2 = n2 < V - p.e1 ? n2 : V - p.e1; p.e3 = n3 < V - p.e1 - p.e2 ? n3 : V - p.e1 - p.e2;
             int c1 = cap1 < wpb ? cap1 : wpb, c2 = cap2 < wpb ? cap2 : wpb, c3 = cap3 < wpb ? cap3 : wpb;
@@ -167,8 +175,8 @@ __global__ void __launch_bounds__(FJ_PACK_THREADS) fjsp_pack_kernel(FjParams P, 
     }
     __syncthreads();
     const FjPackPlan p = s_plan;
-    unsigned long long before = wsum[tid >> 5] + inc - cnt;   // per-class likely envs before this thread's chunk
-    int r1 = (int)(before & 0x1fffff), r2 = (int)((before >> 21) & 0x1fffff), r3 = (int)((before >> 42) & 0x1fffff);
+    // per-class likely envs before this thread's chunk
+    int r1 = wsum[0][tid >> 5] + inc[0] - cnt[0], r2 = wsum[1][tid >> 5] + inc[1] - cnt[1], r3 = wsum[2][tid >> 5] + inc[2] - cnt[2];
     for (int i = lo; i < hi; ++i) {
         const int env = static_order[i], c = flags[i];
         int slot = -1;
@@ -270,7 +278,8 @@ struct fjsp_vec {
     long long launches;
     // staging for the host-buffer entry points
     cudaStream_t stream, copy_stream;
-    cudaEvent_t chunk_done;
+    cudaEvent_t chunk_done, dev_done;   // dev_done: last work queued through the device entry points (caller's stream)
+    int dev_pending;
     int stage_T;
     int32_t *d_actions, *d_done, *d_rec;
     uint32_t *d_rnd;
@@ -302,10 +311,27 @@ template <typename F> static int dispatch(fjsp_vec *v, F f)
     return -2;
 }
 
+// One handle can be driven through the device entry points (caller's stream) and the host-buffer entry
+// points (the handle's own stream): work queued on the caller's stream is recorded here and waited
+// for by the host calls; the host calls end synchronised, so the reverse order needs nothing.
+static void note_device_work(fjsp_vec *v, cudaStream_t st)
+{
+    if (st == v->stream) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+    if (cudaEventRecord(v->dev_done, st) == cudaSuccess) v->dev_pending = 1; else cudaGetLastError();
+}
+static void wait_device_work(fjsp_vec *v)
+{
+    if (v->dev_pending) { cudaStreamWaitEvent(v->stream, v->dev_done, 0); v->dev_pending = 0; }
+}
+
 extern "C" {
 
 const char *fjsp_last_error(void) { return g_err.c_str(); }
 int fjsp_abi_version(void) { return 2; }
+
+int fjsp_vec_destroy(fjsp_vec *v);
 
 int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_instances,
                     const int32_t *env_instance, int n_envs, int variant, int sum_mode, int device,
@@ -323,9 +349,22 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         g_err = "fjsp_vec_create: no CUDA device (this library has no CPU path)"; return -3;
     }
+    if (n_envs >= FJ_SLOT_DETACHED) { g_err = "fjsp_vec_create: more than 2^30 - 1 environment copies"; return -1; }
     CK(cudaSetDevice(device));
     fjsp_vec *v = new fjsp_vec();
     if (!fj_build_tables(blobs, blob_offsets, n_instances, v->tb, g_err, variant)) { delete v; return -1; }
+    // from here on a failure frees what has been allocated so far
+#undef CK
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            cudaGetLastError();                                                                    \
+            fjsp_vec_destroy(v);                                                                   \
+            return -10;                                                                            \
+        }                                                                                          \
+    } while (0)
     v->variant = variant; v->sum_mode = sum_mode ? 1 : 0; v->B = n_envs; v->device = device; v->launches = 0;
     v->nstate = (variant == FJSP_SO_DFJSP || variant == FJSP_SO_FJSSP) ? 20 : 30;
     cudaDeviceProp prop;
@@ -479,8 +518,16 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     v->step_smem_bytes = v->stage_bytes + (size_t)P.team_smem;
     v->detach = getenv("FJSP_NO_DETACH") ? 0 : 1;
     if (dispatch(v, [&](auto V, auto SM) {
-            cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->step_smem_bytes);
+            auto kern = fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->step_smem_bytes) != cudaSuccess) {
+                // the device refuses that much dynamic shared memory: no LP scratch, then no staging
+                cudaGetLastError();
+                v->P.team_smem = 0; v->step_smem_bytes = v->stage_bytes;
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->step_smem_bytes) != cudaSuccess) {
+                    cudaGetLastError();
+                    v->P.stage = 0; v->stage_bytes = 0; v->step_smem_bytes = 0;
+                }
+            }
             if (getenv("FJSP_CARVEOUT"))   // percent of the unified L1 / shared memory given to shared memory
                 cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,
                                      cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("FJSP_CARVEOUT")));
@@ -489,11 +536,22 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&v->chunk_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&v->dev_done, cudaEventDisableTiming));
+    v->dev_pending = 0;
     v->stage_T = 0;
     v->d_actions = v->d_done = v->d_rec = nullptr; v->d_rnd = nullptr;
     v->d_state64 = v->d_reward = nullptr; v->d_state32 = nullptr;
     *out = v;
     return 0;
+#undef CK
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return -10;                                                                            \
+        }                                                                                          \
+    } while (0)
 }
 
 static void free_stage(fjsp_vec *v)
@@ -515,7 +573,10 @@ int fjsp_vec_destroy(fjsp_vec *v)
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
     cudaFree(v->d_trace); cudaFree(v->d_cta_x);
     cudaFree(v->d_rep_env); cudaFree(v->d_plan_x); cudaFree(v->d_plan_meta); cudaFree(v->d_plan_ok);
-    cudaStreamDestroy(v->stream); cudaStreamDestroy(v->copy_stream); cudaEventDestroy(v->chunk_done);
+    if (v->stream) cudaStreamDestroy(v->stream);
+    if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
+    if (v->chunk_done) cudaEventDestroy(v->chunk_done);
+    if (v->dev_done) cudaEventDestroy(v->dev_done);
     delete v;
     return 0;
 }
@@ -549,6 +610,7 @@ int fjsp_vec_reset(fjsp_vec *v, void *stream, double *d_state64, float *d_state3
     if (rc) return rc;
     v->launches += 3;
     CK(cudaGetLastError());
+    note_device_work(v, st);
     return 0;
 }
 
@@ -594,6 +656,7 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     if (rc) return rc;
     v->launches += 1 + ((v->P.cta_lp == 1 && v->plan_ready && v->plan_all) ? 0 : 2 * FJ_ROUNDS) + 2 * v->pack;
     CK(cudaGetLastError());
+    note_device_work(v, st);
     return 0;
 }
 
@@ -623,6 +686,7 @@ int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint3
     if (rc) return rc;
     const size_t n = (size_t)T * v->B;
     cudaStream_t st = v->stream, cp = v->copy_stream;
+    wait_device_work(v);
     CK(cudaMemcpyAsync(v->d_actions, h_actions, n * 2 * 4, cudaMemcpyHostToDevice, st));
     if (h_rnd) CK(cudaMemcpyAsync(v->d_rnd, h_rnd, n * 2 * 4, cudaMemcpyHostToDevice, st));
     // long rollouts are cut into chunks of 32 steps: the device-to-host copy of one chunk's
@@ -659,6 +723,7 @@ int fjsp_vec_reset_host(fjsp_vec *v, double *h_state64, float *h_state32)
     int rc = ensure_stage(v, 1);
     if (rc) return rc;
     cudaStream_t st = v->stream;
+    wait_device_work(v);
     rc = fjsp_vec_reset(v, st, h_state64 ? v->d_state64 : nullptr, h_state32 ? v->d_state32 : nullptr);
     if (rc) return rc;
     const size_t n = (size_t)v->B * v->nstate;

@@ -25,6 +25,8 @@ static inline bool fj_parse_blob(const int32_t *b, FjBlobView &v, std::string &e
     if (v.KT < 1 || v.KT > FJSP_MAX_KT) { err = "instance blob: operation types outside 1..256"; return false; }
     if (v.S < 1 || v.S > FJSP_MAX_S) { err = "instance blob: order count outside 1..16"; return false; }
     if (v.Nmax > 65000) { err = "instance blob: more than 65000 jobs of one kind"; return false; }
+    if (v.K < 1 || v.K > v.KT || v.K > 255) { err = "instance blob: job kinds outside 1..min(KT, 255)"; return false; }
+    if (v.NP < v.KT || v.NP > v.KT * v.M || v.NBD < 0) { err = "instance blob: pair / breakdown counts out of range"; return false; }
     const int32_t *p = b + 16;
     v.ntask = p; p += v.K;
     v.rj_kind = p; p += v.KT;
@@ -42,6 +44,26 @@ static inline bool fj_parse_blob(const int32_t *b, FjBlobView &v, std::string &e
     v.bd_end = p; p += v.NBD;
     v.pair_order = p; p += v.NP;
     if (p - b != b[1]) { err = "instance blob: length does not match header"; return false; }
+    // every field the table builder indexes with (the blob comes through a public C ABI)
+    for (int r = 0; r < v.K; ++r)
+        if (v.ntask[r] < 1 || v.ntask[r] > 128) { err = "instance blob: operations per job kind outside 1..128"; return false; }
+    for (int q = 0; q < v.KT; ++q) {
+        if (v.rj_kind[q] < 0 || v.rj_kind[q] >= v.K || v.rj_stage[q] < 0 || v.rj_stage[q] >= v.ntask[v.rj_kind[q]]) {
+            err = "instance blob: rj_kind / rj_stage out of range"; return false;
+        }
+        if (v.nelig[q] < 1 || v.nelig[q] > v.M) { err = "instance blob: eligible machines of an operation type outside 1..M"; return false; }
+        unsigned seen = 0;
+        for (int k = 0; k < v.nelig[q]; ++k) {
+            const int m = v.mt_order[q * v.M + k];
+            if (m < 0 || m >= v.M || (seen >> m & 1u)) { err = "instance blob: mt_order entry out of range or repeated"; return false; }
+            seen |= 1u << m;
+            if (v.ptime[q * v.M + m] < 1) { err = "instance blob: processing time of an eligible pair < 1"; return false; }
+        }
+    }
+    for (int k = 0; k < v.NP; ++k)
+        if (v.pair_order[k] < 0 || v.pair_order[k] >= v.KT * v.M) { err = "instance blob: pair_order entry out of range"; return false; }
+    for (int m = 0; m <= v.M; ++m)
+        if (v.bd_ptr[m] < 0 || v.bd_ptr[m] > v.NBD || (m && v.bd_ptr[m] < v.bd_ptr[m - 1])) { err = "instance blob: bd_ptr not a prefix array"; return false; }
     for (int i = 0; i < v.S * v.K; ++i)
         if (v.count[i] < 1 || v.count[i] > 65000) { err = "instance blob: per-order job count outside 1..65000"; return false; }
     return true;
