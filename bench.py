@@ -506,9 +506,9 @@ def main():
                            "launches_per_step": LPS, "machines": cfg.get("machines"), "orders": cfg.get("orders"), "variant": variant,
                            "distinct_instances_per_gpu": len(blobs),
                            "l2": "flushed between timed steps (256 MiB fill)",
-                           "kernels_per_step": "flag + pack kernels (LP-aware env-to-warp map), step kernel (lockstep env warps + LP team)",
+                           "kernels_per_step": "flag + pack kernels (LP-aware env-to-warp map), step kernel (env CTAs of lockstep warps + LP-server CTAs)",
                            "parallelism": f"shard{world}", "env_record_bytes": q["env_record_bytes"], "grid": q["grid"],
-                           "block": q["block"], "env_warps": q["env_warps"], "lp_team_warps": q["team_warps"],
+                           "block": q["block"], "env_warps": q["env_warps"], "lp_server_ctas": q["lp_server_ctas"],
                            "step_kernel_dynamic_smem": q["step_smem_bytes"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "link_gbs": (h2d + d2h) * K / e2e_s / 1e9,

@@ -38,41 +38,47 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
     fj_params_to_shared(P);
     extern __shared__ __align__(16) unsigned char stage_smem[];
     __shared__ FjLpBoard board;
-    __shared__ int4 red4[64];
     const int warp = threadIdx.x >> 5;
-    const int nenv = P.env_warps;                 // env warps of the CTA (= warp slots of a virtual CTA)
-    const int nteam = (blockDim.x >> 5) - nenv;   // LP team: the CTA's last warps (0 in the free-running / parking modes)
-    for (int k = threadIdx.x; k < 32; k += blockDim.x) {
-        board.req[k] = -1; board.resp[k] = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fj_smem_addr(&board.mbar[k])) : "memory");
+    const int nenv = P.env_warps;                 // env warps of an env CTA (= warp slots of a virtual CTA)
+    const int nsrv = P.cta_lp == 1 ? P.srv_ctas : 0;
+    if ((int)blockIdx.x < nsrv) {
+        // LP-server CTA (the first CTAs of the grid: scheduled first, so an env CTA never waits for a
+        // server that is not resident): groups of warps serve the LP queue until every env CTA is done
+        const int gw = P.srv_group_warps, gid = warp / gw;
+        if (gid >= P.srv_groups) return;
+        FjCtaGroup g;
+        g.red = nullptr; g.flip = 0; g.base = gid * gw * 32; g.nthr = gw * 32; g.bar = FJ_BAR_SRV0 + gid;
+        fj_lp_server_loop(P, g, stage_smem + (size_t)gid * P.srv_group_smem, (int)gridDim.x - nsrv, (int)blockIdx.x * P.srv_groups + gid);
+        return;
     }
-    if (threadIdx.x == 0) { board.quit = 0; board.cur[0] = board.cur[1] = -1; }
+    const int ecta = (int)blockIdx.x - nsrv, nectas = (int)gridDim.x - nsrv;
+    for (int k = threadIdx.x; k < 32; k += blockDim.x)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(fj_smem_addr(&board.mbar[k])) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     unsigned char *hotbuf = P.stage && warp < nenv ? stage_smem + (size_t)warp * P.stage_stride : nullptr;
     FjCtaCtx K;
-    K.warp = warp; K.nwarps = nenv; K.cta_lp = P.cta_lp == 1 && nteam > 0;
-    K.slab = P.lp + (size_t)blockIdx.x * P.lp_stride;
-    K.xbuf = P.cta_x + (size_t)blockIdx.x * nenv * P.d.NPx;
-    K.team_smem = P.team_smem ? stage_smem + (P.stage ? (size_t)nenv * P.stage_stride : 0) : nullptr;
+    K.warp = warp; K.nwarps = nenv; K.cta_lp = nsrv > 0;
+    K.gslot = ecta * nenv + warp;
+    K.slab = nullptr;
+    K.xbuf = P.cta_x + (size_t)K.gslot * P.d.NPx;
     K.board = &board;
-    K.group.red = red4; K.group.flip = 0; K.group.base = nenv * 32; K.group.nthr = nteam * 32; K.group.bar = FJ_BAR_TEAM;
-    const int total = gridDim.x * nenv;
-    // P.order maps warp slots to envs: slot = virtual CTA * nenv + warp, -1 = empty.  CTA b plays
-    // the virtual CTAs b, b + gridDim, ...
+    K.group.red = nullptr; K.group.flip = 0; K.group.base = 0; K.group.nthr = 32; K.group.bar = 0;
+    const int total = nectas * nenv;
+    // P.order maps warp slots to envs: slot = virtual CTA * nenv + warp, -1 = empty.  Env CTA b plays
+    // the virtual CTAs b, b + env CTAs, ...
     if (P.cta_lp == 2) {
         // free-running warps: no CTA coupling at all; a warp that reaches an order arrival solves
         // the fluid LP itself on its own scratch slab (diagnostic mode, FJSP_FREE_RUN)
-        unsigned char *lp = P.lp + (size_t)(blockIdx.x * nenv + warp) * P.lp_stride;
-        for (int slot = blockIdx.x * nenv + warp; slot < P.n_slots; slot += total) {
+        unsigned char *lp = P.lp + (size_t)(ecta * nenv + warp) * P.lp_stride;
+        for (int slot = ecta * nenv + warp; slot < P.n_slots; slot += total) {
             const int env = P.order[slot];
             if (env >= 0) fj_env_rollout<VARIANT, SUM_MODE, 0>(P, A, env, lp, nullptr);
         }
         return;
     }
-    if (warp >= nenv) { fj_lp_team_loop(P, K); return; }
     unsigned uses = 0;
-    for (int base = blockIdx.x * nenv; base < P.n_slots; base += total) {
+    for (int base = ecta * nenv; base < P.n_slots; base += total) {
         const int raw = P.order[base + warp];
         const int env = raw < 0 ? -1 : raw & (FJ_SLOT_DETACHED - 1);
         const int detached = raw >= 0 && (raw & FJ_SLOT_DETACHED);
@@ -85,9 +91,9 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
         fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env, 1, hotbuf, next_env, uses & 1u, detached ? 0 : lock_threads);
         if (hotbuf) ++uses;
     }
-    // every env warp (the free-running ones included) has finished its last round: release the LP team
+    // every env warp (the free-running ones included) has finished its last round: one more CTA the servers need not wait for
     fj_env_count(0, nenv * 32);
-    if (threadIdx.x == 0) *(volatile int *)&board.quit = 1;
+    if (threadIdx.x == 0 && nsrv > 0) { __threadfence(); atomicAdd(P.lpq + 2, 1u); }
 }
 
 // LP-aware packing, run before every step launch.  The warps of a CTA serve each other's fluid
@@ -227,7 +233,10 @@ __global__ void __launch_bounds__(FJ_LP_THREADS) fjsp_lp_kernel(const __grid_con
     unsigned char *red = smem + ((SMEM_BINV ? binv_bytes : 0) + fj_lp_small_bytes(P.d) + 15) / 16 * 16;   // 16-byte aligned
     FjCtaGroup g;
     g.red = (int4 *)red; g.flip = 0; g.whole_cta();
-    for (int i = blockIdx.x; i < n; i += gridDim.x) fj_lp_service(P, g, list_in, i, binv, small_, P.lp + (size_t)blockIdx.x * P.lp_stride);
+    // the fast path carves the same dynamic shared memory its own way (it is one or the other per LP)
+    const int fast_bytes = (int)(red - smem);
+    for (int i = blockIdx.x; i < n; i += gridDim.x)
+        fj_lp_service(P, g, list_in, i, binv, small_, P.lp + (size_t)blockIdx.x * P.lp_stride, smem, fast_bytes);
 }
 
 // after the first reset(): copy each instance's order-0 LP solution from its representative env
@@ -270,8 +279,9 @@ struct fjsp_vec {
     double *d_lp_x, *d_plan_x;
     int n_inst, plan_ready, plan_all;   // plan_all: every instance's order-0 LP solution gets cached by the first reset
     int32_t *d_inst, *d_env_inst, *d_order, *d_order_dyn;
-    int n_slots, pack_cap[3], pack_rows[2], multi_round, env_warps, team_warps, detach;
+    int n_slots, pack_cap[3], pack_rows[2], multi_round, env_warps, srv_ctas, env_ctas, detach;
     double *d_cta_x;
+    unsigned int *d_lpq; unsigned long long *d_lpq_ring; int *d_lp_req, *d_lp_resp;
     unsigned char *d_flags;
     int pack;
     unsigned char *d_env, *d_lp;
@@ -374,30 +384,65 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     int cap = prop.multiProcessorCount * 8;
     if (getenv("FJSP_GRID_PER_SM")) cap = prop.multiProcessorCount * atoi(getenv("FJSP_GRID_PER_SM"));
     v->grid = want < cap ? want : cap;
-    const int lp_mode = getenv("FJSP_FREE_RUN") ? 2 : getenv("FJSP_NO_CTA_LP") ? 0 : 1;
+    int lp_mode = getenv("FJSP_FREE_RUN") ? 2 : getenv("FJSP_NO_CTA_LP") ? 0 : 1;
+    int srv_groups = 0, srv_group_warps = 0;
     {
-        // CTA shape at run time: `env_warps` env warps (one environment copy each, lockstep slots) plus
-        // an LP team of 4 warps (8 when an LP can have more than 128 rows).  One CTA per SM; a batch
-        // larger than grid x env_warps is played in rounds.
-        const int gmax = prop.multiProcessorCount, wmax = FJ_STEP_THREADS / 32;
-        int team = lp_mode == 1 ? (v->tb.d.Rx > 128 ? 8 : 4) : 0;
-        if (getenv("FJSP_LP_TEAM") && lp_mode == 1) team = atoi(getenv("FJSP_LP_TEAM"));
-        if (team < 1 && lp_mode == 1) team = 1;
-        if (team > wmax / 2) team = wmax / 2;
+        // Shape of the main kernel at run time.  One CTA per SM: `srv_ctas` LP-server CTAs and env CTAs of
+        // `env_warps` warps (one environment copy each, lockstep slots); a batch larger than
+        // env CTAs x env_warps is played in rounds.
+        const int nsm = prop.multiProcessorCount, wmax = FJ_STEP_THREADS / 32;
+        // LP load per env step (group-cycles): an episode meets S - 1 order-arrival LPs in `ops` steps; an LP
+        // takes ~0.7 R iterations of ~(2500 + R^2 / 16) cycles on a server group (profiles/README.md r02)
+        double load = 0.0; int any_arrival = 0;
+        for (int i = 0; i < n_instances; ++i) {
+            const int32_t *b = blobs + blob_offsets[i];
+            const int M = b[2], K = b[3], KT = b[4], S = b[5];
+            const int32_t *ntask = b + 16, *count = b + 16 + K + 3 * KT + 3 * KT * M + M + 2 * S;
+            double ops = 0.0;
+            for (int r = 0; r < K; ++r) { double c = 0.0; for (int s2 = 0; s2 < S; ++s2) c += count[s2 * K + r]; ops += c * ntask[r]; }
+            const double R = M + KT + 0.5 * (KT - K);
+            if (S > 1) any_arrival = 1;
+            load += (S - 1) / (ops > 1.0 ? ops : 1.0) * 0.7 * R * (2500.0 + R * R / 16.0);
+        }
+        load /= n_instances;
+        if (lp_mode == 1 && !any_arrival) lp_mode = 0;   // no order ever arrives after reset(): nothing to serve
+        int srv = 0;
+        if (lp_mode == 1) {
+            // an env CTA retires one env step per ~2200 SM cycles; a server CTA runs 4 groups; 2.5x headroom for bursts
+            const double per_env_cta = load / 2200.0 / 4.0 * 2.5;
+            srv = (int)(nsm * per_env_cta / (1.0 + per_env_cta) + 0.999);
+            if (srv < 2) srv = 2;
+            if (srv > nsm / 3) srv = nsm / 3;
+            if (n_envs <= 32) srv = 1;
+            if (getenv("FJSP_LP_SERVERS")) srv = atoi(getenv("FJSP_LP_SERVERS"));
+            if (srv < 1) srv = 1;
+            if (srv > nsm - 1) srv = nsm - 1;
+        }
+        const int gmax = nsm - srv;
         const long long want_slots = (long long)n_envs + (getenv("FJSP_SPARE") ? n_envs * (long long)atoi(getenv("FJSP_SPARE")) / 100 : 0);
-        v->multi_round = (long long)n_envs > (long long)gmax * (wmax - team);
+        v->multi_round = (long long)n_envs > (long long)gmax * wmax;
         int wpb = (int)((want_slots + gmax - 1) / gmax);
-        if (wpb > wmax - team) wpb = wmax - team;
+        if (wpb > wmax) wpb = wmax;
         if (wpb < 4) wpb = 4;
         if (getenv("FJSP_STEP_WARPS")) wpb = atoi(getenv("FJSP_STEP_WARPS"));
-        if (wpb > wmax - team) wpb = wmax - team;
+        if (wpb > wmax) wpb = wmax;
         if (wpb < 1) wpb = 1;
-        v->env_warps = wpb; v->team_warps = team;
-        v->step_threads = (wpb + team) * 32;
+        v->env_warps = wpb; v->srv_ctas = srv;
+        v->step_threads = wpb * 32;
         long long ctas = (want_slots + wpb - 1) / wpb;              // virtual CTAs
-        v->step_grid = (int)(ctas < gmax ? ctas : gmax);
-        const long long rounds = (ctas + v->step_grid - 1) / v->step_grid;
-        v->n_slots = (int)(rounds * v->step_grid * wpb);
+        v->env_ctas = (int)(ctas < gmax ? ctas : gmax);
+        v->step_grid = v->env_ctas + srv;
+        const long long rounds = (ctas + v->env_ctas - 1) / v->env_ctas;
+        v->n_slots = (int)(rounds * v->env_ctas * wpb);
+        if (srv) {
+            // server groups: 4 per CTA when the CTA has the warps for it (a driver warp + helpers each)
+            srv_groups = wpb >= 16 ? 4 : wpb >= 8 ? 2 : 1;
+            if (getenv("FJSP_LP_GROUPS")) srv_groups = atoi(getenv("FJSP_LP_GROUPS"));
+            if (srv_groups < 1) srv_groups = 1;
+            if (srv_groups > 12) srv_groups = 12;
+            if (srv_groups > wpb) srv_groups = wpb;
+            srv_group_warps = wpb / srv_groups;
+        }
     }
     const unsigned long long lp_stride = fj_lp_scratch_bytes(v->tb.d);
     // the resume kernel (in-line LP fallback) and the LP kernel (global Binv fallback) share the slabs
@@ -412,8 +457,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (v->lp_smem_binv && binv_b + small_b > 100 * 1024) v->lp_grid = prop.multiProcessorCount;
     int slabs = v->resume_grid * FJ_WARPS_PER_BLOCK;
     if (v->lp_grid > slabs) slabs = v->lp_grid;
-    if (v->step_grid > slabs) slabs = v->step_grid;   // one slab per CTA of the main kernel (in-CTA LP service)
-    if (lp_mode == 2 && v->step_grid * v->env_warps > slabs) slabs = v->step_grid * v->env_warps;
+    if (v->srv_ctas * srv_groups > slabs) slabs = v->srv_ctas * srv_groups;   // one slab per server group of the main kernel
+    if (lp_mode == 2 && v->env_ctas * v->env_warps > slabs) slabs = v->env_ctas * v->env_warps;
     const size_t lp_bytes = (size_t)lp_stride * slabs;
     const size_t env_bytes = (size_t)n_envs * v->tb.eo.stride;
     CK(cudaMalloc(&v->d_inst, v->tb.inst.size() * 4));
@@ -437,7 +482,22 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     }
     CK(cudaMalloc(&v->d_env, env_bytes));
     CK(cudaMalloc(&v->d_lp, lp_bytes));
-    CK(cudaMalloc(&v->d_cta_x, (size_t)v->step_grid * v->env_warps * v->tb.d.NPx * 8 + 16));
+    {   // LP service of the main kernel: queue, one request / response record and one solution buffer per env warp
+        const size_t gslots = (size_t)v->env_ctas * v->env_warps;
+        const int req_stride = 2 + v->tb.d.KTx + v->tb.d.KTW + 1;
+        CK(cudaMalloc(&v->d_cta_x, gslots * v->tb.d.NPx * 8 + 16));
+        CK(cudaMalloc(&v->d_lpq, 16));
+        CK(cudaMalloc(&v->d_lpq_ring, (size_t)FJ_LPQ_RING * 8));
+        CK(cudaMalloc(&v->d_lp_req, gslots * req_stride * 4));
+        CK(cudaMalloc(&v->d_lp_resp, gslots * 16));
+        CK(cudaMemset(v->d_lpq, 0, 16));
+        CK(cudaMemset(v->d_lpq_ring, 0, (size_t)FJ_LPQ_RING * 8));
+        CK(cudaMemset(v->d_lp_req, 0, gslots * req_stride * 4));
+        CK(cudaMemset(v->d_lp_resp, 0, gslots * 16));
+        v->P.lpq = v->d_lpq; v->P.lpq_ring = v->d_lpq_ring; v->P.lp_req = v->d_lp_req; v->P.lp_resp = v->d_lp_resp;
+        v->P.lp_req_stride = req_stride;
+        v->P.srv_ctas = v->srv_ctas; v->P.srv_groups = srv_groups; v->P.srv_group_warps = srv_group_warps;
+    }
     CK(cudaMemcpy(v->d_inst, v->tb.inst.data(), v->tb.inst.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(v->d_env_inst, env_instance, (size_t)n_envs * 4, cudaMemcpyHostToDevice));
     CK(cudaMemset(v->d_env, 0, env_bytes));
@@ -500,39 +560,41 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         v->pack_rows[0] = 70; v->pack_rows[1] = 45;
         if (getenv("FJSP_PACK")) sscanf(getenv("FJSP_PACK"), "%d,%d,%d,%d,%d", &v->pack_cap[0], &v->pack_cap[1], &v->pack_cap[2], &v->pack_rows[0], &v->pack_rows[1]);
     }
-    {   // LP team scratch in shared memory: column descriptors, positions and B^-1 of the largest LP the
-        // batch can meet (rows <= M + 2 KT - K), capped by what the SM has left
-        // (FJSP_TEAM_SMEM_KB overrides the cap; 0 keeps the LP scratch in HBM/L2)
-        size_t rub = 1;
-        for (int i = 0; i < n_instances; ++i) { const int32_t *b = blobs + blob_offsets[i]; const size_t r = (size_t)b[2] + 2 * b[4] - b[3]; if (r > rub) rub = r; }
-        const size_t C = (size_t)v->tb.d.NPx + 1;
-        const size_t small_b = (C * 24 + ((C + rub + 1) & ~(size_t)1) * 4 + rub * 8 + 15) / 16 * 16;
-        const size_t want = small_b + ((rub + 1) * (rub | 1) * 8 + 15) / 16 * 16;
-        size_t cap = (size_t)(getenv("FJSP_TEAM_SMEM_KB") ? atoi(getenv("FJSP_TEAM_SMEM_KB")) : 64) * 1024;
-        const size_t room = (size_t)200 * 1024 > v->stage_bytes ? (size_t)200 * 1024 - v->stage_bytes : 0;
-        if (cap > room) cap = room;
-        size_t give = want <= cap ? want : (small_b <= cap ? cap : 0);
-        if (P.cta_lp != 1) give = 0;
-        P.team_smem = (int)(give / 16 * 16);
+    {   // shared memory of a server group: the solver's vectors, the column descriptors and positions, and B^-1
+        // when it still fits (else B^-1 stays on the group's slab in HBM/L2).  Env and server CTAs are one
+        // launch: the dynamic shared memory is the larger of the two needs (FJSP_SRV_SMEM_KB overrides the
+        // servers' share).
+        P.srv_group_smem = 0;
+        v->step_smem_bytes = v->stage_bytes;
+        if (P.cta_lp == 1 && v->srv_ctas > 0) {
+            size_t rub = 1;
+            for (int i = 0; i < n_instances; ++i) { const int32_t *b = blobs + blob_offsets[i]; const size_t r = (size_t)b[2] + 2 * b[4] - b[3]; if (r > rub) rub = r; }
+            const size_t C = (size_t)v->tb.d.NPx + 1;
+            const size_t state_b = ((4 * ((size_t)v->tb.d.Rx + 2)) * 8 + ((size_t)v->tb.d.Rx + 2) * 4 + 16 + (size_t)v->tb.d.KTx * 2 + 15) / 16 * 16;
+            const size_t small_b = (C * 24 + ((C + rub + 1) & ~(size_t)1) * 4 + 15) / 16 * 16;
+            const size_t want = state_b + small_b + ((rub + 1) * (rub | 1) * 8 + 15) / 16 * 16;
+            size_t cap = (size_t)(getenv("FJSP_SRV_SMEM_KB") ? atoi(getenv("FJSP_SRV_SMEM_KB")) : 200) * 1024 / P.srv_groups;
+            size_t give = want <= cap ? want : cap;
+            if (give < state_b + small_b) give = state_b + small_b;      // the vectors and descriptors must be on chip
+            give = (give + 15) / 16 * 16;
+            if (give * P.srv_groups > (size_t)200 * 1024) { g_err = "fjsp_vec_create: instance too large for the LP servers' shared memory"; fjsp_vec_destroy(v); return -5; }
+            P.srv_group_smem = (int)give;
+            if (give * P.srv_groups > v->step_smem_bytes) v->step_smem_bytes = give * P.srv_groups;
+        }
     }
-    v->step_smem_bytes = v->stage_bytes + (size_t)P.team_smem;
     v->detach = getenv("FJSP_NO_DETACH") ? 0 : 1;
     if (dispatch(v, [&](auto V, auto SM) {
             auto kern = fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->step_smem_bytes) != cudaSuccess) {
-                // the device refuses that much dynamic shared memory: no LP scratch, then no staging
                 cudaGetLastError();
-                v->P.team_smem = 0; v->step_smem_bytes = v->stage_bytes;
-                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->step_smem_bytes) != cudaSuccess) {
-                    cudaGetLastError();
-                    v->P.stage = 0; v->stage_bytes = 0; v->step_smem_bytes = 0;
-                }
+                g_err = "fjsp_vec_create: the device refuses the step kernel's dynamic shared memory";
+                return -5;
             }
             if (getenv("FJSP_CARVEOUT"))   // percent of the unified L1 / shared memory given to shared memory
                 cudaFuncSetAttribute(fjsp_step_kernel<decltype(V)::value, decltype(SM)::value>,
                                      cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("FJSP_CARVEOUT")));
             return 0;
-        })) return -2;
+        })) { fjsp_vec_destroy(v); return -5; }
     CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&v->chunk_done, cudaEventDisableTiming));
@@ -572,6 +634,7 @@ int fjsp_vec_destroy(fjsp_vec *v)
     cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
     cudaFree(v->d_trace); cudaFree(v->d_cta_x);
+    cudaFree(v->d_lpq); cudaFree(v->d_lpq_ring); cudaFree(v->d_lp_req); cudaFree(v->d_lp_resp);
     cudaFree(v->d_rep_env); cudaFree(v->d_plan_x); cudaFree(v->d_plan_meta); cudaFree(v->d_plan_ok);
     if (v->stream) cudaStreamDestroy(v->stream);
     if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
@@ -586,7 +649,7 @@ int fjsp_vec_query(fjsp_vec *v, int64_t *o)
     if (!v || !o) { g_err = "fjsp_vec_query: null argument"; return -1; }
     o[0] = v->B; o[1] = v->nstate; o[2] = v->tb.eo.stride; o[3] = (int64_t)v->tb.io.stride * 4;
     o[4] = v->step_grid; o[5] = v->step_threads; o[6] = (int64_t)v->P.lp_stride; o[7] = v->launches;
-    o[8] = v->env_warps; o[9] = v->team_warps; o[10] = v->n_slots; o[11] = (int64_t)v->step_smem_bytes;
+    o[8] = v->env_warps; o[9] = v->srv_ctas; o[10] = v->n_slots; o[11] = (int64_t)v->step_smem_bytes;
     return 0;
 }
 
@@ -630,6 +693,7 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     A.park_count = nullptr; A.park_env = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(v->d_pend_count, 0, 4 * (FJ_ROUNDS + 1), st));
+    CK(cudaMemsetAsync(v->d_lpq + 2, 0, 4, st));   // env CTAs finished in this launch (the queue's tickets are never reset)
     int rc = dispatch(v, [&](auto V, auto SM) {
         constexpr int VV = decltype(V)::value, MM = decltype(SM)::value;
         A.park_count = v->d_pend_count; A.park_env = v->d_pend_env;

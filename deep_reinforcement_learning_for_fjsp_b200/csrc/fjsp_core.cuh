@@ -524,8 +524,8 @@ FJ_FN double fj_lp_colvec_dot(const FjCtx &c, const FjLp &L, const double *brow,
 #define FJ_LPT_DECL long long lt_ = clock64(), la_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define FJ_LPT(k) do { const long long n_ = clock64(); la_[k] += n_ - lt_; lt_ = n_; } while (0)
 #define FJ_LPT_ITER() (la_[7] += 1)
-#define FJ_LPT_FLUSH() do { if (g.rank() == 0 && g.size() > FJ_NL && c.P->trace) { \
-    for (int k_ = 0; k_ < 8; ++k_) c.P->trace[((size_t)blockIdx.x * FJ_TRACE_ROWS + FJ_TRACE_ROWS - 1) * 8 + k_] += la_[k_]; } } while (0)
+#define FJ_LPT_FLUSH() do { if (g.rank() == 0 && g.size() > FJ_NL && fj_sP.trace) { \
+    for (int k_ = 0; k_ < 8; ++k_) atomicAdd((unsigned long long *)&fj_sP.trace[((size_t)blockIdx.x * FJ_TRACE_ROWS + FJ_TRACE_ROWS - 1) * 8 + k_], (unsigned long long)la_[k_]); } } while (0)
 #else
 #define FJ_LPT_DECL
 #define FJ_LPT(k)
@@ -681,34 +681,79 @@ FJ_FN int fj_lp_solve(const G &g_in, FjCtx &c, FjLp &L, double *x_out, int *iter
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- group fast path of the LP
 // The same pivoting rules and the same floating-point operations as fj_lp_solve (results are
-// bit-identical; tests/test_gpu_parity.py compares both with the oracle), organised for a SMALL
-// group (the step kernel's 4- or 8-warp LP team, the LP kernel's 8-warp CTA).  An LP iteration is
-// a chain of short dependent phases and a warp retires one instruction per 10-25 cycles, so what
-// counts is the number of instructions every warp executes per iteration:
+// bit-identical; tests/test_gpu_parity.py compares both with the oracle), organised around what
+// bounds a small dense simplex on an SM: the LENGTH OF THE DEPENDENT CHAIN of one iteration.  A
+// warp retires one dependent instruction per ~10 cycles, a CTA-wide argmin costs two warp
+// reductions, a trip through shared memory and a barrier, and with "thread i owns row i" most
+// phases run one element per thread: the round-1/2 team version spent 11.8 k cycles per iteration
+// on ~600 dependent instructions (profiles/README.md).  Here
+//   * ONE warp -- the DRIVER -- runs the whole decision chain of an iteration: pricing over all
+//     columns (a lane owns columns lane, lane + 32, ...: independent 4-term dot products, so the
+//     loads and the multiply-add chains of several columns are in flight together), the entering
+//     argmin (three redux.sync, no shared-memory exchange, no barrier), w = B^-1 A_q and the ratio
+//     test for rows lane, lane + 32, ..., the leaving argmin, x_B, the scaled pivot row and the new
+//     pricing vector;
+//   * the group's other warps -- the HELPERS -- apply the rank-1 update of the pivot the driver has
+//     just published while the driver already prices the next iteration (pricing needs only the
+//     mirrored t row y of B^-1, which the driver updates itself);
+//   * two group barriers per iteration tie them together: A "update of pivot n-1 done" (before the
+//     driver reads B^-1 for w) and B "pivot n published";
 //   * every structural column carries a descriptor: its four row indices (machine row, demand
 //     row, the two precedence rows; a missing row points at a padding column of B^-1 that is
 //     always 0, which adds +-0 and leaves the accumulator unchanged) and its two coefficients:
 //     a reduced cost or an entry of w is 4 loads, 4 multiplies, 4 adds, no branch;
-//   * thread i owns ROW i of B^-1 (x_B, the basic variable and w of the row stay in its
-//     registers) and B^-1 is stored COLUMN-major with an odd column stride: "thread i reads
-//     B^-1[i][k]" is a conflict-free shared-memory access (coalesced when the scratch is global),
-//     and so is "thread k reads B^-1[p][k]" of the pivot-row scaling;
-//   * the rank-1 update is flat: a warp owns 32 rows and a chunk of the columns, a thread runs
-//     B^-1[i][k] -= w_i * pr[k] over its chunk with pr broadcast from shared memory -- 5
-//     instructions per element (round 1's row-block version spent 30 instructions of set-up per row
-//     on one inner iteration: 68 % of all LP instructions);
-//   * the t row of B^-1 (the pricing vector y) is mirrored in shared memory and updated by the
-//     threads that scale the pivot row, so the rank-1 update of pivot n runs after the pricing
-//     of iteration n+1 without a barrier in between: three group barriers per iteration.
-#define FJ_LPF_RMAX 256
+//   * B^-1 is stored COLUMN-major with an odd column stride: "lane i reads B^-1[i][k]" and "lane k
+//     reads B^-1[p][k]" are conflict-free shared-memory accesses (coalesced when the scratch is
+//     global); the update skips 32-row groups whose w is all zero and column quadruples whose
+//     pivot-row entries are all zero (x - w * 0 = x: only the sign of a zero could differ, and a
+//     zero's sign never reaches a comparison, a non-zero value or the flushed solution).
+// per-group state of the fast path, carved from the group's shared memory for the batch's largest LP
+// (rows <= Rx): w = B^-1 A_q, the scaled pivot row, the pricing vector y (+ the zero padding entry),
+// x_B, the basic variable of every row, the precedence row of every operation type, control words
 struct FjLpFastSmem {
-    double w[FJ_LPF_RMAX];
-    double pr[FJ_LPF_RMAX];
-    double y[2][FJ_LPF_RMAX + 2];
-    short prec[FJSP_MAX_KT];
-    int nprec;
+    double *base; int n, ktx;   // n = Rx + 2 entries per double array
+    FJ_MFN double *w() const { return base; }
+    FJ_MFN double *pr() const { return base + n; }
+    FJ_MFN double *y() const { return base + 2 * n; }
+    FJ_MFN double *xb() const { return base + 3 * n; }
+    FJ_MFN int *bvar() const { return (int *)(base + 4 * n); }
+    FJ_MFN int *ctl() const { return bvar() + n; }                 // [0] nprec [1] pivot row for the helpers (-1: leave) [2] ticket [3] requester
+    FJ_MFN short *prec() const { return (short *)(ctl() + 4); }
 };
-static __shared__ FjLpFastSmem fj_sLpf;
+FJ_FN size_t fj_lpf_state_bytes(const FjDims &d)
+{
+    const size_t n = (size_t)d.Rx + 2;
+    return (4 * n * 8 + n * 4 + 16 + (size_t)d.KTx * 2 + 15) / 16 * 16;
+}
+FJ_FN FjLpFastSmem fj_lpf_state(unsigned char *p, const FjDims &d)
+{
+    FjLpFastSmem S; S.base = (double *)p; S.n = d.Rx + 2; S.ktx = d.KTx;
+    return S;
+}
+
+// What the LP is built from: the instance's statics and, of the environment's state at the order
+// arrival, the unprocessed operations per type and which waiting queues are empty.  Either the env
+// record itself (qlen != null: the LP kernel after reset() / for parked envs) or the request an env
+// warp posted for the LP servers (empty != null; written by another SM: read through L2).
+struct FjLpIn {
+    const int32_t *I;
+    int M, KT, NP;
+    const int32_t *fstart;
+    const uint16_t *qlen;
+    const uint32_t *empty;
+};
+FJ_FN int fj_lpin_fstart(const FjLpIn &in, int q) { return in.qlen ? in.fstart[q] : __ldcg(in.fstart + q); }
+FJ_FN int fj_lpin_prec(const FjLpIn &in, const FjParams &P, int q)   // a precedence row: not a last stage and nothing waits at the next one
+{
+    if (__ldg(in.I + P.io.rjlast + q)) return 0;
+    if (in.qlen) return in.qlen[q + 1] == 0;
+    return (int)(__ldcg(in.empty + ((q + 1) >> 5)) >> ((q + 1) & 31) & 1u);
+}
+FJ_FN void fj_lpin_from_ctx(FjLpIn &in, const FjCtx &c)
+{
+    in.I = c.I; in.M = c.M; in.KT = c.KT; in.NP = c.I[c.P->io.hdr + 7];
+    in.fstart = c.fstart; in.qlen = c.qlen; in.empty = nullptr;
+}
 
 // sum over the column's four rows of  (negate ? -v[row] : v[row]) * coefficient,  v = a vector indexed by row
 // (stride 1: the pricing vector) or row i of the column-major B^-1 (stride = column stride)
@@ -722,176 +767,205 @@ FJ_FN double fj_lpf_dot(const double *v, int stride, uint2 ix, double a, double 
     return acc;
 }
 
+// rank-1 update of pivot row p by helper h of nh:  B^-1[i][k] -= w[i] * pr[k]  for rows i != p with
+// w[i] != 0; lanes own the rows of a 32-row group, helpers interleave the columns
+FJ_FN void fj_lpf_rank1(const FjLpFastSmem &S, double *BT, int Rs, int R, int p, int h, int nh, int lane)
+{
+    const int ngrp = (R + 31) >> 5;
+    for (int grp = 0; grp < ngrp; ++grp) {
+        const int i = grp * 32 + lane;
+        const double wv = (i < R && i != p) ? S.w()[i] : 0.0;
+        const bool on = wv != 0.0;
+        if (!__any_sync(0xffffffffu, on)) continue;
+        double *b = BT + i;
+        int k = h;
+        for (; k + 3 * nh < R; k += 4 * nh) {
+            const double p0 = S.pr()[k], p1 = S.pr()[k + nh], p2 = S.pr()[k + 2 * nh], p3 = S.pr()[k + 3 * nh];
+            if (p0 == 0.0 && p1 == 0.0 && p2 == 0.0 && p3 == 0.0) continue;
+            if (on) {
+                double *b0 = b + (size_t)k * Rs, *b1 = b0 + (size_t)nh * Rs, *b2 = b1 + (size_t)nh * Rs, *b3 = b2 + (size_t)nh * Rs;
+                const double e0 = *b0, e1 = *b1, e2 = *b2, e3 = *b3;
+                *b0 = fj_sub(e0, fj_mul(wv, p0));
+                *b1 = fj_sub(e1, fj_mul(wv, p1));
+                *b2 = fj_sub(e2, fj_mul(wv, p2));
+                *b3 = fj_sub(e3, fj_mul(wv, p3));
+            }
+        }
+        for (; k < R; k += nh) {
+            const double p0 = S.pr()[k];
+            if (p0 != 0.0 && on) { double *b0 = b + (size_t)k * Rs; *b0 = fj_sub(*b0, fj_mul(wv, p0)); }
+        }
+    }
+}
+
 // returns -1 when the LP does not fit the fast path (the caller then runs fj_lp_solve).
-// `smem` / `smem_bytes`: shared-memory scratch of the calling group (the step kernel's LP team).  The
-// column descriptors and positions go there when they fit, and B^-1 too when it still fits; the
-// rest lives on `slab` (HBM/L2).
-FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, FjCtx &c, unsigned char *slab, double *x_out, int *iters_out,
-                           unsigned char *smem = nullptr, int smem_bytes = 0)
+// `smem` / `smem_bytes`: shared-memory scratch of the calling group (the step kernel's LP team, the LP
+// kernel's CTA).  The column descriptors and positions go there when they fit, and B^-1 too when it
+// still fits; the rest lives on `slab` (HBM/L2).
+FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, const FjParams &P, const FjLpIn &in, const FjLpFastSmem &S, unsigned char *slab, double *x_out,
+                           int *iters_out, unsigned char *smem = nullptr, int smem_bytes = 0)
 {
     FjCtaGroup g = g_in;
-    FjLpFastSmem &S = fj_sLpf;
-    const int tid = g.rank(), nt = g.size();
-    const int M = c.M, KT = c.KT, Mx = c.Mx;
-    const FjRO ptime = FJ_I(c, ptime);
-    const FjEligRO elig = fj_elig(c);
-    const FjLastRO rjlast = fj_rjlast(c);
-    const FjStageRO rjstage = fj_rjstage(c);
-    const FjRO colbase = FJ_I(c, colbase);
+    const int tid = g.rank(), nt = g.size(), lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int M = in.M, KT = in.KT;
     FJ_LPT_DECL;
     if (tid < 32) {   // precedence rows, numbered in ascending operation-type order
         int base = 0;
         for (int q0 = 0; q0 < KT; q0 += 32) {
             const int q = q0 + tid;
-            const int f = q < KT && !rjlast[q] && c.qlen[q + 1] == 0;
+            const int f = q < KT && fj_lpin_prec(in, P, q);
             const unsigned bal = __ballot_sync(0xffffffffu, f);
-            if (q < KT) S.prec[q] = (short)(f ? M + KT + base + __popc(bal & ((1u << tid) - 1u)) : -1);
+            if (q < KT) S.prec()[q] = (short)(f ? M + KT + base + __popc(bal & ((1u << tid) - 1u)) : -1);
             base += __popc(bal);
         }
-        if (tid == 0) S.nprec = base;
+        if (tid == 0) S.ctl()[0] = base;
     }
     g.sync();
-    const int NP = FJ_I(c, hdr)[7], R = M + KT + S.nprec, C = NP + 1, Rs = R | 1;   // odd column stride
-    if (R > FJ_LPF_RMAX || R > nt || R >= 0xffff) { g.sync(); return -1; }
-    // carve: B^-1 (R + 1 columns of Rs entries: column R is the all-zero padding), column descriptors,
-    // positions, final x_B
+    const int NP = in.NP, R = M + KT + S.ctl()[0], C = NP + 1, Rs = R | 1;   // odd column stride
+    if (R + 2 > S.n || R >= 0xffff) { g.sync(); return -1; }   // (cannot happen: S is sized for the batch's largest LP)
+    // carve: B^-1 (R + 1 columns of Rs entries: column R is the all-zero padding), column descriptors, positions
     const size_t binv_bytes = ((size_t)(R + 1) * Rs * 8 + 15) / 16 * 16;
-    const size_t small_bytes = (size_t)C * 24 + (size_t)((C + R + 1) & ~1) * 4 + (size_t)R * 8;
+    const size_t small_bytes = (size_t)C * 24 + (size_t)((C + R + 1) & ~1) * 4;
     const bool small_sm = smem && (size_t)smem_bytes >= small_bytes;
     const bool binv_sm = small_sm && (size_t)smem_bytes >= ((small_bytes + 15) / 16 * 16) + binv_bytes;
     double *BT = (double *)(binv_sm ? smem + (small_bytes + 15) / 16 * 16 : slab);
     double2 *coef = (double2 *)(small_sm ? smem : slab + binv_bytes);
     uint2 *cidx = (uint2 *)(coef + C);
     int *pos = (int *)(cidx + C);
-    double *xBm = (double *)(pos + ((C + R + 1) & ~1));
-    for (int q = tid; q < KT; q += nt) {
-        unsigned em = (unsigned)elig[q];
-        int col = colbase[q];
-        const double fs = (double)c.fstart[q];
-        const int p_prev = (rjstage[q] > 0 && S.prec[q - 1] >= 0) ? S.prec[q - 1] : R;
-        const int p_own = S.prec[q] >= 0 ? S.prec[q] : R;
-        while (em) {
-            const int m = fj_ffs0(em); em &= em - 1;
-            const double rate = fj_div(1.0, (double)ptime[q * Mx + m]);
-            coef[col] = make_double2(-fj_div(rate, fs), rate);
-            cidx[col] = make_uint2((unsigned)m | ((unsigned)(M + q) << 16), (unsigned)p_prev | ((unsigned)p_own << 16));
-            ++col;
+    {   // one thread per structural column: descriptor and coefficients (the per-pair rate 1/p is a static of the instance)
+        const int32_t *colqm = in.I + P.io.colqm, *rjstage = in.I + P.io.rjstage;
+        const double *colrate = (const double *)(in.I + P.io.colrate);
+        for (int j = tid; j < NP; j += nt) {
+            const int qm = __ldg(colqm + j), q = qm >> 8, m = qm & 0xff;
+            const double rate = __ldg(colrate + j);
+            const double fs = (double)fj_lpin_fstart(in, q);
+            const int p_prev = (__ldg(rjstage + q) > 0 && S.prec()[q - 1] >= 0) ? S.prec()[q - 1] : R;
+            const int p_own = S.prec()[q] >= 0 ? S.prec()[q] : R;
+            coef[j] = make_double2(-__ddiv_rn(rate, fs), rate);
+            cidx[j] = make_uint2((unsigned)m | ((unsigned)(M + q) << 16), (unsigned)p_prev | ((unsigned)p_own << 16));
         }
     }
     for (int j = tid; j < C + R; j += nt) pos[j] = j >= C ? j - C : -1;
     for (int e = tid; e < (R + 1) * Rs; e += nt) BT[e] = 0.0;
-    for (int k = tid; k < R + 2; k += nt) { S.y[0][k] = 0.0; S.y[1][k] = 0.0; }
-    double xb = tid < M ? 1.0 : 0.0;        // x_B of row tid (tid < R)
-    int bvar = C + tid;                     // basic variable of row tid
+    for (int k = tid; k < R + 2; k += nt) S.y()[k] = 0.0;
+    for (int i = tid; i < R; i += nt) { S.xb()[i] = i < M ? 1.0 : 0.0; S.bvar()[i] = C + i; }
     g.sync();
-    if (tid < R) BT[(size_t)tid * Rs + tid] = 1.0;
+    for (int i = tid; i < R; i += nt) BT[(size_t)i * Rs + i] = 1.0;
     g.sync();
     const int dantzig_iters = 20 * R + 100, hard_iters = 200 * R + 1000;
-    const int nvar = C + R, t_col = NP;
-    // rank-1 update: a warp owns a group of 32 rows and one chunk of the columns
-    const int lane = tid & 31, nw = nt >> 5, ngrp = (R + 31) >> 5;
-    const int nchunk = nw >= ngrp ? nw / ngrp : 1;                 // column chunks per row group
-    const int csize = (R + nchunk - 1) / nchunk;
-    const int my_grp0 = nw >= ngrp ? (tid >> 5) % ngrp : (tid >> 5);   // first row group of this warp
-    const int grp_step = nw >= ngrp ? ngrp : nw;                       // (a warp loops over groups only when there are more groups than warps)
-    const int my_chunk = nw >= ngrp ? (tid >> 5) / ngrp : 0;
-    const int k_lo = my_chunk < nchunk ? my_chunk * csize : R, k_hi = k_lo + csize < R ? k_lo + csize : R;
-    int it = 0, rc = 0, cur = 0, pt = -1, p_last = -1;
+    const int t_col = NP;
+    int it = 0, rc = 0;
     FJ_LPT(0);
-    for (;; ++it) {
-        FJ_LPT_ITER();
-        if (it >= hard_iters) { rc = 2; break; }
-        // ---- pricing on the mirrored t row: most negative reduced cost (lowest column on
-        // ties) / Bland: lowest column
-        const double *y = S.y[cur];
-        const int bland = it >= dantzig_iters;
-        double ek = 0.0; int ei = FJ_EMPTY, ea = 0;
-        for (int j = tid; j < nvar; j += nt) {
-            if (pos[j] >= 0) continue;
-            double d;
-            if (j < NP) {
-                const double2 cf = coef[j];
-                d = fj_sub(0.0, pt >= 0 ? fj_lpf_dot(y, 1, cidx[j], cf.x, cf.y, true) : 0.0);
-            } else if (j == NP) {
-                double acc = 0.0;
-                if (pt >= 0) for (int q = 0; q < KT; ++q) acc = fj_add(acc, fj_mul(-y[M + q], 1.0));
-                d = fj_sub(-1.0, acc);
-            } else {
-                d = pt >= 0 ? -(-y[j - C]) : -0.0;
-            }
-            if (d < -FJ_LP_EPS_D) {
-                if (bland) { if (ei == FJ_EMPTY) { ek = d; ei = j; } }
-                else if (ei == FJ_EMPTY || d < ek) { ek = d; ei = j; }
-            }
-        }
-        FJ_LPT(1);
-        // ---- rank-1 update of the previous pivot (rows != p_last; rows with w == 0 are left alone);
-        // the pricing above did not need it
-        if (p_last >= 0) {
-            for (int grp = my_grp0; grp < ngrp; grp += grp_step) {
-                const int i = grp * 32 + lane;
-                const double wv = i < R && i != p_last ? S.w[i] : 0.0;
-                if (wv != 0.0) {
-                    double *b = BT + i + k_lo * Rs;       // entry (i, k) of the column-major inverse, k = k_lo ..
-                    const double *pv = S.pr + k_lo;
-                    int n = k_hi - k_lo;
-                    for (; n >= 4; n -= 4, b += 4 * Rs, pv += 4) {
-                        const double p0 = pv[0], p1 = pv[1], p2 = pv[2], p3 = pv[3];
-                        const double e0 = b[0], e1 = b[Rs], e2 = b[2 * Rs], e3 = b[3 * Rs];
-                        b[0] = fj_sub(e0, fj_mul(wv, p0));
-                        b[Rs] = fj_sub(e1, fj_mul(wv, p1));
-                        b[2 * Rs] = fj_sub(e2, fj_mul(wv, p2));
-                        b[3 * Rs] = fj_sub(e3, fj_mul(wv, p3));
+    if (wid == 0) {
+        // ------------------------------------------------ driver
+        int pt = -1;   // row of t in the basis, -1: nonbasic
+        for (;; ++it) {
+            FJ_LPT_ITER();
+            int qin = FJ_EMPTY;
+            if (it >= hard_iters) rc = 2;
+            else if (pt < 0) qin = t_col;   // y = 0: every structural / slack reduced cost is 0 and t prices at -1
+            else {
+                // ---- pricing on the mirrored t row: most negative reduced cost (lowest column on
+                // ties) / Bland: lowest column.  t itself is basic here.
+                const double *y = S.y();
+                const int bland = it >= dantzig_iters;
+                double ek = 0.0; int ei = FJ_EMPTY;
+#pragma unroll 2
+                for (int j = lane; j < NP; j += 32) {
+                    const double2 cf = coef[j];
+                    const double d = fj_sub(0.0, fj_lpf_dot(y, 1, cidx[j], cf.x, cf.y, true));
+                    if (pos[j] < 0 && d < -FJ_LP_EPS_D) {
+                        if (bland) { if (ei == FJ_EMPTY) { ek = d; ei = j; } }
+                        else if (ei == FJ_EMPTY || d < ek) { ek = d; ei = j; }
                     }
-                    for (; n > 0; --n, b += Rs, ++pv) b[0] = fj_sub(b[0], fj_mul(wv, pv[0]));
+                }
+                for (int i = lane; i < R; i += 32) {
+                    const double d = -(-y[i]);
+                    if (pos[C + i] < 0 && d < -FJ_LP_EPS_D) {
+                        if (bland) { if (ei == FJ_EMPTY) { ek = d; ei = C + i; } }
+                        else if (ei == FJ_EMPTY || d < ek) { ek = d; ei = C + i; }
+                    }
+                }
+                if (bland) ei = (int)__reduce_min_sync(0xffffffffu, (unsigned)ei);
+                else {
+                    unsigned hi, lo, id; int ea = 0;
+                    fj_lex_pack(ek, ei, 0, hi, lo, id);
+                    fj_warp_lexmin(hi, lo, id);
+                    fj_lex_unpack(hi, lo, id, ek, ei, ea);
+                }
+                qin = ei;
+            }
+            FJ_LPT(1);
+            g.sync();   // A: the helpers have applied the previous pivot
+            FJ_LPT(2);
+            if (qin == FJ_EMPTY) break;   // optimal (or rc = 2)
+            // ---- w = B^-1 A_q and the ratio test  min max(xB, 0) / w  over w > eps (ties: lowest basic variable)
+            double rk = 0.0; int ri = FJ_EMPTY, rrow = 0;
+            {
+                double2 cf = make_double2(0.0, 0.0); uint2 ix = make_uint2(0u, 0u);
+                if (qin < NP) { cf = coef[qin]; ix = cidx[qin]; }
+                for (int i = lane; i < R; i += 32) {
+                    const double *brow = BT + i;      // row i: entry k at brow[k * Rs]
+                    double wi;
+                    if (qin < NP) wi = fj_lpf_dot(brow, Rs, ix, cf.x, cf.y, false);
+                    else if (qin == NP) { double acc = 0.0; for (int q = 0; q < KT; ++q) acc = fj_add(acc, fj_mul(brow[(size_t)(M + q) * Rs], 1.0)); wi = acc; }
+                    else wi = brow[(size_t)(qin - C) * Rs];
+                    S.w()[i] = wi;
+                    if (wi > FJ_LP_EPS_PIV) {
+                        const double xv = S.xb()[i];
+                        const double r = __ddiv_rn(xv > 0.0 ? xv : 0.0, wi);
+                        const int bi = S.bvar()[i];
+                        if (ri == FJ_EMPTY || r < rk || (r == rk && bi < ri)) { rk = r; ri = bi; rrow = i; }
+                    }
                 }
             }
-        }
-        FJ_LPT(6);
-        if (bland) ei = g.min_i(ei); else g.argmin(ek, ei, ea);   // barrier: the rank-1 update is complete
-        FJ_LPT(2);
-        const int qin = ei;
-        if (qin == FJ_EMPTY) break;   // optimal
-        // ---- w = B^-1 A_q and the ratio test, row tid
-        double wi = 0.0, rk = 0.0; int ri = FJ_EMPTY, rrow = 0;
-        if (tid < R) {
-            const double *brow = BT + tid;      // row tid: entry k at brow[k * Rs]
-            if (qin < NP) { const double2 cf = coef[qin]; wi = fj_lpf_dot(brow, Rs, cidx[qin], cf.x, cf.y, false); }
-            else if (qin == NP) { double acc = 0.0; for (int q = 0; q < KT; ++q) acc = fj_add(acc, fj_mul(brow[(size_t)(M + q) * Rs], 1.0)); wi = acc; }
-            else wi = brow[(size_t)(qin - C) * Rs];
-            S.w[tid] = wi;
-            if (wi > FJ_LP_EPS_PIV) { rk = fj_div(xb > 0.0 ? xb : 0.0, wi); ri = bvar; rrow = tid; }
-        }
-        FJ_LPT(3);
-        g.argmin(rk, ri, rrow);       // barrier: publishes w
-        FJ_LPT(4);
-        if (ri == FJ_EMPTY) { rc = 3; break; }
-        const int p = rrow;
-        const double theta = rk, wp = S.w[p];
-        if (tid < R) {
-            if (tid == p) { xb = theta; bvar = qin; }
-            else xb = fj_sub(xb, fj_mul(theta, wi));
-            // pivot row (entry tid of it), and the new t row of B^-1 for the next pricing
-            const double pr = fj_div(BT[(size_t)tid * Rs + p], wp);
-            BT[(size_t)tid * Rs + p] = pr;
-            S.pr[tid] = pr;
+            FJ_LPT(3);
+            {
+                unsigned hi, lo, id;
+                fj_lex_pack(rk, ri, rrow, hi, lo, id);
+                fj_warp_lexmin(hi, lo, id);
+                fj_lex_unpack(hi, lo, id, rk, ri, rrow);
+            }
+            __syncwarp();   // every lane's w is visible to the warp
+            FJ_LPT(4);
+            if (ri == FJ_EMPTY) { rc = 3; break; }
+            const int p = rrow;
+            const double theta = rk, wp = S.w()[p];
             const int pt_new = qin == t_col ? p : (ri == t_col ? -1 : pt);
-            double yn = 0.0;
-            if (pt_new == p) yn = pr;
-            else if (pt_new >= 0) { const double wt = S.w[pt_new], yo = S.y[cur][tid]; yn = wt != 0.0 ? fj_sub(yo, fj_mul(wt, pr)) : yo; }
-            S.y[cur ^ 1][tid] = yn;
+            const double wt = (pt_new >= 0 && pt_new != p) ? S.w()[pt_new] : 0.0;
+            for (int i = lane; i < R; i += 32) {
+                // x_B, the scaled pivot row (entry i of it) and the t row of B^-1 for the next pricing
+                if (i == p) { S.xb()[i] = theta; S.bvar()[i] = qin; }
+                else S.xb()[i] = fj_sub(S.xb()[i], fj_mul(theta, S.w()[i]));
+                const double pr = __ddiv_rn(BT[(size_t)i * Rs + p], wp);
+                BT[(size_t)i * Rs + p] = pr;
+                S.pr()[i] = pr;
+                double yn = 0.0;
+                if (pt_new == p) yn = pr;
+                else if (pt_new >= 0) { const double yo = S.y()[i]; yn = wt != 0.0 ? fj_sub(yo, fj_mul(wt, pr)) : yo; }
+                S.y()[i] = yn;
+            }
+            if (lane == 0) { pos[ri] = -1; pos[qin] = p; S.ctl()[1] = p; }
+            pt = pt_new;
+            FJ_LPT(5);
+            if (nw == 1) { __syncwarp(); fj_lpf_rank1(S, BT, Rs, R, p, 0, 1, lane); __syncwarp(); }
+            g.sync();   // B: pivot published
+            FJ_LPT(6);
         }
-        if (tid == 0) { pos[ri] = -1; pos[qin] = p; }
-        pt = qin == t_col ? p : (ri == t_col ? -1 : pt);
-        p_last = p; cur ^= 1;
-        g.sync();
-        FJ_LPT(5);
+        if (lane == 0) S.ctl()[1] = -1;
+        g.sync();       // B of the last round: the helpers leave
+    } else {
+        // ------------------------------------------------ helpers
+        for (;;) {
+            g.sync();   // A
+            g.sync();   // B
+            const int p = *(volatile int *)&S.ctl()[1];
+            if (p < 0) break;
+            fj_lpf_rank1(S, BT, Rs, R, p, wid - 1, nw - 1, lane);
+        }
     }
-    // the update of the last pivot was folded into the pricing pass that found no entering column
-    if (tid < R) xBm[tid] = xb;
-    g.sync();
     for (int j = tid; j < NP; j += nt) {
-        double x = pos[j] >= 0 ? xBm[pos[j]] : 0.0;
+        double x = pos[j] >= 0 ? S.xb()[pos[j]] : 0.0;
         if (x < FJ_LP_EPS_ZERO) x = 0.0;
         x_out[j] = x;
     }
@@ -966,61 +1040,114 @@ FJ_FN void fj_arrival_begin(FjCtx &c, int s)
 
 FJ_OUTLINE unsigned fj_small_set_order(unsigned seq, int n);
 
-// class_FJSP.py:292-316 update_fluid_parameter from the LP solution x (canonical columns)
+// exclusive prefix sum of one int per lane (and the warp total)
+FJ_FN int fj_excl_scan_i(int v, int &total)
+{
+#ifdef FJ_DEVICE_CODE
+    int inc = v;
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (fj_lane() >= d) inc += o; }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+#else
+    total = v;
+    return 0;
+#endif
+}
+FJ_FN double fj_ld_x(const double *x, int j)   // an LP solution entry: possibly written by another SM, so never from L1
+{
+#ifdef FJ_DEVICE_CODE
+    return __ldcg(x + j);
+#else
+    return x[j];
+#endif
+}
+FJ_FN double fj_inst_d(const FjCtx &c, int off, int i)   // double i of an 8-byte aligned array of the instance record
+{
+    const double *p = (const double *)(c.I + off) + i;
+#ifdef FJ_DEVICE_CODE
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// class_FJSP.py:292-316 update_fluid_parameter from the LP solution x (canonical columns).  Lanes own
+// operation types; the fluid slots (canonical column order) are numbered with a warp prefix sum and
+// filled by their types' lanes (one division per fluid pair, all types at once).
 template <int SUM_MODE>
 FJ_FN void fj_arrival_finish(FjCtx &c, const double *x, int iters, int rc)
 {
     const int lane = fj_lane();
-    const int KT = c.KT, Mx = c.Mx;
-    const FjRO ptime = FJ_I(c, ptime), poord = FJ_I(c, poord), nelig = FJ_I(c, nelig);
+    const int KT = c.KT, Mx = c.Mx, NFx = c.P->d.NFx;
+    const FjRO poord = FJ_I(c, poord), nelig = FJ_I(c, nelig);
     const FjEligRO elig = fj_elig(c);
     const FjRO colbase = FJ_I(c, colbase);
+    const int rate_off = c.P->io.colrate;   // 1.0 / processing time of every column
     if (lane == 0) {
         c.scal[FJ_S_LPSOLVES] += 1; c.scal[FJ_S_LPITERS] += iters;
         if (rc) c.scal[FJ_S_ERROR] |= FJ_E_LP;
     }
+    int base = 0, overflow = 0;
     FJ_NOUNROLL
-    for (int q = lane; q < KT; q += FJ_NL) {
-        unsigned em = (unsigned)elig[q], fm = 0, fseq = 0;
-        int nfq = 0;
-        FjPySum ps; fj_pysum_init(ps);
-        FJ_NOUNROLL
-        for (int k = 0; k < nelig[q]; ++k) {
-            int m = poord[q * Mx + k];
-            int col = colbase[q] + fj_popc(em & ((1u << m) - 1u));
-            double xv = x[col];
-            double fr = fj_mul(xv, fj_div(1.0, (double)ptime[q * Mx + m]));
-            fj_pysum_add<SUM_MODE>(ps, fr);
-            if (xv != 0.0) { fm |= 1u << m; if (nfq < 4) fseq |= (unsigned)m << (8 * nfq); ++nfq; }
+    for (int q0 = 0; q0 < KT; q0 += FJ_NL) {
+        const int q = q0 + lane;
+        unsigned em = 0, fm = 0;
+        int nfq = 0, cb = 0;
+        double rs = 0.0;
+        if (q < KT) {
+            em = (unsigned)elig[q]; cb = colbase[q];
+            unsigned fseq = 0;
+            FjPySum ps; fj_pysum_init(ps);
+            FJ_NOUNROLL
+            for (int k = 0; k < nelig[q]; ++k) {
+                const int m = poord[q * Mx + k];
+                const int col = cb + fj_popc(em & ((1u << m) - 1u));
+                const double xv = fj_ld_x(x, col);
+                const double fr = fj_mul(xv, fj_inst_d(c, rate_off, col));
+                fj_pysum_add<SUM_MODE>(ps, fr);
+                if (xv != 0.0) { fm |= 1u << m; if (nfq < 4) fseq |= (unsigned)m << (8 * nfq); ++nfq; }
+            }
+            // set(fluid_machine_list) is built from x.items() order: its iteration order (what machine_select
+            // walks) is fixed until the next arrival
+            c.h_fo[q] = nfq < 5 ? fj_small_set_order(fseq, nfq) : 0u;
+            rs = fj_pysum_result<SUM_MODE>(ps);
+            c.rsum[q] = rs;
+            c.tsum[q] = fj_div(1.0, rs);
+            c.flmask[q] = fm;
         }
-        // set(fluid_machine_list) is built from x.items() order: its iteration order (what machine_select
-        // walks) is fixed until the next arrival
-        c.h_fo[q] = nfq < 5 ? fj_small_set_order(fseq, nfq) : 0u;
-        double rs = fj_pysum_result<SUM_MODE>(ps);
-        c.rsum[q] = rs;
-        c.tsum[q] = fj_div(1.0, rs);
-        c.flmask[q] = fm;
-    }
-    fj_sync();
-    if (lane == 0) {   // fluid slots in canonical column order
-        int nfl = 0;
-        FJ_NOUNROLL
-        for (int q = 0; q < KT && nfl >= 0; ++q) {
-            unsigned fm = c.flmask[q], em = (unsigned)elig[q];
+        int tot;
+        int sl = base + fj_excl_scan_i(nfq, tot);
+        base += tot;
+        if (base > NFx) overflow = 1;
+        if (q < KT && !overflow) {
+            const double fs = (double)c.fstart[q];
             FJ_NOUNROLL
             while (fm) {
-                int m = fj_ffs0(fm); fm &= fm - 1;
-                if (nfl >= c.P->d.NFx) { c.scal[FJ_S_ERROR] |= FJ_E_OVERFLOW; nfl = -1; break; }
-                int col = colbase[q] + fj_popc(em & ((1u << m) - 1u));
-                double fr = fj_mul(x[col], fj_div(1.0, (double)ptime[q * Mx + m]));
-                double arr = fj_div(fj_mul((double)c.fstart[q], fr), c.rsum[q]);
-                c.slot[q * Mx + m] = (uint16_t)nfl;
-                c.ff[nfl] = fr; c.fa[nfl] = arr; c.fu[nfl] = arr;
-                c.mF[m] = fj_add(c.mF[m], fr);
-                ++nfl;
+                const int m = fj_ffs0(fm); fm &= fm - 1;
+                const int col = cb + fj_popc(em & ((1u << m) - 1u));
+                const double fr = fj_mul(fj_ld_x(x, col), fj_inst_d(c, rate_off, col));
+                const double arr = fj_div(fj_mul(fs, fr), rs);
+                c.slot[q * Mx + m] = (uint16_t)sl;
+                c.ff[sl] = fr; c.fa[sl] = arr; c.fu[sl] = arr;
+                ++sl;
             }
         }
-        c.scal[FJ_S_NFL] = nfl < 0 ? 0 : nfl;
+    }
+    fj_sync();
+    // a machine's fluid rate sum: its pairs in ascending operation-type order (canonical column order)
+    if (!overflow) {
+        FJ_NOUNROLL
+        for (int m = lane; m < c.M; m += FJ_NL) {
+            double acc = c.mF[m];
+            FJ_NOUNROLL
+            for (int q = 0; q < KT; ++q)
+                if (c.flmask[q] >> m & 1u) acc = fj_add(acc, c.ff[c.slot[q * Mx + m]]);
+            c.mF[m] = acc;
+        }
+    }
+    if (lane == 0) {
+        if (overflow) c.scal[FJ_S_ERROR] |= FJ_E_OVERFLOW;
+        c.scal[FJ_S_NFL] = overflow ? 0 : base;
     }
     fj_sync();
 }
@@ -2073,20 +2200,25 @@ FJ_FN void fj_env_rollout_body(const FjParams &P, const FjStepArgs &A, int env, 
 }
 
 // ---------------------------------------------------------------- main kernel driver
-// The step kernel's CTA has two roles.
-//   * ENV warps (one environment copy each) run in LOCKSTEP slots, one named barrier per slot:
-//     all of them execute the same few KB of straight-line code at the same time and share its
-//     instruction-cache lines (free-running warps re-fetched the per-step code from L2: "no
-//     instruction" was the top stall, profiles/README.md).  A slot is one env step.
-//   * the LP TEAM (the CTA's last 4 or 8 warps, own named barrier) serves fluid LPs.  An env warp
-//     whose clock reaches an order arrival posts a request on the CTA's board and keeps taking the
-//     slot barriers WITHOUT working until the solution is there; its CTA-mates keep stepping.
-//     Every env warp counts its own steps, the CTA leaves the loop when all have done T.
-//     (Round 1 stopped the whole CTA for every LP: 45 % of all warp stalls were that barrier and
-//     the two 1024-thread argmin reductions were 2.5 k of an iteration's 6.4 k cycles.)
+// The step kernel's CTAs have two roles.
+//   * ENV CTAs: every warp plays one environment copy.  The warps run in LOCKSTEP slots, one named
+//     barrier per slot: all of them execute the same few KB of straight-line code at the same time and
+//     share its instruction-cache lines (the per-step code is ~70 KB against a 32 KB L1.5 instruction
+//     cache; free-running warps re-fetched it from L2: "no instruction" was the top stall,
+//     profiles/README.md).  A slot is one env step.
+//   * LP-SERVER CTAs (the grid's first P.srv_ctas CTAs) play no environment: their warps form groups
+//     that serve fluid LPs.  An env warp whose clock reaches an order arrival writes what the LP is
+//     built from (unprocessed operations per type, which waiting queues are empty) to its request
+//     record in HBM/L2, takes a ticket on the queue and leaves the lockstep group: it free-runs,
+//     polling for the solution, while its CTA-mates keep stepping.  A server group claims the ticket,
+//     solves the LP with B^-1 in its shared memory and flags the solution ready.
+//     (Round 1 stopped the whole CTA for every LP: 45 % of all warp stalls were that barrier.  The
+//     first round-2 version kept a 4-warp LP team inside every env CTA: its warps ran code no other
+//     warp of the SM was running and starved on instruction fetch -- "no instruction" was their top
+//     stall, 23 cycles per instruction, 0.5 M cycles per LP.  On a server SM only LP code runs.)
 #define FJ_BAR_ENV 1
-#define FJ_BAR_TEAM 2
 #define FJ_BAR_ROUND 3
+#define FJ_BAR_SRV0 4                  // server groups: barrier FJ_BAR_SRV0 + group
 #define FJ_SLOT_DETACHED 0x40000000   // P.order flag: the env free-runs (it is expected to meet a fluid LP or a reset in this launch)
 
 FJ_FN void fj_emit_state(const FjCtx &c, const FjStepArgs &A, size_t i, int nobs, int terminal)
@@ -2103,25 +2235,20 @@ FJ_FN void fj_emit_state(const FjCtx &c, const FjStepArgs &A, size_t i, int nobs
     }
 }
 
-// the CTA's LP request board (shared memory)
+// per-CTA shared state of the env role
 struct FjLpBoard {
-    int req[32];      // env a warp wants an LP for, -1 none (written by the owner, cleared by the team)
-    int resp[32];     // 1: the warp's solution is ready (set by the team, cleared by the owner)
-    int meta[64];     // per warp: iterations, return code
-    int cur[2];       // the team leader's pick for this team iteration (double-buffered)
-    int quit;         // set by the env warps after their last round
-    int pad;
+    int meta[64];     // host build: iterations, return code of the in-line LP
     unsigned long long mbar[32];   // one mbarrier per env warp: TMA stage-in of its record's hot prefix
 };
 
-// per-CTA context of the main kernel
+// per-warp view of the main kernel's env role
 struct FjCtaCtx {
-    int warp, nwarps, cta_lp;    // env warp index, env warps of the CTA
-    unsigned char *slab;         // the CTA's LP scratch in HBM/L2: B^-1 and the small arrays
-    unsigned char *team_smem;    // the LP team's shared-memory scratch (P.team_smem bytes), or null
-    double *xbuf;                // [nwarps][NPx] LP solutions, one per env warp
+    int warp, nwarps, cta_lp;    // env warp index, env warps of the CTA, 1: LP servers present
+    int gslot;                   // env-warp slot of the launch: env CTA index * env warps + warp (request / response records)
+    unsigned char *slab;         // host build: LP scratch of the in-line solve
+    double *xbuf;                // this warp's LP solution buffer [NPx] (host build: the one buffer)
     FjLpBoard *board;
-    FjCtaGroup group;            // the LP team (device) / one thread (host build)
+    FjCtaGroup group;            // host build: one thread
 };
 
 #ifdef __CUDACC__
@@ -2194,54 +2321,93 @@ FJ_FN void fj_tma_prefetch_l2(const unsigned char *src, unsigned bytes)   // one
 #define FJ_TR_FLUSH(P, K)
 #endif
 
-// one LP for the env whose context is c2, solved by group g on `slab`; x and (iterations, rc) out
-FJ_FN void fj_lp_for_ctx(const FjParams &P, const FjCtaGroup &g, FjCtx &c2, unsigned char *slab, double *x, int *meta,
-                         unsigned char *smem = nullptr, int smem_bytes = 0)
+// one LP for the env whose context is c2, solved in line by group g on `slab` (the one-lane host build)
+FJ_FN void fj_lp_for_ctx(const FjParams &P, const FjCtaGroup &g, FjCtx &c2, unsigned char *slab, double *x, int *meta)
 {
     FjLp L;
     fj_lp_carve(L, slab, slab + (size_t)P.d.Rx * P.d.Rx * 8, P.d);
-    int iters = 0, rc = -1;
-#ifdef FJ_DEVICE_CODE
-    rc = fj_lp_solve_fast(g, c2, slab, x, &iters, smem, smem_bytes);
-#endif
-    (void)smem; (void)smem_bytes;
-    if (rc < 0) rc = fj_lp_solve(g, c2, L, x, &iters);
+    int iters = 0;
+    const int rc = fj_lp_solve(g, c2, L, x, &iters);
     if (g.rank() == 0) { meta[0] = iters; meta[1] = rc; }
     g.sync();
 }
 
 #ifdef __CUDACC__
-// The LP team's loop: the leader warp scans the request board, the team solves the picked LP
-// into the owner's solution buffer and flags it ready.  Leaves when the env warps set `quit`.
-FJ_FN void fj_lp_team_loop(const FjParams &Pin, const FjCtaCtx &K)
+// ---- the LP queue (HBM/L2).  Tickets are 32-bit and never reset: an entry carries ticket + 1, so a
+// stale entry of an earlier lap (or launch) never matches.
+// env warp (all lanes): write the request, take a ticket
+FJ_FN void fj_lp_post(const FjParams &P, const FjCtx &c, int gslot, int env)
+{
+    const int lane = fj_lane();
+    int *rq = P.lp_req + (size_t)gslot * P.lp_req_stride;
+    const int KT = c.KT, KTx = P.d.KTx;
+    for (int q0 = 0; q0 < KT + 1; q0 += 32) {   // (the mask's last word covers bit KT, which nothing reads)
+        const int q = q0 + lane;
+        if (q < KT) rq[2 + q] = c.fstart[q];
+        const unsigned e = __ballot_sync(0xffffffffu, q < KT && c.qlen[q] == 0);
+        if (lane == 0) rq[2 + KTx + (q0 >> 5)] = (int)e;
+    }
+    if (lane == 0) { rq[0] = env; P.lp_resp[4 * gslot] = 0; }
+    __threadfence();      // the request is in L2 before its ticket
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned t = atomicAdd(P.lpq + 1, 1u);
+        *(volatile unsigned long long *)(P.lpq_ring + (t & (FJ_LPQ_RING - 1))) = ((unsigned long long)(t + 1u) << 32) | (unsigned)gslot;
+    }
+}
+
+// A server group's loop: the leader claims a ticket, the group solves that LP into the requester's
+// solution buffer and flags it ready.  Leaves when every env CTA has finished its launch.
+FJ_FN void fj_lp_server_loop(const FjParams &Pin, const FjCtaGroup &g, unsigned char *gsmem, int env_ctas, int slab_index)
 {
     const FjParams &P = fj_params_bind(Pin);
-    FjLpBoard &bd = *K.board;
-    const FjCtaGroup &g = K.group;
-    volatile int *req = bd.req, *resp = bd.resp, *cur = bd.cur, *quit = &bd.quit;
-    for (int it = 0;; ++it) {
-        if (g.rank() < 32) {
-            const int l = g.rank();
-            const int r = l < K.nwarps ? req[l] : -1;
-            const unsigned b = __ballot_sync(0xffffffffu, r >= 0);
-            int w = -1;
-            if (b) w = __ffs((int)b) - 1;
-            else if (*quit) w = -2;
-            else __nanosleep(64);
-            if (l == 0) cur[it & 1] = w;
+    const FjLpFastSmem S = fj_lpf_state(gsmem, P.d);
+    unsigned char *scratch = gsmem + fj_lpf_state_bytes(P.d);
+    const int scratch_bytes = P.srv_group_smem - (int)fj_lpf_state_bytes(P.d);
+    unsigned char *slab = P.lp + (size_t)slab_index * P.lp_stride;
+    volatile unsigned *q = P.lpq;
+    for (;;) {
+        if (g.rank() == 0) {
+            int got = -1;
+            const unsigned h = q[0], t = q[1];
+            if ((int)(t - h) > 0) { if (atomicCAS(P.lpq, h, h + 1u) == h) got = (int)(h & 0x3fffffffu); }
+            else if (q[2] >= (unsigned)env_ctas) {
+                // every env CTA has finished (all their requests were answered before): leave unless a ticket slipped in between
+                const unsigned h2 = q[0], t2 = q[1];
+                if (h2 == t2) got = -2;
+            } else __nanosleep(200);
+            S.ctl()[2] = got;
+            if (got >= 0) {
+                // wait for the entry of ticket h (its poster writes it right after taking the ticket)
+                const volatile unsigned long long *e = P.lpq_ring + (h & (FJ_LPQ_RING - 1));
+                unsigned long long v;
+                do { v = *e; } while ((unsigned)(v >> 32) != h + 1u);
+                S.ctl()[3] = (int)(unsigned)v;     // the requester's env-warp slot
+                __threadfence();
+            }
         }
         g.sync();
-        const int w = cur[it & 1];
-        if (w == -2) break;
-        if (w < 0) continue;
-        __threadfence_block();
-        fj_lp_for_ctx(P, g, fj_sC[w], K.slab, K.xbuf + (size_t)w * P.d.NPx, bd.meta + 2 * w, K.team_smem, P.team_smem);
+        const int got = S.ctl()[2];
+        const int gslot = S.ctl()[3];
+        g.sync();               // everyone has read the two words before the leader's next round rewrites them
+        if (got == -2) break;
+        if (got < 0) continue;
+        const int *rq = P.lp_req + (size_t)gslot * P.lp_req_stride;
+        FjLpIn in;
+        const int env = __ldcg(rq);
+        in.I = P.inst + (size_t)P.env_inst[env] * P.io.stride;
+        in.M = __ldg(in.I + P.io.hdr); in.KT = __ldg(in.I + P.io.hdr + 2); in.NP = __ldg(in.I + P.io.hdr + 7);
+        in.fstart = rq + 2; in.qlen = nullptr; in.empty = (const uint32_t *)(rq + 2 + P.d.KTx);
+        double *x = P.cta_x + (size_t)gslot * P.d.NPx;
+        int iters = 0;
+        int rc = fj_lp_solve_fast(g, P, in, S, slab, x, &iters, scratch, scratch_bytes);
         if (g.rank() == 0) {
-            __threadfence_block();
-            req[w] = -1;
-            __threadfence_block();
-            resp[w] = 1;
+            if (rc < 0) { rc = 4; iters = 0; }   // beyond the fast path's row limit: reported as an LP error of the env
+            P.lp_resp[4 * gslot + 1] = iters; P.lp_resp[4 * gslot + 2] = rc;
         }
+        __threadfence();        // every thread's part of x is in L2 ...
+        g.sync();
+        if (g.rank() == 0) *(volatile int *)(P.lp_resp + 4 * gslot) = 1;   // ... before the flag
     }
 }
 #endif
@@ -2279,11 +2445,8 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
     size_t i = (size_t)env;             // row of this env in the [T][B] inputs / outputs of its step tt
     int tt = 0;
     int st = active && A.T > 0 ? FJ_ST_FRONT : FJ_ST_IDLE;
-#ifdef FJ_DEVICE_CODE
     // lock_threads: threads of this round's lockstep group (this warp is one of them), 0: this warp
     // free-runs (no slot barrier; it polls for its LP solutions)
-    volatile int *req = K.board->req, *resp = K.board->resp;
-#endif
     for (;;) {
         if (st != FJ_ST_IDLE) {
             int kind = 0;       // 0 nothing to emit, 1 dispatched (clock, observation), 2 nothing dispatchable (emit unchanged)
@@ -2291,12 +2454,11 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
             FJ_TR_MARK();
 #ifdef FJ_DEVICE_CODE
             if (st == FJ_ST_WAIT) {
-                int ready = lane == 0 ? resp[K.warp] : 0;
+                int ready = lane == 0 ? *(volatile int *)(P.lp_resp + 4 * K.gslot) : 0;
                 ready = fj_bcast_i(ready, 0);
                 if (!ready) { __nanosleep(lock_threads ? 200 : 100); FJ_TR_ACC(2); goto vote; }
-                __threadfence_block();
-                fj_arrival_finish<SUM_MODE>(c, K.xbuf + (size_t)K.warp * P.d.NPx, K.board->meta[2 * K.warp], K.board->meta[2 * K.warp + 1]);
-                if (lane == 0) resp[K.warp] = 0;
+                __threadfence();   // the solution was written by another SM: fj_arrival_finish reads it through L2
+                fj_arrival_finish<SUM_MODE>(c, K.xbuf, __ldcg(P.lp_resp + 4 * K.gslot + 1), __ldcg(P.lp_resp + 4 * K.gslot + 2));
                 resume = 1; kind = 1; st = FJ_ST_FRONT;
                 FJ_TR_ACC(2);
             } else
@@ -2341,9 +2503,7 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
                     }
 #ifdef FJ_DEVICE_CODE
                     FJ_TR_COUNT(4);
-                    __threadfence_block();
-                    fj_sync();
-                    if (lane == 0) req[K.warp] = env;
+                    fj_lp_post(P, c, K.gslot, env);
                     st = FJ_ST_WAIT; kind = 0;
                     break;
 #else
@@ -2439,7 +2599,8 @@ FJ_FN void fj_env_reset_finish(const FjParams &Pin, int env, unsigned char *lp, 
 }
 
 // one parked LP, solved by a whole CTA (device) / one thread (host build)
-FJ_FN void fj_lp_service(const FjParams &Pin, const FjCtaGroup &g, const int *list, int idx, unsigned char *binv, unsigned char *small_, unsigned char *fast_slab = nullptr)
+FJ_FN void fj_lp_service(const FjParams &Pin, const FjCtaGroup &g, const int *list, int idx, unsigned char *binv, unsigned char *small_, unsigned char *fast_slab = nullptr,
+                         unsigned char *fast_smem = nullptr, int fast_smem_bytes = 0)
 {
     const FjParams &P = fj_params_bind(Pin);
     const int env = list[idx];
@@ -2449,8 +2610,15 @@ FJ_FN void fj_lp_service(const FjParams &Pin, const FjCtaGroup &g, const int *li
     int iters = 0;
     int rc = -1;
 #ifdef FJ_DEVICE_CODE
-    if (fast_slab) rc = fj_lp_solve_fast(g, c, fast_slab, P.lp_x + (size_t)idx * P.d.NPx, &iters);
+    if (fast_slab && fast_smem && (size_t)fast_smem_bytes >= fj_lpf_state_bytes(P.d)) {
+        const FjLpFastSmem S = fj_lpf_state(fast_smem, P.d);
+        FjLpIn in;
+        fj_lpin_from_ctx(in, c);
+        const int sb = (int)fj_lpf_state_bytes(P.d);
+        rc = fj_lp_solve_fast(g, P, in, S, fast_slab, P.lp_x + (size_t)idx * P.d.NPx, &iters, fast_smem + sb, fast_smem_bytes - sb);
+    }
 #endif
+    (void)fast_slab; (void)fast_smem; (void)fast_smem_bytes;
     if (rc < 0) rc = fj_lp_solve(g, c, L, P.lp_x + (size_t)idx * P.d.NPx, &iters);
     if (g.rank() == 0) { P.lp_meta[2 * idx] = iters; P.lp_meta[2 * idx + 1] = rc; }
     g.sync();

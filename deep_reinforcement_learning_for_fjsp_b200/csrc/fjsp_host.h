@@ -155,6 +155,9 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
     io.bdptr = o; o += d.Mx + 1;
     io.bds = o; o += d.NBDx;
     io.bde = o; o += d.NBDx;
+    io.colqm = o; o += d.NPx;
+    o = fj_align(o, 2);
+    io.colrate = o; o += 2 * d.NPx;
     io.stride = fj_align(o, 4);
     t.io = io;
     // env offsets (bytes)
@@ -276,7 +279,17 @@ static inline bool fj_build_tables(const int32_t *blobs, const int64_t *offsets,
         }
         {
             int cb = 0;
-            for (int q = 0; q < v.KT; ++q) { w[io.colbase + q] = cb; cb += v.nelig[q]; }
+            for (int q = 0; q < v.KT; ++q) {
+                w[io.colbase + q] = cb;
+                // LP columns of the type: machine ascending; 1.0 / p is the IEEE quotient the kernels used to divide for
+                for (int m = 0; m < v.M; ++m) if ((unsigned)w[io.elig + q] >> m & 1u) {
+                    if (cb >= v.NP) { err = "instance blob: NP != sum(nelig)"; return false; }
+                    w[io.colqm + cb] = (q << 8) | m;
+                    const double rate = 1.0 / (double)v.ptime[q * v.M + m];
+                    memcpy(&w[io.colrate + 2 * cb], &rate, 8);
+                    ++cb;
+                }
+            }
             if (cb != v.NP) { err = "instance blob: NP != sum(nelig)"; return false; }
         }
         for (int m = 0; m < v.M; ++m) {

@@ -51,6 +51,8 @@ struct FjInstOff {
     int bde;       // [NBDx]
     int mnkt;      // [Mx] operation types a machine can process (len(kind_task_tuple))
     int colbase;   // [KTx] first LP column of an operation type (prefix of popcount(elig))
+    int colqm;     // [NPx] operation type << 8 | machine of every LP column (canonical order: type ascending, machine ascending)
+    int colrate;   // [2*NPx] double 1.0 / processing time of every LP column (even word offset: 8-byte aligned)
     int hotw;      // words of the record's hot head (everything a step reads except the per-pair tables)
     int stride;    // words per instance
 };
@@ -139,10 +141,17 @@ struct FjParams {
     const int *plan_meta;       // [n_instances][2]
     const int *plan_ok;         // [n_instances] 1 once cached (null before the first reset)
     int stage_stride;           // bytes of one warp's shared-memory slab (env hot prefix + instance hot words)
-    int env_warps;              // env warps per CTA of the main kernel (= warp slots of a virtual CTA); the CTA's other warps are its LP team
-    int cta_lp;                 // 1: the LP team of an env's CTA solves its order-arrival LPs; 0: park for the LP / resume kernels; 2: free-running warps
-    int team_smem;              // bytes of shared-memory LP scratch of the CTA's LP team (after the env warps' slabs)
-    double *cta_x;              // [step grid][env_warps][NPx] LP solutions of the in-CTA service, one buffer per env warp
+    int env_warps;              // env warps per CTA of the main kernel (= warp slots of a virtual CTA)
+    int cta_lp;                 // 1: the LP-server CTAs of the main kernel solve the order-arrival LPs; 0: park for the LP / resume kernels; 2: free-running warps
+    // LP service inside the main kernel (cta_lp == 1): its first `srv_ctas` CTAs run no environments; their warps
+    // form `srv_groups` groups of `srv_group_warps` warps that serve the requests the env warps post on a queue in HBM/L2
+    int srv_ctas, srv_groups, srv_group_warps, srv_group_smem;   // srv_group_smem: bytes of dynamic shared memory per group
+    unsigned int *lpq;          // [0] head (claimed tickets), [1] tail (issued tickets): never reset; [2] env CTAs that have finished this launch (zeroed per launch)
+    unsigned long long *lpq_ring;   // [FJ_LPQ_RING] (ticket + 1) << 32 | env-warp slot
+    int *lp_req;                // [env CTAs x env_warps][lp_req_stride]: env, then fstart[KTx], then the empty-queue mask [KTW + 1]
+    int lp_req_stride;
+    int *lp_resp;               // [env CTAs x env_warps][4]: ready flag, iterations, return code
+    double *cta_x;              // [env CTAs][env_warps][NPx] LP solutions, one buffer per env warp
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory
     int B, variant, sum_mode, nobs;
     long long *trace;           // FJ_TRACE builds: [grid][33][8] per-warp cycle counters + one row of LP phase cycles per CTA (null otherwise)
@@ -163,4 +172,5 @@ struct FjStepArgs {
     int *park_env;
 };
 
+#define FJ_LPQ_RING 8192   // power of two, larger than the env warps of a launch (each has at most one request outstanding)
 #define FJ_ROUNDS 2   // resume rounds per launch; a third LP of one env inside a launch is solved in line

@@ -161,7 +161,7 @@ class FJSPVecEnv:
         a = np.zeros(12, np.int64)
         _lib.check(self._L.fjsp_vec_query(self._h, a.ctypes.data))
         keys = ["n_envs", "state_size", "env_record_bytes", "instance_record_bytes", "grid", "block",
-                "lp_scratch_bytes_per_slab", "launches", "env_warps", "team_warps", "n_slots", "step_smem_bytes"]
+                "lp_scratch_bytes_per_slab", "launches", "env_warps", "lp_server_ctas", "n_slots", "step_smem_bytes"]
         return dict(zip(keys, (int(x) for x in a)))
 
 

@@ -71,7 +71,7 @@ static void run_step(HostVec *h, const FjStepArgs &A)
     FjCtaCtx K;
     static FjLpBoard board;
     K.warp = 0; K.nwarps = 1; K.cta_lp = h->P.cta_lp;
-    K.slab = h->lp.data(); K.team_smem = nullptr;
+    K.slab = h->lp.data(); K.gslot = 0;
     K.xbuf = (double *)(K.slab + (size_t)h->tb.d.Rx * h->tb.d.Rx * 8 + (fj_lp_small_bytes(h->tb.d) + 7) / 8 * 8);
     K.board = &board; K.group.red = nullptr; K.group.flip = 0; K.group.whole_cta();
     for (int e = 0; e < h->P.B; ++e) fj_cta_rollout<V, SM>(h->P, B_, K, e, 1, stage);               // main kernel
@@ -125,7 +125,7 @@ int fjsp_hostsim_create(const int32_t *blobs, const int64_t *offsets, int n_inst
     P.lp_slots = ov ? atoi(ov) : n_envs;
     h->lp_x.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * h->tb.d.NPx, 0.0);
     h->lp_meta.assign((size_t)(P.lp_slots > 0 ? P.lp_slots : 1) * 2, 0);
-    P.stage = 0; P.env_warps = 1; P.cta_x = nullptr; P.team_smem = 0; P.stage_stride = h->tb.eo.hot;
+    P.stage = 0; P.env_warps = 1; P.cta_x = nullptr; P.stage_stride = h->tb.eo.hot;
     P.cta_lp = getenv("FJSP_HOSTSIM_NO_CTA_LP") ? 0 : 1;
     P.plan_x = nullptr; P.plan_meta = nullptr; P.plan_ok = nullptr;
     h->pend_count = 0;

@@ -43,18 +43,21 @@ def main():
     for i in range(a.burnin // T):
         vec.rollout(sets[i % 4][0], sets[(i + 1) % 4][1], reward_policy=1, out=out, state_dtype=torch.float32)
     q = vec.query()
-    grid = q["grid"]
+    srv = q["lp_server_ctas"]
+    grid = q["grid"] - srv          # env CTAs (the grid's first CTAs are the LP servers)
     inf = vec.info()
     ops = np.array([x.total_operations for x in insts]); rub = np.array([x.machine_count + 2 * sum(x.ntask) - x.kind_count for x in insts])
     likely = (inf["done"] != 0) | (inf["next_order"] < 3) | (ops - inf["step_count"] <= T - 8)
     print("predicted LP envs: %d of %d (done %d, young %d, ending %d); heavy %d medium %d light %d" % (
         likely.sum(), B, (inf["done"] != 0).sum(), (inf["next_order"] < 3).sum(), (ops - inf["step_count"] <= T - 8).sum(),
         (likely & (rub >= 85)).sum(), (likely & (rub >= 55) & (rub < 85)).sum(), (likely & (rub < 55)).sum()))
-    tr = np.zeros((grid, 33, 8), dtype=np.int64)
+    tr_all = np.zeros((grid + srv, 33, 8), dtype=np.int64)
+    tr = tr_all[srv:]
     L = _lib.load()
-    _lib.check(L.fjsp_vec_trace(vec._h, tr.ctypes.data, 1))
+    _lib.check(L.fjsp_vec_trace(vec._h, tr_all.ctypes.data, 1))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     acc = np.zeros_like(tr)
+    acc_lp = np.zeros(8, dtype=np.int64)
     ms = 0.0
     for i in range(a.launches):
         ev0.record()
@@ -63,7 +66,7 @@ def main():
         torch.cuda.synchronize()
         ms_i = ev0.elapsed_time(ev1)
         ms += ms_i / a.launches
-        _lib.check(L.fjsp_vec_trace(vec._h, tr.ctypes.data, 1))
+        _lib.check(L.fjsp_vec_trace(vec._h, tr_all.ctypes.data, 1))
         nwi = q["env_warps"]
         ct = tr[:, :nwi, 0].max(1)
         nl = tr[:, :nwi, 5].sum(1)
@@ -81,6 +84,7 @@ def main():
             print("   single-env CTAs: %d, total mean %.2f M max %.2f M, LP mean %.2f M, LPs mean %.1f" % (
                 len(ones), ct[ones].mean() / 1e6, ct[ones].max() / 1e6, tr[ones, :nwi, 3].max(1).mean() / 1e6, nl[ones].mean()))
         acc += tr
+        acc_lp += tr_all[:, 32, :].sum(0)
         if i == 0:
             ns = L.fjsp_vec_slots(vec._h, None, 0)
             sl = np.zeros(ns, dtype=np.int32)
@@ -93,9 +97,9 @@ def main():
     tr = tr.astype(np.float64) / a.launches
     nw = q["env_warps"]
     if True:
-        lpt = tr[:, 32, :].sum(0) * a.launches
+        lpt = acc_lp.astype(np.float64)
         solves = tr[:, :nw, 5].sum() * a.launches
-        names = ["setup", "pricing", "argmin-in", "w+ratio", "argmin-out", "xB/pivot-row", "rank-1 update"]
+        names = ["setup", "pricing+argmin", "wait A (helpers: previous rank-1)", "w+ratio", "argmin-out", "xB/pivot-row/y", "barrier B"]
         print("LP phases (cycles per iteration): " + ", ".join("%s %.0f" % (n, lpt[k] / max(lpt[7], 1)) for k, n in enumerate(names) if k)
               + "; setup per LP %.0f; iterations per LP %.1f; LPs %d" % (lpt[0] / max(solves, 1), lpt[7] / max(solves, 1), solves))
     tr = tr[:, :nw]
