@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the T=1 / T=128 rollout-length lines")
     ap.add_argument("--no-policy", dest="policy", action="store_false", help="skip the policy-in-the-loop lines")
     ap.add_argument("--parity-envs", type=int, default=16, help="environments replayed on the CPU oracle after timing")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic: do not evict L2 between timed steps (the line says so)")
     a = ap.parse_args()
     cfg = dict(CONFIGS[a.config])
     if a.envs is not None:
@@ -359,7 +360,8 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     t_wall0 = time.perf_counter()
     for i in range(K):
-        flush.fill_(i & 0xff)                       # evict L2 between timed steps (not timed)
+        if not args.no_flush:
+            flush.fill_(i & 0xff)                   # evict L2 between timed steps (not timed)
         ev[i][0].record(stream)
         for j in range(LPS):
             launch((W + i * LPS + j) % NP_, (W + i * LPS + j) % NP_)
@@ -505,7 +507,7 @@ def main():
                 "config": {"workload": cfg["workload"], "name": args.config, "envs_per_gpu": B, "env_steps_per_step": T * LPS,
                            "launches_per_step": LPS, "machines": cfg.get("machines"), "orders": cfg.get("orders"), "variant": variant,
                            "distinct_instances_per_gpu": len(blobs),
-                           "l2": "flushed between timed steps (256 MiB fill)",
+                           "l2": "NOT flushed (diagnostic run)" if args.no_flush else "flushed between timed steps (256 MiB fill)",
                            "kernels_per_step": "flag + pack kernels (LP-aware env-to-warp map), step kernel (env CTAs of lockstep warps + LP-server CTAs)",
                            "parallelism": f"shard{world}", "env_record_bytes": q["env_record_bytes"], "grid": q["grid"],
                            "block": q["block"], "env_warps": q["env_warps"], "lp_server_ctas": q["lp_server_ctas"],
@@ -530,7 +532,8 @@ def main():
                 "episode_stats_all_ranks": {"copies": int(stats.shape[0]), "mean_completion_time": float(stats[:, 0].mean()),
                                             "mean_delay_time_sum": float(stats[:, 1].mean()),
                                             "gathered_with": "sharding.gather_episode_stats (" + (dist.get_backend() if world > 1 else "single rank") + ")"},
-                "step_ms_min_max": [min(per_step_ms), max(per_step_ms)], "large_batch": large,
+                "step_ms_min_max": [min(per_step_ms), max(per_step_ms)], "step_ms_all": [round(x, 4) for x in per_step_ms],
+                "large_batch": large,
                 "rollout_sweep": sweep, "policy_in_loop": pol}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_port_throughput(blobs[:64], variant, args.cpu_seconds, T, args.seed)

@@ -46,9 +46,7 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
         // server that is not resident): groups of warps serve the LP queue until every env CTA is done
         const int gw = P.srv_group_warps, gid = warp / gw;
         if (gid >= P.srv_groups) return;
-        FjCtaGroup g;
-        g.red = nullptr; g.flip = 0; g.base = gid * gw * 32; g.nthr = gw * 32; g.bar = FJ_BAR_SRV0 + gid;
-        fj_lp_server_loop(P, g, stage_smem + (size_t)gid * P.srv_group_smem, (int)gridDim.x - nsrv, (int)blockIdx.x * P.srv_groups + gid);
+        fj_lp_server_loop(gid, gw, stage_smem + (size_t)gid * P.srv_group_smem, (int)gridDim.x - nsrv, (int)blockIdx.x * P.srv_groups + gid);
         return;
     }
     const int ecta = (int)blockIdx.x - nsrv, nectas = (int)gridDim.x - nsrv;
@@ -290,7 +288,7 @@ struct fjsp_vec {
     cudaStream_t stream, copy_stream;
     cudaEvent_t chunk_done, dev_done;   // dev_done: last work queued through the device entry points (caller's stream)
     int dev_pending;
-    int stage_T;
+    int stage_T, stage_out_T;
     int32_t *d_actions, *d_done, *d_rec;
     uint32_t *d_rnd;
     double *d_state64, *d_reward;
@@ -391,8 +389,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         // `env_warps` warps (one environment copy each, lockstep slots); a batch larger than
         // env CTAs x env_warps is played in rounds.
         const int nsm = prop.multiProcessorCount, wmax = FJ_STEP_THREADS / 32;
-        // LP load per env step (group-cycles): an episode meets S - 1 order-arrival LPs in `ops` steps; an LP
-        // takes ~0.7 R iterations of ~(2500 + R^2 / 16) cycles on a server group (profiles/README.md r02)
+        // LP load per env step (group-cycles): an episode meets S - 1 order-arrival LPs in `ops` steps; model of an
+        // LP: ~0.7 R iterations of ~(2500 + R^2 / 16) cycles
         double load = 0.0; int any_arrival = 0;
         for (int i = 0; i < n_instances; ++i) {
             const int32_t *b = blobs + blob_offsets[i];
@@ -408,9 +406,11 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         if (lp_mode == 1 && !any_arrival) lp_mode = 0;   // no order ever arrives after reset(): nothing to serve
         int srv = 0;
         if (lp_mode == 1) {
-            // an env CTA retires one env step per ~2200 SM cycles; a server CTA runs 4 groups; 2.5x headroom for bursts
-            const double per_env_cta = load / 2200.0 / 4.0 * 2.5;
-            srv = (int)(nsm * per_env_cta / (1.0 + per_env_cta) + 0.999);
+            // Measured (profiles/README.md r02): an LP costs ~2.5 x that model on a server group; an env CTA retires
+            // one env step per ~2000 cycles; the queue stays short while the groups are busy < 55 % of the time;
+            // two groups per server CTA.  10 machines / 3 orders (Instance_generate.py profile): 12-13 of 148 SMs.
+            const double groups_per_env_cta = load * 2.5 / 2000.0 / 0.55;
+            srv = (int)(nsm * groups_per_env_cta / (2.0 + groups_per_env_cta) + 0.5);
             if (srv < 2) srv = 2;
             if (srv > nsm / 3) srv = nsm / 3;
             if (n_envs <= 32) srv = 1;
@@ -436,10 +436,12 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         v->n_slots = (int)(rounds * v->env_ctas * wpb);
         if (srv) {
             // server groups: 4 per CTA when the CTA has the warps for it (a driver warp + helpers each)
-            srv_groups = wpb >= 16 ? 4 : wpb >= 8 ? 2 : 1;
+            // server groups: two per CTA (up to 16 warps and ~100 KB of shared memory each: B^-1 of a 110-row LP
+            // fits; four of the group's warps drive the iteration, the others apply the rank-1 updates)
+            srv_groups = wpb >= 12 ? 2 : 1;
             if (getenv("FJSP_LP_GROUPS")) srv_groups = atoi(getenv("FJSP_LP_GROUPS"));
             if (srv_groups < 1) srv_groups = 1;
-            if (srv_groups > 12) srv_groups = 12;
+            if (srv_groups > 6) srv_groups = 6;
             if (srv_groups > wpb) srv_groups = wpb;
             srv_group_warps = wpb / srv_groups;
         }
@@ -600,7 +602,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaEventCreateWithFlags(&v->chunk_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&v->dev_done, cudaEventDisableTiming));
     v->dev_pending = 0;
-    v->stage_T = 0;
+    v->stage_T = 0; v->stage_out_T = 0;
     v->d_actions = v->d_done = v->d_rec = nullptr; v->d_rnd = nullptr;
     v->d_state64 = v->d_reward = nullptr; v->d_state32 = nullptr;
     *out = v;
@@ -622,7 +624,7 @@ static void free_stage(fjsp_vec *v)
     cudaFree(v->d_state64); cudaFree(v->d_state32); cudaFree(v->d_reward);
     v->d_actions = v->d_done = v->d_rec = nullptr; v->d_rnd = nullptr;
     v->d_state64 = v->d_reward = nullptr; v->d_state32 = nullptr;
-    v->stage_T = 0;
+    v->stage_T = 0; v->stage_out_T = 0;
 }
 
 int fjsp_vec_destroy(fjsp_vec *v)
@@ -724,20 +726,40 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     return 0;
 }
 
-static int ensure_stage(fjsp_vec *v, int T)
+// staging for the host-buffer entry points: inputs always (H2D copies), outputs only for host buffers
+// the device cannot write directly
+static int ensure_stage(fjsp_vec *v, int T, bool outputs)
 {
-    if (T <= v->stage_T) return 0;
-    free_stage(v);
     const size_t n = (size_t)T * v->B;
-    CK(cudaMalloc(&v->d_actions, n * 2 * 4));
-    CK(cudaMalloc(&v->d_rnd, n * 2 * 4));
-    CK(cudaMalloc(&v->d_done, n * 4));
-    CK(cudaMalloc(&v->d_rec, n * 8 * 4));
-    CK(cudaMalloc(&v->d_state64, n * v->nstate * 8));
-    CK(cudaMalloc(&v->d_state32, n * v->nstate * 4));
-    CK(cudaMalloc(&v->d_reward, n * 8));
-    v->stage_T = T;
+    if (T > v->stage_T) {
+        cudaFree(v->d_actions); cudaFree(v->d_rnd); v->d_actions = nullptr; v->d_rnd = nullptr;
+        v->stage_T = 0;
+        CK(cudaMalloc(&v->d_actions, n * 2 * 4));
+        CK(cudaMalloc(&v->d_rnd, n * 2 * 4));
+        v->stage_T = T;
+    }
+    if (outputs && T > v->stage_out_T) {
+        cudaFree(v->d_done); cudaFree(v->d_rec); cudaFree(v->d_state64); cudaFree(v->d_state32); cudaFree(v->d_reward);
+        v->d_done = v->d_rec = nullptr; v->d_state64 = v->d_reward = nullptr; v->d_state32 = nullptr;
+        v->stage_out_T = 0;
+        CK(cudaMalloc(&v->d_done, n * 4));
+        CK(cudaMalloc(&v->d_rec, n * 8 * 4));
+        CK(cudaMalloc(&v->d_state64, n * v->nstate * 8));
+        CK(cudaMalloc(&v->d_state32, n * v->nstate * 4));
+        CK(cudaMalloc(&v->d_reward, n * 8));
+        v->stage_out_T = T;
+    }
     return 0;
+}
+
+// device address of a host buffer the kernel can write directly (page-locked and mapped: cudaHostAlloc /
+// cudaHostRegister memory under unified addressing), or null
+static void *mapped_host(void *h)
+{
+    if (!h) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (a.type == cudaMemoryTypeHost && a.devicePointer) ? a.devicePointer : nullptr;
 }
 
 int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint32_t *h_rnd,
@@ -746,37 +768,50 @@ int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint3
 {
     if (!v || !h_actions || T < 1) { g_err = "fjsp_vec_step_host: null handle/actions or T < 1"; return -1; }
     CK(cudaSetDevice(v->device));
-    int rc = ensure_stage(v, T);
-    if (rc) return rc;
     const size_t n = (size_t)T * v->B;
     cudaStream_t st = v->stream, cp = v->copy_stream;
+    // Page-locked output buffers are written by the step kernel itself while it runs (stores over the link,
+    // no staging, no device-to-host copy after the launch: the memory pipes are idle anyway); pageable ones go
+    // through device staging and copies.  FJSP_ZEROCOPY=0 forces staging, =state maps only the observation.
+    const char *zc = getenv("FJSP_ZEROCOPY");
+    const int zmode = !zc ? 2 : (zc[0] == '0' ? 0 : (zc[0] == 's' ? 1 : 2));
+    double *m_state64 = zmode ? (double *)mapped_host(h_state64) : nullptr, *m_reward = zmode == 2 ? (double *)mapped_host(h_reward) : nullptr;
+    float *m_state32 = zmode ? (float *)mapped_host(h_state32) : nullptr;
+    int32_t *m_done = zmode == 2 ? (int32_t *)mapped_host(h_done) : nullptr, *m_rec = zmode == 2 ? (int32_t *)mapped_host(h_rec) : nullptr;
+    const bool staged = (h_state64 && !m_state64) || (h_state32 && !m_state32) || (h_reward && !m_reward) || (h_done && !m_done) || (h_rec && !m_rec);
+    int rc = ensure_stage(v, T, staged);
+    if (rc) return rc;
     wait_device_work(v);
     CK(cudaMemcpyAsync(v->d_actions, h_actions, n * 2 * 4, cudaMemcpyHostToDevice, st));
     if (h_rnd) CK(cudaMemcpyAsync(v->d_rnd, h_rnd, n * 2 * 4, cudaMemcpyHostToDevice, st));
-    // long rollouts are cut into chunks of 32 steps: the device-to-host copy of one chunk's
-    // outputs (copy stream) overlaps the kernels of the next chunk (compute stream).  Shorter
+    // long rollouts are cut into chunks of 32 steps when outputs are staged: the device-to-host copy of one
+    // chunk's outputs (copy stream) overlaps the kernels of the next chunk (compute stream).  Shorter
     // chunks measured slower (per-launch staging and launch overheads), so T < 64 is one chunk.
-    const int nchunk = T >= 64 ? T / 32 : 1;
+    const int nchunk = staged && T >= 64 ? T / 32 : 1;
     const size_t B = (size_t)v->B, ns = (size_t)v->nstate;
     for (int c = 0; c < nchunk; ++c) {
         const int t0 = (int)((long long)T * c / nchunk), t1 = (int)((long long)T * (c + 1) / nchunk);
         if (t1 == t0) continue;
         const size_t o = (size_t)t0 * B, m = (size_t)(t1 - t0) * B;
         rc = fjsp_vec_step(v, st, t1 - t0, v->d_actions + o * 2, h_rnd ? v->d_rnd + o * 2 : nullptr, reward_policy,
-                           completion, tardiness, energy, autoreset, h_state64 ? v->d_state64 + o * ns : nullptr,
-                           h_state32 ? v->d_state32 + o * ns : nullptr, h_reward ? v->d_reward + o : nullptr,
-                           h_done ? v->d_done + o : nullptr, h_rec ? v->d_rec + o * 8 : nullptr);
+                           completion, tardiness, energy, autoreset,
+                           h_state64 ? (m_state64 ? m_state64 : v->d_state64) + o * ns : nullptr,
+                           h_state32 ? (m_state32 ? m_state32 : v->d_state32) + o * ns : nullptr,
+                           h_reward ? (m_reward ? m_reward : v->d_reward) + o : nullptr,
+                           h_done ? (m_done ? m_done : v->d_done) + o : nullptr,
+                           h_rec ? (m_rec ? m_rec : v->d_rec) + o * 8 : nullptr);
         if (rc) return rc;
+        if (!staged) continue;
         CK(cudaEventRecord(v->chunk_done, st));
         CK(cudaStreamWaitEvent(cp, v->chunk_done, 0));
-        if (h_state64) CK(cudaMemcpyAsync(h_state64 + o * ns, v->d_state64 + o * ns, m * ns * 8, cudaMemcpyDeviceToHost, cp));
-        if (h_state32) CK(cudaMemcpyAsync(h_state32 + o * ns, v->d_state32 + o * ns, m * ns * 4, cudaMemcpyDeviceToHost, cp));
-        if (h_reward) CK(cudaMemcpyAsync(h_reward + o, v->d_reward + o, m * 8, cudaMemcpyDeviceToHost, cp));
-        if (h_done) CK(cudaMemcpyAsync(h_done + o, v->d_done + o, m * 4, cudaMemcpyDeviceToHost, cp));
-        if (h_rec) CK(cudaMemcpyAsync(h_rec + o * 8, v->d_rec + o * 8, m * 8 * 4, cudaMemcpyDeviceToHost, cp));
+        if (h_state64 && !m_state64) CK(cudaMemcpyAsync(h_state64 + o * ns, v->d_state64 + o * ns, m * ns * 8, cudaMemcpyDeviceToHost, cp));
+        if (h_state32 && !m_state32) CK(cudaMemcpyAsync(h_state32 + o * ns, v->d_state32 + o * ns, m * ns * 4, cudaMemcpyDeviceToHost, cp));
+        if (h_reward && !m_reward) CK(cudaMemcpyAsync(h_reward + o, v->d_reward + o, m * 8, cudaMemcpyDeviceToHost, cp));
+        if (h_done && !m_done) CK(cudaMemcpyAsync(h_done + o, v->d_done + o, m * 4, cudaMemcpyDeviceToHost, cp));
+        if (h_rec && !m_rec) CK(cudaMemcpyAsync(h_rec + o * 8, v->d_rec + o * 8, m * 8 * 4, cudaMemcpyDeviceToHost, cp));
     }
     CK(cudaStreamSynchronize(st));
-    CK(cudaStreamSynchronize(cp));
+    if (staged) CK(cudaStreamSynchronize(cp));
     return 0;
 }
 
@@ -784,7 +819,7 @@ int fjsp_vec_reset_host(fjsp_vec *v, double *h_state64, float *h_state32)
 {
     if (!v) { g_err = "fjsp_vec_reset_host: null handle"; return -1; }
     CK(cudaSetDevice(v->device));
-    int rc = ensure_stage(v, 1);
+    int rc = ensure_stage(v, 1, true);
     if (rc) return rc;
     cudaStream_t st = v->stream;
     wait_device_work(v);

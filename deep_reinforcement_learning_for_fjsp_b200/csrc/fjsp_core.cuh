@@ -394,7 +394,8 @@ struct FjCtaGroup {
     int4 *red;    // shared scratch: two buffers of one entry per warp (<= 32 warps)
     int flip;     // which buffer the next reduction uses (same value in every thread)
     int base, nthr, bar;   // first thread, threads (multiple of 32), hardware barrier id
-    FJ_MFN void whole_cta() { base = 0; nthr = (int)blockDim.x; bar = 0; }
+    int dbar;              // a second barrier id of the group (the LP fast path's driver warps)
+    FJ_MFN void whole_cta() { base = 0; nthr = (int)blockDim.x; bar = 0; dbar = 1; }
     FJ_MFN int rank() const { return (int)threadIdx.x - base; }
     FJ_MFN int size() const { return nthr; }
     FJ_MFN int lane() const { return threadIdx.x & 31; }
@@ -432,8 +433,8 @@ struct FjCtaGroup {
 #else
 struct int4 { int x, y, z, w; };
 struct FjCtaGroup {   // host simulation: one thread
-    int4 *red; int flip; int base, nthr, bar;
-    FJ_MFN void whole_cta() { base = 0; nthr = 1; bar = 0; }
+    int4 *red; int flip; int base, nthr, bar, dbar;
+    FJ_MFN void whole_cta() { base = 0; nthr = 1; bar = 0; dbar = 1; }
     FJ_MFN int rank() const { return 0; }
     FJ_MFN int size() const { return 1; }
     FJ_MFN int lane() const { return 0; }
@@ -717,13 +718,13 @@ struct FjLpFastSmem {
     FJ_MFN double *y() const { return base + 2 * n; }
     FJ_MFN double *xb() const { return base + 3 * n; }
     FJ_MFN int *bvar() const { return (int *)(base + 4 * n); }
-    FJ_MFN int *ctl() const { return bvar() + n; }                 // [0] nprec [1] pivot row for the helpers (-1: leave) [2] ticket [3] requester
-    FJ_MFN short *prec() const { return (short *)(ctl() + 4); }
+    FJ_MFN int *ctl() const { return bvar() + n; }                 // [0] nprec [1] pivot row for the helpers (-1: leave) [2] ticket [3] requester [4..16) argmin partials of the driver warps
+    FJ_MFN short *prec() const { return (short *)(ctl() + 16); }
 };
 FJ_FN size_t fj_lpf_state_bytes(const FjDims &d)
 {
     const size_t n = (size_t)d.Rx + 2;
-    return (4 * n * 8 + n * 4 + 16 + (size_t)d.KTx * 2 + 15) / 16 * 16;
+    return (4 * n * 8 + n * 4 + 64 + (size_t)d.KTx * 2 + 15) / 16 * 16;
 }
 FJ_FN FjLpFastSmem fj_lpf_state(unsigned char *p, const FjDims &d)
 {
@@ -755,23 +756,32 @@ FJ_FN void fj_lpin_from_ctx(FjLpIn &in, const FjCtx &c)
     in.fstart = c.fstart; in.qlen = c.qlen; in.empty = nullptr;
 }
 
-// sum over the column's four rows of  (negate ? -v[row] : v[row]) * coefficient,  v = a vector indexed by row
-// (stride 1: the pricing vector) or row i of the column-major B^-1 (stride = column stride)
-FJ_FN double fj_lpf_dot(const double *v, int stride, uint2 ix, double a, double r, bool negate)
+// The 4-term dot product of a structural column with a row-indexed vector v (the pricing vector, or a
+// row of B^-1):  ((v0 + v1 * a) + v2 * r) + v3 * (-r),  every multiply and add rounded separately.
+// The specification (oracle/fjsp_lp.c) writes it  (((0 + v0 * 1) + v1 * a) + v2 * r) + v3 * (-r)  and, for the
+// reduced cost,  0 - sum((-y) * coefficient):  x * 1 = x and 0 + x = x exactly, and rounding to nearest is
+// symmetric under negation, so this is the same number (only the sign of a zero can differ, and a zero's
+// sign never reaches a comparison, a non-zero value or the flushed solution).
+FJ_FN double fj_lpf_dot4(double v0, double v1, double v2, double v3, double a, double r)
 {
-    const double b0 = v[(ix.x & 0xffffu) * stride], b1 = v[(ix.x >> 16) * stride], b2 = v[(ix.y & 0xffffu) * stride], b3 = v[(ix.y >> 16) * stride];
-    double acc = fj_add(0.0, fj_mul(negate ? -b0 : b0, 1.0));
-    acc = fj_add(acc, fj_mul(negate ? -b1 : b1, a));
-    acc = fj_add(acc, fj_mul(negate ? -b2 : b2, r));
-    acc = fj_add(acc, fj_mul(negate ? -b3 : b3, -r));
-    return acc;
+    double acc = fj_add(v0, fj_mul(v1, a));
+    acc = fj_add(acc, fj_mul(v2, r));
+    return fj_add(acc, fj_mul(v3, -r));
 }
+// column descriptor: the four rows of the column as BYTE offsets into a row-indexed double vector
+// (row * 8, 16 bits each; a missing precedence row points at the padding entry R, which is always 0);
+// bit 0 of the first word: the column is basic
+FJ_FN double fj_lpf_at(const double *v, unsigned off) { return *(const double *)((const char *)v + (off & 0xfff8u)); }
 
 // rank-1 update of pivot row p by helper h of nh:  B^-1[i][k] -= w[i] * pr[k]  for rows i != p with
-// w[i] != 0; lanes own the rows of a 32-row group, helpers interleave the columns
+// w[i] != 0; lanes own the rows of a 32-row group (w in a register), helpers interleave the columns;
+// a quad of columns whose pivot-row entries are all zero is skipped (the pivot row is sparse).
+// (Lanes-own-columns with the rows interleaved was measured 20-40 % slower: w is much denser than the
+// pivot row, so nothing could be skipped.)
 FJ_FN void fj_lpf_rank1(const FjLpFastSmem &S, double *BT, int Rs, int R, int p, int h, int nh, int lane)
 {
     const int ngrp = (R + 31) >> 5;
+    const double *pr = S.pr();
     for (int grp = 0; grp < ngrp; ++grp) {
         const int i = grp * 32 + lane;
         const double wv = (i < R && i != p) ? S.w()[i] : 0.0;
@@ -780,7 +790,7 @@ FJ_FN void fj_lpf_rank1(const FjLpFastSmem &S, double *BT, int Rs, int R, int p,
         double *b = BT + i;
         int k = h;
         for (; k + 3 * nh < R; k += 4 * nh) {
-            const double p0 = S.pr()[k], p1 = S.pr()[k + nh], p2 = S.pr()[k + 2 * nh], p3 = S.pr()[k + 3 * nh];
+            const double p0 = pr[k], p1 = pr[k + nh], p2 = pr[k + 2 * nh], p3 = pr[k + 3 * nh];
             if (p0 == 0.0 && p1 == 0.0 && p2 == 0.0 && p3 == 0.0) continue;
             if (on) {
                 double *b0 = b + (size_t)k * Rs, *b1 = b0 + (size_t)nh * Rs, *b2 = b1 + (size_t)nh * Rs, *b3 = b2 + (size_t)nh * Rs;
@@ -792,23 +802,204 @@ FJ_FN void fj_lpf_rank1(const FjLpFastSmem &S, double *BT, int Rs, int R, int p,
             }
         }
         for (; k < R; k += nh) {
-            const double p0 = S.pr()[k];
+            const double p0 = pr[k];
             if (p0 != 0.0 && on) { double *b0 = b + (size_t)k * Rs; *b0 = fj_sub(*b0, fj_mul(wv, p0)); }
         }
     }
 }
 
+// lexicographic minimum over the group's D driver warps: warp minimum, partials through shared memory,
+// one barrier of the drivers, warp minimum of the partials (every driver lane gets the result)
+FJ_FN void fj_lpf_lexmin(unsigned &hi, unsigned &lo, unsigned &id, int *part, int dw, int D, int dbar, int lane)
+{
+    fj_warp_lexmin(hi, lo, id);
+    if (D == 1) return;
+    if (lane == 0) { part[3 * dw] = (int)hi; part[3 * dw + 1] = (int)lo; part[3 * dw + 2] = (int)id; }
+    asm volatile("bar.sync %0, %1;" ::"r"(dbar), "r"(D * 32) : "memory");
+    hi = lo = id = 0xffffffffu;
+    if (lane < D) { hi = (unsigned)part[3 * lane]; lo = (unsigned)part[3 * lane + 1]; id = (unsigned)part[3 * lane + 2]; }
+    fj_warp_lexmin(hi, lo, id);
+}
+
+// the simplex iterations (everything is set up: all-slack basis, B^-1 = I).  BINV_SM only tells the
+// compiler which address space BT is in.  The group's first D warps are the drivers: driver dw owns the
+// columns and rows  lane + 32 (dw + D k);  the other warps are the helpers.
+template <bool BINV_SM>
+FJ_FN int fj_lpf_iterate(FjCtaGroup g, const FjLpFastSmem &S, double *BT, const double2 *coef, uint2 *cidx, int *pos, int M, int KT, int NP, int R, int *iters_out)
+{
+    const int tid = g.rank(), lane = tid & 31, wid = tid >> 5, nw = g.size() >> 5;
+    const int D = nw >= 12 ? 4 : nw >= 6 ? 2 : 1;
+    const int C = NP + 1, Rs = R | 1, t_col = NP;
+    const int dantzig_iters = 20 * R + 100, hard_iters = 200 * R + 1000;
+    int it = 0, rc = 0;
+    FJ_LPT_DECL;
+    if (wid < D) {
+        // ------------------------------------------------ drivers
+        const int dw = wid, first = lane + 32 * dw, step = 32 * D;
+        int pt = -1;               // row of t in the basis, -1: nonbasic
+        unsigned slack_nb = 0;     // bit k: the slack of row first + step k is nonbasic (all slacks start basic)
+        double *const y = S.y(), *const w = S.w(), *const xb = S.xb(), *const prow = S.pr();
+        int *const bvar = S.bvar(), *const part = S.ctl() + 4;
+        for (;; ++it) {
+            FJ_LPT_ITER();
+            int qin = FJ_EMPTY;
+            if (it >= hard_iters) rc = 2;
+            else if (pt < 0) qin = t_col;   // y = 0: every structural / slack reduced cost is 0 and t prices at -1
+            else {
+                // ---- pricing on the mirrored t row: most negative reduced cost, lowest column on ties (Dantzig);
+                // after dantzig_iters the lowest column with a negative reduced cost (Bland: every key equal).
+                // t itself is basic here.  Two columns per pass: their loads and chains overlap.
+                const bool bland = it >= dantzig_iters;
+                double ek = 0.0; int ei = FJ_EMPTY;
+                int j = first;
+                for (; j + step < NP; j += 2 * step) {
+                    const uint2 xa = cidx[j], xc = cidx[j + step];
+                    const double2 ca = coef[j], cc = coef[j + step];
+                    const double a0 = fj_lpf_at(y, xa.x), a1 = fj_lpf_at(y, xa.x >> 16), a2 = fj_lpf_at(y, xa.y), a3 = fj_lpf_at(y, xa.y >> 16);
+                    const double c0 = fj_lpf_at(y, xc.x), c1 = fj_lpf_at(y, xc.x >> 16), c2 = fj_lpf_at(y, xc.y), c3 = fj_lpf_at(y, xc.y >> 16);
+                    const double da = fj_lpf_dot4(a0, a1, a2, a3, ca.x, ca.y), dc = fj_lpf_dot4(c0, c1, c2, c3, cc.x, cc.y);
+                    const double ka = bland ? -1.0 : da, kc = bland ? -1.0 : dc;
+                    if (!(xa.x & 1u) && da < -FJ_LP_EPS_D && (ei == FJ_EMPTY || ka < ek)) { ek = ka; ei = j; }
+                    if (!(xc.x & 1u) && dc < -FJ_LP_EPS_D && (ei == FJ_EMPTY || kc < ek)) { ek = kc; ei = j + step; }
+                }
+                if (j < NP) {
+                    const uint2 xa = cidx[j];
+                    const double2 ca = coef[j];
+                    const double da = fj_lpf_dot4(fj_lpf_at(y, xa.x), fj_lpf_at(y, xa.x >> 16), fj_lpf_at(y, xa.y), fj_lpf_at(y, xa.y >> 16), ca.x, ca.y);
+                    const double ka = bland ? -1.0 : da;
+                    if (!(xa.x & 1u) && da < -FJ_LP_EPS_D && (ei == FJ_EMPTY || ka < ek)) { ek = ka; ei = j; }
+                }
+                for (unsigned nb = slack_nb, k = 0; __any_sync(0xffffffffu, nb != 0u); nb >>= 1, ++k) {
+                    if (nb & 1u) {
+                        const int i = first + step * (int)k;
+                        const double d = y[i], kd = bland ? -1.0 : d;
+                        if (d < -FJ_LP_EPS_D && (ei == FJ_EMPTY || kd < ek)) { ek = kd; ei = C + i; }
+                    }
+                }
+                unsigned hi, lo, id; int ea = 0;
+                fj_lex_pack(ek, ei, 0, hi, lo, id);
+                fj_lpf_lexmin(hi, lo, id, part, dw, D, g.dbar, lane);
+                fj_lex_unpack(hi, lo, id, ek, ei, ea);
+                qin = ei;
+            }
+            FJ_LPT(1);
+            g.sync();   // A: the helpers have applied the previous pivot
+            FJ_LPT(2);
+            if (qin == FJ_EMPTY) break;   // optimal (or rc = 2)
+            // ---- w = B^-1 A_q and the ratio test  min max(xB, 0) / w  over w > eps (ties: lowest basic variable)
+            double rk = 0.0; int ri = FJ_EMPTY, rrow = 0;
+            if (qin < NP) {
+                const uint2 ix = cidx[qin];
+                const double2 cf = coef[qin];
+                const double *c0 = BT + (size_t)((ix.x & 0xfff8u) >> 3) * Rs, *c1 = BT + (size_t)((ix.x >> 16 & 0xfff8u) >> 3) * Rs;
+                const double *c2 = BT + (size_t)((ix.y & 0xfff8u) >> 3) * Rs, *c3 = BT + (size_t)((ix.y >> 16 & 0xfff8u) >> 3) * Rs;
+                for (int i = first; i < R; i += 2 * step) {
+                    // two rows per pass (the second may be past the end: it is computed on row i again and dropped)
+                    const int i2 = i + step < R ? i + step : i;
+                    const double w1 = fj_lpf_dot4(c0[i], c1[i], c2[i], c3[i], cf.x, cf.y);
+                    const double w2 = fj_lpf_dot4(c0[i2], c1[i2], c2[i2], c3[i2], cf.x, cf.y);
+                    const double x1 = xb[i], x2 = xb[i2];
+                    const int b1 = bvar[i], b2 = bvar[i2];
+                    w[i] = w1;
+                    if (i2 != i) w[i2] = w2;
+                    const bool t1 = w1 > FJ_LP_EPS_PIV, t2 = i2 != i && w2 > FJ_LP_EPS_PIV;
+                    if (__any_sync(__activemask(), t1 || t2)) {
+                        const double r1 = __ddiv_rn(x1 > 0.0 ? x1 : 0.0, t1 ? w1 : 1.0), r2 = __ddiv_rn(x2 > 0.0 ? x2 : 0.0, t2 ? w2 : 1.0);
+                        if (t1 && (ri == FJ_EMPTY || r1 < rk || (r1 == rk && b1 < ri))) { rk = r1; ri = b1; rrow = i; }
+                        if (t2 && (ri == FJ_EMPTY || r2 < rk || (r2 == rk && b2 < ri))) { rk = r2; ri = b2; rrow = i2; }
+                    }
+                }
+            } else {
+                // t (sum of the demand-row columns, ascending) or a slack (one column of B^-1) enters: rare
+                for (int i = first; i < R; i += step) {
+                    const double *brow = BT + i;
+                    double wi;
+                    if (qin == NP) { double acc = 0.0; for (int q = 0; q < KT; ++q) acc = fj_add(acc, brow[(size_t)(M + q) * Rs]); wi = acc; }
+                    else wi = brow[(size_t)(qin - C) * Rs];
+                    w[i] = wi;
+                    if (wi > FJ_LP_EPS_PIV) {
+                        const double xv = xb[i];
+                        const double r = __ddiv_rn(xv > 0.0 ? xv : 0.0, wi);
+                        const int bi = bvar[i];
+                        if (ri == FJ_EMPTY || r < rk || (r == rk && bi < ri)) { rk = r; ri = bi; rrow = i; }
+                    }
+                }
+            }
+            FJ_LPT(3);
+            {
+                unsigned hi, lo, id;
+                fj_lex_pack(rk, ri, rrow, hi, lo, id);
+                __syncwarp();
+                fj_lpf_lexmin(hi, lo, id, part, dw, D, g.dbar, lane);
+                fj_lex_unpack(hi, lo, id, rk, ri, rrow);
+            }
+            __syncwarp();   // every lane's w is visible to the warp (other drivers' rows: the drivers' barrier above)
+            FJ_LPT(4);
+            if (ri == FJ_EMPTY) { rc = 3; break; }
+            const int p = rrow;
+            const double theta = rk, wp = w[p];
+            const int pt_new = qin == t_col ? p : (ri == t_col ? -1 : pt);
+            const double wt = (pt_new >= 0 && pt_new != p) ? w[pt_new] : 0.0;
+            const double *bp = BT + p;      // row p: entry k at bp[k * Rs]
+            for (int i = first; i < R; i += 2 * step) {
+                // x_B, the scaled pivot row (entry i of it) and the t row of B^-1 for the next pricing; two entries per pass
+                const int i2 = i + step < R ? i + step : i;
+                const double e1 = bp[(size_t)i * Rs], e2 = bp[(size_t)i2 * Rs];
+                const double x1 = xb[i], x2 = xb[i2], w1 = w[i], w2 = w[i2], y1 = y[i], y2 = y[i2];
+                double p1 = e1, p2 = e2;       // 0 / wp = 0 (wp > 0): a pass of zeros needs no division
+                if (__any_sync(__activemask(), e1 != 0.0 || e2 != 0.0)) { p1 = __ddiv_rn(e1, wp); p2 = __ddiv_rn(e2, wp); }
+                const double nx1 = i == p ? theta : fj_sub(x1, fj_mul(theta, w1)), nx2 = i2 == p ? theta : fj_sub(x2, fj_mul(theta, w2));
+                double n1 = 0.0, n2 = 0.0;
+                if (pt_new == p) { n1 = p1; n2 = p2; }
+                else if (pt_new >= 0) { n1 = wt != 0.0 ? fj_sub(y1, fj_mul(wt, p1)) : y1; n2 = wt != 0.0 ? fj_sub(y2, fj_mul(wt, p2)) : y2; }
+                xb[i] = nx1; BT[(size_t)i * Rs + p] = p1; prow[i] = p1; y[i] = n1;
+                if (i == p) bvar[i] = qin;
+                if (i2 != i) {
+                    xb[i2] = nx2; BT[(size_t)i2 * Rs + p] = p2; prow[i2] = p2; y[i2] = n2;
+                    if (i2 == p) bvar[i2] = qin;
+                }
+            }
+            // bookkeeping: positions (for the final read-out), basic flags of the structural columns, nonbasic slacks
+            if (tid == 0) {
+                pos[ri] = -1; pos[qin] = p; S.ctl()[1] = p;
+                if (qin < NP) cidx[qin].x |= 1u;
+                if (ri < NP) cidx[ri].x &= ~1u;
+            }
+            if (ri >= C) { const int s_ = ri - C, g_ = s_ >> 5; if ((s_ & 31) == lane && g_ % D == dw) slack_nb |= 1u << (g_ / D); }
+            if (qin >= C) { const int s_ = qin - C, g_ = s_ >> 5; if ((s_ & 31) == lane && g_ % D == dw) slack_nb &= ~(1u << (g_ / D)); }
+            pt = pt_new;
+            FJ_LPT(5);
+            if (nw == 1) { __syncwarp(); fj_lpf_rank1(S, BT, Rs, R, p, 0, 1, lane); __syncwarp(); }
+            g.sync();   // B: pivot published
+            FJ_LPT(6);
+        }
+        if (tid == 0) S.ctl()[1] = -1;
+        g.sync();       // B of the last round: the helpers leave
+    } else {
+        // ------------------------------------------------ helpers
+        for (;;) {
+            g.sync();   // A
+            g.sync();   // B
+            const int p = *(volatile int *)&S.ctl()[1];
+            if (p < 0) break;
+            fj_lpf_rank1(S, BT, Rs, R, p, wid - D, nw - D, lane);
+        }
+    }
+    FJ_LPT_FLUSH();
+    if (iters_out) *iters_out = it;
+    return rc;
+}
+
 // returns -1 when the LP does not fit the fast path (the caller then runs fj_lp_solve).
-// `smem` / `smem_bytes`: shared-memory scratch of the calling group (the step kernel's LP team, the LP
-// kernel's CTA).  The column descriptors and positions go there when they fit, and B^-1 too when it
-// still fits; the rest lives on `slab` (HBM/L2).
+// `smem` / `smem_bytes`: shared-memory scratch of the calling group (a server group of the step kernel, the
+// LP kernel's CTA): the column descriptors and positions live there, and B^-1 too when it still fits (else on
+// `slab` in HBM/L2).
 FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, const FjParams &P, const FjLpIn &in, const FjLpFastSmem &S, unsigned char *slab, double *x_out,
-                           int *iters_out, unsigned char *smem = nullptr, int smem_bytes = 0)
+                           int *iters_out, unsigned char *smem, int smem_bytes)
 {
     FjCtaGroup g = g_in;
-    const int tid = g.rank(), nt = g.size(), lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int tid = g.rank(), nt = g.size();
     const int M = in.M, KT = in.KT;
-    FJ_LPT_DECL;
     if (tid < 32) {   // precedence rows, numbered in ascending operation-type order
         int base = 0;
         for (int q0 = 0; q0 < KT; q0 += 32) {
@@ -822,27 +1013,27 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, const FjParams &P, const FjLp
     }
     g.sync();
     const int NP = in.NP, R = M + KT + S.ctl()[0], C = NP + 1, Rs = R | 1;   // odd column stride
-    if (R + 2 > S.n || R >= 0xffff) { g.sync(); return -1; }   // (cannot happen: S is sized for the batch's largest LP)
-    // carve: B^-1 (R + 1 columns of Rs entries: column R is the all-zero padding), column descriptors, positions
+    // carve: column descriptors, positions, then B^-1 (R + 1 columns of Rs entries: column R is the all-zero padding)
     const size_t binv_bytes = ((size_t)(R + 1) * Rs * 8 + 15) / 16 * 16;
-    const size_t small_bytes = (size_t)C * 24 + (size_t)((C + R + 1) & ~1) * 4;
-    const bool small_sm = smem && (size_t)smem_bytes >= small_bytes;
-    const bool binv_sm = small_sm && (size_t)smem_bytes >= ((small_bytes + 15) / 16 * 16) + binv_bytes;
-    double *BT = (double *)(binv_sm ? smem + (small_bytes + 15) / 16 * 16 : slab);
-    double2 *coef = (double2 *)(small_sm ? smem : slab + binv_bytes);
+    const size_t small_bytes = ((size_t)C * 24 + (size_t)((C + R + 1) & ~1) * 4 + 15) / 16 * 16;
+    if (R + 2 > S.n || R >= 0xfff || !smem || (size_t)smem_bytes < small_bytes) { g.sync(); return -1; }
+    const bool binv_sm = (size_t)smem_bytes >= small_bytes + binv_bytes;
+    double2 *coef = (double2 *)smem;
     uint2 *cidx = (uint2 *)(coef + C);
     int *pos = (int *)(cidx + C);
+    double *BT = (double *)(binv_sm ? smem + small_bytes : slab);
     {   // one thread per structural column: descriptor and coefficients (the per-pair rate 1/p is a static of the instance)
         const int32_t *colqm = in.I + P.io.colqm, *rjstage = in.I + P.io.rjstage;
         const double *colrate = (const double *)(in.I + P.io.colrate);
+        const short *prec = S.prec();
         for (int j = tid; j < NP; j += nt) {
             const int qm = __ldg(colqm + j), q = qm >> 8, m = qm & 0xff;
             const double rate = __ldg(colrate + j);
             const double fs = (double)fj_lpin_fstart(in, q);
-            const int p_prev = (__ldg(rjstage + q) > 0 && S.prec()[q - 1] >= 0) ? S.prec()[q - 1] : R;
-            const int p_own = S.prec()[q] >= 0 ? S.prec()[q] : R;
+            const int p_prev = (__ldg(rjstage + q) > 0 && prec[q - 1] >= 0) ? prec[q - 1] : R;
+            const int p_own = prec[q] >= 0 ? prec[q] : R;
             coef[j] = make_double2(-__ddiv_rn(rate, fs), rate);
-            cidx[j] = make_uint2((unsigned)m | ((unsigned)(M + q) << 16), (unsigned)p_prev | ((unsigned)p_own << 16));
+            cidx[j] = make_uint2(((unsigned)m << 3) | ((unsigned)(M + q) << 19), ((unsigned)p_prev << 3) | ((unsigned)p_own << 19));
         }
     }
     for (int j = tid; j < C + R; j += nt) pos[j] = j >= C ? j - C : -1;
@@ -852,126 +1043,15 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, const FjParams &P, const FjLp
     g.sync();
     for (int i = tid; i < R; i += nt) BT[(size_t)i * Rs + i] = 1.0;
     g.sync();
-    const int dantzig_iters = 20 * R + 100, hard_iters = 200 * R + 1000;
-    const int t_col = NP;
-    int it = 0, rc = 0;
-    FJ_LPT(0);
-    if (wid == 0) {
-        // ------------------------------------------------ driver
-        int pt = -1;   // row of t in the basis, -1: nonbasic
-        for (;; ++it) {
-            FJ_LPT_ITER();
-            int qin = FJ_EMPTY;
-            if (it >= hard_iters) rc = 2;
-            else if (pt < 0) qin = t_col;   // y = 0: every structural / slack reduced cost is 0 and t prices at -1
-            else {
-                // ---- pricing on the mirrored t row: most negative reduced cost (lowest column on
-                // ties) / Bland: lowest column.  t itself is basic here.
-                const double *y = S.y();
-                const int bland = it >= dantzig_iters;
-                double ek = 0.0; int ei = FJ_EMPTY;
-#pragma unroll 2
-                for (int j = lane; j < NP; j += 32) {
-                    const double2 cf = coef[j];
-                    const double d = fj_sub(0.0, fj_lpf_dot(y, 1, cidx[j], cf.x, cf.y, true));
-                    if (pos[j] < 0 && d < -FJ_LP_EPS_D) {
-                        if (bland) { if (ei == FJ_EMPTY) { ek = d; ei = j; } }
-                        else if (ei == FJ_EMPTY || d < ek) { ek = d; ei = j; }
-                    }
-                }
-                for (int i = lane; i < R; i += 32) {
-                    const double d = -(-y[i]);
-                    if (pos[C + i] < 0 && d < -FJ_LP_EPS_D) {
-                        if (bland) { if (ei == FJ_EMPTY) { ek = d; ei = C + i; } }
-                        else if (ei == FJ_EMPTY || d < ek) { ek = d; ei = C + i; }
-                    }
-                }
-                if (bland) ei = (int)__reduce_min_sync(0xffffffffu, (unsigned)ei);
-                else {
-                    unsigned hi, lo, id; int ea = 0;
-                    fj_lex_pack(ek, ei, 0, hi, lo, id);
-                    fj_warp_lexmin(hi, lo, id);
-                    fj_lex_unpack(hi, lo, id, ek, ei, ea);
-                }
-                qin = ei;
-            }
-            FJ_LPT(1);
-            g.sync();   // A: the helpers have applied the previous pivot
-            FJ_LPT(2);
-            if (qin == FJ_EMPTY) break;   // optimal (or rc = 2)
-            // ---- w = B^-1 A_q and the ratio test  min max(xB, 0) / w  over w > eps (ties: lowest basic variable)
-            double rk = 0.0; int ri = FJ_EMPTY, rrow = 0;
-            {
-                double2 cf = make_double2(0.0, 0.0); uint2 ix = make_uint2(0u, 0u);
-                if (qin < NP) { cf = coef[qin]; ix = cidx[qin]; }
-                for (int i = lane; i < R; i += 32) {
-                    const double *brow = BT + i;      // row i: entry k at brow[k * Rs]
-                    double wi;
-                    if (qin < NP) wi = fj_lpf_dot(brow, Rs, ix, cf.x, cf.y, false);
-                    else if (qin == NP) { double acc = 0.0; for (int q = 0; q < KT; ++q) acc = fj_add(acc, fj_mul(brow[(size_t)(M + q) * Rs], 1.0)); wi = acc; }
-                    else wi = brow[(size_t)(qin - C) * Rs];
-                    S.w()[i] = wi;
-                    if (wi > FJ_LP_EPS_PIV) {
-                        const double xv = S.xb()[i];
-                        const double r = __ddiv_rn(xv > 0.0 ? xv : 0.0, wi);
-                        const int bi = S.bvar()[i];
-                        if (ri == FJ_EMPTY || r < rk || (r == rk && bi < ri)) { rk = r; ri = bi; rrow = i; }
-                    }
-                }
-            }
-            FJ_LPT(3);
-            {
-                unsigned hi, lo, id;
-                fj_lex_pack(rk, ri, rrow, hi, lo, id);
-                fj_warp_lexmin(hi, lo, id);
-                fj_lex_unpack(hi, lo, id, rk, ri, rrow);
-            }
-            __syncwarp();   // every lane's w is visible to the warp
-            FJ_LPT(4);
-            if (ri == FJ_EMPTY) { rc = 3; break; }
-            const int p = rrow;
-            const double theta = rk, wp = S.w()[p];
-            const int pt_new = qin == t_col ? p : (ri == t_col ? -1 : pt);
-            const double wt = (pt_new >= 0 && pt_new != p) ? S.w()[pt_new] : 0.0;
-            for (int i = lane; i < R; i += 32) {
-                // x_B, the scaled pivot row (entry i of it) and the t row of B^-1 for the next pricing
-                if (i == p) { S.xb()[i] = theta; S.bvar()[i] = qin; }
-                else S.xb()[i] = fj_sub(S.xb()[i], fj_mul(theta, S.w()[i]));
-                const double pr = __ddiv_rn(BT[(size_t)i * Rs + p], wp);
-                BT[(size_t)i * Rs + p] = pr;
-                S.pr()[i] = pr;
-                double yn = 0.0;
-                if (pt_new == p) yn = pr;
-                else if (pt_new >= 0) { const double yo = S.y()[i]; yn = wt != 0.0 ? fj_sub(yo, fj_mul(wt, pr)) : yo; }
-                S.y()[i] = yn;
-            }
-            if (lane == 0) { pos[ri] = -1; pos[qin] = p; S.ctl()[1] = p; }
-            pt = pt_new;
-            FJ_LPT(5);
-            if (nw == 1) { __syncwarp(); fj_lpf_rank1(S, BT, Rs, R, p, 0, 1, lane); __syncwarp(); }
-            g.sync();   // B: pivot published
-            FJ_LPT(6);
-        }
-        if (lane == 0) S.ctl()[1] = -1;
-        g.sync();       // B of the last round: the helpers leave
-    } else {
-        // ------------------------------------------------ helpers
-        for (;;) {
-            g.sync();   // A
-            g.sync();   // B
-            const int p = *(volatile int *)&S.ctl()[1];
-            if (p < 0) break;
-            fj_lpf_rank1(S, BT, Rs, R, p, wid - 1, nw - 1, lane);
-        }
-    }
+    int rc;
+    if (binv_sm) rc = fj_lpf_iterate<true>(g, S, BT, coef, cidx, pos, M, KT, NP, R, iters_out);
+    else rc = fj_lpf_iterate<false>(g, S, BT, coef, cidx, pos, M, KT, NP, R, iters_out);
     for (int j = tid; j < NP; j += nt) {
         double x = pos[j] >= 0 ? S.xb()[pos[j]] : 0.0;
         if (x < FJ_LP_EPS_ZERO) x = 0.0;
         x_out[j] = x;
     }
     g.sync();
-    FJ_LPT_FLUSH();
-    if (iters_out) *iters_out = it;
     return rc;
 }
 #endif
@@ -2358,9 +2438,12 @@ FJ_FN void fj_lp_post(const FjParams &P, const FjCtx &c, int gslot, int env)
 
 // A server group's loop: the leader claims a ticket, the group solves that LP into the requester's
 // solution buffer and flags it ready.  Leaves when every env CTA has finished its launch.
-FJ_FN void fj_lp_server_loop(const FjParams &Pin, const FjCtaGroup &g, unsigned char *gsmem, int env_ctas, int slab_index)
+// (out of line: its register allocation is its own, not the env role's)
+FJ_FN_NOINLINE void fj_lp_server_loop(int gid, int gw, unsigned char *gsmem, int env_ctas, int slab_index)
 {
-    const FjParams &P = fj_params_bind(Pin);
+    const FjParams &P = fj_sP;
+    FjCtaGroup g;
+    g.red = nullptr; g.flip = 0; g.base = gid * gw * 32; g.nthr = gw * 32; g.bar = FJ_BAR_SRV0 + gid; g.dbar = FJ_BAR_SRV0 + 6 + gid;
     const FjLpFastSmem S = fj_lpf_state(gsmem, P.d);
     unsigned char *scratch = gsmem + fj_lpf_state_bytes(P.d);
     const int scratch_bytes = P.srv_group_smem - (int)fj_lpf_state_bytes(P.d);
