@@ -235,15 +235,26 @@ def parity_sample(vec, blobs, env_inst, variant, history, sample, dev, rng):
     rec_eq = bool(np.array_equal(o["rec"][:, sample].cpu().numpy(), ref["rec"]))
     rew_eq = bool(np.array_equal(o["reward"][:, sample].cpu().numpy(), ref["reward"]))
     done_eq = bool(np.array_equal(o["done"][:, sample].cpu().numpy(), ref["done"]))
-    rel = float(np.max(np.abs(st - ref["state"]) / np.maximum(np.abs(ref["state"]), 1e-3)))   # relative; absolute x 1e3 below 1e-3
+    # float features: 1e-5 relative (the north star's bar) with an absolute floor of 1e-9 for features that are
+    # (numerically) zero in the reference, e.g. the spread of identical values
+    rs = ref["state"]
+    diff = np.abs(st - rs)
+    big = np.abs(rs) >= 1e-6
+    rel = float(np.max(diff[big] / np.abs(rs[big]))) if big.any() else 0.0
+    mabs = float(diff.max())
+    state_ok = bool(np.all(diff <= 1e-5 * np.abs(rs) + 1e-9))
+    w = np.unravel_index(int(np.argmax(diff - 1e-5 * np.abs(rs))), diff.shape)
     info = vec.info()
     oi = [e.info() for e in envs]
     time_eq = bool(np.array_equal(info["step_time"][sample], [x["step_time"] for x in oi]))
     return {"envs": len(sample), "env_steps_replayed_per_env": steps + T, "schedule_records_equal": rec_eq,
             "rewards_equal": rew_eq, "dones_equal": done_eq, "clock_equal": time_eq, "state_max_rel_err": rel,
-            "ok": rec_eq and rew_eq and done_eq and time_eq and rel <= 1e-5,
+            "state_max_abs_err": mabs, "state_within_tolerance": state_ok,
+            "state_worst_entry": {"t": int(w[0]), "env": int(sample[w[1]]), "feature": int(w[2]), "b200": float(st[w]), "oracle": float(rs[w])},
+            "ok": rec_eq and rew_eq and done_eq and time_eq and state_ok,
             "how": "oracle/fjsp_oracle.c replayed from reset() through the burn-in, warm-up and timed launches, "
-                   "then one more launch compared output for output (float64 states; bar 1e-5 relative)"}
+                   "then one more launch compared output for output (schedule records, rewards, dones, clocks: equal; "
+                   "float64 states: |diff| <= 1e-5 |ref| + 1e-9; state_max_rel_err is over |ref| >= 1e-6)"}
 
 
 def policy_in_loop(blobs, env_inst, variant, local_rank, world, n_steps=200, seed=0):
@@ -460,8 +471,11 @@ def main():
             evL[i][1].record(stream)
         torch.cuda.synchronize(dev)
         msL, stepsL = sharding.reduce_timing(sum(a.elapsed_time(b) for a, b in evL), BL * T * KL, dev)
+        infL = vecL.info()
+        badL = np.nonzero(infL["error"])[0]
         large = {"envs_per_gpu": BL, "value": stepsL / (msL / 1e3), "unit": UNIT, "launches": KL,
-                 "ms_per_launch": msL / KL, "env_errors": int((vecL.info()["error"] != 0).sum()),
+                 "ms_per_launch": msL / KL, "env_errors": int(len(badL)),
+                 "env_error_flags": [(int(e), int(infL["error"][e]), int(infL["step_count"][e]), int(infL["lp_solves"][e]), int(infL["lp_iterations"][e])) for e in badL[:8]],
                  "note": "instances replicated; env table > L2, no flush needed"}
         vecL.close()
         del vecL, outL, aL, rL

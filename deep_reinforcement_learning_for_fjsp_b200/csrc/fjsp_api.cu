@@ -249,12 +249,12 @@ __global__ void fjsp_plan_kernel(FjParams P, const int *rep_env, int n_inst, dou
     if (threadIdx.x == 0) { plan_meta[2 * ii] = P.lp_meta[2 * env]; plan_meta[2 * ii + 1] = P.lp_meta[2 * env + 1]; plan_ok[ii] = 1; }
 }
 
-__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(const __grid_constant__ FjParams P)
+__global__ void __launch_bounds__(FJ_BLOCK) fjsp_reset_begin_kernel(const __grid_constant__ FjParams P, int fresh)
 {
     fj_params_to_shared(P);
     const int gw = blockIdx.x * FJ_WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const int total = gridDim.x * FJ_WARPS_PER_BLOCK;
-    for (int env = gw; env < P.B; env += total) fj_env_reset_begin(P, env);
+    for (int env = gw; env < P.B; env += total) fj_env_reset_begin(P, env, fresh);
     if (blockIdx.x == 0 && threadIdx.x == 0) *P.pend_count = P.B;
 }
 
@@ -275,6 +275,7 @@ struct fjsp_vec {
     size_t lp_smem_bytes, stage_bytes, step_smem_bytes;
     int *d_pend_count, *d_pend_env, *d_lp_meta, *d_rep_env, *d_plan_meta, *d_plan_ok;
     double *d_lp_x, *d_plan_x;
+    int n_resets;
     int n_inst, plan_ready, plan_all;   // plan_all: every instance's order-0 LP solution gets cached by the first reset
     int32_t *d_inst, *d_env_inst, *d_order, *d_order_dyn;
     int n_slots, pack_cap[3], pack_rows[2], multi_round, env_warps, srv_ctas, env_ctas, detach;
@@ -660,7 +661,9 @@ int fjsp_vec_reset(fjsp_vec *v, void *stream, double *d_state64, float *d_state3
     if (!v) { g_err = "fjsp_vec_reset: null handle"; return -1; }
     CK(cudaSetDevice(v->device));
     cudaStream_t st = (cudaStream_t)stream;
-    fjsp_reset_begin_kernel<<<v->grid, FJ_BLOCK, 0, st>>>(v->P);
+    // the first reset() is that of a new environment object; later ones reset a used object (reference quirks included)
+    fjsp_reset_begin_kernel<<<v->grid, FJ_BLOCK, 0, st>>>(v->P, v->n_resets == 0 ? 1 : 0);
+    v->n_resets += 1;
     launch_lp(v, st, 0);
     if (!v->plan_ready) {
         fjsp_plan_kernel<<<v->n_inst, 128, 0, st>>>(v->P, v->d_rep_env, v->n_inst, v->d_plan_x, v->d_plan_meta, v->d_plan_ok);

@@ -2651,11 +2651,14 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
 }
 
 // reset() entry: phase 1 parks every env on its order-0 LP, phase 2 finishes
-FJ_FN void fj_env_reset_begin(const FjParams &Pin, int env)
+// `fresh`: the first reset() after creation (a new environment object); later calls are reset() of a USED
+// object, with the reference's quirks (busy flags, order_arrive_time and the `done` seen by the first
+// observation survive), exactly like the fused auto-reset
+FJ_FN void fj_env_reset_begin(const FjParams &Pin, int env, int fresh = 1)
 {
     const FjParams &P = fj_params_bind(Pin);
     FjCtx &c = fj_ctx_init(P, env, nullptr);
-    fj_reset_begin(c, 1);
+    fj_reset_begin(c, fresh);
     if (fj_lane() == 0) {
         c.scal[FJ_S_PHASE] = FJ_PH_LP_RESET;
         c.scal[FJ_S_LPSLOT] = env < P.lp_slots ? env : -1;

@@ -21,6 +21,7 @@ struct HostVec {
     std::vector<int32_t> plan_meta, plan_ok;
     int pend_count;
     int variant, sum_mode;
+    int n_resets = 0;
 };
 
 static void run_lp_service(HostVec *h, int round = 0)
@@ -41,7 +42,8 @@ static std::string g_err;
 template <int V, int SM>
 static void run_reset(HostVec *h, double *state)
 {
-    for (int e = 0; e < h->P.B; ++e) fj_env_reset_begin(h->P, e);
+    for (int e = 0; e < h->P.B; ++e) fj_env_reset_begin(h->P, e, h->n_resets == 0 ? 1 : 0);
+    h->n_resets += 1;
     h->pend_counts[0] = h->P.B;
     run_lp_service(h, 0);
     if (!h->P.plan_ok && !getenv("FJSP_HOSTSIM_NO_PLAN")) {   // cache each instance's order-0 LP solution

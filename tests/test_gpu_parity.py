@@ -235,3 +235,43 @@ def test_lp_aware_packing_places_every_env_once(n_inst, copies):
         assert np.array_equal(rw[:, sample], ref["reward"])
         assert np.allclose(st[:, sample], ref["state"], rtol=1e-9, atol=1e-12)
     assert (vec.info()["error"] == 0).all()
+
+
+def test_bench_scale_instances_three_rounds_whole_episodes():
+    """The bench workload itself (Instance_generate.py distributions at full size, scale = 1.0) on a batch of
+    more than three rounds of the step kernel's warp slots (multi-round packing, TMA staging with the next
+    round's prefetch, LP servers under load), from reset() through whole episodes into the next ones: a sample
+    of environments is compared with the oracle output for output, every launch."""
+    import torch
+    import oracle_py
+    from deep_reinforcement_learning_for_fjsp_b200.instance import FJSPInstance
+    n_inst, T, launches = 96, 64, 44                      # 2816 steps: episodes of this profile take ~1500-3500
+    insts = [FJSPInstance.generate(7000 + i, [0.5, 1.0, 1.5][i % 3], 10, 3, "DA3C") for i in range(n_inst)]
+    blobs = [i.to_blob() for i in insts]
+    B = 3 * 148 * 32 + 777                                # > 3 full rounds whatever the CTA shape
+    env_instance = (np.arange(B) % n_inst).astype(np.int32)
+    vec = make_vec(blobs, env_instance, "MO_DFJSP")
+    q = vec.query()
+    assert q["n_slots"] >= 3 * (q["grid"] - q["lp_server_ctas"]) * q["env_warps"]
+    sample = np.unique(np.concatenate([np.linspace(0, B - 1, 10).astype(np.int64), [1, B // 2 + 5]]))
+    envs = [oracle_py.OracleEnv(blobs[env_instance[e]], "MO_DFJSP") for e in sample]
+    s0 = vec.reset().cpu().numpy()
+    pc.assert_states_close(s0[sample], np.stack([e.reset() for e in envs]), "reset")
+    rng = np.random.default_rng(12)
+    dev = vec.dev
+    idx = torch.from_numpy(sample).to(dev)
+    episodes = 0
+    for L in range(launches):
+        actions = np.stack([rng.integers(0, 12, (T, B)), rng.integers(0, 10, (T, B))], -1).astype(np.int32)
+        rnd = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
+        o = vec.rollout(torch.from_numpy(actions).to(dev), torch.from_numpy(rnd.view(np.int32)).to(dev), reward_policy=1, want_rec=True)
+        ref = oracle_py.batch_rollout(envs, actions[:, sample], rnd[:, sample], 1)
+        assert np.array_equal(o["rec"][:, idx].cpu().numpy(), ref["rec"]), f"launch {L}: schedule records differ"
+        assert np.array_equal(o["done"][:, idx].cpu().numpy(), ref["done"]), f"launch {L}"
+        assert np.array_equal(o["reward"][:, idx].cpu().numpy(), ref["reward"]), f"launch {L}"
+        pc.assert_states_close(o["state"][:, idx].cpu().numpy(), ref["state"], f"launch {L}")
+        episodes += int(ref["done"].sum())
+    info = vec.info()
+    assert (info["error"] == 0).all()
+    assert episodes >= len(sample) // 2, "the run must carry the sample through whole episodes"
+    assert np.array_equal(info["step_time"][sample], [e.info()["step_time"] for e in envs])
