@@ -509,6 +509,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     size_t slots = (size_t)n_envs;
     const size_t per_slot = (size_t)v->tb.d.NPx * 8;
     if (slots * per_slot > ((size_t)2 << 30)) slots = ((size_t)2 << 30) / per_slot;
+    if (getenv("FJSP_LP_SLOTS") && (size_t)atoi(getenv("FJSP_LP_SLOTS")) < slots) slots = (size_t)(atoi(getenv("FJSP_LP_SLOTS")) > 1 ? atoi(getenv("FJSP_LP_SLOTS")) : 1);   // test knob: force the no-slot fallback paths
     CK(cudaMalloc(&v->d_pend_count, 4 * (FJ_ROUNDS + 1)));
     CK(cudaMalloc(&v->d_pend_env, (size_t)n_envs * 4 * 2));
     CK(cudaMalloc(&v->d_lp_x, slots * per_slot));
@@ -553,6 +554,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (getenv("FJSP_NO_STAGE")) P.stage = 0;
     if (!P.stage) v->stage_bytes = 0;
     P.cta_lp = lp_mode;
+    P.lock_mask = 0;
+    if (getenv("FJSP_LOCKSTEP_K")) { int k = atoi(getenv("FJSP_LOCKSTEP_K")); int m = 1; while (m * 2 <= k) m *= 2; P.lock_mask = m - 1; }
     v->pack = (P.cta_lp == 1 && !getenv("FJSP_NO_PACK")) ? 1 : 0;
     {   // The packing kernel deals the envs that will meet an LP in this launch one per virtual CTA first
         // (one LP team per CTA serves them one at a time) and fills the rest in the static order.
@@ -576,7 +579,10 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
             const size_t state_b = ((4 * ((size_t)v->tb.d.Rx + 2)) * 8 + ((size_t)v->tb.d.Rx + 2) * 4 + 16 + (size_t)v->tb.d.KTx * 2 + 15) / 16 * 16;
             const size_t small_b = (C * 24 + ((C + rub + 1) & ~(size_t)1) * 4 + 15) / 16 * 16;
             const size_t want = state_b + small_b + ((rub + 1) * (rub | 1) * 8 + 15) / 16 * 16;
-            size_t cap = (size_t)(getenv("FJSP_SRV_SMEM_KB") ? atoi(getenv("FJSP_SRV_SMEM_KB")) : 200) * 1024 / P.srv_groups;
+            // by default no more than the env CTAs stage (or 100 KB): a larger request moves the whole launch to a
+            // bigger shared-memory carve-out, i.e. less L1 for the env CTAs (164 KB -> 228 KB: -4 %)
+            const size_t dflt = v->stage_bytes > (size_t)100 * 1024 ? v->stage_bytes : (size_t)100 * 1024;
+            size_t cap = (getenv("FJSP_SRV_SMEM_KB") ? (size_t)atoi(getenv("FJSP_SRV_SMEM_KB")) * 1024 : dflt) / P.srv_groups;
             size_t give = want <= cap ? want : cap;
             if (give < state_b + small_b) give = state_b + small_b;      // the vectors and descriptors must be on chip
             give = (give + 15) / 16 * 16;

@@ -2630,7 +2630,9 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
         // slot barrier of the lockstep group.  A warp stays in the group only while it steps: one that
         // has done its T steps leaves, and so does one that waits for an LP (it free-runs from here
         // on: its mates must not slip a slot per poll); the vote tells the others the new group size.
-        if (lock_threads) {
+        // (P.lock_mask = K - 1: the group meets every K steps only; a warp that leaves announces it at the
+        // group's next meeting)
+        if (lock_threads && ((tt & P.lock_mask) == 0 || st != FJ_ST_FRONT)) {
             const int stay = st == FJ_ST_FRONT;
             const int n = fj_env_vote(stay, lock_threads);
             lock_threads = stay ? n : 0;

@@ -152,6 +152,7 @@ struct FjParams {
     int lp_req_stride;
     int *lp_resp;               // [env CTAs x env_warps][4]: ready flag, iterations, return code
     double *cta_x;              // [env CTAs][env_warps][NPx] LP solutions, one buffer per env warp
+    int lock_mask;              // the lockstep group of an env CTA meets at a barrier every lock_mask + 1 steps (power of two - 1)
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory
     int B, variant, sum_mode, nobs;
     long long *trace;           // FJ_TRACE builds: [grid][33][8] per-warp cycle counters + one row of LP phase cycles per CTA (null otherwise)
