@@ -192,6 +192,10 @@ def run_reference(args, cfg, rank):
     def one():
         a, r = make_actions(rng, Tc, B, variant)
         oracle_py.batch_rollout(envs, a, r, 1, want_rec=False, threads=threads)
+    # untimed burn-in so the sample sits in the same mix of episode phases as the GPU arm's timed region
+    burn = min(cfg["burnin"], 1024)
+    for _ in range((burn + Tc - 1) // Tc):
+        one()
     for _ in range(args.warmup):
         one()
     t0 = time.perf_counter()
@@ -200,8 +204,8 @@ def run_reference(args, cfg, rank):
     dt = time.perf_counter() - t0
     value = args.steps * Tc * B / dt
     sample = (f"{B} of the config's {cfg['envs']} environment copies x {args.steps * Tc} steps in {dt:.1f}s on {threads} host "
-              f"threads (C port of the reference env, oracle/fjsp_oracle.c; the Python reference itself needs CPLEX and runs "
-              f"~20-200 steps/s on one core, see BASELINE.md)")
+              f"threads after {burn} burn-in steps per copy (C port of the reference env, oracle/fjsp_oracle.c; the Python "
+              f"reference itself needs CPLEX and runs 150-630 steps/s on one core, see BASELINE.md)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
