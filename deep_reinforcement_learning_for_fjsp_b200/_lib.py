@@ -8,7 +8,7 @@ LIB_PATH = os.environ.get("FJSP_B200_LIB", os.path.join(HERE, "libfjsp_b200.so")
 _lib = None
 
 SYMBOLS = ["fjsp_last_error", "fjsp_abi_version", "fjsp_vec_create", "fjsp_vec_destroy", "fjsp_vec_query",
-           "fjsp_vec_reset", "fjsp_vec_step", "fjsp_vec_step_host", "fjsp_vec_reset_host", "fjsp_vec_info", "fjsp_vec_trace", "fjsp_vec_slots"]
+           "fjsp_vec_reset", "fjsp_vec_step", "fjsp_vec_step_host", "fjsp_vec_step_host_begin", "fjsp_vec_step_host_wait", "fjsp_vec_reset_host", "fjsp_vec_info", "fjsp_vec_trace", "fjsp_vec_slots"]
 
 
 class ExtensionMissing(RuntimeError):
@@ -33,6 +33,8 @@ def load():
     L.fjsp_vec_reset.argtypes = [vp, vp, vp, vp]
     L.fjsp_vec_step.argtypes = [vp, vp, i, vp, vp, i, d, d, d, i, vp, vp, vp, vp, vp]
     L.fjsp_vec_step_host.argtypes = [vp, i, vp, vp, i, d, d, d, i, vp, vp, vp, vp, vp]
+    L.fjsp_vec_step_host_begin.argtypes = [vp, i, vp, vp, i, d, d, d, i, vp, vp, vp, vp, vp]
+    L.fjsp_vec_step_host_wait.argtypes = [vp]
     L.fjsp_vec_reset_host.argtypes = [vp, vp, vp]
     L.fjsp_vec_info.argtypes = [vp, vp]
     L.fjsp_vec_trace.argtypes = [vp, vp, i]
@@ -40,7 +42,7 @@ def load():
     L.fjsp_vec_slots.restype = i
     L.fjsp_vec_trace.restype = i
     for f in ("fjsp_vec_create", "fjsp_vec_destroy", "fjsp_vec_query", "fjsp_vec_reset", "fjsp_vec_step",
-              "fjsp_vec_step_host", "fjsp_vec_reset_host", "fjsp_vec_info"):
+              "fjsp_vec_step_host", "fjsp_vec_step_host_begin", "fjsp_vec_step_host_wait", "fjsp_vec_reset_host", "fjsp_vec_info"):
         getattr(L, f).restype = i
     _lib = L
     return L

@@ -290,6 +290,9 @@ struct fjsp_vec {
     cudaEvent_t chunk_done, dev_done;   // dev_done: last work queued through the device entry points (caller's stream)
     int dev_pending;
     int stage_T, stage_out_T;
+    // pipelined host calls (fjsp_vec_step_host_begin / _wait): two input staging slots
+    int32_t *d_actions2[2]; uint32_t *d_rnd2[2]; unsigned char *d_out2[2]; int pipe_T; cudaEvent_t pipe_in[2], pipe_k[2], pipe_done[2];
+    long long pipe_begun, pipe_waited; cudaStream_t copy_out_stream;
     int32_t *d_actions, *d_done, *d_rec;
     uint32_t *d_rnd;
     double *d_state64, *d_reward;
@@ -608,6 +611,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaStreamCreateWithFlags(&v->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&v->chunk_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&v->dev_done, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&v->copy_out_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) { CK(cudaEventCreateWithFlags(&v->pipe_in[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&v->pipe_k[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&v->pipe_done[k], cudaEventDisableTiming)); }
     v->dev_pending = 0;
     v->stage_T = 0; v->stage_out_T = 0;
     v->d_actions = v->d_done = v->d_rec = nullptr; v->d_rnd = nullptr;
@@ -649,6 +654,8 @@ int fjsp_vec_destroy(fjsp_vec *v)
     if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
     if (v->chunk_done) cudaEventDestroy(v->chunk_done);
     if (v->dev_done) cudaEventDestroy(v->dev_done);
+    if (v->copy_out_stream) cudaStreamDestroy(v->copy_out_stream);
+    for (int k = 0; k < 2; ++k) { if (v->pipe_in[k]) cudaEventDestroy(v->pipe_in[k]); if (v->pipe_k[k]) cudaEventDestroy(v->pipe_k[k]); if (v->pipe_done[k]) cudaEventDestroy(v->pipe_done[k]); cudaFree(v->d_actions2[k]); cudaFree(v->d_rnd2[k]); cudaFree(v->d_out2[k]); }
     delete v;
     return 0;
 }
@@ -821,6 +828,74 @@ int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint3
     }
     CK(cudaStreamSynchronize(st));
     if (staged) CK(cudaStreamSynchronize(cp));
+    return 0;
+}
+
+// Pipelined form of fjsp_vec_step_host for callers whose actions do not depend on the previous call's
+// outputs (rule-based rollouts, replays): _begin queues the host-to-device copy of the inputs (input copy
+// stream), the launch (compute stream, outputs into one of two device staging slots) and the device-to-host
+// copy of the outputs (output copy stream) and returns; _wait blocks until the OLDEST call begun has
+// delivered its outputs.  Up to two calls in flight: the copies of one run beside the kernels of the other,
+// each direction on its own copy engine.  (Outputs go through staging + DMA here, not through kernel stores
+// into host memory: SM stores of 120-byte rows reach ~10 GB/s on the link, the copy engine 2-3 x that, and
+// with two calls in flight the copy is hidden anyway.)  Host buffers should be page-locked; pageable ones
+// make the copies synchronous (correct, not overlapped).
+int fjsp_vec_step_host_begin(fjsp_vec *v, int T, const int32_t *h_actions, const uint32_t *h_rnd,
+                             int reward_policy, double completion, double tardiness, double energy, int autoreset,
+                             double *h_state64, float *h_state32, double *h_reward, int32_t *h_done, int32_t *h_rec)
+{
+    if (!v || !h_actions || T < 1) { g_err = "fjsp_vec_step_host_begin: null handle/actions or T < 1"; return -1; }
+    if (v->pipe_begun - v->pipe_waited >= 2) { g_err = "fjsp_vec_step_host_begin: two calls already in flight (call fjsp_vec_step_host_wait first)"; return -7; }
+    CK(cudaSetDevice(v->device));
+    const int slot = (int)(v->pipe_begun & 1);
+    const size_t n = (size_t)T * v->B, ns = (size_t)v->nstate;
+    if (T > v->pipe_T) {
+        CK(cudaDeviceSynchronize());
+        for (int k = 0; k < 2; ++k) {
+            cudaFree(v->d_actions2[k]); cudaFree(v->d_rnd2[k]); cudaFree(v->d_out2[k]);
+            v->d_actions2[k] = nullptr; v->d_rnd2[k] = nullptr; v->d_out2[k] = nullptr;
+            CK(cudaMalloc(&v->d_actions2[k], n * 2 * 4));
+            CK(cudaMalloc(&v->d_rnd2[k], n * 2 * 4));
+            CK(cudaMalloc(&v->d_out2[k], n * (ns * 12 + 8 + 4 + 32)));   // state64 | state32 | reward | done | rec
+        }
+        v->pipe_T = T;
+    }
+    unsigned char *o = v->d_out2[slot];
+    double *d_state64 = (double *)o; o += n * ns * 8;
+    double *d_reward = (double *)o; o += n * 8;
+    float *d_state32 = (float *)o; o += n * ns * 4;
+    int32_t *d_done = (int32_t *)o; o += n * 4;
+    int32_t *d_rec = (int32_t *)o;
+    cudaStream_t st = v->stream, cin = v->copy_stream, cout = v->copy_out_stream;
+    wait_device_work(v);
+    // the slot's previous user (call begun - 2) was waited for by the host: its copies are done
+    CK(cudaMemcpyAsync(v->d_actions2[slot], h_actions, n * 2 * 4, cudaMemcpyHostToDevice, cin));
+    if (h_rnd) CK(cudaMemcpyAsync(v->d_rnd2[slot], h_rnd, n * 2 * 4, cudaMemcpyHostToDevice, cin));
+    CK(cudaEventRecord(v->pipe_in[slot], cin));
+    CK(cudaStreamWaitEvent(st, v->pipe_in[slot], 0));
+    int rc = fjsp_vec_step(v, st, T, v->d_actions2[slot], h_rnd ? v->d_rnd2[slot] : nullptr, reward_policy, completion, tardiness, energy,
+                           autoreset, h_state64 ? d_state64 : nullptr, h_state32 ? d_state32 : nullptr, h_reward ? d_reward : nullptr,
+                           h_done ? d_done : nullptr, h_rec ? d_rec : nullptr);
+    if (rc) return rc;
+    CK(cudaEventRecord(v->pipe_k[slot], st));
+    CK(cudaStreamWaitEvent(cout, v->pipe_k[slot], 0));
+    if (h_state64) CK(cudaMemcpyAsync(h_state64, d_state64, n * ns * 8, cudaMemcpyDeviceToHost, cout));
+    if (h_state32) CK(cudaMemcpyAsync(h_state32, d_state32, n * ns * 4, cudaMemcpyDeviceToHost, cout));
+    if (h_reward) CK(cudaMemcpyAsync(h_reward, d_reward, n * 8, cudaMemcpyDeviceToHost, cout));
+    if (h_done) CK(cudaMemcpyAsync(h_done, d_done, n * 4, cudaMemcpyDeviceToHost, cout));
+    if (h_rec) CK(cudaMemcpyAsync(h_rec, d_rec, n * 8 * 4, cudaMemcpyDeviceToHost, cout));
+    CK(cudaEventRecord(v->pipe_done[slot], cout));
+    v->pipe_begun += 1;
+    return 0;
+}
+
+int fjsp_vec_step_host_wait(fjsp_vec *v)
+{
+    if (!v) { g_err = "fjsp_vec_step_host_wait: null handle"; return -1; }
+    if (v->pipe_waited >= v->pipe_begun) return 0;
+    CK(cudaSetDevice(v->device));
+    CK(cudaEventSynchronize(v->pipe_done[v->pipe_waited & 1]));
+    v->pipe_waited += 1;
     return 0;
 }
 

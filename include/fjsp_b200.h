@@ -49,7 +49,7 @@ int fjsp_vec_destroy(fjsp_vec *v);
 
 /* out[0..11] = n_envs, state_size (20 SO / 30 MO), env record bytes, instance record bytes,
  * grid blocks, threads per block, LP scratch bytes per slab, kernel launches so far,
- * env warps per block (= warp slots of a virtual CTA), LP-team warps per block, warp slots,
+ * env warps per block (= warp slots of a virtual CTA), LP-server blocks of the grid, warp slots,
  * dynamic shared memory bytes per block of the step kernel */
 int fjsp_vec_query(fjsp_vec *v, int64_t *out12);
 
@@ -77,6 +77,17 @@ int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint3
                        int reward_policy, double completion, double tardiness, double energy, int autoreset,
                        double *h_state64, float *h_state32, double *h_reward, int32_t *h_done, int32_t *h_rec);
 int fjsp_vec_reset_host(fjsp_vec *v, double *h_state64, float *h_state32);
+
+/* Pipelined form of fjsp_vec_step_host (same arguments) for callers whose actions do not depend on
+ * the previous call's outputs -- the `for worker in pool` of Parallel_Experience_Generator.play_n_episodes
+ * (:28-40) with rule-based or replayed actions: _begin queues the input copy and the launch and returns,
+ * _wait blocks until the OLDEST call begun has finished (its outputs are then complete).  At most two
+ * calls in flight; the copies of one (each direction on its own copy engine) overlap the kernels of the
+ * other.  Host buffers should be page-locked (pageable ones make the copies synchronous). */
+int fjsp_vec_step_host_begin(fjsp_vec *v, int T, const int32_t *h_actions, const uint32_t *h_rnd,
+                             int reward_policy, double completion, double tardiness, double energy, int autoreset,
+                             double *h_state64, float *h_state32, double *h_reward, int32_t *h_done, int32_t *h_rec);
+int fjsp_vec_step_host_wait(fjsp_vec *v);
 
 /* Per environment 12 int64: step_time, step_count, completion_time, delay_time_sum,
  * energy_consumption, lp_solves, lp_iterations, error flags, done, next order, episodes,

@@ -287,3 +287,41 @@ def test_fallback_paths_vs_oracle(knobs, monkeypatch):
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     pc.compare_with_oracle(make_vec, "MO_DFJSP", 23, n_inst=6, copies=4, T=48, launches=3, reward_policy=1)
+
+
+def test_pipelined_host_calls_equal_blocking_calls():
+    """fjsp_vec_step_host_begin / _wait (two calls in flight, outputs written by the kernel into page-locked
+    host memory) deliver exactly what the blocking fjsp_vec_step_host delivers."""
+    import torch
+    from deep_reinforcement_learning_for_fjsp_b200 import _lib
+    insts, env_instance = pc.random_batch(33, "MO_DFJSP", 5, 30)
+    blobs = [i.to_blob() for i in insts]
+    a, b = make_vec(blobs, env_instance, "MO_DFJSP"), make_vec(blobs, env_instance, "MO_DFJSP")
+    B, T, calls = len(env_instance), 24, 5
+    rng = np.random.default_rng(2)
+    acts = [np.stack([rng.integers(0, 12, (T, B)), rng.integers(0, 10, (T, B))], -1).astype(np.int32) for _ in range(calls)]
+    rnds = [rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32) for _ in range(calls)]
+    assert np.array_equal(a.reset_host(), b.reset_host())
+    want = [a.step_host(acts[k], rnds[k], 1) for k in range(calls)]
+    L = b._L
+    pa = [torch.from_numpy(x).pin_memory() for x in acts]
+    pr = [torch.from_numpy(x.view(np.int32)).pin_memory() for x in rnds]
+    st = [torch.empty((T, B, b.state_size), dtype=torch.float64).pin_memory() for _ in range(calls)]
+    rw = [torch.empty((T, B), dtype=torch.float64).pin_memory() for _ in range(calls)]
+    dn = [torch.empty((T, B), dtype=torch.int32).pin_memory() for _ in range(calls)]
+    rec = [torch.empty((T, B, 8), dtype=torch.int32).pin_memory() for _ in range(calls)]
+
+    def begin(k):
+        _lib.check(L.fjsp_vec_step_host_begin(b._h, T, pa[k].data_ptr(), pr[k].data_ptr(), 1, 1.0, 1.0, 1.0, 1,
+                                              st[k].data_ptr(), None, rw[k].data_ptr(), dn[k].data_ptr(), rec[k].data_ptr()))
+    begin(0)
+    for k in range(1, calls):
+        begin(k)
+        _lib.check(L.fjsp_vec_step_host_wait(b._h))
+        assert np.array_equal(rec[k - 1].numpy(), want[k - 1][3]) and np.array_equal(st[k - 1].numpy(), want[k - 1][0])
+    with pytest.raises(RuntimeError):
+        begin(0); begin(1)                  # a third call in flight is refused
+    _lib.check(L.fjsp_vec_step_host_wait(b._h))
+    _lib.check(L.fjsp_vec_step_host_wait(b._h))
+    assert np.array_equal(rw[calls - 1].numpy(), want[calls - 1][1]) and np.array_equal(dn[calls - 1].numpy(), want[calls - 1][2])
+    assert np.array_equal(rec[calls - 1].numpy(), want[calls - 1][3])
