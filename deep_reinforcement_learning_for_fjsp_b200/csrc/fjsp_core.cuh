@@ -771,6 +771,16 @@ FJ_FN double fj_lpf_dot4(double v0, double v1, double v2, double v3, double a, d
 // column descriptor: the four rows of the column as BYTE offsets into a row-indexed double vector
 // (row * 8, 16 bits each; a missing precedence row points at the padding entry R, which is always 0);
 // bit 0 of the first word: the column is basic
+// a / b for b > 0 (exactly __ddiv_rn's result): a zero numerator -- the common case in this degenerate LP: most
+// x_B and most entries of a pivot row are 0 -- would send the whole warp through the division's special-operand
+// slow path (measured: the ratio test and the pivot-row scaling took 2.6 k and 1.5 k cycles, most of an iteration);
+// 0 / b = 0 with the numerator's sign, so those lanes divide 1.0 instead and keep their zero
+FJ_FN double fj_lpf_div(double a, double b)
+{
+    const bool z = a == 0.0;
+    const double q = __ddiv_rn(z ? 1.0 : a, b);
+    return z ? a : q;
+}
 FJ_FN double fj_lpf_at(const double *v, unsigned off) { return *(const double *)((const char *)v + (off & 0xfff8u)); }
 
 // rank-1 update of pivot row p by helper h of nh:  B^-1[i][k] -= w[i] * pr[k]  for rows i != p with
@@ -852,6 +862,7 @@ FJ_FN int fj_lpf_iterate(FjCtaGroup g, const FjLpFastSmem &S, double *BT, const 
                 const bool bland = it >= dantzig_iters;
                 double ek = 0.0; int ei = FJ_EMPTY;
                 int j = first;
+                FJ_NOUNROLL
                 for (; j + step < NP; j += 2 * step) {
                     const uint2 xa = cidx[j], xc = cidx[j + step];
                     const double2 ca = coef[j], cc = coef[j + step];
@@ -869,6 +880,7 @@ FJ_FN int fj_lpf_iterate(FjCtaGroup g, const FjLpFastSmem &S, double *BT, const 
                     const double ka = bland ? -1.0 : da;
                     if (!(xa.x & 1u) && da < -FJ_LP_EPS_D && (ei == FJ_EMPTY || ka < ek)) { ek = ka; ei = j; }
                 }
+                FJ_NOUNROLL
                 for (unsigned nb = slack_nb, k = 0; __any_sync(0xffffffffu, nb != 0u); nb >>= 1, ++k) {
                     if (nb & 1u) {
                         const int i = first + step * (int)k;
@@ -893,6 +905,7 @@ FJ_FN int fj_lpf_iterate(FjCtaGroup g, const FjLpFastSmem &S, double *BT, const 
                 const double2 cf = coef[qin];
                 const double *c0 = BT + (size_t)((ix.x & 0xfff8u) >> 3) * Rs, *c1 = BT + (size_t)((ix.x >> 16 & 0xfff8u) >> 3) * Rs;
                 const double *c2 = BT + (size_t)((ix.y & 0xfff8u) >> 3) * Rs, *c3 = BT + (size_t)((ix.y >> 16 & 0xfff8u) >> 3) * Rs;
+                FJ_NOUNROLL
                 for (int i = first; i < R; i += 2 * step) {
                     // two rows per pass (the second may be past the end: it is computed on row i again and dropped)
                     const int i2 = i + step < R ? i + step : i;
@@ -904,22 +917,36 @@ FJ_FN int fj_lpf_iterate(FjCtaGroup g, const FjLpFastSmem &S, double *BT, const 
                     if (i2 != i) w[i2] = w2;
                     const bool t1 = w1 > FJ_LP_EPS_PIV, t2 = i2 != i && w2 > FJ_LP_EPS_PIV;
                     if (__any_sync(__activemask(), t1 || t2)) {
-                        const double r1 = __ddiv_rn(x1 > 0.0 ? x1 : 0.0, t1 ? w1 : 1.0), r2 = __ddiv_rn(x2 > 0.0 ? x2 : 0.0, t2 ? w2 : 1.0);
+                        const double r1 = fj_lpf_div(x1 > 0.0 ? x1 : 0.0, t1 ? w1 : 1.0), r2 = fj_lpf_div(x2 > 0.0 ? x2 : 0.0, t2 ? w2 : 1.0);
                         if (t1 && (ri == FJ_EMPTY || r1 < rk || (r1 == rk && b1 < ri))) { rk = r1; ri = b1; rrow = i; }
                         if (t2 && (ri == FJ_EMPTY || r2 < rk || (r2 == rk && b2 < ri))) { rk = r2; ri = b2; rrow = i2; }
                     }
                 }
             } else {
-                // t (sum of the demand-row columns, ascending) or a slack (one column of B^-1) enters: rare
+                // t (sum of the demand-row columns, ascending) or a slack (one column of B^-1) enters.  t enters
+                // OFTEN: a degenerate ratio test (ratio 0) is won by the lowest basic variable, t ranks below
+                // every slack, so t keeps leaving and re-entering.  Its w is a sum in ascending operation-type
+                // order per row: the adds are a serial chain, the loads are not -- eight in flight.
+                FJ_NOUNROLL
                 for (int i = first; i < R; i += step) {
                     const double *brow = BT + i;
                     double wi;
-                    if (qin == NP) { double acc = 0.0; for (int q = 0; q < KT; ++q) acc = fj_add(acc, brow[(size_t)(M + q) * Rs]); wi = acc; }
-                    else wi = brow[(size_t)(qin - C) * Rs];
+                    if (qin == NP) {
+                        double acc = 0.0;
+                        const double *b = brow + (size_t)M * Rs;
+                        int q = 0;
+                        for (; q + 8 <= KT; q += 8, b += (size_t)8 * Rs) {
+                            const double v0 = b[0], v1 = b[Rs], v2 = b[2 * (size_t)Rs], v3 = b[3 * (size_t)Rs];
+                            const double v4 = b[4 * (size_t)Rs], v5 = b[5 * (size_t)Rs], v6 = b[6 * (size_t)Rs], v7 = b[7 * (size_t)Rs];
+                            acc = fj_add(fj_add(fj_add(fj_add(fj_add(fj_add(fj_add(fj_add(acc, v0), v1), v2), v3), v4), v5), v6), v7);
+                        }
+                        for (; q < KT; ++q, b += Rs) acc = fj_add(acc, b[0]);
+                        wi = acc;
+                    } else wi = brow[(size_t)(qin - C) * Rs];
                     w[i] = wi;
                     if (wi > FJ_LP_EPS_PIV) {
                         const double xv = xb[i];
-                        const double r = __ddiv_rn(xv > 0.0 ? xv : 0.0, wi);
+                        const double r = fj_lpf_div(xv > 0.0 ? xv : 0.0, wi);
                         const int bi = bvar[i];
                         if (ri == FJ_EMPTY || r < rk || (r == rk && bi < ri)) { rk = r; ri = bi; rrow = i; }
                     }
@@ -941,13 +968,14 @@ FJ_FN int fj_lpf_iterate(FjCtaGroup g, const FjLpFastSmem &S, double *BT, const 
             const int pt_new = qin == t_col ? p : (ri == t_col ? -1 : pt);
             const double wt = (pt_new >= 0 && pt_new != p) ? w[pt_new] : 0.0;
             const double *bp = BT + p;      // row p: entry k at bp[k * Rs]
+            FJ_NOUNROLL
             for (int i = first; i < R; i += 2 * step) {
                 // x_B, the scaled pivot row (entry i of it) and the t row of B^-1 for the next pricing; two entries per pass
                 const int i2 = i + step < R ? i + step : i;
                 const double e1 = bp[(size_t)i * Rs], e2 = bp[(size_t)i2 * Rs];
                 const double x1 = xb[i], x2 = xb[i2], w1 = w[i], w2 = w[i2], y1 = y[i], y2 = y[i2];
                 double p1 = e1, p2 = e2;       // 0 / wp = 0 (wp > 0): a pass of zeros needs no division
-                if (__any_sync(__activemask(), e1 != 0.0 || e2 != 0.0)) { p1 = __ddiv_rn(e1, wp); p2 = __ddiv_rn(e2, wp); }
+                if (__any_sync(__activemask(), e1 != 0.0 || e2 != 0.0)) { p1 = fj_lpf_div(e1, wp); p2 = fj_lpf_div(e2, wp); }
                 const double nx1 = i == p ? theta : fj_sub(x1, fj_mul(theta, w1)), nx2 = i2 == p ? theta : fj_sub(x2, fj_mul(theta, w2));
                 double n1 = 0.0, n2 = 0.0;
                 if (pt_new == p) { n1 = p1; n2 = p2; }

@@ -33,6 +33,18 @@ def main():
         ev[1].record()
         torch.cuda.synchronize()
         ms.append(ev[0].elapsed_time(ev[1]))
+    if os.environ.get('FJSP_B200_LIB', '').endswith('trace.so'):
+        from deep_reinforcement_learning_for_fjsp_b200 import _lib
+        q = vec.query()
+        tr = np.zeros((q['grid'], 33, 8), dtype=np.int64)
+        L = _lib.load()
+        _lib.check(L.fjsp_vec_trace(vec._h, tr.ctypes.data, 1))
+        vec.reset()
+        torch.cuda.synchronize()
+        _lib.check(L.fjsp_vec_trace(vec._h, tr.ctypes.data, 1))
+        lpt = tr[:, 32, :].sum(0).astype(np.float64)
+        names = ['setup', 'pricing+argmin', 'wait A', 'w+ratio', 'argmin-out', 'xB/pivot-row/y', 'barrier B']
+        print('LP kernel phases (cycles per iteration, trace build): ' + ', '.join('%s %.0f' % (n, lpt[k] / max(lpt[7], 1)) for k, n in enumerate(names) if k) + '; iterations %d' % lpt[7])
     inf = vec.info()
     iters = inf["lp_iterations"].astype(np.float64) / np.maximum(inf["lp_solves"], 1)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
