@@ -345,6 +345,11 @@ def main():
     if args.impl == "reference":
         run_reference(args, cfg, rank)
         return
+    # rank 0 prints ONE JSON line on stdout: everything else a library writes to fd 1 (NCCL's version banner is a
+    # plain printf) goes to stderr for the whole run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from deep_reinforcement_learning_for_fjsp_b200.vec_env import FJSPVecEnv
@@ -354,7 +359,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / debug lines go to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     variant, B, T, LPS = cfg["variant"], cfg["envs"], cfg["T"], cfg["launches_per_step"]
@@ -619,7 +623,8 @@ def main():
                 "rollout_sweep": sweep, "policy_in_loop": pol}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_port_throughput(blobs[:64], variant, args.cpu_seconds, T, args.seed)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
