@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(FJ_BLOCK) fjsp_resume_kernel(const __grid_cons
 
 // LP kernel: one CTA per parked LP, basis inverse in shared memory when it fits
 #ifndef FJ_LP_THREADS
+#ifndef FJ_LP_THREADS
 #define FJ_LP_THREADS 256
+#endif
 #endif
 static_assert(FJ_STEP_THREADS / 32 <= FJ_CTX_WARPS && FJ_LP_THREADS / 32 <= FJ_CTX_WARPS && FJ_BLOCK / 32 <= FJ_CTX_WARPS,
               "fj_sC holds one context per warp of a CTA");

@@ -44,7 +44,7 @@ def main():
         _lib.check(L.fjsp_vec_trace(vec._h, tr.ctypes.data, 1))
         lpt = tr[:, 32, :].sum(0).astype(np.float64)
         names = ['setup', 'pricing+argmin', 'wait A', 'w+ratio', 'argmin-out', 'xB/pivot-row/y', 'barrier B']
-        print('LP kernel phases (cycles per iteration, trace build): ' + ', '.join('%s %.0f' % (n, lpt[k] / max(lpt[7], 1)) for k, n in enumerate(names) if k) + '; iterations %d' % lpt[7])
+        print('LP kernel phases (cycles per iteration; NOTE the trace build keeps its counters in local memory, every mark costs ~1.5 k cycles: relative only): ' + ', '.join('%s %.0f' % (n, lpt[k] / max(lpt[7], 1)) for k, n in enumerate(names)) + '; iterations %d' % lpt[7])
     inf = vec.info()
     iters = inf["lp_iterations"].astype(np.float64) / np.maximum(inf["lp_solves"], 1)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
