@@ -565,7 +565,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (getenv("FJSP_LOCKSTEP_K")) { int k = atoi(getenv("FJSP_LOCKSTEP_K")); int m = 1; while (m * 2 <= k) m *= 2; P.lock_mask = m - 1; }
     v->pack = (P.cta_lp == 1 && !getenv("FJSP_NO_PACK")) ? 1 : 0;
     {   // The packing kernel deals the envs that will meet an LP in this launch one per virtual CTA first
-        // (one LP team per CTA serves them one at a time) and fills the rest in the static order.
+        // (they free-run and wait for the LP servers; their CTA-mates keep stepping) and fills the rest in the static order.
         // FJSP_PACK="cap1,cap2,cap3,rows_heavy,rows_medium" limits the env warps of a virtual CTA that
         // holds an env with a heavy / medium / light LP ahead (needs spare slots, FJSP_SPARE).
         const int w = v->env_warps;

@@ -388,8 +388,8 @@ struct FjWarpGroup {
 
 #ifdef __CUDACC__
 // A group of whole warps of one CTA that synchronises on its own named barrier: the whole CTA
-// (base 0, blockDim.x threads, barrier 0 = __syncthreads) in the LP kernel, or the LP team of the
-// step kernel (the CTA's last warps, barrier FJ_BAR_TEAM) while the env warps keep stepping.
+// (base 0, blockDim.x threads, barrier 0 = __syncthreads) in the LP kernel, or one LP group of a server
+// CTA of the step kernel (barriers FJ_BAR_SRV0 + group for the group, + 6 for its driver warps).
 struct FjCtaGroup {
     int4 *red;    // shared scratch: two buffers of one entry per warp (<= 32 warps)
     int flip;     // which buffer the next reduction uses (same value in every thread)
@@ -2601,13 +2601,13 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
                 FJ_TR_ACC(0);
             }
             // ---- discrete-event clock.  At an order arrival the env needs the fluid LP of its
-            // new state: the CTA's LP team solves it (device) / it is solved in line (host build)
+            // new state: an LP-server group solves it (device) / it is solved in line (host build)
             int done = 0;
             if (kind == 1) {
                 for (;;) {
                     const int ck = fj_clock<SUM_MODE, 1>(resume);
                     if (ck != FJ_CLK_PARKED) { done = ck == FJ_CLK_DONE; break; }
-                    if (!K.cta_lp) {             // no in-CTA service configured: park for the LP / resume kernels
+                    if (!K.cta_lp) {             // no LP servers in this launch: park for the LP / resume kernels
                         fj_suspend(c, P, A, env, FJ_PH_LP_STEP, tt);
                         st = FJ_ST_IDLE; kind = 0;
                         break;

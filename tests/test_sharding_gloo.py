@@ -28,8 +28,17 @@ def _worker(rank, world, port, blobs, env_instance, actions, rnd, q):
     info = vec.info()
     stats = sharding.gather_episode_stats(info["completion"], info["delay_sum"], info["energy"])
     ms, steps = sharding.reduce_timing(10.0 + rank, rec.shape[0] * rec.shape[1])
+    # the agents' data-parallel update: every rank's gradients averaged in one flat bucket
+    import torch
+    net = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        for p_ in net.parameters():
+            p_.fill_(0.5)
+    net(torch.full((4, 3), float(rank + 1))).sum().backward()
+    n_el = sharding.allreduce_gradients(net.parameters())
+    grads = torch.cat([p_.grad.reshape(-1) for p_ in net.parameters()]).numpy()
     if rank == 0:
-        q.put((stats, ms, steps))
+        q.put((stats, ms, steps, n_el, grads))
     q.put(("rec", lo, hi, rec))
     dist.barrier()
     dist.destroy_process_group()
@@ -67,7 +76,9 @@ def test_two_ranks_equal_one_process():
             _, lo, hi, part = item
             rec[:, lo:hi] = part
         else:
-            stats, ms, steps = item
+            stats, ms, steps, n_el, grads = item
     assert np.array_equal(rec, rec_all)
     assert ms == 11.0 and steps == T * B
+    # d(sum of outputs)/dW = 4 * x per output row, averaged over the ranks' x = 1 and x = 2; bias gradient 4
+    assert n_el == 8 and np.allclose(grads, [6.0] * 6 + [4.0] * 2)
     assert np.array_equal(stats[:, 0], info_all["completion"]) and np.array_equal(stats[:, 2], info_all["energy"])

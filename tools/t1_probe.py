@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """T=1 launches (one reference step() per launch) on the bench workload: per-launch device times and
 the LP work they contain.  Diagnostic; also the target of `ncu -k regex:fjsp_step_kernel` captures of the
-LP team (python tools/t1_probe.py --launches 40)."""
+LP servers (python tools/t1_probe.py --launches 40)."""
 import argparse
 import os
 import sys
