@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
     }
     // every env warp (the free-running ones included) has finished its last round: one more CTA the servers need not wait for
     fj_env_count(0, nenv * 32);
-    if (threadIdx.x == 0 && nsrv > 0) { __threadfence(); atomicAdd(P.lpq + 2, 1u); }
+    if (threadIdx.x == 0 && nsrv > 0) { __threadfence(); atomicAdd((unsigned *)P.pend_count + FJ_ROUNDS + 1, 1u); }
 }
 
 // LP-aware packing, run before every step launch.  The warps of a CTA serve each other's fluid
@@ -281,7 +281,7 @@ struct fjsp_vec {
     double *d_lp_x, *d_plan_x;
     int n_resets;
     int n_inst, plan_ready, plan_all;   // plan_all: every instance's order-0 LP solution gets cached by the first reset
-    int32_t *d_inst, *d_env_inst, *d_order, *d_order_dyn;
+    int32_t *d_inst, *d_env_inst, *d_order, *d_order_dyn, *d_order_static, *last_order;
     int n_slots, pack_cap[3], pack_rows[2], multi_round, env_warps, srv_ctas, env_ctas, detach;
     double *d_cta_x;
     unsigned int *d_lpq; unsigned long long *d_lpq_ring; int *d_lp_req, *d_lp_resp;
@@ -489,6 +489,9 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         CK(cudaMemcpy(v->d_order, order.data(), (size_t)n_envs * 4, cudaMemcpyHostToDevice));
         order.resize(v->n_slots, -1);   // without packing: the static order, spare slots empty
         CK(cudaMemcpy(v->d_order_dyn, order.data(), (size_t)v->n_slots * 4, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&v->d_order_static, (size_t)v->n_slots * 4));
+        CK(cudaMemcpy(v->d_order_static, order.data(), (size_t)v->n_slots * 4, cudaMemcpyHostToDevice));
+        v->last_order = v->d_order_dyn;
     }
     CK(cudaMalloc(&v->d_env, env_bytes));
     CK(cudaMalloc(&v->d_lp, lp_bytes));
@@ -517,11 +520,11 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     const size_t per_slot = (size_t)v->tb.d.NPx * 8;
     if (slots * per_slot > ((size_t)2 << 30)) slots = ((size_t)2 << 30) / per_slot;
     if (getenv("FJSP_LP_SLOTS") && (size_t)atoi(getenv("FJSP_LP_SLOTS")) < slots) slots = (size_t)(atoi(getenv("FJSP_LP_SLOTS")) > 1 ? atoi(getenv("FJSP_LP_SLOTS")) : 1);   // test knob: force the no-slot fallback paths
-    CK(cudaMalloc(&v->d_pend_count, 4 * (FJ_ROUNDS + 1)));
+    CK(cudaMalloc(&v->d_pend_count, 4 * (FJ_ROUNDS + 2)));
     CK(cudaMalloc(&v->d_pend_env, (size_t)n_envs * 4 * 2));
     CK(cudaMalloc(&v->d_lp_x, slots * per_slot));
     CK(cudaMalloc(&v->d_lp_meta, slots * 8));
-    CK(cudaMemset(v->d_pend_count, 0, 4 * (FJ_ROUNDS + 1)));
+    CK(cudaMemset(v->d_pend_count, 0, 4 * (FJ_ROUNDS + 2)));
     {   // per-instance cache of the order-0 LP solution (filled by the first reset)
         std::vector<int> rep(n_instances, -1);
         for (int e = n_envs - 1; e >= 0; --e) rep[env_instance[e]] = e;
@@ -648,7 +651,7 @@ int fjsp_vec_destroy(fjsp_vec *v)
     if (!v) return 0;
     cudaSetDevice(v->device);
     free_stage(v);
-    cudaFree(v->d_order); cudaFree(v->d_order_dyn); cudaFree(v->d_flags);
+    cudaFree(v->d_order); cudaFree(v->d_order_dyn); cudaFree(v->d_order_static); cudaFree(v->d_flags);
     cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
     cudaFree(v->d_trace); cudaFree(v->d_cta_x);
@@ -714,17 +717,23 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     A.state = d_state64; A.state32 = d_state32; A.reward = d_reward; A.done = d_done; A.rec = d_rec;
     A.park_count = nullptr; A.park_env = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemsetAsync(v->d_pend_count, 0, 4 * (FJ_ROUNDS + 1), st));
-    CK(cudaMemsetAsync(v->d_lpq + 2, 0, 4, st));   // env CTAs finished in this launch (the queue's tickets are never reset)
+    // parked-LP counts of the fallback rounds + the env CTAs finished in this launch (the LP queue's tickets are never reset)
+    CK(cudaMemsetAsync(v->d_pend_count, 0, 4 * (FJ_ROUNDS + 2), st));
     int rc = dispatch(v, [&](auto V, auto SM) {
         constexpr int VV = decltype(V)::value, MM = decltype(SM)::value;
         A.park_count = v->d_pend_count; A.park_env = v->d_pend_env;
-        if (v->pack) {
+        // LP-aware packing pays for itself on rollouts (T >= 8: 16 us against >= 0.3 ms); a launch of a few steps
+        // (T = 1 is the agents' step()) uses the static map: an env that meets an LP leaves its lockstep group anyway
+        const bool pack = v->pack && T >= 8;
+        FjParams Pl = v->P;
+        if (pack) {
             fjsp_flag_kernel<<<(v->B + 255) / 256, 256, 0, st>>>(v->P, v->d_order, v->d_flags, T, v->pack_rows[0], v->pack_rows[1]);
             fjsp_pack_kernel<<<1, FJ_PACK_THREADS, 0, st>>>(v->P, v->d_order, v->d_flags, v->d_order_dyn, v->env_warps,
                                                             v->pack_cap[0], v->pack_cap[1], v->pack_cap[2], v->detach);
-        }
-        fjsp_step_kernel<VV, MM><<<v->step_grid, v->step_threads, v->step_smem_bytes, st>>>(v->P, A);
+        } else Pl.order = v->d_order_static;
+        v->last_order = (int32_t *)Pl.order;
+        v->launches += 1 + 2 * (pack ? 1 : 0);
+        fjsp_step_kernel<VV, MM><<<v->step_grid, v->step_threads, v->step_smem_bytes, st>>>(Pl, A);
         // resume rounds: an env can meet a reset and further order arrivals inside one launch; the
         // last round solves whatever is left in line
         // With the CTA-served LP and every instance's order-0 solution cached nothing can park
@@ -740,7 +749,7 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
         return 0;
     });
     if (rc) return rc;
-    v->launches += 1 + ((v->P.cta_lp == 1 && v->plan_ready && v->plan_all) ? 0 : 2 * FJ_ROUNDS) + 2 * v->pack;
+    v->launches += (v->P.cta_lp == 1 && v->plan_ready && v->plan_all) ? 0 : 2 * FJ_ROUNDS;
     CK(cudaGetLastError());
     note_device_work(v, st);
     return 0;
@@ -927,7 +936,7 @@ int fjsp_vec_slots(fjsp_vec *v, int32_t *h_out, int capacity)
     if (capacity < v->n_slots) { g_err = "fjsp_vec_slots: buffer too small"; return -1; }
     CK(cudaSetDevice(v->device));
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(h_out, v->d_order_dyn, (size_t)v->n_slots * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_out, v->last_order, (size_t)v->n_slots * 4, cudaMemcpyDeviceToHost));
     for (int i = 0; i < v->n_slots; ++i) if (h_out[i] >= 0) h_out[i] &= FJ_SLOT_DETACHED - 1;   // bit 30: the env free-runs in that launch
     return v->n_slots;
 }

@@ -2477,12 +2477,13 @@ FJ_FN_NOINLINE void fj_lp_server_loop(int gid, int gw, unsigned char *gsmem, int
     const int scratch_bytes = P.srv_group_smem - (int)fj_lpf_state_bytes(P.d);
     unsigned char *slab = P.lp + (size_t)slab_index * P.lp_stride;
     volatile unsigned *q = P.lpq;
+    volatile unsigned *finished = (volatile unsigned *)P.pend_count + FJ_ROUNDS + 1;   // env CTAs done in this launch (zeroed per launch)
     for (;;) {
         if (g.rank() == 0) {
             int got = -1;
             const unsigned h = q[0], t = q[1];
             if ((int)(t - h) > 0) { if (atomicCAS(P.lpq, h, h + 1u) == h) got = (int)(h & 0x3fffffffu); }
-            else if (q[2] >= (unsigned)env_ctas) {
+            else if (*finished >= (unsigned)env_ctas) {
                 // every env CTA has finished (all their requests were answered before): leave unless a ticket slipped in between
                 const unsigned h2 = q[0], t2 = q[1];
                 if (h2 == t2) got = -2;

@@ -132,7 +132,7 @@ struct FjParams {
     unsigned char *env;         // env table
     unsigned char *lp;          // LP scratch slabs (one per CTA of the main kernel / per warp of the resume kernel)
     unsigned long long lp_stride;
-    int *pend_count;            // [FJ_ROUNDS + 1] parked LPs per resume round of the current launch
+    int *pend_count;            // [FJ_ROUNDS + 1] parked LPs per resume round of the current launch; [FJ_ROUNDS + 1]: env CTAs finished
     int *pend_env;              // [2][B] env of each parked LP (ping-pong between rounds)
     double *lp_x;               // [lp_slots][NPx] LP solutions
     int *lp_meta;               // [lp_slots][2] iterations, return code
@@ -146,7 +146,7 @@ struct FjParams {
     // LP service inside the main kernel (cta_lp == 1): its first `srv_ctas` CTAs run no environments; their warps
     // form `srv_groups` groups of `srv_group_warps` warps that serve the requests the env warps post on a queue in HBM/L2
     int srv_ctas, srv_groups, srv_group_warps, srv_group_smem;   // srv_group_smem: bytes of dynamic shared memory per group
-    unsigned int *lpq;          // [0] head (claimed tickets), [1] tail (issued tickets): never reset; [2] env CTAs that have finished this launch (zeroed per launch)
+    unsigned int *lpq;          // [0] head (claimed tickets), [1] tail (issued tickets): never reset
     unsigned long long *lpq_ring;   // [FJ_LPQ_RING] (ticket + 1) << 32 | env-warp slot
     int *lp_req;                // [env CTAs x env_warps][lp_req_stride]: env, then fstart[KTx], then the empty-queue mask [KTW + 1]
     int lp_req_stride;
