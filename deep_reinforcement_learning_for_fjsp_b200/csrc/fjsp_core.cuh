@@ -708,6 +708,14 @@ FJ_FN int fj_lp_solve(const G &g_in, FjCtx &c, FjLp &L, double *x_out, int *iter
 //     global); the update skips 32-row groups whose w is all zero and column quadruples whose
 //     pivot-row entries are all zero (x - w * 0 = x: only the sign of a zero could differ, and a
 //     zero's sign never reaches a comparison, a non-zero value or the flushed solution).
+// tells the compiler that p points into shared memory (a round trip through the shared window: the generic
+// pointer came through a noinline call or a select and lost its address space; with it loads / stores are
+// LDS / STS with 32-bit addresses instead of generic LD / ST with 64-bit address arithmetic)
+template <typename T> FJ_FN T *fj_as_shared(T *p)
+{
+    return (T *)__cvta_shared_to_generic(__cvta_generic_to_shared(p));
+}
+
 // per-group state of the fast path, carved from the group's shared memory for the batch's largest LP
 // (rows <= Rx): w = B^-1 A_q, the scaled pivot row, the pricing vector y (+ the zero padding entry),
 // x_B, the basic variable of every row, the precedence row of every operation type, control words
@@ -728,7 +736,7 @@ FJ_FN size_t fj_lpf_state_bytes(const FjDims &d)
 }
 FJ_FN FjLpFastSmem fj_lpf_state(unsigned char *p, const FjDims &d)
 {
-    FjLpFastSmem S; S.base = (double *)p; S.n = d.Rx + 2; S.ktx = d.KTx;
+    FjLpFastSmem S; S.base = fj_as_shared((double *)p); S.n = d.Rx + 2; S.ktx = d.KTx;
     return S;
 }
 
@@ -840,7 +848,11 @@ FJ_FN int fj_lpf_iterate(FjCtaGroup g, const FjLpFastSmem &S, double *BT, const 
     const int tid = g.rank(), lane = tid & 31, wid = tid >> 5, nw = g.size() >> 5;
     const int D = nw >= 12 ? 4 : nw >= 6 ? 2 : 1;
     const int C = NP + 1, Rs = R | 1, t_col = NP;
+#ifdef FJ_LP_DEBUG_MAXIT   // timing probe only (tools/lp_probe.py): stop after a few iterations
+    const int dantzig_iters = 20 * R + 100, hard_iters = FJ_LP_DEBUG_MAXIT;
+#else
     const int dantzig_iters = 20 * R + 100, hard_iters = 200 * R + 1000;
+#endif
     int it = 0, rc = 0;
     FJ_LPT_DECL;
     if (wid < D) {
@@ -1046,7 +1058,7 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, const FjParams &P, const FjLp
     const size_t small_bytes = ((size_t)C * 24 + (size_t)((C + R + 1) & ~1) * 4 + 15) / 16 * 16;
     if (R + 2 > S.n || R >= 0xfff || !smem || (size_t)smem_bytes < small_bytes) { g.sync(); return -1; }
     const bool binv_sm = (size_t)smem_bytes >= small_bytes + binv_bytes;
-    double2 *coef = (double2 *)smem;
+    double2 *coef = fj_as_shared((double2 *)smem);
     uint2 *cidx = (uint2 *)(coef + C);
     int *pos = (int *)(cidx + C);
     double *BT = (double *)(binv_sm ? smem + small_bytes : slab);
@@ -1072,7 +1084,7 @@ FJ_FN int fj_lp_solve_fast(const FjCtaGroup &g_in, const FjParams &P, const FjLp
     for (int i = tid; i < R; i += nt) BT[(size_t)i * Rs + i] = 1.0;
     g.sync();
     int rc;
-    if (binv_sm) rc = fj_lpf_iterate<true>(g, S, BT, coef, cidx, pos, M, KT, NP, R, iters_out);
+    if (binv_sm) rc = fj_lpf_iterate<true>(g, S, fj_as_shared(BT), coef, cidx, pos, M, KT, NP, R, iters_out);
     else rc = fj_lpf_iterate<false>(g, S, BT, coef, cidx, pos, M, KT, NP, R, iters_out);
     for (int j = tid; j < NP; j += nt) {
         double x = pos[j] >= 0 ? S.xb()[pos[j]] : 0.0;
