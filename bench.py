@@ -239,8 +239,10 @@ def run_reference(args, cfg, rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": cfg["workload"], "envs_per_gpu": cfg["envs"], "envs_sampled": B, "env_steps_per_step": Tc,
-                       "variant": variant, "machines": cfg.get("machines"), "orders": cfg.get("orders")},
+            "config": {"workload": cfg["workload"], "name": args.config, "envs_per_gpu": cfg["envs"], "envs_sampled": B,
+                       "env_steps_per_step": Tc, "launches_per_step": lps, "machines": cfg.get("machines"),
+                       "orders": cfg.get("orders"), "variant": variant, "distinct_instances_per_gpu": len(blobs),
+                       "parallelism": f"host threads x{threads}"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
