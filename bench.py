@@ -466,14 +466,24 @@ def main():
     barrier()
     e2e_sync_s = time.perf_counter() - t0
     if LPS == 1:
+        for i in range(W):                                           # warm-up: the pipeline's staging buffers are allocated on first use
+            e2e_begin(i)
+            _lib.check(L.fjsp_vec_step_host_wait(vec._h))
         barrier()
         t0 = time.perf_counter()
         checksum = 0.0
+        dbg = []
         e2e_begin(0)
         for i in range(1, K):
+            ta = time.perf_counter()
             e2e_begin(i)
+            tb = time.perf_counter()
             _lib.check(L.fjsp_vec_step_host_wait(vec._h))          # call i - 1 is complete: its outputs are in host memory
+            tc = time.perf_counter()
             checksum += float(hrw[(i - 1) % 2][-1, 0])               # the device-to-host read of the step's result
+            dbg.append((round((tb - ta) * 1e3, 3), round((tc - tb) * 1e3, 3), round((time.perf_counter() - tc) * 1e3, 3)))
+        if os.environ.get("FJSP_BENCH_DEBUG"):
+            print("pipelined calls (begin, wait, read) ms:", dbg, file=sys.stderr)
         _lib.check(L.fjsp_vec_step_host_wait(vec._h))
         checksum += float(hrw[(K - 1) % 2][-1, 0])
         barrier()
@@ -484,7 +494,19 @@ def main():
         e2e_s, e2e_api = e2e_sync_s, "fjsp_vec_step_host (C ABI, one blocking call per step(), pinned host buffers)"
     h2d = ha[0].numel() * 4 + hr[0].numel() * 4
     d2h = hs[0].numel() * 4 + hrw[0].numel() * 8 + hdn[0].numel() * 4
-    del ha, hr, hs, hrw, hdn
+    # what the link of THIS box gives a plain device-to-host copy into page-locked memory (the e2e numbers are
+    # bound by it: 148 bytes cross the link per env step)
+    dsrc = torch.empty(hs[0].numel(), dtype=torch.float32, device=dev)
+    lk = []
+    for _ in range(4):
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        hs[0].view(-1).copy_(dsrc, non_blocking=True)
+        l1.record(stream)
+        torch.cuda.synchronize(dev)
+        lk.append(dsrc.numel() * 4 / (l0.elapsed_time(l1) / 1e3) / 1e9)
+    link_d2h_gbs = max(lk[1:])
+    del ha, hr, hs, hrw, hdn, dsrc
     # ---- other rollout lengths on the same batch (not the headline): T = 1 is one reference
     # step() per launch, T = 128 a PPO-style rollout
     sweep = []
@@ -601,6 +623,8 @@ def main():
                            "step_kernel_dynamic_smem": q["step_smem_bytes"]},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "link_gbs": (h2d + d2h) * K / e2e_s / 1e9, "api": e2e_api,
+                        "link_d2h_copy_gbs_measured": link_d2h_gbs,
+                        "link_bound_value": link_d2h_gbs * 1e9 / (d2h / (B * Te)) * world,
                         "modes": e2e_modes,
                         "note": "value = the faster of the two public host-buffer APIs on this run; both move every input and output over the link inside the timed region (the link of a shared box is the noisy part: see link_gbs)"},
                 "gpu_launches": int(launches),

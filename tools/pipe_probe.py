@@ -18,7 +18,15 @@ if 'burn' in MODE:
         vec.rollout(torch.from_numpy(a).to(dev), torch.from_numpy(r.view(np.int32)).to(dev), reward_policy=1, state_dtype=torch.float32)
     torch.cuda.synchronize()
 if 'flush' in MODE:
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda'); flush.fill_(1)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    if 'nofill' not in MODE:
+        flush.fill_(1)
+    torch.cuda.synchronize()
+    if 'free' in MODE:
+        del flush
+        torch.cuda.empty_cache()
+if 'small' in MODE:
+    small = torch.empty(1024, dtype=torch.uint8, device='cuda'); small.fill_(1); torch.cuda.synchronize()
 
 rng = np.random.default_rng(1)
 ha = [torch.from_numpy(bench.make_actions(rng, T, B, "MO_DFJSP")[0]).pin_memory() for _ in range(2)]
@@ -28,7 +36,7 @@ hrw = [torch.empty((T, B), dtype=torch.float64).pin_memory() for _ in range(2)]
 hdn = [torch.empty((T, B), dtype=torch.int32).pin_memory() for _ in range(2)]
 L = vec._L
 def begin(k):
-    _lib.check(L.fjsp_vec_step_host_begin(vec._h, T, ha[k].data_ptr(), hr[k].data_ptr(), 1, 1.0, 1.0, 1.0, 1, None, hs[k].data_ptr(), hrw[k].data_ptr(), hdn[k].data_ptr(), None))
+    _lib.check(L.fjsp_vec_step_host_begin(vec._h, T, ha[k].data_ptr(), hr[k].data_ptr(), 1, 1.0, 1.0, 1.0, 1, None, None if 'nostate' in MODE else hs[k].data_ptr(), hrw[k].data_ptr(), hdn[k].data_ptr(), None))
 for i in range(30):
     _lib.check(L.fjsp_vec_step_host(vec._h, T, ha[i%2].data_ptr(), hr[i%2].data_ptr(), 1, 1.0, 1.0, 1.0, 1, None, hs[i%2].data_ptr(), hrw[i%2].data_ptr(), hdn[i%2].data_ptr(), None))
 torch.cuda.synchronize()
