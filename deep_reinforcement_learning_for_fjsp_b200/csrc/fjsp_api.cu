@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
     FjCtaCtx K;
     K.warp = warp; K.nwarps = nenv; K.cta_lp = nsrv > 0;
     K.gslot = ecta * nenv + warp;
-    K.slab = nullptr;
+    K.slab = (P.lp_own && K.gslot < P.lp_own_slots) ? P.lp_own + (size_t)K.gslot * P.lp_stride : nullptr;   // overflow path: solve in line
     K.xbuf = P.cta_x + (size_t)K.gslot * P.d.NPx;
     K.board = &board;
     K.group.red = nullptr; K.group.flip = 0; K.group.base = 0; K.group.nthr = 32; K.group.bar = 0;
@@ -284,7 +284,7 @@ struct fjsp_vec {
     int32_t *d_inst, *d_env_inst, *d_order, *d_order_dyn, *d_order_static, *last_order;
     int n_slots, pack_cap[3], pack_rows[2], multi_round, env_warps, srv_ctas, env_ctas, detach;
     double *d_cta_x;
-    unsigned int *d_lpq; unsigned long long *d_lpq_ring; int *d_lp_req, *d_lp_resp;
+    unsigned int *d_lpq; unsigned long long *d_lpq_ring; int *d_lp_req, *d_lp_resp; unsigned char *d_lp_own;
     unsigned char *d_flags;
     int pack;
     unsigned char *d_env, *d_lp;
@@ -510,6 +510,21 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         v->P.lpq = v->d_lpq; v->P.lpq_ring = v->d_lpq_ring; v->P.lp_req = v->d_lp_req; v->P.lp_resp = v->d_lp_resp;
         v->P.lp_req_stride = req_stride;
         v->P.srv_ctas = v->srv_ctas; v->P.srv_groups = srv_groups; v->P.srv_group_warps = srv_group_warps;
+        // Overflow: when every copy meets its order arrivals at once (right after reset(): 2 x 4096 LPs in the first
+        // launch against ~26 server groups = 70 ms) an env warp that finds the queue long solves its LP itself, on
+        // a scratch slab of its own in HBM/L2 (the warp-level generic solver: ~1-3 ms, but every warp at once).
+        v->P.lp_own = nullptr; v->P.lp_own_slots = 0; v->P.lp_overflow = 0;
+        if (v->srv_ctas > 0) {
+            size_t own = gslots;
+            const size_t budget = (size_t)(getenv("FJSP_LP_OWN_MB") ? atoi(getenv("FJSP_LP_OWN_MB")) : 4096) << 20;
+            if (own * lp_stride > budget) own = budget / lp_stride;
+            if (own > 0) {
+                CK(cudaMalloc(&v->d_lp_own, own * lp_stride));
+                v->P.lp_own = v->d_lp_own; v->P.lp_own_slots = (int)own;
+                v->P.lp_overflow = 16 * v->srv_ctas * srv_groups;
+                if (getenv("FJSP_LP_OVERFLOW")) v->P.lp_overflow = atoi(getenv("FJSP_LP_OVERFLOW"));
+            }
+        }
     }
     CK(cudaMemcpy(v->d_inst, v->tb.inst.data(), v->tb.inst.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(v->d_env_inst, env_instance, (size_t)n_envs * 4, cudaMemcpyHostToDevice));
@@ -655,7 +670,7 @@ int fjsp_vec_destroy(fjsp_vec *v)
     cudaFree(v->d_inst); cudaFree(v->d_env_inst); cudaFree(v->d_env); cudaFree(v->d_lp);
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
     cudaFree(v->d_trace); cudaFree(v->d_cta_x);
-    cudaFree(v->d_lpq); cudaFree(v->d_lpq_ring); cudaFree(v->d_lp_req); cudaFree(v->d_lp_resp);
+    cudaFree(v->d_lpq); cudaFree(v->d_lpq_ring); cudaFree(v->d_lp_req); cudaFree(v->d_lp_resp); cudaFree(v->d_lp_own);
     cudaFree(v->d_rep_env); cudaFree(v->d_plan_x); cudaFree(v->d_plan_meta); cudaFree(v->d_plan_ok);
     if (v->stream) cudaStreamDestroy(v->stream);
     if (v->copy_stream) cudaStreamDestroy(v->copy_stream);

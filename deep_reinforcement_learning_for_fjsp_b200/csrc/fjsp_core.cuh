@@ -2560,7 +2560,7 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
             fj_stage_copy(hotbuf, G, P.eo.hot);
 #endif
         }
-        fj_ctx_init(P, env, nullptr, hotbuf);
+        fj_ctx_init(P, env, K.slab, hotbuf);
     }
     (void)next_env; (void)parity;
     const int nobs = P.nobs;
@@ -2627,6 +2627,18 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
                     }
 #ifdef FJ_DEVICE_CODE
                     FJ_TR_COUNT(4);
+                    {   // a long queue (every copy meeting its arrivals at once): solve in line, every warp its own LP
+                        int over = 0;
+                        if (lane == 0 && K.slab && P.lp_overflow > 0) {
+                            const volatile unsigned *q = P.lpq;
+                            over = (int)(q[1] - q[0]) >= P.lp_overflow;
+                        }
+                        if (fj_bcast_i(over, 0)) {
+                            fj_order_arrives_inline<SUM_MODE>(0, 0);
+                            resume = 1;
+                            continue;
+                        }
+                    }
                     fj_lp_post(P, c, K.gslot, env);
                     st = FJ_ST_WAIT; kind = 0;
                     break;

@@ -151,6 +151,9 @@ struct FjParams {
     int *lp_req;                // [env CTAs x env_warps][lp_req_stride]: env, then fstart[KTx], then the empty-queue mask [KTW + 1]
     int lp_req_stride;
     int *lp_resp;               // [env CTAs x env_warps][4]: ready flag, iterations, return code
+    unsigned char *lp_own;      // one LP scratch slab (lp_stride bytes) per env warp of the launch for the overflow path, or null
+    int lp_own_slots;           // env warps that have one
+    int lp_overflow;            // queue depth from which an env warp solves its LP itself (0: never)
     double *cta_x;              // [env CTAs][env_warps][NPx] LP solutions, one buffer per env warp
     int lock_mask;              // the lockstep group of an env CTA meets at a barrier every lock_mask + 1 steps (power of two - 1)
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory

@@ -157,3 +157,39 @@ def check_edge_cases(make_vec, variant):
         assert np.array_equal(st[3:, b, :n], np.broadcast_to(st[2, b, :n], (T2 - 3, n)))
         assert (st[3:, b, n:] == 0).all()
     assert (vec2.info()["error"] == 0).all()
+
+
+def check_reset_of_used_env(make_vec, variant, seed=91):
+    """reset() on a USED environment object -- after a finished episode, and in the middle of one (agents only do
+    the former; the latter must still do what the reference's reset() does to a half-played object: busy flags,
+    order_arrive_time and the `done` seen by the first observation survive) -- against the oracle doing the same,
+    error flags included."""
+    insts, env_instance = random_batch(seed, variant, 3, 2)
+    blobs = [i.to_blob() for i in insts]
+    B = len(env_instance)
+    vec = make_vec(blobs, env_instance, variant)
+    envs = [oracle_py.OracleEnv(blobs[k], variant) for k in env_instance]
+    rng = np.random.default_rng(seed)
+    nt, nm = NRULES[variant]
+    for phase, T in enumerate((25, 40, 30)):                   # reset, 25 steps, reset mid-episode, 40 steps, reset, 30 steps
+        s0 = vec.reset_host()
+        o0 = np.stack([e.reset() for e in envs])
+        assert_states_close(s0, o0, f"reset {phase}")
+        actions = np.stack([rng.integers(0, nt, (T, B)), rng.integers(0, nm, (T, B))], -1).astype(np.int32)
+        rnd = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
+        st, rw, dn, rec = vec.step_host(actions, rnd, 1, 1.0, 1.0, 1.0, False)
+        # the oracle steps one by one so that an error flag (a rule that finds nothing to dispatch) does not abort the run
+        for t in range(T):
+            for b, e in enumerate(envs):
+                if e.info()["done"]:
+                    continue
+                try:
+                    so, ro, do, reco = e.step(actions[t, b], rnd[t, b], 1)
+                except AssertionError:
+                    continue
+                assert np.array_equal(rec[t, b], reco), (phase, t, b)
+                assert rw[t, b] == ro and dn[t, b] == int(do), (phase, t, b)
+                assert_states_close(st[t, b], so, f"phase {phase} step {t} env {b}")
+    info = vec.info()
+    assert np.array_equal(info["error"], [e.info()["error"] for e in envs])
+    assert np.array_equal(info["step_time"], [e.info()["step_time"] for e in envs])

@@ -325,3 +325,8 @@ def test_pipelined_host_calls_equal_blocking_calls():
     _lib.check(L.fjsp_vec_step_host_wait(b._h))
     assert np.array_equal(rw[calls - 1].numpy(), want[calls - 1][1]) and np.array_equal(dn[calls - 1].numpy(), want[calls - 1][2])
     assert np.array_equal(rec[calls - 1].numpy(), want[calls - 1][3])
+
+
+@pytest.mark.parametrize("variant", ["SO_DFJSP", "MO_DFJSP"])
+def test_reset_of_a_used_environment(variant):
+    pc.check_reset_of_used_env(make_vec, variant)

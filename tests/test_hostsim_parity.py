@@ -84,3 +84,8 @@ def test_left_to_right_sum_mode_vs_oracle():
     """sum_mode 0 (CPython <= 3.11 builtin sum) is a separate template instantiation: it must
     agree with the oracle run in the same mode."""
     pc.compare_with_oracle(make_vec, "MO_DFJSP", 9, n_inst=3, copies=2, T=40, launches=2, sum_mode=0)
+
+
+@pytest.mark.parametrize("variant", ["SO_DFJSP", "MO_DFJSP"])
+def test_reset_of_a_used_environment(variant):
+    pc.check_reset_of_used_env(make_vec, variant)

@@ -49,3 +49,25 @@ t0 = time.perf_counter(); _lib.check(L.fjsp_vec_step_host_wait(vec._h)); tw.appe
 print(MODE, 'per call ms', round((sum(tb) + sum(tw)) / len(tb) * 1e3, 3))
 print("begin ms", [round(x * 1e3, 3) for x in tb])
 print("wait  ms", [round(x * 1e3, 3) for x in tw])
+
+# ---- the step launch alone: outputs in device memory vs written by the kernel into page-locked host memory
+dev = torch.device('cuda', 0)
+da = torch.from_numpy(bench.make_actions(rng, T, B, 'MO_DFJSP')[0]).to(dev)
+dr = torch.from_numpy(bench.make_actions(rng, T, B, 'MO_DFJSP')[1].view(np.int32)).to(dev)
+ds = torch.empty((T, B, 30), dtype=torch.float32, device=dev)
+drw = torch.empty((T, B), dtype=torch.float64, device=dev)
+ddn = torch.empty((T, B), dtype=torch.int32, device=dev)
+st = torch.cuda.current_stream(dev)
+import ctypes
+for name, (ps, prw, pdn) in (("device outputs", (ds.data_ptr(), drw.data_ptr(), ddn.data_ptr())),
+                             ("host-mapped outputs", (hs[0].data_ptr(), hrw[0].data_ptr(), hdn[0].data_ptr())),
+                             ("host-mapped state only", (hs[0].data_ptr(), drw.data_ptr(), ddn.data_ptr()))):
+    ts = []
+    for i in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        _lib.check(L.fjsp_vec_step(vec._h, ctypes.c_void_p(st.cuda_stream), T, da.data_ptr(), dr.data_ptr(), 1, 1.0, 1.0, 1.0, 1, None, ps, prw, pdn, None))
+        e1.record(st)
+        torch.cuda.synchronize()
+        ts.append(round(e0.elapsed_time(e1), 3))
+    print("step launch (flag + pack + step kernel),", name, "ms:", ts)
