@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Longer randomized parity run than the test-suite (GPU box): many seeds, all four environment classes, batch
+shapes from one warp to several rounds, with the run-time knobs that force the rarely taken paths (overflow
+in-line LPs, one server group, no LP servers, no staging).  Every output of every step against the oracle.
+usage: python tools/fuzz_parity.py [--minutes 3]"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--minutes", type=float, default=3.0)
+    a = ap.parse_args()
+    import parity_common as pc
+    from deep_reinforcement_learning_for_fjsp_b200.vec_env import FJSPVecEnv
+
+    def make_vec(blobs, env_instance, variant, sum_mode=1):
+        return FJSPVecEnv(None, env_instance, variant, blobs=blobs, sum_mode=sum_mode)
+    knobs = [{}, {"FJSP_LP_OVERFLOW": "1"}, {"FJSP_LP_SERVERS": "1", "FJSP_LP_GROUPS": "1"}, {"FJSP_NO_CTA_LP": "1"},
+             {"FJSP_NO_STAGE": "1"}, {"FJSP_LP_OVERFLOW": "3", "FJSP_LP_SERVERS": "2"}, {"FJSP_LOCKSTEP_K": "4"}]
+    variants = [("SO_DFJSP", False), ("MO_DFJSP", False), ("MO_DFJSP_breakdown", True), ("SO_FJSSP", False)]
+    t0, n, seed = time.time(), 0, 1000
+    rng = np.random.default_rng(7)
+    while time.time() - t0 < a.minutes * 60:
+        kn = knobs[n % len(knobs)]
+        variant, bd = variants[(n // len(knobs)) % len(variants)]
+        n_inst, copies = int(rng.integers(1, 9)), int(rng.choice([1, 3, 17, 80]))
+        T, launches = int(rng.choice([1, 7, 32, 64])), int(rng.integers(2, 5))
+        if T == 1:
+            launches = 40
+        for k in list(os.environ):
+            if k.startswith("FJSP_") and k != "FJSP_B200_LIB":
+                del os.environ[k]
+        os.environ.update(kn)
+        seed += 1
+        try:
+            pc.compare_with_oracle(make_vec, variant, seed, n_inst=n_inst, copies=copies, T=T, launches=launches,
+                                   reward_policy=int(rng.integers(0, 4)), breakdowns=bd)
+        except Exception as e:
+            print("FAIL", dict(variant=variant, seed=seed, n_inst=n_inst, copies=copies, T=T, launches=launches, knobs=kn), repr(e)[:300])
+            raise
+        n += 1
+    print("fuzz ok: %d random batches in %.0f s (all four classes, %d knob sets)" % (n, time.time() - t0, len(knobs)))
+
+
+if __name__ == "__main__":
+    main()
