@@ -69,6 +69,7 @@ def parse():
     ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the T=1 / T=128 rollout-length lines")
     ap.add_argument("--no-policy", dest="policy", action="store_false", help="skip the policy-in-the-loop lines")
     ap.add_argument("--parity-envs", type=int, default=16, help="environments replayed on the CPU oracle after timing")
+    ap.add_argument("--e2e-all", action="store_true", help="also time fjsp_vec_step_host with kernel stores into host memory (FJSP_ZEROCOPY=1)")
     ap.add_argument("--no-flush", action="store_true", help="diagnostic: do not evict L2 between timed steps (the line says so)")
     a = ap.parse_args()
     cfg = dict(CONFIGS[a.config])
@@ -375,12 +376,14 @@ def main():
     history = []                                    # what the sample environments were fed, launch by launch
     # inputs for every launch, resident in HBM before the timed region (a pool that the burn-in cycles through)
     NP_ = min(W + K, 8) if B * T > 2_000_000 else W + K
-    acts, rnds, acts_h, rnds_h = [], [], [], []
+    acts, rnds, acts_h, rnds_h, acts_full, rnds_full = [], [], [], [], [], []
     for _ in range(NP_):
         a, r = make_actions(rng, T, B, variant)
         acts.append(torch.from_numpy(a).to(dev))
         rnds.append(torch.from_numpy(r.view(np.int32)).to(dev))
         acts_h.append(a[:, sample].copy())
+        acts_full.append(a)
+        rnds_full.append(r)
         rnds_h.append(r[:, sample].copy())
     out = {"state": torch.empty((T, B, vec.state_size), dtype=torch.float32, device=dev),
            "reward": torch.empty((T, B), dtype=torch.float64, device=dev),
@@ -430,69 +433,89 @@ def main():
     parity = parity_sample(vec, blobs, env_inst, variant, history, sample, dev, rng) if len(sample) else None
     # ---- e2e: the host-buffer C-ABI calls, pinned host buffers, every copy inside the timed region.  Each
     # call copies that step's actions / draws host-to-device and delivers state, reward and done in page-locked
-    # host memory.  Headline: the pipelined pair fjsp_vec_step_host_begin / _wait (two calls in flight: the
-    # input copy of one beside the kernels of the other -- the rule-based rollouts of this workload do not need
-    # call k's outputs to form call k + 1's actions); `sync_call` is the plain blocking fjsp_vec_step_host.
+    # host memory.  The launch time of this workload depends on which environments meet their order arrivals in
+    # the launch (1.1-2.3 ms over a few hundred launches: tools/e2e_probe.py), so every e2e mode runs on a TWIN
+    # batch -- the same instances, brought through the same burn-in and warm-up launches -- and is fed the very
+    # launches of the device-timed region, from host memory: `e2e` and `value` time the same env steps.
     Te = T * LPS
-    ha = [torch.from_numpy(make_actions(rng, Te, B, variant)[0]).pin_memory() for _ in range(2)]
-    hr = [torch.from_numpy(make_actions(rng, Te, B, variant)[1].view(np.int32)).pin_memory() for _ in range(2)]
-    hs = [torch.empty((Te, B, vec.state_size), dtype=torch.float32).pin_memory() for _ in range(2)]
-    hrw = [torch.empty((Te, B), dtype=torch.float64).pin_memory() for _ in range(2)]
-    hdn = [torch.empty((Te, B), dtype=torch.int32).pin_memory() for _ in range(2)]
+    nburn = (cfg["burnin"] + T - 1) // T
+    ha = [torch.from_numpy(a).pin_memory() for a in acts_full]
+    hr = [torch.from_numpy(r.view(np.int32)).pin_memory() for r in rnds_full]
+    hs = [torch.empty((LPS, T, B, vec.state_size), dtype=torch.float32).pin_memory() for _ in range(2)]
+    hrw = [torch.empty((LPS, T, B), dtype=torch.float64).pin_memory() for _ in range(2)]
+    hdn = [torch.empty((LPS, T, B), dtype=torch.int32).pin_memory() for _ in range(2)]
     L = vec._L
 
-    def e2e_call(i):
-        k = i % 2
-        if LPS == 1:
-            _lib.check(L.fjsp_vec_step_host(vec._h, T, ha[k].data_ptr(), hr[k].data_ptr(), 1, 1.0, 1.0, 1.0, 1,
-                                            None, hs[k].data_ptr(), hrw[k].data_ptr(), hdn[k].data_ptr(), None))
-        else:   # one step() per call, as a single-environment agent loop makes them
-            for j in range(LPS):
-                o = j * B
-                _lib.check(L.fjsp_vec_step_host(vec._h, 1, ha[k].data_ptr() + o * 8, hr[k].data_ptr() + o * 8, 1, 1.0, 1.0,
-                                                1.0, 1, None, hs[k].data_ptr() + o * vec.state_size * 4, hrw[k].data_ptr() + o * 8,
-                                                hdn[k].data_ptr() + o * 4, None))
+    def twin():
+        tv = FJSPVecEnv(None, env_inst, variant, device=local_rank, blobs=blobs)
+        tv.reset()
+        for i in range(nburn):
+            tv.rollout(acts[i % NP_], rnds[(i * 7 + 3) % NP_], reward_policy=1, out=out, state_dtype=torch.float32)
+        torch.cuda.synchronize(dev)
+        return tv
 
-    def e2e_begin(i):
-        k = i % 2
-        _lib.check(L.fjsp_vec_step_host_begin(vec._h, T, ha[k].data_ptr(), hr[k].data_ptr(), 1, 1.0, 1.0, 1.0, 1,
-                                              None, hs[k].data_ptr(), hrw[k].data_ptr(), hdn[k].data_ptr(), None))
-    for i in range(W):
-        e2e_call(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        e2e_call(i)
-    barrier()
-    e2e_sync_s = time.perf_counter() - t0
+    def host_call(tv, n, k, fn, j=0):
+        """the launch that used input set n % NP_ as one host-buffer call into slice j of buffer set k"""
+        s_ = n % NP_
+        _lib.check(fn(tv._h, T, ha[s_].data_ptr(), hr[s_].data_ptr(), 1, 1.0, 1.0, 1.0, 1,
+                      None, hs[k][j].data_ptr(), hrw[k][j].data_ptr(), hdn[k][j].data_ptr(), None))
+
+    def e2e_blocking(no_kernel_stores):
+        if no_kernel_stores:
+            os.environ["FJSP_ZEROCOPY"] = "0"
+        tv = twin()
+        for n in range(W * LPS):
+            host_call(tv, n, 0, L.fjsp_vec_step_host)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            for j in range(LPS):
+                host_call(tv, W + i * LPS + j, i % 2, L.fjsp_vec_step_host, j)
+        barrier()
+        dt = time.perf_counter() - t0
+        same = bool(np.array_equal(tv.info()["step_time"], info1["step_time"]))
+        tv.close()
+        if no_kernel_stores:
+            del os.environ["FJSP_ZEROCOPY"]
+        return dt, same
+
+    e2e_sync_s, same_sync = e2e_blocking(False)
+    # the same call with the outputs copied out in chunks while the kernel runs (the route buffers the device cannot map take)
+    e2e_zc_s = None
+    if args.e2e_all and LPS == 1 and T >= 16 and "FJSP_ZEROCOPY" not in os.environ:
+        e2e_zc_s, _ = e2e_blocking(True)
+    same_pipe = None
     if LPS == 1:
-        for i in range(W):                                           # warm-up: the pipeline's staging buffers are allocated on first use
-            e2e_begin(i)
-            _lib.check(L.fjsp_vec_step_host_wait(vec._h))
+        tv = twin()
+        for n in range(W):                                           # warm-up (the pipeline's staging buffers are allocated on first use)
+            host_call(tv, n, 0, L.fjsp_vec_step_host_begin)
+            _lib.check(L.fjsp_vec_step_host_wait(tv._h))
         barrier()
         t0 = time.perf_counter()
         checksum = 0.0
         dbg = []
-        e2e_begin(0)
+        host_call(tv, W, 0, L.fjsp_vec_step_host_begin)
         for i in range(1, K):
             ta = time.perf_counter()
-            e2e_begin(i)
+            host_call(tv, W + i, i % 2, L.fjsp_vec_step_host_begin)
             tb = time.perf_counter()
-            _lib.check(L.fjsp_vec_step_host_wait(vec._h))          # call i - 1 is complete: its outputs are in host memory
+            _lib.check(L.fjsp_vec_step_host_wait(tv._h))           # call i - 1 is complete: its outputs are in host memory
             tc = time.perf_counter()
-            checksum += float(hrw[(i - 1) % 2][-1, 0])               # the device-to-host read of the step's result
+            checksum += float(hrw[(i - 1) % 2][0, -1, 0])            # the device-to-host read of the step's result
             dbg.append((round((tb - ta) * 1e3, 3), round((tc - tb) * 1e3, 3), round((time.perf_counter() - tc) * 1e3, 3)))
         if os.environ.get("FJSP_BENCH_DEBUG"):
             print("pipelined calls (begin, wait, read) ms:", dbg, file=sys.stderr)
-        _lib.check(L.fjsp_vec_step_host_wait(vec._h))
-        checksum += float(hrw[(K - 1) % 2][-1, 0])
+        _lib.check(L.fjsp_vec_step_host_wait(tv._h))
+        checksum += float(hrw[(K - 1) % 2][0, -1, 0])
         barrier()
         e2e_s = time.perf_counter() - t0
+        same_pipe = bool(np.array_equal(tv.info()["step_time"], info1["step_time"]))
+        tv.close()
         e2e_api = ("fjsp_vec_step_host_begin / _wait (C ABI, two calls in flight, pinned host buffers: input copy, kernels and "
                    "output copy of consecutive calls overlap; float32 state out)")
     else:
         e2e_s, e2e_api = e2e_sync_s, "fjsp_vec_step_host (C ABI, one blocking call per step(), pinned host buffers)"
-    h2d = ha[0].numel() * 4 + hr[0].numel() * 4
+    h2d = (ha[0].numel() * 4 + hr[0].numel() * 4) * LPS
     d2h = hs[0].numel() * 4 + hrw[0].numel() * 8 + hdn[0].numel() * 4
     # what the link of THIS box gives a plain device-to-host copy into page-locked memory (the e2e numbers are
     # bound by it: 148 bytes cross the link per env step)
@@ -587,9 +610,14 @@ def main():
     value = total_steps / (dev_ms_max / 1e3)
     e2e_value = total_steps / (e2e_ms_max / 1e3)
     e2e_sync_value = total_steps / (e2e_sync_ms_max / 1e3)
+    blocking_api = "fjsp_vec_step_host (one blocking call per bench step; the kernel stores its outputs into the page-locked buffers while it runs)"
     e2e_modes = {"pipelined_calls": {"value": e2e_value, "unit": UNIT, "api": e2e_api},
-                 "blocking_call": {"value": e2e_sync_value, "unit": UNIT,
-                                   "api": "fjsp_vec_step_host (one blocking call per bench step; the kernel writes page-locked outputs itself)"}}
+                 "blocking_call": {"value": e2e_sync_value, "unit": UNIT, "api": blocking_api}}
+    if e2e_zc_s is not None:
+        e2e_zc_ms_max, _ = sharding.reduce_timing(e2e_zc_s * 1e3, 0, dev)
+        e2e_modes["blocking_call_chunked_copies"] = {"value": total_steps / (e2e_zc_ms_max / 1e3), "unit": UNIT,
+                                                     "api": "fjsp_vec_step_host with FJSP_ZEROCOPY=0 (device staging; chunks of 8 steps leave through the copy "
+                                                            "engine while the kernel runs, the host polling the kernel's progress words)"}
     if e2e_sync_value > e2e_value:
         e2e_value, e2e_api, e2e_s = e2e_sync_value, e2e_modes["blocking_call"]["api"], e2e_sync_s
     if rank == 0:
@@ -626,6 +654,10 @@ def main():
                         "link_d2h_copy_gbs_measured": link_d2h_gbs,
                         "link_bound_value": link_d2h_gbs * 1e9 / (d2h / (B * Te)) * world,
                         "modes": e2e_modes,
+                        "same_env_steps_as_value": {"blocking_call": same_sync, "pipelined_calls": same_pipe,
+                                                    "how": "each mode runs on a twin batch (same instances, same burn-in and warm-up launches) and "
+                                                           "replays the device-timed region's launches from host memory; true = the twin's clocks "
+                                                           "after its timed region equal the device-timed batch's"},
                         "note": "value = the faster of the two public host-buffer APIs on this run; both move every input and output over the link inside the timed region (the link of a shared box is the noisy part: see link_gbs)"},
                 "gpu_launches": int(launches),
                 "clocks": clocks,

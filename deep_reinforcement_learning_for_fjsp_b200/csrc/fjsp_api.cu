@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -12,6 +14,7 @@
 #include "fjsp_core.cuh"
 
 #define FJ_BLOCK 128
+#define FJ_PROG_CHUNKS 64    // progress chunks of one launch (fjsp_vec_step_host)
 #define FJ_WARPS_PER_BLOCK (FJ_BLOCK / 32)
 
 static thread_local std::string g_err;
@@ -92,6 +95,14 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
     // every env warp (the free-running ones included) has finished its last round: one more CTA the servers need not wait for
     fj_env_count(0, nenv * 32);
     if (threadIdx.x == 0 && nsrv > 0) { __threadfence(); atomicAdd((unsigned *)P.pend_count + FJ_ROUNDS + 1, 1u); }
+    // ... and from here on this CTA serves too: the envs that are still playing are the ones that wait for LPs, and
+    // the launch ends with the last of them.  (Every warp's staging slab has been stored and waited for; the group
+    // barriers and the groups' shared memory are laid out as in a server CTA, slabs after the servers'.)
+    if (nsrv > 0 && P.srv_join) {
+        const int gw = P.srv_group_warps, gid = warp / gw;
+        if (gid < P.srv_groups)
+            fj_lp_server_loop(gid, gw, stage_smem + (size_t)gid * P.srv_group_smem, nectas, (nsrv + ecta) * P.srv_groups + gid);
+    }
 }
 
 // LP-aware packing, run before every step launch.  The warps of a CTA serve each other's fluid
@@ -294,6 +305,8 @@ struct fjsp_vec {
     cudaEvent_t chunk_done, dev_done;   // dev_done: last work queued through the device entry points (caller's stream)
     int dev_pending;
     int stage_T, stage_out_T;
+    // progress reporting of a launch (fjsp_vec_step_host: chunks of steps copied out while the kernel runs)
+    unsigned *d_prog, *h_prog, *h_prog_dev; unsigned prog_seq; int prog_shift;   // prog_shift < 0: off for the next launch
     // pipelined host calls (fjsp_vec_step_host_begin / _wait): two input staging slots
     int32_t *d_actions2[2]; uint32_t *d_rnd2[2]; unsigned char *d_out2[2]; int pipe_T; cudaEvent_t pipe_in[2], pipe_k[2], pipe_done[2];
     long long pipe_begun, pipe_waited; cudaStream_t copy_out_stream;
@@ -467,7 +480,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (v->lp_smem_binv && binv_b + small_b > 100 * 1024) v->lp_grid = prop.multiProcessorCount;
     int slabs = v->resume_grid * FJ_WARPS_PER_BLOCK;
     if (v->lp_grid > slabs) slabs = v->lp_grid;
-    if (v->srv_ctas * srv_groups > slabs) slabs = v->srv_ctas * srv_groups;   // one slab per server group of the main kernel
+    if ((v->srv_ctas + v->env_ctas) * srv_groups > slabs) slabs = (v->srv_ctas + v->env_ctas) * srv_groups;   // one slab per server group of the main kernel (env CTAs serve once their envs are done)
     if (lp_mode == 2 && v->env_ctas * v->env_warps > slabs) slabs = v->env_ctas * v->env_warps;
     const size_t lp_bytes = (size_t)lp_stride * slabs;
     const size_t env_bytes = (size_t)n_envs * v->tb.eo.stride;
@@ -514,6 +527,7 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         // launch against ~26 server groups = 70 ms) an env warp that finds the queue long solves its LP itself, on
         // a scratch slab of its own in HBM/L2 (the warp-level generic solver: ~1-3 ms, but every warp at once).
         v->P.lp_own = nullptr; v->P.lp_own_slots = 0; v->P.lp_overflow = 0;
+        v->P.srv_join = getenv("FJSP_SRV_JOIN") ? atoi(getenv("FJSP_SRV_JOIN")) : 1;
         if (v->srv_ctas > 0) {
             size_t own = gslots;
             const size_t budget = (size_t)(getenv("FJSP_LP_OWN_MB") ? atoi(getenv("FJSP_LP_OWN_MB")) : 4096) << 20;
@@ -634,6 +648,11 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     CK(cudaEventCreateWithFlags(&v->chunk_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&v->dev_done, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&v->copy_out_stream, cudaStreamNonBlocking));
+    v->prog_shift = -1;
+    CK(cudaMalloc(&v->d_prog, 4 * FJ_PROG_CHUNKS));
+    CK(cudaHostAlloc(&v->h_prog, 4 * FJ_PROG_CHUNKS, cudaHostAllocMapped));
+    memset(v->h_prog, 0, 4 * FJ_PROG_CHUNKS);
+    CK(cudaHostGetDevicePointer(&v->h_prog_dev, v->h_prog, 0));
     for (int k = 0; k < 2; ++k) { CK(cudaEventCreateWithFlags(&v->pipe_in[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&v->pipe_k[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&v->pipe_done[k], cudaEventDisableTiming)); }
     v->dev_pending = 0;
     v->stage_T = 0; v->stage_out_T = 0;
@@ -671,6 +690,7 @@ int fjsp_vec_destroy(fjsp_vec *v)
     cudaFree(v->d_pend_count); cudaFree(v->d_pend_env); cudaFree(v->d_lp_x); cudaFree(v->d_lp_meta);
     cudaFree(v->d_trace); cudaFree(v->d_cta_x);
     cudaFree(v->d_lpq); cudaFree(v->d_lpq_ring); cudaFree(v->d_lp_req); cudaFree(v->d_lp_resp); cudaFree(v->d_lp_own);
+    cudaFree(v->d_prog); if (v->h_prog) cudaFreeHost(v->h_prog);
     cudaFree(v->d_rep_env); cudaFree(v->d_plan_x); cudaFree(v->d_plan_meta); cudaFree(v->d_plan_ok);
     if (v->stream) cudaStreamDestroy(v->stream);
     if (v->copy_stream) cudaStreamDestroy(v->copy_stream);
@@ -732,6 +752,10 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     A.state = d_state64; A.state32 = d_state32; A.reward = d_reward; A.done = d_done; A.rec = d_rec;
     A.park_count = nullptr; A.park_env = nullptr;
     cudaStream_t st = (cudaStream_t)stream;
+    if (v->prog_shift >= 0 && v->d_prog) {
+        CK(cudaMemsetAsync(v->d_prog, 0, 4 * FJ_PROG_CHUNKS, st));
+        A.prog_count = v->d_prog; A.prog_flag = v->h_prog_dev; A.prog_seq = v->prog_seq; A.prog_shift = v->prog_shift;
+    }
     // parked-LP counts of the fallback rounds + the env CTAs finished in this launch (the LP queue's tickets are never reset)
     CK(cudaMemsetAsync(v->d_pend_count, 0, 4 * (FJ_ROUNDS + 2), st));
     int rc = dispatch(v, [&](auto V, auto SM) {
@@ -768,6 +792,13 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
     CK(cudaGetLastError());
     note_device_work(v, st);
     return 0;
+}
+
+static double fj_now_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
 // staging for the host-buffer entry points: inputs always (H2D copies), outputs only for host buffers
@@ -811,18 +842,27 @@ int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint3
                        double *h_state64, float *h_state32, double *h_reward, int32_t *h_done, int32_t *h_rec)
 {
     if (!v || !h_actions || T < 1) { g_err = "fjsp_vec_step_host: null handle/actions or T < 1"; return -1; }
+    const double t_enter = getenv("FJSP_HOST_DEBUG") ? fj_now_ms() : 0.0;
     CK(cudaSetDevice(v->device));
     const size_t n = (size_t)T * v->B;
     cudaStream_t st = v->stream, cp = v->copy_stream;
-    // Page-locked output buffers are written by the step kernel itself while it runs (stores over the link,
-    // no staging, no device-to-host copy after the launch: the memory pipes are idle anyway); pageable ones go
-    // through device staging and copies.  FJSP_ZEROCOPY=0 forces staging, =state maps only the observation.
-    const char *zc = getenv("FJSP_ZEROCOPY");
+    // How the outputs reach the host buffers:
+    //  * page-locked (mapped) buffers are written by the step kernel itself while it runs: stores over the link, no
+    //    staging and no copy after the launch (measured on the same env steps: 0.97 x the device-timed rate, against
+    //    0.88 x for the chunked copies below).  FJSP_ZEROCOPY=0 turns this off, =state maps only the observation.
+    //  * other buffers, T >= 16: the kernel writes device staging and reports, per chunk of 8 steps, when every env
+    //    has written it; this thread polls the report (a word per chunk in page-locked memory) and queues the
+    //    chunk's device-to-host copies on the copy stream while the kernel plays the next steps, so that only the
+    //    last chunk's copy is left when the kernel ends (FJSP_PROGRESSIVE=0: off).
+    //  * otherwise: device staging, copies after the launch (rollouts of T >= 64 in chunks of 32 steps).
+    const char *zc = getenv("FJSP_ZEROCOPY"), *pg = getenv("FJSP_PROGRESSIVE");
+    const bool can_park = !(v->P.cta_lp == 1 && v->plan_ready && v->plan_all);
     const int zmode = !zc ? 2 : (zc[0] == '0' ? 0 : (zc[0] == 's' ? 1 : 2));
     double *m_state64 = zmode ? (double *)mapped_host(h_state64) : nullptr, *m_reward = zmode == 2 ? (double *)mapped_host(h_reward) : nullptr;
     float *m_state32 = zmode ? (float *)mapped_host(h_state32) : nullptr;
     int32_t *m_done = zmode == 2 ? (int32_t *)mapped_host(h_done) : nullptr, *m_rec = zmode == 2 ? (int32_t *)mapped_host(h_rec) : nullptr;
     const bool staged = (h_state64 && !m_state64) || (h_state32 && !m_state32) || (h_reward && !m_reward) || (h_done && !m_done) || (h_rec && !m_rec);
+    const bool progressive = staged && T >= 16 && !can_park && v->d_prog && !(pg && pg[0] == '0');
     int rc = ensure_stage(v, T, staged);
     if (rc) return rc;
     wait_device_work(v);
@@ -833,6 +873,54 @@ int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint3
     // chunks measured slower (per-launch staging and launch overheads), so T < 64 is one chunk.
     const int nchunk = staged && T >= 64 ? T / 32 : 1;
     const size_t B = (size_t)v->B, ns = (size_t)v->nstate;
+    if (progressive) {
+        int shift = 3;
+        while (((T - 1) >> shift) + 1 > FJ_PROG_CHUNKS) ++shift;
+        const int nprog = ((T - 1) >> shift) + 1;
+        v->prog_seq += 1;
+        v->prog_shift = shift;
+        rc = fjsp_vec_step(v, st, T, v->d_actions, h_rnd ? v->d_rnd : nullptr, reward_policy, completion, tardiness, energy, autoreset,
+                           h_state64 ? (m_state64 ? m_state64 : v->d_state64) : nullptr, h_state32 ? (m_state32 ? m_state32 : v->d_state32) : nullptr,
+                           h_reward ? (m_reward ? m_reward : v->d_reward) : nullptr, h_done ? (m_done ? m_done : v->d_done) : nullptr,
+                           h_rec ? (m_rec ? m_rec : v->d_rec) : nullptr);
+        v->prog_shift = -1;
+        if (rc) return rc;
+        auto copy_chunk = [&](int c) -> int {
+            const int t0 = c << shift, t1 = std::min(T, (c + 1) << shift);
+            const size_t o = (size_t)t0 * B, m = (size_t)(t1 - t0) * B;
+            if (h_state64 && !m_state64) CK(cudaMemcpyAsync(h_state64 + o * ns, v->d_state64 + o * ns, m * ns * 8, cudaMemcpyDeviceToHost, cp));
+            if (h_state32 && !m_state32) CK(cudaMemcpyAsync(h_state32 + o * ns, v->d_state32 + o * ns, m * ns * 4, cudaMemcpyDeviceToHost, cp));
+            if (h_reward && !m_reward) CK(cudaMemcpyAsync(h_reward + o, v->d_reward + o, m * 8, cudaMemcpyDeviceToHost, cp));
+            if (h_done && !m_done) CK(cudaMemcpyAsync(h_done + o, v->d_done + o, m * 4, cudaMemcpyDeviceToHost, cp));
+            if (h_rec && !m_rec) CK(cudaMemcpyAsync(h_rec + o * 8, v->d_rec + o * 8, m * 8 * 4, cudaMemcpyDeviceToHost, cp));
+            return 0;
+        };
+        const volatile unsigned *flag = v->h_prog;
+        int next = 0;
+        unsigned spins = 0;
+        const bool dbg = getenv("FJSP_HOST_DEBUG") != nullptr;      // host-side time line of the call on stderr
+        double t_flag[FJ_PROG_CHUNKS];
+        const double t_launched = dbg ? fj_now_ms() : 0.0;
+        while (next < nprog) {
+            if (flag[next] == v->prog_seq) { if (dbg) t_flag[next] = fj_now_ms(); if (copy_chunk(next)) return -10; ++next; continue; }
+            if ((++spins & 1023u) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) break;   // finished (or failed): no more reports to wait for
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        const int seen = next;
+        CK(cudaStreamSynchronize(st));
+        const double t_kernel = dbg ? fj_now_ms() : 0.0;
+        for (; next < nprog; ++next) if (copy_chunk(next)) return -10;
+        CK(cudaStreamSynchronize(cp));
+        if (dbg) {
+            const double t_end = fj_now_ms();
+            fprintf(stderr, "step_host T=%d: enter->launched %.3f ms, chunks reported %d/%d at", T, t_launched - t_enter, seen, nprog);
+            for (int c = 0; c < seen; ++c) fprintf(stderr, " %.3f", t_flag[c] - t_launched);
+            fprintf(stderr, ", kernel done %.3f, copies done %.3f (ms after launch)\n", t_kernel - t_launched, t_end - t_launched);
+        }
+        return 0;
+    }
     for (int c = 0; c < nchunk; ++c) {
         const int t0 = (int)((long long)T * c / nchunk), t1 = (int)((long long)T * (c + 1) / nchunk);
         if (t1 == t0) continue;

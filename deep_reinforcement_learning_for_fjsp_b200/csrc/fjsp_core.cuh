@@ -2677,6 +2677,21 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
             FJ_TR_ACC(3);
             ++tt; i += batch;
             if (tt >= A.T) st = FJ_ST_IDLE;
+#ifdef FJ_DEVICE_CODE
+            if (A.prog_count && ((tt & ((1 << A.prog_shift) - 1)) == 0 || tt >= A.T)) {
+                // this env's outputs of a whole chunk of steps are written: count it; the last env of the batch
+                // tells the host (which copies the chunk out while the launch goes on)
+                __syncwarp();
+                if (lane == 0) {
+                    const int ch = (tt - 1) >> A.prog_shift;
+                    __threadfence();
+                    if (atomicAdd(A.prog_count + ch, 1u) + 1u == (unsigned)P.B) {
+                        __threadfence_system();
+                        *(volatile unsigned *)(A.prog_flag + ch) = A.prog_seq;
+                    }
+                }
+            }
+#endif
         }
     vote:
 #ifdef FJ_DEVICE_CODE

@@ -154,6 +154,7 @@ struct FjParams {
     unsigned char *lp_own;      // one LP scratch slab (lp_stride bytes) per env warp of the launch for the overflow path, or null
     int lp_own_slots;           // env warps that have one
     int lp_overflow;            // queue depth from which an env warp solves its LP itself (0: never)
+    int srv_join;               // an env CTA whose envs have all finished the launch serves LPs until the launch ends
     double *cta_x;              // [env CTAs][env_warps][NPx] LP solutions, one buffer per env warp
     int lock_mask;              // the lockstep group of an env CTA meets at a barrier every lock_mask + 1 steps (power of two - 1)
     int stage;                  // 1: kernels stage the hot part of the env record in shared memory
@@ -174,6 +175,14 @@ struct FjStepArgs {
     int32_t *rec;               // [T][B][8] or null
     int *park_count;            // where this kernel parks envs that need a fluid LP
     int *park_env;
+    // progress of the launch for the host-buffer entry point (null: off).  Every env adds one to
+    // prog_count[c] when its outputs of steps [c << prog_shift, (c + 1) << prog_shift) are written; the env that
+    // completes a chunk stores prog_seq into prog_flag[c] (page-locked host memory): the host then copies that
+    // chunk's outputs out with the copy engine while the kernel plays the next steps
+    unsigned *prog_count = nullptr;
+    unsigned *prog_flag = nullptr;
+    unsigned prog_seq = 0;
+    int prog_shift = 0;
 };
 
 #define FJ_LPQ_RING 8192   // power of two, larger than the env warps of a launch (each has at most one request outstanding)

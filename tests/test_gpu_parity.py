@@ -327,6 +327,53 @@ def test_pipelined_host_calls_equal_blocking_calls():
     assert np.array_equal(rec[calls - 1].numpy(), want[calls - 1][3])
 
 
+@pytest.mark.parametrize("T", [16, 43, 600])
+def test_host_output_routes_agree(T, monkeypatch):
+    """fjsp_vec_step_host delivers its outputs by one of three routes: kernel stores into page-locked host memory
+    (the default for such buffers), chunks copied out while the kernel runs (progress words polled by the host: other
+    buffers from T = 16 on), device staging copied after the launch (FJSP_PROGRESSIVE=0).  All three must deliver the same
+    bytes -- on a batch of more than one round of warp slots, with page-locked and with pageable buffers, for a
+    ragged last chunk (T = 43) and for more steps than progress words at 8 steps per chunk (T = 600)."""
+    import torch
+    from deep_reinforcement_learning_for_fjsp_b200 import _lib
+    copies = 1300 if T < 100 else 40
+    insts, env_instance = pc.random_batch(35, "MO_DFJSP", 4, copies)
+    blobs = [i.to_blob() for i in insts]
+    B = len(env_instance)
+    rng = np.random.default_rng(3)
+    calls = 3
+    acts = [np.stack([rng.integers(0, 12, (T, B)), rng.integers(0, 10, (T, B))], -1).astype(np.int32) for _ in range(calls)]
+    rnds = [rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32) for _ in range(calls)]
+    got = {}
+    for route, knobs in (("progressive", {"FJSP_ZEROCOPY": "0"}), ("zero_copy", {}), ("staged", {"FJSP_ZEROCOPY": "0", "FJSP_PROGRESSIVE": "0"})):
+        for k in ("FJSP_ZEROCOPY", "FJSP_PROGRESSIVE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, x in knobs.items():
+            monkeypatch.setenv(k, x)
+        vec = make_vec(blobs, env_instance, "MO_DFJSP")
+        vec.reset_host()
+        out = []
+        for k in range(calls):
+            pa, pr = torch.from_numpy(acts[k]).pin_memory(), torch.from_numpy(rnds[k].view(np.int32)).pin_memory()
+            st = torch.full((T, B, vec.state_size), -7.0, dtype=torch.float32).pin_memory()
+            rw = torch.full((T, B), -7.0, dtype=torch.float64).pin_memory()
+            dn = torch.full((T, B), -7, dtype=torch.int32).pin_memory()
+            rec = torch.full((T, B, 8), -7, dtype=torch.int32).pin_memory()
+            _lib.check(vec._L.fjsp_vec_step_host(vec._h, T, pa.data_ptr(), pr.data_ptr(), 2, 1.0, 1.0, 1.0, 1,
+                                                 None, st.data_ptr(), rw.data_ptr(), dn.data_ptr(), rec.data_ptr()))
+            out.append([x.numpy().copy() for x in (st, rw, dn, rec)])
+        # pageable buffers, float64 state
+        out.append(list(vec.step_host(acts[0], rnds[0], 2)))
+        assert (vec.info()["error"] == 0).all()
+        got[route] = out
+        vec.close()
+    for route in ("zero_copy", "staged"):
+        for k in range(calls + 1):
+            for a, b in zip(got["progressive"][k], got[route][k]):
+                assert np.array_equal(a, b), (route, k)
+    assert (got["progressive"][0][2] >= 0).all() and not (got["progressive"][0][0] == -7.0).all(axis=-1).any()
+
+
 @pytest.mark.parametrize("variant", ["SO_DFJSP", "MO_DFJSP"])
 def test_reset_of_a_used_environment(variant):
     pc.check_reset_of_used_env(make_vec, variant)
