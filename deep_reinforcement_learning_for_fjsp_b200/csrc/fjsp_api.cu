@@ -448,10 +448,17 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         if (getenv("FJSP_STEP_WARPS")) wpb = atoi(getenv("FJSP_STEP_WARPS"));
         if (wpb > wmax) wpb = wmax;
         if (wpb < 1) wpb = 1;
-        v->env_warps = wpb; v->srv_ctas = srv;
-        v->step_threads = wpb * 32;
         long long ctas = (want_slots + wpb - 1) / wpb;              // virtual CTAs
         v->env_ctas = (int)(ctas < gmax ? ctas : gmax);
+        // SMs the env CTAs leave over serve LPs too (4096 copies: 133 env CTAs of 31 warps whether 13 or 15 SMs serve)
+        if (lp_mode == 1 && !getenv("FJSP_LP_SERVERS") && n_envs > 32 && srv < nsm - v->env_ctas) {
+            const int model = srv;
+            srv = nsm - v->env_ctas;
+            if (srv > 2 * model) srv = 2 * model;                   // (a small batch leaves most SMs over: no use for them)
+            if (srv > nsm / 3) srv = nsm / 3;
+        }
+        v->env_warps = wpb; v->srv_ctas = srv;
+        v->step_threads = wpb * 32;
         v->step_grid = v->env_ctas + srv;
         const long long rounds = (ctas + v->env_ctas - 1) / v->env_ctas;
         v->n_slots = (int)(rounds * v->env_ctas * wpb);
@@ -527,7 +534,10 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
         // launch against ~26 server groups = 70 ms) an env warp that finds the queue long solves its LP itself, on
         // a scratch slab of its own in HBM/L2 (the warp-level generic solver: ~1-3 ms, but every warp at once).
         v->P.lp_own = nullptr; v->P.lp_own_slots = 0; v->P.lp_overflow = 0;
-        v->P.srv_join = getenv("FJSP_SRV_JOIN") ? atoi(getenv("FJSP_SRV_JOIN")) : 1;
+        // FJSP_SRV_JOIN=1: env CTAs whose envs are done serve LPs until the launch ends.  Off by default: measured
+        // neutral at the default server count (102.4 vs 101.8 M env-steps/s: the launch ends with the env CTAs'
+        // lockstep steps, not with a queue of LPs), a gain only when the servers are under-provisioned (3 servers: 79 M)
+        v->P.srv_join = getenv("FJSP_SRV_JOIN") ? atoi(getenv("FJSP_SRV_JOIN")) : 0;
         if (v->srv_ctas > 0) {
             size_t own = gslots;
             const size_t budget = (size_t)(getenv("FJSP_LP_OWN_MB") ? atoi(getenv("FJSP_LP_OWN_MB")) : 4096) << 20;

@@ -278,12 +278,13 @@ def test_bench_scale_instances_three_rounds_whole_episodes():
 
 
 @pytest.mark.parametrize("knobs", [{"FJSP_LP_SLOTS": "5"}, {"FJSP_NO_CTA_LP": "1"}, {"FJSP_LP_SLOTS": "3", "FJSP_NO_CTA_LP": "1"},
-                                   {"FJSP_LP_SERVERS": "1", "FJSP_LP_GROUPS": "1"}, {"FJSP_NO_STAGE": "1"}])
+                                   {"FJSP_LP_SERVERS": "1", "FJSP_LP_GROUPS": "1"}, {"FJSP_NO_STAGE": "1"},
+                                   {"FJSP_SRV_JOIN": "1", "FJSP_LP_SERVERS": "1"}])
 def test_fallback_paths_vs_oracle(knobs, monkeypatch):
     """The paths a default run does not take: fewer LP solution slots than environments (an env without a
     slot solves its LP in line on its warp's scratch slab, in reset() and in the resume kernel; no cached
     order-0 solution for some instances), parking for the LP / resume kernels instead of the LP servers, a
-    single one-group server, and no shared-memory staging."""
+    single one-group server, no shared-memory staging, and env CTAs that serve LPs once their envs are done."""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     pc.compare_with_oracle(make_vec, "MO_DFJSP", 23, n_inst=6, copies=4, T=48, launches=3, reward_policy=1)
