@@ -91,6 +91,41 @@ def make_instances(n, seed, M, S, profile="DA3C", breakdowns=False):
             for i in range(n)]
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank's host thread on the CPUs of its GPU's NUMA node, so that the page-locked buffers it
+    allocates afterwards (first touch) and the link traffic stay on that node.  Only narrows the CPU set the
+    process already has; does nothing (and says why) when the box exposes no such topology."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id      # torch >= 2.x: "0000:1B:00.0"
+    except Exception:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        except Exception as e:
+            return {"bound": False, "why": "no PCI bus id (%s)" % type(e).__name__}
+    try:
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return {"bound": False, "why": "numa_node = -1 (single node)", "pci": bus}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        local = cpus & allowed
+        if not local:
+            return {"bound": False, "why": "the process may not run on node %d's CPUs" % node, "pci": bus, "node": node, "allowed_cpus": len(allowed)}
+        os.sched_setaffinity(0, local)
+        return {"bound": True, "pci": bus, "node": node, "cpus": len(local), "_previous": sorted(allowed)}
+    except Exception as e:
+        return {"bound": False, "why": "%s: %s" % (type(e).__name__, e)}
+
+
 def config_blobs(cfg, seed, rank=0):
     """(instance blobs, env -> instance map) of one rank's shard."""
     B = cfg["envs"]
@@ -360,6 +395,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
+    host_numa = bind_to_gpu_numa_node(torch, local_rank)
+    prev_affinity = host_numa.pop("_previous", None)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -659,6 +696,7 @@ def main():
                                                            "replays the device-timed region's launches from host memory; true = the twin's clocks "
                                                            "after its timed region equal the device-timed batch's"},
                         "note": "value = the faster of the two public host-buffer APIs on this run; both move every input and output over the link inside the timed region (the link of a shared box is the noisy part: see link_gbs)"},
+                "host_numa": host_numa,
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -680,6 +718,8 @@ def main():
                 "large_batch": large,
                 "rollout_sweep": sweep, "policy_in_loop": pol}
         if not args.no_cpu_baseline:
+            if host_numa.get("bound"):
+                os.sched_setaffinity(0, prev_affinity)             # the CPU baseline gets every core the process had
             line["cpu_baseline"] = cpu_port_throughput(blobs[:64], variant, args.cpu_seconds, T, args.seed)
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -87,9 +87,17 @@ __global__ void __launch_bounds__(FJ_STEP_THREADS, FJ_STEP_MIN_BLOCKS) fjsp_step
         if (next_env >= 0) next_env &= FJ_SLOT_DETACHED - 1;
         // the round's lockstep group: env warps that hold an env which is not expected to meet an LP or
         // a reset (those free-run: their long steps would stall every mate at the slot barrier)
-        const int lock_threads = fj_env_count(env >= 0 && !detached, nenv * 32);
+        // (P.lock_groups = 2 / 4: the warps of each pair of SM sub-partitions / of each sub-partition form a group
+        // of their own -- a shorter wait for the group's slowest warp, two / four instruction streams per SM)
+        const int lg = P.lock_groups, mygrp = lg == 4 ? (warp & 3) : lg == 2 ? ((warp >> 1) & 1) : 0;
+        int lock_threads = 0;
+        for (int gi = 0; gi < lg; ++gi) {
+            const int n = fj_env_count(env >= 0 && !detached && mygrp == gi, nenv * 32);
+            if (mygrp == gi) lock_threads = n;
+        }
         if (env < 0) continue;
-        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env, 1, hotbuf, next_env, uses & 1u, detached ? 0 : lock_threads);
+        const int lock_bar = mygrp == 0 ? FJ_BAR_ENV : mygrp == 1 ? 2 : 10 + mygrp;
+        fj_cta_rollout<VARIANT, SUM_MODE>(P, A, K, env, 1, hotbuf, next_env, uses & 1u, detached ? 0 : lock_threads, lock_bar);
         if (hotbuf) ++uses;
     }
     // every env warp (the free-running ones included) has finished its last round: one more CTA the servers need not wait for
@@ -604,6 +612,8 @@ int fjsp_vec_create(const int32_t *blobs, const int64_t *blob_offsets, int n_ins
     if (!P.stage) v->stage_bytes = 0;
     P.cta_lp = lp_mode;
     P.lock_mask = 0;
+    P.lock_groups = 1;
+    if (getenv("FJSP_LOCK_GROUPS")) { const int k = atoi(getenv("FJSP_LOCK_GROUPS")); P.lock_groups = k >= 4 ? 4 : k >= 2 ? 2 : 1; }
     if (getenv("FJSP_LOCKSTEP_K")) { int k = atoi(getenv("FJSP_LOCKSTEP_K")); int m = 1; while (m * 2 <= k) m *= 2; P.lock_mask = m - 1; }
     v->pack = (P.cta_lp == 1 && !getenv("FJSP_NO_PACK")) ? 1 : 0;
     {   // The packing kernel deals the envs that will meet an LP in this launch one per virtual CTA first

@@ -2372,11 +2372,11 @@ struct FjCtaCtx {
 };
 
 #ifdef __CUDACC__
-FJ_FN int fj_env_vote(int pred, int nthreads)   // barrier of the lockstep group + number of its threads with pred
+FJ_FN int fj_env_vote(int pred, int nthreads, int bar)   // barrier `bar` of the lockstep group + number of its threads with pred
 {
     unsigned r;
     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %1, 0;\n bar.red.popc.u32 %0, %2, %3, q;\n}"
-                 : "=r"(r) : "r"(pred), "n"(FJ_BAR_ENV), "r"(nthreads) : "memory");
+                 : "=r"(r) : "r"(pred), "r"(bar), "r"(nthreads) : "memory");
     return (int)r;
 }
 FJ_FN int fj_env_count(int pred, int nthreads)   // barrier of ALL env warps + number of threads with pred
@@ -2545,7 +2545,7 @@ enum { FJ_ST_IDLE = 0, FJ_ST_FRONT = 1, FJ_ST_WAIT = 2 };
 // prefetched into L2 while this round runs.
 template <int VARIANT, int SUM_MODE>
 FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaCtx &K, int env, int active, unsigned char *hotbuf = nullptr,
-                          int next_env = -1, unsigned parity = 0, int lock_threads = 0)
+                          int next_env = -1, unsigned parity = 0, int lock_threads = 0, int lock_bar = FJ_BAR_ENV)
 {
     const FjParams &P = fj_params_bind(Pin);
     const int lane = fj_lane();
@@ -2702,7 +2702,7 @@ FJ_FN void fj_cta_rollout(const FjParams &Pin, const FjStepArgs &A, const FjCtaC
         // group's next meeting)
         if (lock_threads && ((tt & P.lock_mask) == 0 || st != FJ_ST_FRONT)) {
             const int stay = st == FJ_ST_FRONT;
-            const int n = fj_env_vote(stay, lock_threads);
+            const int n = fj_env_vote(stay, lock_threads, lock_bar);
             lock_threads = stay ? n : 0;
         }
         if (st == FJ_ST_IDLE) break;

@@ -154,6 +154,7 @@ struct FjParams {
     unsigned char *lp_own;      // one LP scratch slab (lp_stride bytes) per env warp of the launch for the overflow path, or null
     int lp_own_slots;           // env warps that have one
     int lp_overflow;            // queue depth from which an env warp solves its LP itself (0: never)
+    int lock_groups;            // lockstep groups of an env CTA: 1, 2 (warps by pairs of SM sub-partitions) or 4 (one per sub-partition)
     int srv_join;               // an env CTA whose envs have all finished the launch serves LPs until the launch ends
     double *cta_x;              // [env CTAs][env_warps][NPx] LP solutions, one buffer per env warp
     int lock_mask;              // the lockstep group of an env CTA meets at a barrier every lock_mask + 1 steps (power of two - 1)

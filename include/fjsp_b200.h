@@ -71,8 +71,11 @@ int fjsp_vec_step(fjsp_vec *v, void *stream, int T, const int32_t *d_actions, co
                   int reward_policy, double completion, double tardiness, double energy, int autoreset,
                   double *d_state64, float *d_state32, double *d_reward, int32_t *d_done, int32_t *d_rec);
 
-/* Same with HOST buffers: copies actions/draws in, runs the launch, copies the requested
- * outputs back and synchronises.  This is the call a Python/ctypes agent loop makes. */
+/* Same with HOST buffers: copies actions/draws in, runs the launch, delivers the requested
+ * outputs and synchronises.  This is the call a Python/ctypes agent loop makes.  Page-locked
+ * (mapped) output buffers are stored by the kernel itself while it runs; other buffers are
+ * copied out of device staging in chunks of steps while the kernel plays the following ones
+ * (T >= 16), or after the launch. */
 int fjsp_vec_step_host(fjsp_vec *v, int T, const int32_t *h_actions, const uint32_t *h_rnd,
                        int reward_policy, double completion, double tardiness, double energy, int autoreset,
                        double *h_state64, float *h_state32, double *h_reward, int32_t *h_done, int32_t *h_rec);
