@@ -96,7 +96,8 @@ def bind_to_gpu_numa_node(torch, local_rank):
     allocates afterwards (first touch) and the link traffic stay on that node.  Only narrows the CPU set the
     process already has; does nothing (and says why) when the box exposes no such topology."""
     try:
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id      # torch >= 2.x: "0000:1B:00.0"
+        pr = torch.cuda.get_device_properties(local_rank)                 # torch: three integers
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
     except Exception:
         try:
             import pynvml
@@ -107,8 +108,10 @@ def bind_to_gpu_numa_node(torch, local_rank):
             return {"bound": False, "why": "no PCI bus id (%s)" % type(e).__name__}
     try:
         bus = bus.lower()
-        if len(bus.split(":")[0]) == 8:
+        if len(bus.split(":")[0]) == 8:                                    # NVML: 8-digit domain
             bus = bus[4:]
+        if not os.path.exists("/sys/bus/pci/devices/%s/numa_node" % bus):
+            return {"bound": False, "why": "no /sys/bus/pci/devices/%s/numa_node" % bus}
         node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
         if node < 0:
             return {"bound": False, "why": "numa_node = -1 (single node)", "pci": bus}
