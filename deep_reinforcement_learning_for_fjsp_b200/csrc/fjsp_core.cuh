@@ -2492,14 +2492,22 @@ FJ_FN_NOINLINE void fj_lp_server_loop(int gid, int gw, unsigned char *gsmem, int
     volatile unsigned *finished = (volatile unsigned *)P.pend_count + FJ_ROUNDS + 1;   // env CTAs done in this launch (zeroed per launch)
     for (;;) {
         if (g.rank() == 0) {
+            // the leader alone polls (the group's other threads wait at the barrier below: an idle group executes
+            // no instructions but its leader's; with the whole group going round the loop per poll the idle servers
+            // were 20 % of the launch's warp instructions)
             int got = -1;
-            const unsigned h = q[0], t = q[1];
-            if ((int)(t - h) > 0) { if (atomicCAS(P.lpq, h, h + 1u) == h) got = (int)(h & 0x3fffffffu); }
-            else if (*finished >= (unsigned)env_ctas) {
-                // every env CTA has finished (all their requests were answered before): leave unless a ticket slipped in between
-                const unsigned h2 = q[0], t2 = q[1];
-                if (h2 == t2) got = -2;
-            } else __nanosleep(200);
+            unsigned h = 0;
+            for (;;) {
+                h = q[0];
+                const unsigned t = q[1];
+                if ((int)(t - h) > 0) {
+                    if (atomicCAS(P.lpq, h, h + 1u) == h) { got = (int)(h & 0x3fffffffu); break; }
+                } else if (*finished >= (unsigned)env_ctas) {
+                    // every env CTA has finished (all their requests were answered before): leave unless a ticket slipped in between
+                    const unsigned h2 = q[0], t2 = q[1];
+                    if (h2 == t2) { got = -2; break; }
+                } else __nanosleep(200);
+            }
             S.ctl()[2] = got;
             if (got >= 0) {
                 // wait for the entry of ticket h (its poster writes it right after taking the ticket)

@@ -26,9 +26,11 @@ def main():
     def make_vec(blobs, env_instance, variant, sum_mode=1):
         return FJSPVecEnv(None, env_instance, variant, blobs=blobs, sum_mode=sum_mode)
     knobs = [{}, {"FJSP_LP_OVERFLOW": "1"}, {"FJSP_LP_SERVERS": "1", "FJSP_LP_GROUPS": "1"}, {"FJSP_NO_CTA_LP": "1"},
-             {"FJSP_NO_STAGE": "1"}, {"FJSP_LP_OVERFLOW": "3", "FJSP_LP_SERVERS": "2"}, {"FJSP_LOCKSTEP_K": "4"}]
+             {"FJSP_NO_STAGE": "1"}, {"FJSP_LP_OVERFLOW": "3", "FJSP_LP_SERVERS": "2"}, {"FJSP_LOCKSTEP_K": "4"},
+             {"FJSP_SRV_JOIN": "1", "FJSP_LP_SERVERS": "2"}, {"FJSP_LOCK_GROUPS": "2"}, {"FJSP_LOCK_GROUPS": "4", "FJSP_SRV_JOIN": "1"},
+             {"FJSP_PROGRESSIVE": "0"}]
     variants = [("SO_DFJSP", False), ("MO_DFJSP", False), ("MO_DFJSP_breakdown", True), ("SO_FJSSP", False)]
-    t0, n, seed = time.time(), 0, 1000
+    t0, n, seed, skipped = time.time(), 0, 1000, 0
     rng = np.random.default_rng(7)
     while time.time() - t0 < a.minutes * 60:
         kn = knobs[n % len(knobs)]
@@ -45,11 +47,19 @@ def main():
         try:
             pc.compare_with_oracle(make_vec, variant, seed, n_inst=n_inst, copies=copies, T=T, launches=launches,
                                    reward_policy=int(rng.integers(0, 4)), breakdowns=bd)
+        except AssertionError as e:
+            if not str(e).startswith("oracle error flags"):
+                print("FAIL", dict(variant=variant, seed=seed, n_inst=n_inst, copies=copies, T=T, launches=launches, knobs=kn), repr(e)[:300])
+                raise
+            # the reference itself raises on this input (a rule finds nothing to dispatch after the reset() of a used
+            # object: DESIGN.md section 1); tests/parity_common.py:check_reset_of_used_env compares those flags
+            skipped += 1
+            print("skipped (the reference raises here):", dict(variant=variant, seed=seed, n_inst=n_inst, copies=copies, T=T, launches=launches), str(e))
         except Exception as e:
             print("FAIL", dict(variant=variant, seed=seed, n_inst=n_inst, copies=copies, T=T, launches=launches, knobs=kn), repr(e)[:300])
             raise
         n += 1
-    print("fuzz ok: %d random batches in %.0f s (all four classes, %d knob sets)" % (n, time.time() - t0, len(knobs)))
+    print("fuzz ok: %d random batches in %.0f s (all four classes, %d knob sets; %d skipped because the reference raises)" % (n, time.time() - t0, len(knobs), skipped))
 
 
 if __name__ == "__main__":
