@@ -102,8 +102,11 @@ class OracleEnv:
         return a
 
 
-def batch_rollout(envs, actions, rnd, reward_policy=1, want_state=True, want_rec=True, threads=0):
-    """actions, rnd: [T, B, 2].  Returns dict of [T, B, ...] arrays.  Auto-resets finished envs."""
+def batch_rollout(envs, actions, rnd, reward_policy=1, want_state=True, want_rec=True, threads=0, allow_errors=False):
+    """actions, rnd: [T, B, 2].  Returns dict of [T, B, ...] arrays.  Auto-resets finished envs.
+    allow_errors: do not raise when an environment raised its error flag (the reference would raise an
+    exception there); the caller reads the flags with info() -- that environment's outputs are undefined from
+    the failing step on."""
     T, B = actions.shape[:2]
     nstate = envs[0].nstate
     actions = np.ascontiguousarray(actions, np.int32)
@@ -116,5 +119,5 @@ def batch_rollout(envs, actions, rnd, reward_policy=1, want_state=True, want_rec
     rc = lib().fjsp_oracle_batch_rollout(handles, B, T, actions.ctypes.data, rnd.ctypes.data, reward_policy, nstate,
                                          state.ctypes.data if want_state else None, reward.ctypes.data,
                                          done.ctypes.data, rec.ctypes.data if want_rec else None, threads)
-    assert rc == 0, "oracle error flags %d" % rc
-    return dict(state=state, reward=reward, done=done, rec=rec)
+    assert rc == 0 or allow_errors, "oracle error flags %d" % rc
+    return dict(state=state, reward=reward, done=done, rec=rec, error_flags=rc)

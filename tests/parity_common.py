@@ -72,19 +72,25 @@ def compare_with_oracle(make_vec, variant, seed, n_inst=6, copies=3, T=48, launc
     assert_states_close(s0, o0, "reset")
     rng = np.random.default_rng(seed + 77)
     nt, nm = NRULES[variant]
+    ok = np.ones(B, bool)       # environments the reference has not raised on (it raises where a rule finds nothing
+                                # to dispatch -- e.g. right after the reset() of a used object whose machines are still
+                                # flagged busy; both sides flag the error, outputs are undefined from there on)
     for L in range(launches):
         actions = np.stack([rng.integers(0, nt, (T, B)), rng.integers(0, nm, (T, B))], -1).astype(np.int32)
         rnd = rng.integers(0, 2**32, (T, B, 2), dtype=np.uint64).astype(np.uint32)
         st, rw, dn, rec = vec.step_host(actions, rnd, reward_policy, 1.0, 1.0, 1.0, True)
-        ref = oracle_py.batch_rollout(envs, actions, rnd, reward_policy)
-        assert np.array_equal(rec, ref["rec"]), f"launch {L}: schedule records differ"
-        assert np.array_equal(dn, ref["done"]), f"launch {L}: done flags differ"
-        assert np.array_equal(rw, ref["reward"]), f"launch {L}: rewards differ"
-        assert_states_close(st, ref["state"], f"launch {L}")
+        ref = oracle_py.batch_rollout(envs, actions, rnd, reward_policy, allow_errors=True)
+        if ref["error_flags"]:
+            ok &= np.array([e.info()["error"] == 0 for e in envs])
+        assert np.array_equal(rec[:, ok], ref["rec"][:, ok]), f"launch {L}: schedule records differ"
+        assert np.array_equal(dn[:, ok], ref["done"][:, ok]), f"launch {L}: done flags differ"
+        assert np.array_equal(rw[:, ok], ref["reward"][:, ok]), f"launch {L}: rewards differ"
+        assert_states_close(st[:, ok], ref["state"][:, ok], f"launch {L}")
     info = vec.info()
-    assert (info["error"] == 0).all()
     oi = [e.info() for e in envs]
-    assert np.array_equal(info["step_time"], [x["step_time"] for x in oi])
+    assert np.array_equal(info["error"], [x["error"] for x in oi]), "error flags differ from the reference's"
+    assert ok.sum() >= (B + 1) // 2, "the reference raised on most of the batch: not a useful case"
+    assert np.array_equal(info["step_time"][ok], np.array([x["step_time"] for x in oi])[ok])
     assert np.array_equal(info["lp_solves"] >= 1, np.ones(B, bool))
     return vec, envs
 

@@ -89,3 +89,14 @@ def test_left_to_right_sum_mode_vs_oracle():
 @pytest.mark.parametrize("variant", ["SO_DFJSP", "MO_DFJSP"])
 def test_reset_of_a_used_environment(variant):
     pc.check_reset_of_used_env(make_vec, variant)
+
+
+def test_input_the_reference_raises_on():
+    """Two copies of this batch restart an episode with a machine still flagged busy (reset() of a used object,
+    DESIGN.md section 1) and the first rule finds nothing to dispatch: the reference raises there.  Both sides
+    must flag exactly those copies (error 2 at step 0 of the new episode) and agree on every other copy."""
+    vec, envs = pc.compare_with_oracle(make_vec, "MO_DFJSP_breakdown", 1908, n_inst=7, copies=80, T=32, launches=4,
+                                       reward_policy=2, breakdowns=True)
+    info = vec.info()
+    bad = np.nonzero(info["error"])[0]
+    assert len(bad) == 2 and (info["error"][bad] == 2).all() and (info["step_count"][bad] == 0).all()
