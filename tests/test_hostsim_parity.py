@@ -100,3 +100,22 @@ def test_input_the_reference_raises_on():
     info = vec.info()
     bad = np.nonzero(info["error"])[0]
     assert len(bad) == 2 and (info["error"][bad] == 2).all() and (info["step_count"][bad] == 0).all()
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_random_shapes_vs_oracle(chunk):
+    """The first draws of tools/fuzz_parity.py (which runs them on the GPU): batch shapes from one copy to a few
+    hundred, rollouts of 1 / 7 / 32 / 64 steps, all four environment classes, every reward policy."""
+    variants = [("SO_DFJSP", False), ("MO_DFJSP", False), ("MO_DFJSP_breakdown", True), ("SO_FJSSP", False)]
+    rng = np.random.default_rng(7)
+    for n in range(32):
+        n_inst, copies = int(rng.integers(1, 9)), int(rng.choice([1, 3, 17, 80]))
+        T, launches = int(rng.choice([1, 7, 32, 64])), int(rng.integers(2, 5))
+        if T == 1:
+            launches = 40
+        rp = int(rng.integers(0, 4))
+        if n % 4 != chunk or copies == 80:
+            continue
+        variant, bd = variants[(n // 3) % 4]
+        pc.compare_with_oracle(make_vec, variant, 1001 + n, n_inst=n_inst, copies=copies, T=T, launches=launches,
+                               reward_policy=rp, breakdowns=bd)
