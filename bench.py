@@ -216,28 +216,38 @@ def oracle_mod():
     return oracle_py
 
 
-def cpu_port_throughput(blobs, variant, seconds, T, seed):
-    """The oracle (C port of the reference env) on the host cores, a bounded sample of the
-    same workload: two environments per thread, `T`-step chunks until the budget."""
+def cpu_port_throughput(blobs, env_inst, variant, seconds, T, seed, burnin):
+    """The oracle (C port of the reference env) on the host cores, a bounded sample of the same workload: 64
+    environment copies per host thread (enough work per thread that starting the threads does not show), a
+    burn-in of up to a third of the budget so that the sample sits in the steady mix of episode phases like the
+    GPU arm's timed region, then `T`-step rollouts with the same action distribution until the budget."""
     oracle_py = oracle_mod()
     threads = oracle_py.lib().fjsp_oracle_max_threads()
-    B = max(threads * 2, 8)
-    Tc = max(T, 32)
-    envs = [oracle_py.OracleEnv(blobs[i % len(blobs)], variant) for i in range(B)]
+    B = min(len(env_inst), max(threads * 64, 64))
+    pick = np.unique(np.linspace(0, len(env_inst) - 1, B).astype(np.int64))
+    B = len(pick)
+    Tc = max(T, 32, 65536 // B)      # steps per call: the per-call host work (threads, Python) must not show either
+    envs = [oracle_py.OracleEnv(blobs[env_inst[i]], variant) for i in pick]
     for e in envs:
         e.reset()
     rng = np.random.default_rng(seed)
-    a, r = make_actions(rng, Tc, B, variant)
-    oracle_py.batch_rollout(envs, a, r, 1, want_state=True, want_rec=False, threads=threads)  # warm-up
-    steps, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
+
+    def one():
         a, r = make_actions(rng, Tc, B, variant)
         oracle_py.batch_rollout(envs, a, r, 1, want_state=True, want_rec=False, threads=threads)
+    burned, t0 = 0, time.perf_counter()
+    while burned < burnin and time.perf_counter() - t0 < seconds / 3.0:
+        one()
+        burned += Tc
+    steps, t0 = 0, time.perf_counter()
+    while steps == 0 or time.perf_counter() - t0 < seconds * 2.0 / 3.0:
+        one()
         steps += Tc * B
     dt = time.perf_counter() - t0
-    return {"value": steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{B} envs x {steps // B} steps of the same workload in {dt:.1f}s on {threads} host threads "
-                      f"(oracle/fjsp_oracle.c, the C port pinned bit-exact to the Python reference)"}
+    used = min(threads, B)
+    return {"value": steps / dt, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": f"{B} of the batch's environment copies x {steps // B} steps of the same workload in {dt:.1f}s on {used} host "
+                      f"threads after {burned} burn-in steps per copy (oracle/fjsp_oracle.c, the C port pinned bit-exact to the Python reference)"}
 
 
 def run_reference(args, cfg, rank):
@@ -723,7 +733,7 @@ def main():
         if not args.no_cpu_baseline:
             if host_numa.get("bound"):
                 os.sched_setaffinity(0, prev_affinity)             # the CPU baseline gets every core the process had
-            line["cpu_baseline"] = cpu_port_throughput(blobs[:64], variant, args.cpu_seconds, T, args.seed)
+            line["cpu_baseline"] = cpu_port_throughput(blobs, env_inst, variant, args.cpu_seconds, T, args.seed, cfg["burnin"])
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
