@@ -232,8 +232,12 @@ def cpu_port_throughput(blobs, env_inst, variant, seconds, T, seed, burnin):
         e.reset()
     rng = np.random.default_rng(seed)
 
+    pool = [make_actions(rng, Tc, B, variant) for _ in range(4)]      # generated outside the timed region
+    count = [0]
+
     def one():
-        a, r = make_actions(rng, Tc, B, variant)
+        a, r = pool[count[0] % len(pool)]
+        count[0] += 1
         oracle_py.batch_rollout(envs, a, r, 1, want_state=True, want_rec=False, threads=threads)
     burned, t0 = 0, time.perf_counter()
     while burned < burnin and time.perf_counter() - t0 < seconds / 3.0:
@@ -257,18 +261,22 @@ def run_reference(args, cfg, rank):
     if rank != 0:
         return
     oracle_py = oracle_mod()
-    threads = oracle_py.lib().fjsp_oracle_max_threads()
     variant, T, lps = cfg["variant"], cfg["T"], cfg["launches_per_step"]
     blobs, env_inst = config_blobs(cfg, args.seed, 0)
     B = min(cfg["envs"], 4096)
+    threads = min(oracle_py.lib().fjsp_oracle_max_threads(), B)     # a thread per environment copy at most
     envs = [oracle_py.OracleEnv(blobs[env_inst[i]], variant) for i in range(B)]
     for e in envs:
         e.reset()
     rng = np.random.default_rng(args.seed)
     Tc = T * lps
 
+    pool = [make_actions(rng, Tc, B, variant) for _ in range(8)]      # generated outside the timed region, like the GPU arm's
+    count = [0]
+
     def one():
-        a, r = make_actions(rng, Tc, B, variant)
+        a, r = pool[count[0] % len(pool)]
+        count[0] += 1
         oracle_py.batch_rollout(envs, a, r, 1, want_rec=False, threads=threads)
     # untimed burn-in so the sample sits in the same mix of episode phases as the GPU arm's timed region
     burn = min(cfg["burnin"], 1024)

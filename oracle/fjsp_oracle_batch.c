@@ -61,6 +61,11 @@ int fjsp_oracle_batch_rollout(void **envs, int B, int T, const int *actions, con
     Job jobs[256];
     pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
     int next = 0, err = 0;
+    if (threads == 1) {   /* one environment (or one core): no thread to start */
+        Job j = { envs, B, T, actions, rnd, reward_policy, nstate, state, reward, done, rec, &next, &mu, 0 };
+        worker(&j);
+        return j.err;
+    }
     for (int i = 0; i < threads; ++i) {
         Job j = { envs, B, T, actions, rnd, reward_policy, nstate, state, reward, done, rec, &next, &mu, 0 };
         jobs[i] = j;
