@@ -92,7 +92,12 @@ def run_reference(variant, inst, actions, rnd, reward_policy, episodes=1, max_st
     return {k: np.array(v) for k, v in out.items()}, t
 
 
+ONLY = set(sys.argv[1:])      # python oracle/make_golden.py [case ...]: only these cases (default: all)
+
+
 def make_case(name, variant, inst, seed, episodes=1, max_steps=None, reward_policy=1, fixed_action=None):
+    if ONLY and name not in ONLY:
+        return None
     # the reference reads DDT back through its integer regex (0.5 -> 0, 1.5 -> 1); keep
     # the blob consistent with what the reference saw
     inst.ddt = float(int(inst.ddt))
@@ -137,6 +142,15 @@ def main():
               FJSPInstance.from_csv(os.path.join(ref_data, "benchmark", "Brandimarte_Data"), "Mk01", "SO"), 22)
     make_case("mo_dfjsp_HMPSAC_DDT1.0_M10_S3", "MO_DFJSP",
               FJSPInstance.from_csv(os.path.join(ref_data, "HMPSAC"), "DDT1.0_M10_S3", "MO"), 23, max_steps=250)
+    # full-size instances of the bench workloads (Instance_generate.py distributions, scale = 1): the first steps of an
+    # episode, which hold its order arrivals (fluid LPs of 50-110 rows; ~300 rows for 20 machines / 5 orders)
+    make_case("mo_dfjsp_bench_scale", "MO_DFJSP", G(7000, 0.5, 10, 3, "DA3C"), 24, max_steps=500, reward_policy=1)
+    make_case("mo_breakdown_bench_scale", "MO_DFJSP_breakdown", G(7001, 1.0, 10, 3, "DA3C", breakdowns=True), 25,
+              max_steps=400, reward_policy=2)
+    make_case("mo_dfjsp_m20_s5", "MO_DFJSP", G(8000, 1.0, 20, 5, "HMPSAC"), 26, max_steps=300, reward_policy=1)
+    make_case("so_fjssp_small_b", "SO_FJSSP", G(11, 0.5, 8, 3, "DA3C", scale=0.12), 27, episodes=2)
+    make_case("so_dfjsp_Mk03", "SO_DFJSP",
+              FJSPInstance.from_csv(os.path.join(ref_data, "benchmark", "Brandimarte_Data"), "Mk03", "SO"), 28, max_steps=200)
 
 
 def brandimarte_blobs():
@@ -149,4 +163,5 @@ def brandimarte_blobs():
 
 if __name__ == "__main__":
     main()
-    brandimarte_blobs()
+    if not ONLY:
+        brandimarte_blobs()
