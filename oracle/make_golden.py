@@ -147,6 +147,7 @@ def main():
     make_case("mo_dfjsp_bench_scale", "MO_DFJSP", G(7000, 0.5, 10, 3, "DA3C"), 24, max_steps=500, reward_policy=1)
     make_case("mo_breakdown_bench_scale", "MO_DFJSP_breakdown", G(7001, 1.0, 10, 3, "DA3C", breakdowns=True), 25,
               max_steps=400, reward_policy=2)
+    make_case("mo_dfjsp_bench_scale_two_episodes", "MO_DFJSP", G(7002, 1.5, 10, 3, "DA3C"), 29, episodes=2, reward_policy=1)
     make_case("mo_dfjsp_m20_s5", "MO_DFJSP", G(8000, 1.0, 20, 5, "HMPSAC"), 26, max_steps=300, reward_policy=1)
     make_case("so_fjssp_small_b", "SO_FJSSP", G(11, 0.5, 8, 3, "DA3C", scale=0.12), 27, episodes=2)
     make_case("so_dfjsp_Mk03", "SO_DFJSP",
