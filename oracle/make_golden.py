@@ -2,7 +2,7 @@
 reference environments (imported from /root/reference through oracle/refshim).
 
 Run in the build container (the reference does not exist on the GPU box):
-    python oracle/make_golden.py
+    python oracle/make_golden.py [case ...]      (no names: every case)
 Each fixture holds the instance blob, the action / random-word sequences and what the
 reference returned: states, rewards, dones, and per step the dispatched operation
 (kind, stage, job number), its machine and its begin / end times.  The reference's
